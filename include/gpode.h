@@ -1,0 +1,129 @@
+/*
+ * gpode.h -- C ABI of libgpode.so: the sparse-GP latent vector field of VAE-GP-ODE and its
+ * fixed-step rollout, forward and backward, as hand-written CUDA for sm_100a (NVIDIA B200).
+ *
+ * The reference (IlzeAmandaA/VAE-GP-ODE) has no FFI: the path sits behind Python nn.Modules.  Each
+ * entry point names the reference interface it replaces (paths relative to
+ * experiments/model/ in the reference tree).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - all tensors are fp32, row-major, contiguous DEVICE pointers owned by the caller; the library
+ *     never allocates, frees or retains a pointer after the call returns;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream); no host synchronisation, no global mutable state, re-entrant;
+ *   - return value: 0 ok; <0 argument/shape error (GPODE_E_*), never a silent fallback;
+ *     >0 a cudaError_t raised by a launch.  No C++ exception crosses the ABI.
+ */
+#ifndef GPODE_H_
+#define GPODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPODE_VERSION 100 /* major*100 + minor */
+
+/* kernel variants (core/kernels.py: RBF dimwise=False / dimwise=True :29-195, DivergenceFreeKernel :201-393) */
+enum { GPODE_RBF_SHARED = 0, GPODE_RBF_DIMWISE = 1, GPODE_DF = 2 };
+/* torchdiffeq fixed-grid methods reachable through Flow(solver=...) (core/flow.py:49,78-85) */
+enum { GPODE_EULER = 0, GPODE_MIDPOINT = 1, GPODE_RK4 = 2 /* 3/8 rule */ };
+
+enum {
+  GPODE_OK = 0,
+  GPODE_E_NULL = -1,        /* a required pointer is NULL */
+  GPODE_E_SHAPE = -2,       /* a size is non-positive or inconsistent (e.g. DF with D_in != D_out) */
+  GPODE_E_UNSUPPORTED = -3, /* shape outside the compiled range (D_in > 16, DF D > 8, parameter tile > 227 KB ...) */
+  GPODE_E_WORKSPACE = -4,   /* workspace / save buffer too small or misaligned */
+  GPODE_E_ENUM = -5         /* unknown variant / method / order */
+};
+
+/*
+ * One function sample of the GP per MC sample l = 0..L-1 -- what SVGP_Layer.build_cache() leaves
+ * behind (core/svpy.py:103-121): Z, lengthscales and variance are shared by all samples, the
+ * random-feature draws and nu are per sample.  Layouts are the reference's own, with a leading L.
+ *
+ *   variant            ell            var        eps / omega         phase           w               nu
+ *   RBF_SHARED         (D_in)         (1)        (L,D_in,S)          (L,1,S)         (L,S,D_out)     (L,M,D_out)
+ *   RBF_DIMWISE        (D_out,D_in)   (D_out)    (L,D_in,S,D_out)    (L,1,S,D_out)   (L,S,D_out)     (L,D_out,M,1)
+ *   DF (D_in==D_out=D) (D,D)          (D)        (L,D,S,D)           (L,1,S,D)       (L,2S,D)        (L,M*D,1)
+ *
+ * `eps` are the standard-normal frequency draws; the kernels use omega = eps / ell exactly like
+ * RBF.sample_freq (core/kernels.py:112-124), which is what carries the lengthscale gradient through
+ * the random features.  `B` (DF only) is the state-independent operator B(omega) (L,S,D,D) of
+ * DivergenceFreeKernel.rff_forward (core/kernels.py:327-336), hoisted to once per rollout.
+ */
+typedef struct GpodeProblem {
+  int32_t variant;
+  int32_t L;      /* MC samples (independent function samples) */
+  int32_t N;      /* states (trajectories) per sample */
+  int32_t D_in;   /* GP input dim = ODE state dim (order 1: q, order 2: 2q) */
+  int32_t D_out;  /* GP output dim */
+  int32_t M;      /* inducing points */
+  int32_t S;      /* random Fourier features */
+  int32_t reserved;
+  const float* Z;     /* (M,D_in) */
+  const float* ell;
+  const float* var;
+  const float* eps;
+  const float* phase;
+  const float* w;
+  const float* nu;
+  const float* B;     /* DF only, else NULL */
+} GpodeProblem;
+
+/* Gradients w.r.t. the GpodeProblem tensors (same layouts).  Written (not accumulated).  Any pointer
+ * may be NULL to skip that output.  No gradient exists for eps / phase / w: they are plain draws
+ * in the reference (requires_grad=False).  d_ell holds the DIRECT dependence only (through K(x,Z)
+ * and through omega = eps/ell); the dependence through nu and B is carried by d_nu / d_B. */
+typedef struct GpodeParamGrads {
+  float* d_Z;    /* (M,D_in), summed over samples */
+  float* d_ell;  /* like ell, summed over samples */
+  float* d_var;  /* like var, summed over samples */
+  float* d_nu;   /* like nu (per sample) */
+  float* d_B;    /* DF only: like B (per sample) */
+} GpodeParamGrads;
+
+int gpode_version(void);
+const char* gpode_error_string(int code);
+
+/* bytes of scratch the calls below need for this problem (T, method only matter for the rollout).
+ * `workspace` must be 256-byte aligned and is clobbered by every call. */
+size_t gpode_workspace_bytes(const GpodeProblem* p, int T, int method);
+/* floats of the forward->backward save buffer of a rollout (stage inputs, stage derivatives, prior part) */
+size_t gpode_rollout_save_floats(const GpodeProblem* p, int T, int method);
+
+/* SVGP_Layer.forward (core/svpy.py:123-142) = kern.rff_forward + kern.f_update
+ * (core/kernels.py:140-153,174-181 / 319-351,390-393) for every state of every sample.
+ *   x (L,N,D_in) -> f (L,N,D_out); f_prior (L,N,D_out) receives the rff part (needed by the backward; may be NULL). */
+int gpode_field_fwd(const GpodeProblem* p, const float* x, float* f, float* f_prior,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* autograd backward of SVGP_Layer.forward (implicit in the reference: loss.backward(), main.py:210).
+ *   g = dL/df (L,N,D_out), f / f_prior as returned by gpode_field_fwd -> dx (L,N,D_in) and the parameter gradients. */
+int gpode_field_bwd(const GpodeProblem* p, const float* x, const float* g, const float* f,
+                    const float* f_prior, float* dx, const GpodeParamGrads* grads,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Flow.forward = torchdiffeq.odeint(ODEfunc, z0, ts, method) on the fixed grid ts, for all L samples
+ * in one launch (core/flow.py:30-45,68-86; core/odegpvae.py:37-45).
+ *   z0 (N,D_in) if z0_per_sample == 0 (the reference feeds every sample the same z0), else (L,N,D_in);
+ *   ts (T) fp32 on the device; order 1: dz = f(z); order 2: dz = [z[q:], f(z)] with q = D_out, D_in = 2q;
+ *   traj (L,N,T,D_in) row-major, traj[:,:,0] = z0.
+ *   save: gpode_rollout_save_floats() floats if a backward will follow, else NULL. */
+int gpode_rollout_fwd(const GpodeProblem* p, const float* z0, int z0_per_sample, const float* ts, int T,
+                      int method, int order, float* traj, float* save,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* reverse-mode sweep through the unrolled solver (what autograd does for use_adjoint=False, core/flow.py:76):
+ *   dtraj = dL/dtraj (L,N,T,D_in) -> dz0 (L,N,D_in) (per sample; sum over L if z0 was shared) and parameter gradients. */
+int gpode_rollout_bwd(const GpodeProblem* p, const float* ts, int T, int method, int order,
+                      const float* traj, const float* save, const float* dtraj, float* dz0,
+                      const GpodeParamGrads* grads, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPODE_H_ */

@@ -1,0 +1,122 @@
+"""CPU: the C-ABI library loads and exports every symbol include/gpode.h declares; host-side logic of
+the drop-in modules (state_dict keys, draw order, transforms, errors) -- no compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, rel, t
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gpode_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "gpode.h")).read()
+    declared = sorted(set(re.findall(r"\b(gpode_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.EXPORTS) == declared
+    L = _lib.load()
+    assert L.gpode_version() == 100
+    assert b"NULL" in L.gpode_error_string(-1)
+    # argument checking happens before any CUDA call: NULL problem -> 0 bytes / error code
+    assert L.gpode_workspace_bytes(None, 16, 2) == 0
+    p = _lib.GpodeProblem()
+    assert L.gpode_field_fwd(ctypes.byref(p), None, None, None, None, 0, None) < 0
+
+
+def test_state_dict_keys_match_reference():
+    from gpode_b200.core.flow import Flow
+    from gpode_b200.core.svpy import SVGP_Layer
+    for kernel, d_out, order in (("RBF", 6, 1), ("DF", 6, 1), ("RBF", 3, 2)):
+        gp = SVGP_Layer(D_in=6, D_out=d_out, M=10, S=8, dimwise=True, device="cpu", kernel=kernel)
+        sd = Flow(gp, order=order, solver="euler").state_dict()
+        assert list(sd.keys()) == ["odefunc._num_evals", "odefunc.diffeq.kern.unconstrained_lengthscales",
+                                   "odefunc.diffeq.kern.unconstrained_variance", "odefunc.diffeq.inducing_loc.optvar",
+                                   "odefunc.diffeq.Um.optvar", "odefunc.diffeq.Us_sqrt.optvar"]
+        assert sd["odefunc.diffeq.Us_sqrt.optvar"].shape == (d_out, 55)
+        assert sd["odefunc.diffeq.kern.unconstrained_lengthscales"].shape == (d_out, 6)
+    gp = SVGP_Layer(D_in=6, D_out=6, M=10, S=8, dimwise=False, device="cpu", kernel="RBF")
+    assert gp.kern.unconstrained_lengthscales.shape == (6,) and gp.kern.unconstrained_variance.shape == (1,)
+    assert abs(gp.kern.lengthscales[0].item() - 0.2) < 1e-6 and abs(gp.kern.variance[0].item() - 0.1) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["rbf_dimwise_o1", "rbf_shared_o1", "df_d4"])
+def test_build_cache_setup_matches_reference(name, monkeypatch):
+    """per-rollout setup (torch ops) on CPU: same draw order, nu and kl agree with the reference."""
+    from gpode_b200.core import kernels as K
+    from gpode_b200.core import svpy as SV
+    from oracle import field as OF
+    from helpers import oracle_cache
+    g = load_golden(name)
+    m = g["meta"]
+    gp = SV.SVGP_Layer(D_in=m["D_in"], D_out=m["D_out"], M=m["M"], S=m["S"], dimwise=m["dimwise"], device="cpu", kernel=m["kernel"])
+    with torch.no_grad():
+        gp.kern.unconstrained_lengthscales.copy_(t(g["p_raw_ell"]))
+        gp.kern.unconstrained_variance.copy_(t(g["p_raw_var"]))
+        gp.inducing_loc.optvar.copy_(t(g["p_Z"]))
+        gp.Um.optvar.copy_(t(g["p_Um"]))
+        gp.Us_sqrt.optvar.copy_(t(g["p_Us_sqrt"]))
+    q = [g["draw_w"], g["draw_eps"], g["draw_phase01"], g["draw_eps_u"]]
+    calls = []
+
+    def feed(shape, seed=None):
+        v = q[len(calls)]
+        calls.append(tuple(shape))
+        assert tuple(v.shape) == tuple(shape)
+        return torch.tensor(v)
+
+    monkeypatch.setattr(K, "sample_normal", feed)
+    monkeypatch.setattr(K, "sample_uniform", feed)
+    monkeypatch.setattr(SV, "sample_normal", feed)
+    gp.build_cache()
+    assert len(calls) == 4
+    assert abs(gp.kl().item() - float(g["kl"])) < 1e-5 * abs(float(g["kl"]))
+    # compare nu through the pathwise update it feeds (nu itself is ill-conditioned)
+    c_ref = oracle_cache(g, torch.float64, shared_nu=True)
+    c_new = dict(c_ref)
+    c_new["nu"] = gp.kern.nu.detach().double()
+    x = t(g["x"], torch.float64)
+    assert rel(OF.update(x, c_new), OF.update(x, c_ref)) < 1e-3
+    assert rel(gp.kern.rff_omega, c_ref["omega"]) < 1e-6
+    s = gp.field_sample()
+    assert s.eps.shape[0] == 1 and s.nu.shape[0] == 1
+
+
+def test_transforms_roundtrip():
+    from gpode_b200.misc import transforms
+    from gpode_b200.misc.constraint_utils import invsoftplus, softplus
+    lt = transforms.LowerTriangular(5, 3)
+    packed = np.random.RandomState(0).normal(size=(3, 15)).astype(np.float32)
+    full = lt.forward(packed)
+    assert full.shape == (3, 5, 5) and np.allclose(np.triu(full[1], 1), 0)
+    assert np.array_equal(lt.backward(full), packed)
+    ft = lt.forward_tensor(torch.tensor(packed))
+    assert np.array_equal(ft.numpy(), full)
+    assert torch.equal(lt.backward_tensor(ft), torch.tensor(packed))
+    # row-major tril order, like np.tril_indices
+    assert full[0, 1, 0] == packed[0, 1] and full[0, 1, 1] == packed[0, 2]
+    v = torch.tensor([0.2, 2.0, 1e-3])
+    assert torch.allclose(softplus(invsoftplus(v)), v, rtol=1e-5)
+    sp = transforms.SoftPlus()
+    assert np.allclose(sp.forward(sp.backward(np.array([0.5, 3.0]))), [0.5, 3.0])
+
+
+def test_no_cpu_path():
+    """the product path has no CPU fallback: a CPU tensor raises instead of silently computing."""
+    from gpode_b200.core.svpy import SVGP_Layer
+    gp = SVGP_Layer(D_in=6, D_out=6, M=10, S=8, device="cpu")
+    gp.build_cache()
+    with pytest.raises(RuntimeError):
+        gp(torch.zeros(4, 6))
+    from gpode_b200.core.flow import Flow
+    with pytest.raises(NotImplementedError):
+        Flow(gp, order=1, solver="dopri5")(torch.zeros(4, 6), torch.arange(3.0))
+    with pytest.raises(NotImplementedError):
+        Flow(gp, order=1, solver="rk4", use_adjoint=True)(torch.zeros(4, 6), torch.arange(3.0))

@@ -1,0 +1,100 @@
+"""GPU: the drop-in modules (SVGP_Layer / Flow with the reference's constructor signatures and
+state_dict keys) end to end against the golden vectors of the live reference: own nu (cuSOLVER Cholesky
+on the GPU instead of LAPACK), leaf gradients through build_cache."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ALL_CASES, RBF_CASES, load_golden, rel, t
+
+pytestmark = pytest.mark.gpu
+
+
+class Draws:
+    """Feeds the golden draws to the drop-in's host RNG helpers in the reference's draw order."""
+
+    def __init__(self, g):
+        self.q = [g["draw_w"], g["draw_eps"], g["draw_phase01"], g["draw_eps_u"]]
+        self.i = 0
+
+    def __call__(self, shape, seed=None):
+        v = self.q[self.i % 4]
+        self.i += 1
+        assert tuple(v.shape) == tuple(shape), (v.shape, shape)
+        return torch.tensor(v)
+
+
+def build_flow(g, method, monkeypatch):
+    from gpode_b200.core import kernels as K
+    from gpode_b200.core import svpy as SV
+    from gpode_b200.core.flow import Flow
+    m = g["meta"]
+    np.random.seed(0)
+    gp = SV.SVGP_Layer(D_in=m["D_in"], D_out=m["D_out"], M=m["M"], S=m["S"], q_diag=False, dimwise=m["dimwise"], device="cuda",
+                       kernel=m["kernel"])
+    flow = Flow(diffeq=gp, order=m["order"], solver=method, use_adjoint=False)
+    sd = {"odefunc._num_evals": torch.tensor(0.),
+          "odefunc.diffeq.kern.unconstrained_lengthscales": t(g["p_raw_ell"]),
+          "odefunc.diffeq.kern.unconstrained_variance": t(g["p_raw_var"]),
+          "odefunc.diffeq.inducing_loc.optvar": t(g["p_Z"]),
+          "odefunc.diffeq.Um.optvar": t(g["p_Um"]),
+          "odefunc.diffeq.Us_sqrt.optvar": t(g["p_Us_sqrt"])}
+    flow.load_state_dict(sd, strict=True)   # the reference's checkpoint keys, verbatim
+    d = Draws(g)
+    monkeypatch.setattr(K, "sample_normal", d)
+    monkeypatch.setattr(K, "sample_uniform", d)
+    monkeypatch.setattr(SV, "sample_normal", d)
+    return flow, gp
+
+
+@pytest.mark.parametrize("name", RBF_CASES)
+@pytest.mark.parametrize("method", ["euler", "rk4"])
+def test_flow_end_to_end(name, method, monkeypatch):
+    g = load_golden(name)
+    m = g["meta"]
+    flow, gp = build_flow(g, method, monkeypatch)
+    z0 = t(g["z0"], device="cuda").requires_grad_(True)
+    ts = t(g["ts"], device="cuda")
+    traj = flow(z0, ts)
+    assert traj.shape == (m["N"], m["T"], m["D_in"])
+    assert flow.num_evals() == float(g["nevals_" + method])
+    e = rel(traj, g["traj_" + method])
+    print("%s %s traj (own nu): %.2e" % (name, method, e))
+    assert e < 1e-4
+    kl = flow.kl()
+    assert abs(kl.item() - float(g["kl"])) < 1e-5 * abs(float(g["kl"]))
+    loss = (traj * t(g["G"], device="cuda")).sum() + kl
+    loss.backward()
+    got = {"z0": z0.grad, "raw_ell": gp.kern.unconstrained_lengthscales.grad, "raw_var": gp.kern.unconstrained_variance.grad,
+           "Z": gp.inducing_loc.optvar.grad, "Um": gp.Um.optvar.grad, "Us_sqrt": gp.Us_sqrt.optvar.grad}
+    for k, v in got.items():
+        e = rel(v, g["roll_%s_d%s" % (method, k)])
+        print("%s %s d%s: %.2e" % (name, method, k, e))
+        # the reference's own fp32 gradients carry the noise of an ill-conditioned Cholesky (cond ~1e4..1e6);
+        # kernel-level gradients are held to 1e-4 in test_gpu_rbf.py, here the bar is the reference's noise
+        assert e < 2e-3, (k, e)
+
+
+@pytest.mark.parametrize("name", ["rbf_dimwise_o1", "rbf_dimwise_o2"])
+def test_layer_forward_and_batched_flow(name, monkeypatch):
+    g = load_golden(name)
+    m = g["meta"]
+    flow, gp = build_flow(g, "rk4", monkeypatch)
+    gp.build_cache()
+    f = gp(t(g["x"], device="cuda"))
+    assert rel(f, g["field_f"]) < 5e-5
+    # torchdiffeq-style callable contract
+    sv = t(g["z0"], device="cuda")
+    dy = flow.odefunc(torch.tensor(0.0), sv)
+    assert dy.shape == sv.shape
+    # batched MC samples: same draws fed twice -> both samples equal the single-sample golden trajectory
+    trajL = flow.forward_samples(t(g["z0"], device="cuda"), t(g["ts"], device="cuda"), 2)
+    assert trajL.shape == (2, m["N"], m["T"], m["D_in"])
+    assert rel(trajL[0], g["traj_rk4"]) < 1e-4 and rel(trajL[1], g["traj_rk4"]) < 1e-4
+
+
+def test_unsupported_solver_raises(monkeypatch):
+    g = load_golden("rbf_dimwise_o1")
+    flow, _ = build_flow(g, "dopri5", monkeypatch)
+    with pytest.raises(NotImplementedError):
+        flow(t(g["z0"], device="cuda"), t(g["ts"], device="cuda"))

@@ -1,0 +1,194 @@
+"""GPU parity of the RBF vector-field kernels through the C ABI (ctypes -> libgpode.so).
+
+Tolerances (north_star, fp32): per-evaluation field rel 1e-5, T-step trajectories rel 1e-4, gradients
+rel 1e-4 -- all norm-wise |a-b|_F/|b|_F with nu shared with the reference.
+Kernel-level gradients are checked against autograd through the fp64 oracle with Z, ell, var, nu as
+independent leaves (exactly the tensors the C ABI differentiates)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import field as OF
+from helpers import RBF_CASES, gpu_sample, load_golden, oracle_cache, rel, t
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 1e-5
+TRAJ_TOL = 1e-4
+GRAD_TOL = 1e-4
+
+
+def _gp():
+    import gpode_b200
+    return gpode_b200
+
+
+def _field(s, x, variant):
+    f, fp = _gp().gp_field(x, s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"], variant, s["B"])
+    return f, fp
+
+
+@pytest.mark.parametrize("name", RBF_CASES)
+def test_field_forward(name):
+    g = load_golden(name)
+    c64 = oracle_cache(g)
+    s = gpu_sample(c64)
+    x = t(g["x"], device="cuda")[None]
+    f, fp = _field(s, x, g["meta"]["variant"])
+    truth = OF.field(t(g["x"], torch.float64), c64)
+    e_ref, e_truth, e_floor = rel(f[0], g["field_f"]), rel(f[0], truth), rel(g["field_f"], truth)
+    print("%s field: new-vs-ref %.2e new-vs-fp64 %.2e ref-vs-fp64 %.2e" % (name, e_ref, e_truth, e_floor))
+    assert e_truth < FIELD_TOL, (e_ref, e_truth, e_floor)
+    assert e_ref < FIELD_TOL + e_floor, (e_ref, e_truth, e_floor)
+    assert rel(fp[0], OF.prior(t(g["x"], torch.float64), c64)) < FIELD_TOL
+
+
+@pytest.mark.parametrize("name", RBF_CASES)
+def test_field_backward_kernel_level(name):
+    g = load_golden(name)
+    variant = g["meta"]["variant"]
+    c = oracle_cache(g, leaves=True)
+    x64 = t(g["x"], torch.float64).requires_grad_(True)
+    gout = t(g["g"], torch.float64)
+    loss = (OF.field(x64, c) * gout).sum()
+    want = torch.autograd.grad(loss, [x64, c["Z"], c["nu"], c["ell"], c["var"]])
+    s = gpu_sample(c)
+    for k in ("Z", "nu", "ell", "var"):
+        s[k].requires_grad_(True)
+    x = t(g["x"], device="cuda")[None].requires_grad_(True)
+    f, _ = _field(s, x, variant)
+    (f[0] * t(g["g"], device="cuda")).sum().backward()
+    got = [x.grad[0], s["Z"].grad, s["nu"].grad[0], s["ell"].grad, s["var"].grad]
+    for nm, a, b in zip(("dx", "dZ", "dnu", "dell", "dvar"), got, want):
+        e = rel(a, b)
+        print("%s field-bwd %s: %.2e" % (name, nm, e))
+        assert e < GRAD_TOL, (nm, e)
+    assert rel(x.grad[0], g["field_dx"]) < 5 * GRAD_TOL  # the reference's own fp32 dx
+
+
+@pytest.mark.parametrize("name", RBF_CASES)
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
+def test_rollout_forward(name, method):
+    g = load_golden(name)
+    m = g["meta"]
+    c64 = oracle_cache(g)
+    s = gpu_sample(c64)
+    z0, ts = t(g["z0"], device="cuda"), t(g["ts"], device="cuda")
+    traj = _gp().gp_rollout(z0, ts, s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"], m["variant"], m["order"],
+                            method, s["B"])
+    assert traj.shape == (1, m["N"], m["T"], m["D_in"])
+    truth = OF.rollout(t(g["z0"], torch.float64), t(g["ts"], torch.float64), c64, m["order"], method)
+    e_truth = rel(traj[0], truth)
+    print("%s rollout %s: new-vs-fp64 %.2e" % (name, method, e_truth))
+    assert e_truth < TRAJ_TOL
+    assert torch.equal(traj[0, :, 0].cpu(), t(g["z0"]))
+    if method != "midpoint":
+        assert rel(traj[0], g["traj_" + method]) < TRAJ_TOL
+
+
+@pytest.mark.parametrize("name", RBF_CASES)
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
+def test_rollout_backward_kernel_level(name, method):
+    g = load_golden(name)
+    m = g["meta"]
+    c = oracle_cache(g, leaves=True)
+    z64 = t(g["z0"], torch.float64).requires_grad_(True)
+    G = t(g["G"], torch.float64)
+    loss = (OF.rollout(z64, t(g["ts"], torch.float64), c, m["order"], method) * G).sum()
+    want = torch.autograd.grad(loss, [z64, c["Z"], c["nu"], c["ell"], c["var"]])
+    s = gpu_sample(c)
+    for k in ("Z", "nu", "ell", "var"):
+        s[k].requires_grad_(True)
+    z0 = t(g["z0"], device="cuda").requires_grad_(True)
+    traj = _gp().gp_rollout(z0, t(g["ts"], device="cuda"), s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"],
+                            m["variant"], m["order"], method, s["B"])
+    (traj[0] * t(g["G"], device="cuda")).sum().backward()
+    got = [z0.grad, s["Z"].grad, s["nu"].grad[0], s["ell"].grad, s["var"].grad]
+    for nm, a, b in zip(("dz0", "dZ", "dnu", "dell", "dvar"), got, want):
+        e = rel(a, b)
+        print("%s rollout-bwd %s %s: %.2e" % (name, method, nm, e))
+        assert e < GRAD_TOL, (nm, e)
+
+
+def test_batched_samples_and_per_sample_z0():
+    """L function samples in one launch == L separate launches; shared z0 gradient is the sum over samples."""
+    g = load_golden("rbf_dimwise_o1_pert")
+    m = g["meta"]
+    c = oracle_cache(g)
+    s1 = gpu_sample(c)
+    L = 3
+    rs = np.random.RandomState(0)
+    s = dict(s1)
+    for k in ("eps", "phase", "w", "nu"):
+        s[k] = torch.cat([s1[k]] + [s1[k] * float(1.0 + 0.1 * rs.normal()) for _ in range(L - 1)], 0).contiguous()
+    gp = _gp()
+    z0 = t(g["z0"], device="cuda").requires_grad_(True)
+    ts = t(g["ts"], device="cuda")
+    G = torch.randn(L, m["N"], m["T"], m["D_in"], device="cuda")
+    traj = gp.gp_rollout(z0, ts, s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"], m["variant"], 1, "rk4")
+    (traj * G).sum().backward()
+    dz_sum = torch.zeros_like(z0)
+    for l in range(L):
+        zl = t(g["z0"], device="cuda").requires_grad_(True)
+        tl = gp.gp_rollout(zl, ts, s["Z"], s["nu"][l:l + 1], s["eps"][l:l + 1], s["phase"][l:l + 1], s["w"][l:l + 1], s["ell"],
+                           s["var"], m["variant"], 1, "rk4")
+        assert torch.equal(tl[0], traj[l])
+        (tl[0] * G[l]).sum().backward()
+        dz_sum += zl.grad
+    assert rel(z0.grad, dz_sum) < 1e-6
+    # per-sample initial states
+    z0L = torch.stack([t(g["z0"], device="cuda") * (1 + 0.1 * l) for l in range(L)]).requires_grad_(True)
+    trajL = gp.gp_rollout(z0L, ts, s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"], m["variant"], 1, "euler")
+    assert torch.equal(trajL[0], gp.gp_rollout(z0L[0].detach(), ts, s["Z"], s["nu"][:1], s["eps"][:1], s["phase"][:1], s["w"][:1],
+                                               s["ell"], s["var"], m["variant"], 1, "euler")[0])
+    trajL.sum().backward()
+    assert z0L.grad.shape == z0L.shape
+
+
+@pytest.mark.parametrize("N", [1, 31, 257, 1000, 70001])
+def test_ragged_and_large_state_counts(N):
+    """state counts that do not fill a CTA / warp, and one large enough to use the 2-states-per-thread shape:
+    a random subset is checked against the fp64 oracle."""
+    g = load_golden("rbf_dimwise_o1")
+    c = oracle_cache(g)
+    s = gpu_sample(c)
+    rs = np.random.RandomState(N)
+    x = torch.tensor(1.5 * rs.normal(size=(1, N, 6)), dtype=torch.float32, device="cuda")
+    f, _ = _field(s, x, "rbf_dimwise")
+    idx = np.unique(np.concatenate([[0, N - 1], rs.randint(0, N, size=min(N, 200))]))
+    truth = OF.field(x[0, idx].double().cpu(), c)
+    assert rel(f[0, idx], truth) < FIELD_TOL
+    ts = 0.1 * torch.arange(5, dtype=torch.float, device="cuda")
+    traj = _gp().gp_rollout(x[0], ts, s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"], "rbf_dimwise", 1, "rk4")
+    truth = OF.rollout(x[0, idx].double().cpu(), ts.double().cpu(), c, 1, "rk4")
+    assert rel(traj[0, idx], truth) < TRAJ_TOL
+
+
+def test_zero_field_properties():
+    """size-independent properties: w = 0 and nu = 0 give f = 0, so the trajectory stays at z0 and dz0 = sum_t G_t."""
+    g = load_golden("rbf_dimwise_o1")
+    c = oracle_cache(g)
+    s = gpu_sample(c)
+    s["w"] = torch.zeros_like(s["w"])
+    s["nu"] = torch.zeros_like(s["nu"])
+    N, T = 4099, 7
+    z0 = torch.randn(N, 6, device="cuda").requires_grad_(True)
+    ts = 0.1 * torch.arange(T, dtype=torch.float, device="cuda")
+    traj = _gp().gp_rollout(z0, ts, s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"], "rbf_dimwise", 1, "rk4")
+    assert torch.equal(traj[0], z0.detach()[:, None, :].expand(N, T, 6))
+    G = torch.randn(1, N, T, 6, device="cuda")
+    (traj * G).sum().backward()
+    assert rel(z0.grad, G[0].sum(1)) < 1e-6
+
+
+def test_errors_are_loud():
+    gp = _gp()
+    g = load_golden("rbf_dimwise_o1")
+    c = oracle_cache(g)
+    s = gpu_sample(c)
+    x = t(g["x"])[None]  # CPU tensor: no CPU path exists
+    with pytest.raises(RuntimeError):
+        _field(s, x, "rbf_dimwise")
+    with pytest.raises(RuntimeError):  # order 2 needs D_in == 2 D_out
+        gp.gp_rollout(t(g["z0"], device="cuda"), t(g["ts"], device="cuda"), s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"],
+                      s["var"], "rbf_dimwise", 2, "rk4")

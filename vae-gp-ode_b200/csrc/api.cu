@@ -1,0 +1,348 @@
+// C ABI of libgpode.so (include/gpode.h): argument checking, workspace carving, kernel sequencing.
+// Nothing here allocates, synchronises or keeps state: every call enqueues on the caller's stream.
+#include <cstdio>
+
+#include "common.cuh"
+#include "df.h"
+#include "rbf.h"
+
+using namespace gpode;
+
+namespace {
+
+struct Ws {  // byte offsets inside the workspace (256-B aligned), see gpode_workspace_bytes
+  size_t packed, xs, ks, fps, ybar, ystage, kbar, gsave, acc, acc_bytes, total;
+  size_t a_dnu, a_pg, a_dell_x, a_dvar, a_dell_z;  // offsets inside acc
+};
+
+int check_problem(const GpodeProblem* p) {
+  if (!p) return GPODE_E_NULL;
+  if (p->variant != GPODE_RBF_SHARED && p->variant != GPODE_RBF_DIMWISE && p->variant != GPODE_DF) return GPODE_E_ENUM;
+  if (p->L < 1 || p->N < 1 || p->D_in < 1 || p->D_out < 1 || p->M < 1 || p->S < 1) return GPODE_E_SHAPE;
+  if (!p->Z || !p->ell || !p->var || !p->eps || !p->phase || !p->w || !p->nu) return GPODE_E_NULL;
+  if (p->D_in > kMaxD || p->D_out > kMaxD || p->M > 512) return GPODE_E_UNSUPPORTED;
+  if (static_cast<long>(p->L) * p->N > (1L << 30)) return GPODE_E_UNSUPPORTED;
+  if (p->variant == GPODE_DF) {
+    if (p->D_in != p->D_out) return GPODE_E_SHAPE;
+    if (!p->B) return GPODE_E_NULL;
+    if (p->D_in > kDfMaxD) return GPODE_E_UNSUPPORTED;
+  }
+  return GPODE_OK;
+}
+
+RbfGeom rbf_geom(const GpodeProblem* p, int order) {
+  RbfGeom g;
+  g.L = p->L;
+  g.N = p->N;
+  g.NL = p->L * p->N;
+  g.D_in = p->D_in;
+  g.D_out = p->D_out;
+  g.DP = (p->D_in + 1) / 2 * 2;
+  g.M = p->M;
+  g.S = p->S;
+  g.MP2 = (p->M + 1) / 2;
+  g.SP2 = (p->S + 1) / 2;
+  g.tile_floats = rbf_tile_floats(g.DP, g.SP2, g.MP2);
+  g.order = order;
+  g.off = p->D_in - p->D_out;
+  return g;
+}
+
+size_t packed_floats(const GpodeProblem* p) {
+  if (p->variant == GPODE_DF) return df_packed_floats(df_geom(p));
+  const RbfGeom g = rbf_geom(p, 1);
+  return static_cast<size_t>(g.L) * g.D_out * g.tile_floats;
+}
+
+size_t acc_floats(const GpodeProblem* p, Ws* w) {
+  if (p->variant == GPODE_DF) return df_acc_floats(df_geom(p));
+  const RbfGeom g = rbf_geom(p, 1);
+  size_t o = 0;
+  auto take = [&](size_t n) { const size_t at = o; o += (n + 63) / 64 * 64; return at; };
+  const size_t a_dnu = take(static_cast<size_t>(g.L) * g.D_out * 2 * g.MP2);
+  const size_t a_pg = take(static_cast<size_t>(g.L) * g.D_out * 2 * g.MP2 * g.DP);
+  const size_t a_dell_x = take(static_cast<size_t>(g.D_out) * g.DP);
+  const size_t a_dvar = take(g.D_out);
+  const size_t a_dell_z = take(static_cast<size_t>(g.D_out) * g.DP);
+  if (w) {
+    w->a_dnu = a_dnu;
+    w->a_pg = a_pg;
+    w->a_dell_x = a_dell_x;
+    w->a_dvar = a_dvar;
+    w->a_dell_z = a_dell_z;
+  }
+  return o;
+}
+
+Ws layout(const GpodeProblem* p, int T, int method) {
+  Ws w = {};
+  const size_t NL = static_cast<size_t>(p->L) * p->N;
+  const int stages = method_stages(method);
+  const size_t steps = T > 1 ? static_cast<size_t>(T - 1) : 1;
+  size_t o = 0;
+  auto take = [&](size_t floats) { const size_t at = o; o += align_up(floats * 4, 256); return at; };
+  w.packed = take(packed_floats(p));
+  w.xs = take(stages * p->D_in * NL);   // one step of stage inputs / derivatives / prior parts (forward without saves)
+  w.ks = take(stages * p->D_in * NL);
+  w.fps = take(stages * p->D_out * NL);
+  w.ybar = take(p->D_in * NL);
+  w.ystage = take(stages * p->D_in * NL);
+  w.kbar = take(p->D_in * NL);
+  w.gsave = take(steps * stages * p->D_out * NL);
+  w.acc_bytes = acc_floats(p, &w) * 4;
+  w.acc = take(w.acc_bytes / 4);
+  w.total = o;
+  return w;
+}
+
+RbfAccum rbf_acc(char* ws, const Ws& w) {
+  RbfAccum a;
+  float* base = reinterpret_cast<float*>(ws + w.acc);
+  a.dnu = base + w.a_dnu;
+  a.pg = base + w.a_pg;
+  a.dell_x = base + w.a_dell_x;
+  a.dvar = base + w.a_dvar;
+  a.dell_z = base + w.a_dell_z;
+  return a;
+}
+
+int check_ws(const void* ws, size_t bytes, size_t need) {
+  if (!ws) return GPODE_E_NULL;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0 || bytes < need) return GPODE_E_WORKSPACE;
+  return GPODE_OK;
+}
+
+int rbf_check_smem(const RbfGeom& g) { return rbf_smem_bytes(g) <= kSmemLimit ? GPODE_OK : GPODE_E_UNSUPPORTED; }
+
+cudaError_t rbf_pack(const GpodeProblem* p, const RbfGeom& g, float* packed, cudaStream_t st) {
+  RbfPackArgs a;
+  a.g = g;
+  a.variant = p->variant;
+  a.Z = p->Z; a.ell = p->ell; a.var = p->var; a.eps = p->eps; a.phase = p->phase; a.w = p->w; a.nu = p->nu;
+  a.packed = packed;
+  return rbf_launch_pack(a, st);
+}
+
+int pgrad_chunks(long evals_per_sample, int ctas_per_chunk) {
+  const long target = 148L * 8;
+  long c = (target + ctas_per_chunk - 1) / ctas_per_chunk;
+  const long maxc = (evals_per_sample + 127) / 128;
+  if (c > maxc) c = maxc;
+  if (c < 1) c = 1;
+  return static_cast<int>(c);
+}
+
+cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float* packed, const float* xsave, const float* gsave,
+                            long n_te, const RbfAccum& acc, const GpodeParamGrads* grads, cudaStream_t st) {
+  RbfPgradArgs pa;
+  pa.g = g;
+  pa.packed = packed;
+  pa.xsave = xsave;
+  pa.gsave = gsave;
+  pa.n_te = n_te;
+  pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L);
+  pa.acc = acc;
+  cudaError_t e = rbf_launch_pgrad(pa, st);
+  if (e != cudaSuccess) return e;
+  RbfFinalizeArgs fa;
+  fa.g = g;
+  fa.variant = p->variant;
+  fa.Z = p->Z; fa.ell = p->ell; fa.var = p->var; fa.nu = p->nu;
+  fa.acc = acc;
+  fa.d_Z = grads ? grads->d_Z : nullptr;
+  fa.d_ell = grads ? grads->d_ell : nullptr;
+  fa.d_var = grads ? grads->d_var : nullptr;
+  fa.d_nu = grads ? grads->d_nu : nullptr;
+  return rbf_launch_finalize(fa, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpode_version(void) { return GPODE_VERSION; }
+
+const char* gpode_error_string(int code) {
+  switch (code) {
+    case GPODE_OK: return "ok";
+    case GPODE_E_NULL: return "a required pointer is NULL";
+    case GPODE_E_SHAPE: return "invalid or inconsistent shape";
+    case GPODE_E_UNSUPPORTED: return "shape outside the compiled range (D_in/D_out <= 16, DF D <= 8, M <= 512, parameter tile <= 227 KB)";
+    case GPODE_E_WORKSPACE: return "workspace too small or not 256-byte aligned";
+    case GPODE_E_ENUM: return "unknown variant / method / order";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error";
+  }
+}
+
+size_t gpode_workspace_bytes(const GpodeProblem* p, int T, int method) {
+  if (check_problem(p) != GPODE_OK) return 0;
+  if (method < GPODE_EULER || method > GPODE_RK4) return 0;
+  return layout(p, T, method).total;
+}
+
+size_t gpode_rollout_save_floats(const GpodeProblem* p, int T, int method) {
+  if (check_problem(p) != GPODE_OK || T < 1) return 0;
+  if (method < GPODE_EULER || method > GPODE_RK4) return 0;
+  const size_t NL = static_cast<size_t>(p->L) * p->N;
+  const size_t steps = T > 1 ? T - 1 : 1;
+  return steps * method_stages(method) * (2 * static_cast<size_t>(p->D_in) + p->D_out) * NL;
+}
+
+int gpode_field_fwd(const GpodeProblem* p, const float* x, float* f, float* f_prior, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  int rc = check_problem(p);
+  if (rc) return rc;
+  if (!x || !f) return GPODE_E_NULL;
+  const Ws w = layout(p, 2, GPODE_EULER);
+  if ((rc = check_ws(workspace, workspace_bytes, w.total))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  float* packed = reinterpret_cast<float*>(ws + w.packed);
+  if (p->variant == GPODE_DF) return df_field_fwd(p, x, f, f_prior, packed, st);
+  const RbfGeom g = rbf_geom(p, 1);
+  if ((rc = rbf_check_smem(g))) return rc;
+  cudaError_t e = rbf_pack(p, g, packed, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  RbfFieldFwdArgs a;
+  a.g = g;
+  a.packed = packed;
+  a.x = x;
+  a.f = f;
+  a.f_prior = f_prior;
+  return static_cast<int>(rbf_launch_field_fwd(a, st));
+}
+
+int gpode_field_bwd(const GpodeProblem* p, const float* x, const float* g_out, const float* f, const float* f_prior, float* dx,
+                    const GpodeParamGrads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_problem(p);
+  if (rc) return rc;
+  if (!x || !g_out || !f || !f_prior || !dx) return GPODE_E_NULL;
+  const Ws w = layout(p, 2, GPODE_EULER);
+  if ((rc = check_ws(workspace, workspace_bytes, w.total))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  float* packed = reinterpret_cast<float*>(ws + w.packed);
+  cudaError_t e = cudaMemsetAsync(ws + w.acc, 0, w.acc_bytes, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (p->variant == GPODE_DF)
+    return df_field_bwd(p, x, g_out, f, f_prior, dx, grads, packed, reinterpret_cast<float*>(ws + w.xs), reinterpret_cast<float*>(ws + w.gsave),
+                        reinterpret_cast<float*>(ws + w.acc), st);
+  const RbfGeom g = rbf_geom(p, 1);
+  if ((rc = rbf_check_smem(g))) return rc;
+  if ((e = rbf_pack(p, g, packed, st)) != cudaSuccess) return static_cast<int>(e);
+  RbfFieldBwdArgs a;
+  a.g = g;
+  a.packed = packed;
+  a.x = x;
+  a.gout = g_out;
+  a.f = f;
+  a.f_prior = f_prior;
+  a.dx = dx;
+  a.xsave = reinterpret_cast<float*>(ws + w.xs);
+  a.gsave = reinterpret_cast<float*>(ws + w.gsave);
+  a.acc = rbf_acc(ws, w);
+  if ((e = rbf_launch_field_bwd(a, st)) != cudaSuccess) return static_cast<int>(e);
+  return static_cast<int>(rbf_param_grads(p, g, packed, a.xsave, a.gsave, 1, a.acc, grads, st));
+}
+
+int gpode_rollout_fwd(const GpodeProblem* p, const float* z0, int z0_per_sample, const float* ts, int T, int method, int order,
+                      float* traj, float* save, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_problem(p);
+  if (rc) return rc;
+  if (!z0 || !ts || !traj) return GPODE_E_NULL;
+  if (T < 1) return GPODE_E_SHAPE;
+  if (method < GPODE_EULER || method > GPODE_RK4 || (order != 1 && order != 2)) return GPODE_E_ENUM;
+  if ((order == 1 && p->D_in != p->D_out) || (order == 2 && p->D_in != 2 * p->D_out)) return GPODE_E_SHAPE;
+  if (order == 2 && p->variant == GPODE_DF) return GPODE_E_SHAPE;  // the reference DF kernel needs D_in == D_out
+  const Ws w = layout(p, T, method);
+  if ((rc = check_ws(workspace, workspace_bytes, w.total))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  float* packed = reinterpret_cast<float*>(ws + w.packed);
+  const int stages = method_stages(method);
+  const size_t NL = static_cast<size_t>(p->L) * p->N;
+  const size_t steps = T > 1 ? T - 1 : 1;
+  float *xs, *ks, *fps;
+  if (save) {
+    xs = save;
+    ks = xs + steps * stages * p->D_in * NL;
+    fps = ks + steps * stages * p->D_in * NL;
+  } else {
+    xs = reinterpret_cast<float*>(ws + w.xs);
+    ks = reinterpret_cast<float*>(ws + w.ks);
+    fps = reinterpret_cast<float*>(ws + w.fps);
+  }
+  if (p->variant == GPODE_DF) return df_rollout_fwd(p, z0, z0_per_sample, ts, T, method, traj, xs, ks, fps, save != nullptr, packed, st);
+  const RbfGeom g = rbf_geom(p, order);
+  if ((rc = rbf_check_smem(g))) return rc;
+  cudaError_t e = rbf_pack(p, g, packed, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  RbfRolloutFwdArgs a;
+  a.g = g;
+  a.packed = packed;
+  a.z0 = z0;
+  a.z0_per_sample = z0_per_sample;
+  a.ts = ts;
+  a.T = T;
+  a.method = method;
+  a.keep = save ? 1 : 0;
+  a.traj = traj;
+  a.xsave = xs;
+  a.ksave = ks;
+  a.fpsave = fps;
+  return static_cast<int>(rbf_launch_rollout_fwd(a, st));
+}
+
+int gpode_rollout_bwd(const GpodeProblem* p, const float* ts, int T, int method, int order, const float* traj, const float* save,
+                      const float* dtraj, float* dz0, const GpodeParamGrads* grads, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  int rc = check_problem(p);
+  if (rc) return rc;
+  if (!ts || !save || !dtraj || !dz0) return GPODE_E_NULL;
+  (void)traj;
+  if (T < 1) return GPODE_E_SHAPE;
+  if (method < GPODE_EULER || method > GPODE_RK4 || (order != 1 && order != 2)) return GPODE_E_ENUM;
+  if ((order == 1 && p->D_in != p->D_out) || (order == 2 && p->D_in != 2 * p->D_out)) return GPODE_E_SHAPE;
+  if (order == 2 && p->variant == GPODE_DF) return GPODE_E_SHAPE;
+  const Ws w = layout(p, T, method);
+  if ((rc = check_ws(workspace, workspace_bytes, w.total))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  float* packed = reinterpret_cast<float*>(ws + w.packed);
+  const int stages = method_stages(method);
+  const size_t NL = static_cast<size_t>(p->L) * p->N;
+  const size_t steps = T > 1 ? T - 1 : 1;
+  const float* xs = save;
+  const float* ks = xs + steps * stages * p->D_in * NL;
+  const float* fps = ks + steps * stages * p->D_in * NL;
+  cudaError_t e = cudaMemsetAsync(ws + w.acc, 0, w.acc_bytes, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (p->variant == GPODE_DF)
+    return df_rollout_bwd(p, ts, T, method, xs, ks, fps, dtraj, dz0, grads, packed, reinterpret_cast<float*>(ws + w.gsave),
+                          reinterpret_cast<float*>(ws + w.ybar), reinterpret_cast<float*>(ws + w.ystage),
+                          reinterpret_cast<float*>(ws + w.kbar), reinterpret_cast<float*>(ws + w.acc), st);
+  const RbfGeom g = rbf_geom(p, order);
+  if ((rc = rbf_check_smem(g))) return rc;
+  if ((e = rbf_pack(p, g, packed, st)) != cudaSuccess) return static_cast<int>(e);
+  RbfRolloutBwdArgs a;
+  a.g = g;
+  a.packed = packed;
+  a.ts = ts;
+  a.T = T;
+  a.method = method;
+  a.xsave = xs;
+  a.ksave = ks;
+  a.fpsave = fps;
+  a.dtraj = dtraj;
+  a.dz0 = dz0;
+  a.gsave = reinterpret_cast<float*>(ws + w.gsave);
+  a.ybar = reinterpret_cast<float*>(ws + w.ybar);
+  a.ystage = reinterpret_cast<float*>(ws + w.ystage);
+  a.kbar = reinterpret_cast<float*>(ws + w.kbar);
+  a.acc = rbf_acc(ws, w);
+  if ((e = rbf_launch_rollout_bwd(a, st)) != cudaSuccess) return static_cast<int>(e);
+  if (T < 2) return GPODE_OK;
+  return static_cast<int>(rbf_param_grads(p, g, packed, xs, a.gsave, static_cast<long>(T - 1) * stages, a.acc, grads, st));
+}
+
+}  // extern "C"

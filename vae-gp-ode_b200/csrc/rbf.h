@@ -1,0 +1,133 @@
+// Host-side descriptors of the RBF kernels (shared by the kernel translation units and the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace gpode {
+
+// Save-buffer indexing: entry (te, c, s) with te = t * stages + i (t = 0 when nothing is kept),
+// c a component, s = l * N + n the global state index -> ((te * C + c) * NL + s): coalesced over states.
+struct RbfGeom {
+  int L, N, NL;          // samples, states per sample, L*N
+  int D_in, D_out, DP;   // DP = D_in rounded up to even
+  int M, S, MP2, SP2;    // pairs (rounded up)
+  int tile_floats;       // floats per packed (l,k) tile
+  int order, off;        // ODE order; off = D_in - D_out: where f sits inside the state derivative
+};
+
+struct RbfFieldFwdArgs {
+  RbfGeom g;
+  const float* packed;
+  const float* x;    // (L,N,D_in)
+  float* f;          // (L,N,D_out)
+  float* f_prior;    // (L,N,D_out) or null
+};
+
+struct RbfRolloutFwdArgs {
+  RbfGeom g;
+  const float* packed;
+  const float* z0;
+  int z0_per_sample;
+  const float* ts;
+  int T, method, keep;   // keep = 1: saves hold every step (backward follows); 0: one step of scratch
+  float* traj;           // (L,N,T,D_in)
+  float* xsave;          // stage inputs      [(T-1)*stages][D_in ][NL]
+  float* ksave;          // stage derivatives [(T-1)*stages][D_in ][NL]
+  float* fpsave;         // prior part        [(T-1)*stages][D_out][NL]
+};
+
+struct RbfAccum {        // fp32 accumulators in the workspace, zeroed before the backward
+  float* dnu;            // [L][D_out][2*MP2]          sum_n g E
+  float* pg;             // [L][D_out][2*MP2][DP]      sum_n g E x_d
+  float* dell_x;         // [D_out][DP]                sum_n x_d * dx_k,d
+  float* dvar;           // [D_out]                    sum_n g (f - f_p/2)
+  float* dell_z;         // [D_out][DP]                sum_m z_d * dZ_k,m,d   (filled by the finalize kernel)
+};
+
+struct RbfRolloutBwdArgs {
+  RbfGeom g;
+  const float* packed;
+  const float* ts;
+  int T, method;
+  const float* xsave;
+  const float* ksave;
+  const float* fpsave;
+  const float* dtraj;    // (L,N,T,D_in)
+  float* dz0;            // (L,N,D_in)
+  float* gsave;          // stage adjoints (f part) [(T-1)*stages][D_out][NL]
+  float* ybar;           // scratch [D_in][NL]
+  float* ystage;         // scratch [stages][D_in][NL]
+  float* kbar;           // scratch [D_in][NL]
+  RbfAccum acc;
+};
+
+struct RbfFieldBwdArgs {
+  RbfGeom g;
+  const float* packed;
+  const float* x;        // (L,N,D_in)
+  const float* gout;     // (L,N,D_out)
+  const float* f;        // (L,N,D_out)
+  const float* f_prior;  // (L,N,D_out)
+  float* dx;             // (L,N,D_in)
+  float* xsave;          // [D_in][NL]   transposed copies for the parameter-gradient kernel
+  float* gsave;          // [D_out][NL]
+  RbfAccum acc;
+};
+
+struct RbfPgradArgs {
+  RbfGeom g;
+  const float* packed;
+  const float* xsave;
+  const float* gsave;
+  long n_te;             // number of (step, stage) slabs
+  int chunks;            // CTAs along the state-evaluation axis
+  RbfAccum acc;
+};
+
+struct RbfPackArgs {
+  RbfGeom g;
+  int variant;           // GPODE_RBF_SHARED or GPODE_RBF_DIMWISE
+  const float* Z;
+  const float* ell;
+  const float* var;
+  const float* eps;
+  const float* phase;
+  const float* w;
+  const float* nu;
+  float* packed;
+};
+
+struct RbfFinalizeArgs {
+  RbfGeom g;
+  int variant;
+  const float* Z;
+  const float* ell;
+  const float* var;
+  const float* nu;
+  RbfAccum acc;
+  float* d_Z;
+  float* d_ell;
+  float* d_var;
+  float* d_nu;
+};
+
+// launchers (one per DP instantiation unit); return cudaGetLastError()
+cudaError_t rbf_launch_field_fwd(const RbfFieldFwdArgs& a, cudaStream_t st);
+cudaError_t rbf_launch_field_bwd(const RbfFieldBwdArgs& a, cudaStream_t st);
+cudaError_t rbf_launch_rollout_fwd(const RbfRolloutFwdArgs& a, cudaStream_t st);
+cudaError_t rbf_launch_rollout_bwd(const RbfRolloutBwdArgs& a, cudaStream_t st);
+cudaError_t rbf_launch_pgrad(const RbfPgradArgs& a, cudaStream_t st);
+cudaError_t rbf_launch_pack(const RbfPackArgs& a, cudaStream_t st);
+cudaError_t rbf_launch_finalize(const RbfFinalizeArgs& a, cudaStream_t st);
+int rbf_smem_bytes(const RbfGeom& g);  // dynamic shared memory of the sweep kernels
+
+}  // namespace gpode
+
+namespace gpode {
+// per-DP instantiations (rbf_inst.cu compiled once per GPODE_DP)
+template <int DP> cudaError_t rbf_field_fwd_dp(const RbfFieldFwdArgs& a, cudaStream_t st);
+template <int DP> cudaError_t rbf_field_bwd_dp(const RbfFieldBwdArgs& a, cudaStream_t st);
+template <int DP> cudaError_t rbf_rollout_fwd_dp(const RbfRolloutFwdArgs& a, cudaStream_t st);
+template <int DP> cudaError_t rbf_rollout_bwd_dp(const RbfRolloutBwdArgs& a, cudaStream_t st);
+template <int DP> cudaError_t rbf_pgrad_dp(const RbfPgradArgs& a, cudaStream_t st);
+}  // namespace gpode

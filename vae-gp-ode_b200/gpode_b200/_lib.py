@@ -1,0 +1,104 @@
+"""ctypes binding of libgpode.so (C ABI declared in include/gpode.h).  No torch types cross the ABI:
+only device pointers, sizes and the CUDA stream handle."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libgpode.so")
+
+RBF_SHARED, RBF_DIMWISE, DF = 0, 1, 2
+EULER, MIDPOINT, RK4 = 0, 1, 2
+METHODS = {"euler": EULER, "midpoint": MIDPOINT, "rk4": RK4}
+STAGES = {EULER: 1, MIDPOINT: 2, RK4: 4}
+VARIANTS = {"rbf_shared": RBF_SHARED, "rbf_dimwise": RBF_DIMWISE, "df": DF}
+
+_fp = ctypes.c_void_p
+
+
+class GpodeProblem(ctypes.Structure):
+    _fields_ = [("variant", ctypes.c_int32), ("L", ctypes.c_int32), ("N", ctypes.c_int32), ("D_in", ctypes.c_int32),
+                ("D_out", ctypes.c_int32), ("M", ctypes.c_int32), ("S", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("Z", _fp), ("ell", _fp), ("var", _fp), ("eps", _fp), ("phase", _fp), ("w", _fp), ("nu", _fp), ("B", _fp)]
+
+
+class GpodeParamGrads(ctypes.Structure):
+    _fields_ = [("d_Z", _fp), ("d_ell", _fp), ("d_var", _fp), ("d_nu", _fp), ("d_B", _fp)]
+
+
+EXPORTS = ["gpode_version", "gpode_error_string", "gpode_workspace_bytes", "gpode_rollout_save_floats",
+           "gpode_field_fwd", "gpode_field_bwd", "gpode_rollout_fwd", "gpode_rollout_bwd"]
+
+_lib = None
+
+
+def load():
+    """Load libgpode.so; fails loudly when it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libgpode.so not found at %s -- build it with `make -C vae-gp-ode_b200/csrc -j8` "
+                           "(or python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    P, PG = ctypes.POINTER(GpodeProblem), ctypes.POINTER(GpodeParamGrads)
+    i32, sz = ctypes.c_int, ctypes.c_size_t
+    lib.gpode_version.restype = i32
+    lib.gpode_version.argtypes = []
+    lib.gpode_error_string.restype = ctypes.c_char_p
+    lib.gpode_error_string.argtypes = [i32]
+    lib.gpode_workspace_bytes.restype = sz
+    lib.gpode_workspace_bytes.argtypes = [P, i32, i32]
+    lib.gpode_rollout_save_floats.restype = sz
+    lib.gpode_rollout_save_floats.argtypes = [P, i32, i32]
+    lib.gpode_field_fwd.restype = i32
+    lib.gpode_field_fwd.argtypes = [P, _fp, _fp, _fp, _fp, sz, _fp]
+    lib.gpode_field_bwd.restype = i32
+    lib.gpode_field_bwd.argtypes = [P, _fp, _fp, _fp, _fp, _fp, PG, _fp, sz, _fp]
+    lib.gpode_rollout_fwd.restype = i32
+    lib.gpode_rollout_fwd.argtypes = [P, _fp, i32, _fp, i32, i32, i32, _fp, _fp, _fp, sz, _fp]
+    lib.gpode_rollout_bwd.restype = i32
+    lib.gpode_rollout_bwd.argtypes = [P, _fp, i32, i32, i32, _fp, _fp, _fp, _fp, PG, _fp, sz, _fp]
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().gpode_error_string(int(rc)).decode()
+        raise RuntimeError("%s failed: %s (code %d)" % (what, msg, rc))
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_handle(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("gpode_b200 runs on CUDA devices only (got a %s tensor); there is no CPU path" % t.device)
+        if t.dtype != torch.float32:
+            raise RuntimeError("gpode_b200 computes in fp32 (got %s)" % t.dtype)
+
+
+def make_problem(variant, L, N, D_in, D_out, M, S, Z, ell, var, eps, phase, w, nu, B=None):
+    p = GpodeProblem()
+    p.variant, p.L, p.N, p.D_in, p.D_out, p.M, p.S, p.reserved = variant, L, N, D_in, D_out, M, S, 0
+    p.Z, p.ell, p.var, p.eps, p.phase, p.w, p.nu = ptr(Z), ptr(ell), ptr(var), ptr(eps), ptr(phase), ptr(w), ptr(nu)
+    p.B = ptr(B)
+    return p
+
+
+def workspace(p, T, method, device):
+    nbytes = load().gpode_workspace_bytes(ctypes.byref(p), T, method)
+    if nbytes == 0:
+        raise RuntimeError("gpode: unsupported problem (variant=%d L=%d N=%d D_in=%d D_out=%d M=%d S=%d): "
+                           "D_in/D_out <= 16, DF D <= 8, M <= 512" % (p.variant, p.L, p.N, p.D_in, p.D_out, p.M, p.S))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes

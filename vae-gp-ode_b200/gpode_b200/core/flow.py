@@ -1,0 +1,97 @@
+"""ODEfunc / Flow -- drop-in for experiments/model/core/flow.py:7-102.
+
+``Flow.forward(z0, ts)`` keeps the reference contract (fresh function sample per call, returns
+(N,T,D_s)) but the whole fixed-grid solve -- every stage of every step, plus its reverse sweep -- is
+one CUDA launch per direction instead of a torchdiffeq Python loop.  ``Flow.forward_samples`` is the
+batched form of the serial MC loop in experiments/model/core/odegpvae.py:37-45: L function samples,
+one launch.  Fixed-grid solvers only (euler, midpoint, rk4 = 3/8 rule); adaptive solvers and the
+adjoint method are outside this path and raise."""
+import torch
+import torch.nn as nn
+
+from .. import functional as GF
+from .._lib import METHODS, STAGES
+from .svpy import FieldSample
+
+
+class ODEfunc(nn.Module):
+    def __init__(self, diffeq, order):
+        super().__init__()
+        self.diffeq = diffeq
+        self.order = order
+        self.register_buffer("_num_evals", torch.tensor(0.))
+
+    def before_odeint(self, rebuild_cache):
+        self._num_evals.fill_(0)
+        if rebuild_cache:
+            self.diffeq.build_cache()
+
+    def num_evals(self):
+        return self._num_evals.item()
+
+    def first_order(self, sv):
+        return self.diffeq(sv)
+
+    def second_order(self, sv):
+        q = sv.shape[1] // 2
+        return torch.cat([sv[:, q:], self.diffeq(sv)], 1)
+
+    def forward(self, t, sv):
+        """torchdiffeq-style right-hand side (autonomous: t is ignored), one field evaluation on the GPU."""
+        self._num_evals += 1
+        if self.order == 1:
+            return self.first_order(sv)
+        if self.order == 2:
+            return self.second_order(sv)
+        raise ValueError("order must be 1 or 2")
+
+
+class Flow(nn.Module):
+    def __init__(self, diffeq, order=2, solver="dopri5", atol=1e-6, rtol=1e-6, use_adjoint=False):
+        super().__init__()
+        self.odefunc = ODEfunc(diffeq, order)
+        self.solver = solver
+        self.atol = atol
+        self.rtol = rtol
+        self.use_adjoint = use_adjoint
+
+    def _method(self):
+        if self.solver not in METHODS:
+            raise NotImplementedError("gpode_b200 implements the fixed-grid solvers %s; got %r (adaptive solvers are "
+                                      "outside the CUDA hot path)" % (sorted(METHODS), self.solver))
+        if self.use_adjoint:
+            raise NotImplementedError("use_adjoint=True is not part of the CUDA path: the fused reverse sweep already "
+                                      "differentiates the discrete solver exactly with O(T) saved stages")
+        return METHODS[self.solver]
+
+    def _rollout(self, z0, ts, sample):
+        method = self._method()
+        traj = GF.gp_rollout(z0, ts, sample.Z, sample.nu, sample.eps, sample.phase, sample.w, sample.ell, sample.var,
+                             sample.variant, self.odefunc.order, method, sample.B)
+        self.odefunc._num_evals.fill_((ts.shape[0] - 1) * STAGES[method])
+        return traj
+
+    def forward(self, z0, ts):
+        """(N,D_s), (T,) -> (N,T,D_s) for one fresh function sample."""
+        self.odefunc.before_odeint(rebuild_cache=True)
+        return self._rollout(z0, ts, self.odefunc.diffeq.field_sample())[0]
+
+    def forward_samples(self, z0, ts, L):
+        """(N,D_s) -> (L,N,T,D_s): L fresh function samples (caches drawn in order), a single launch."""
+        samples = []
+        for _ in range(L):
+            self.odefunc.before_odeint(rebuild_cache=True)
+            samples.append(self.odefunc.diffeq.field_sample())
+        return self._rollout(z0, ts, FieldSample.stack(samples))
+
+    def num_evals(self):
+        return self.odefunc.num_evals()
+
+    def kl(self):
+        return self.odefunc.diffeq.kl()
+
+
+def sample_trajectories(flow, z0, T, L=1, dt=0.1):
+    """Batched equivalent of ODEGPVAE.sample_trajectories (odegpvae.py:37-45): (L,N,T,D_s)."""
+    ts = dt * torch.arange(T, dtype=torch.float).to(z0.device)
+    return flow.forward_samples(z0, ts, L)

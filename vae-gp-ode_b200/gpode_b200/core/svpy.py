@@ -1,0 +1,109 @@
+"""SVGP_Layer -- drop-in for experiments/model/core/svpy.py:30-175 (decoupled sampling of a sparse GP
+posterior, Wilson et al. 2020).  Same constructor, parameters (``inducing_loc``, ``Um``, ``Us_sqrt``
+as Param modules -> same state_dict keys), ``build_cache`` / ``forward`` / ``kl`` /
+``sample_inducing``.  ``forward`` evaluates the field with the CUDA kernels of libgpode.so."""
+import sys
+
+import numpy as np
+import torch
+
+from .. import functional as GF
+from ..misc import transforms
+from ..misc.param import Param
+from .kernels import RBF, DivergenceFreeKernel
+
+jitter = 1e-5
+
+
+def sample_normal(shape, seed=None):
+    """host draw ~ N(0,1) from the global numpy RNG (reference svpy.py:12-18; patched by the parity tests)."""
+    rng = np.random if seed is None else np.random.RandomState(seed)
+    return torch.tensor(rng.normal(size=shape).astype(np.float32))
+
+
+class FieldSample:
+    """The tensors that pin one function sample (what build_cache leaves on the kernel), with a leading
+    sample axis so that several samples can share one launch."""
+
+    def __init__(self, variant, Z, ell, var, eps, phase, w, nu, B=None):
+        self.variant, self.Z, self.ell, self.var = variant, Z, ell, var
+        self.eps, self.phase, self.w, self.nu, self.B = eps, phase, w, nu, B
+
+    @staticmethod
+    def stack(samples):
+        s0 = samples[0]
+        cat = lambda name: torch.cat([getattr(s, name) for s in samples], 0)
+        return FieldSample(s0.variant, s0.Z, s0.ell, s0.var, cat("eps"), cat("phase"), cat("w"), cat("nu"),
+                           cat("B") if s0.B is not None else None)
+
+
+class SVGP_Layer(torch.nn.Module):
+    def __init__(self, D_in, D_out, M, S, q_diag=False, dimwise=True, device="cpu", kernel="RBF"):
+        super().__init__()
+        if kernel == "RBF":
+            self.kern = RBF(D_in, D_out, dimwise)
+            self.dimwise = dimwise
+        elif kernel == "DF":
+            self.kern = DivergenceFreeKernel(D_in, D_out)
+            self.dimwise = False
+        else:
+            sys.exit("Invalid kernel selection")
+        self.kernel_n = kernel
+        self.q_diag = q_diag
+        self.D_out, self.D_in, self.M, self.S = D_out, D_in, M, S
+        self.device = device
+        # initial values come from the global numpy RNG in the reference's order (svpy.py:76-86)
+        self.inducing_loc = Param(np.random.normal(size=(M, D_in)), name="Inducing locations", device=device)
+        self.Um = Param(np.random.normal(size=(M, D_out)) * 1e-1, name="Inducing distribution (mean)", device=device)
+        if q_diag:
+            self.Us_sqrt = Param(np.ones((M, D_out)) * 1e-3, transform=transforms.SoftPlus(),
+                                 name="Inducing distribution (scale)", device=device)
+        else:
+            self.Us_sqrt = Param(np.stack([np.eye(M)] * D_out) * 1e-3,
+                                 transform=transforms.LowerTriangular(M, D_out, device=device),
+                                 name="Inducing distribution (scale)", device=device)
+        self.kern.to(device)
+
+    def sample_inducing(self):
+        """u = Lq eps + m, eps ~ N(0,I) (M,D_out) (whitened inducing sample, svpy.py:88-101)."""
+        eps = sample_normal(shape=(self.M, self.D_out)).to(self.device)
+        if self.q_diag:
+            return self.Us_sqrt() * eps + self.Um()
+        return torch.einsum("dnm,md->nd", self.Us_sqrt(), eps) + self.Um()
+
+    def build_cache(self):
+        """Fix one function sample: feature draws, inducing sample, nu (svpy.py:103-121; same draw order)."""
+        self.kern.build_cache(self.S, self.device)
+        u = self.sample_inducing()
+        Z = self.inducing_loc()
+        Ku = self.kern.K(Z)
+        u_prior = self.kern.rff_forward(Z, self.S)
+        self.kern.compute_nu(Ku, u_prior, u)
+
+    def field_sample(self):
+        """Current cache as a FieldSample with L = 1."""
+        k = self.kern
+        if k.nu is None:
+            raise RuntimeError("build_cache() must run before the layer is evaluated")
+        B = k.extra_cache()
+        return FieldSample(k.variant, self.inducing_loc(), k.lengthscales, k.variance, k.rff_eps[None], k.rff_phase[None],
+                           k.rff_weights[None], k.nu[None], None if B is None else B[None])
+
+    def forward(self, x):
+        """f(x) = prior draw + pathwise update for x (N,D_in) -> (N,D_out), on the GPU kernels."""
+        s = self.field_sample()
+        f, _ = GF.gp_field(x[None], s.Z, s.nu, s.eps, s.phase, s.w, s.ell, s.var, s.variant, s.B)
+        return f[0]
+
+    def kl(self):
+        """whitened KL(q(u) || N(0,I)) = 1/2 sum_d(-log|Lq_d Lq_d^T| + |m_d|^2 + |Lq_d|_F^2 - M) (svpy.py:144-175)."""
+        m = self.Um()
+        if self.q_diag:
+            diag = self.Us_sqrt()
+            trace = diag.square().sum(0)
+        else:
+            Lq = torch.tril(self.Us_sqrt())
+            diag = torch.diagonal(Lq, dim1=1, dim2=2).t()
+            trace = Lq.square().sum((1, 2))
+        two_kl = -torch.log(diag.square()).sum(0) + m.square().sum(0) + trace - self.M
+        return 0.5 * two_kl.sum()
