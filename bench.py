@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- GP-ODE RK4 latent trajectory-steps/s, forward + backward, on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+One "step" = one pass of the hot path over one batch: fixed-grid RK4 (3/8 rule) rollout of every
+(trajectory, MC-sample) latent state over the T-point grid and its reverse sweep with all parameter
+gradients.  Default workload = BASELINE.json configs[4] ("scaled data-parallel rollout": 65,536
+trajectories x 8 MC samples, latent_dim 16, M=512 inducing, S=256 features, T=64, RK4) on EVERY GPU
+(weak scaling: ranks hold independent trajectory shards, parameters replicated, one NCCL all-reduce of
+the kernel-level gradients per step).  Unit of work: trajectory-step = one state advanced over one grid
+interval, all 4 stages, forward and backward.
+
+Prints ONE JSON line (rank 0).  `value` = kernel path with inputs resident in HBM; `e2e` = the same
+metric through the public drop-in API (Flow.forward_samples -> build_cache -> rollout -> backward) with
+z0 and the random draws coming from host memory every step and the loss / gradients read back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "vae-gp-ode_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[4]; per GPU
+    "cfg5_rbf_d16_m512_t64_rk4": dict(variant="rbf_dimwise", kernel="RBF", N=65536, L=8, D_in=16, D_out=16, M=512, S=256, T=64,
+                                      order=1, method="rk4", ell=2.0, var=1.0),
+    # smaller shapes for quick looks (not the headline)
+    "cfg5_eighth": dict(variant="rbf_dimwise", kernel="RBF", N=8192, L=8, D_in=16, D_out=16, M=512, S=256, T=64, order=1,
+                        method="rk4", ell=2.0, var=1.0),
+    "cfg4_rbf_d6_m256_t2_euler": dict(variant="rbf_dimwise", kernel="RBF", N=1048576, L=1, D_in=6, D_out=6, M=256, S=256, T=2,
+                                      order=1, method="euler", ell=2.0, var=1.0),
+    "cfg1_rbf_d6_m100_t16_rk4": dict(variant="rbf_dimwise", kernel="RBF", N=25, L=1, D_in=6, D_out=6, M=100, S=256, T=16, order=1,
+                                     method="rk4", ell=2.0, var=1.0),
+}
+DEFAULT_WORKLOAD = "cfg5_rbf_d16_m512_t64_rk4"
+STAGES = {"euler": 1, "midpoint": 2, "rk4": 4}
+# cpu sample of the default workload: same per-trajectory-step work (D, M, S, RK4), fewer trajectories / grid points
+CPU_SAMPLE = dict(N=256, L=1, T=32)
+
+
+def algorithmic_work(w):
+    """per trajectory-step, forward+backward: fwd+bwd = 3x flops, 2x SFU of one forward evaluation."""
+    st = STAGES[w["method"]]
+    if w["variant"] == "df":
+        D = w["D_in"]
+        f1 = 2 * (3 * w["S"] * D * D + w["M"] * (6 * D * D + 2 * D))
+        s1 = 2 * w["S"] * D + w["M"] * D * D
+    elif w["variant"] == "rbf_shared":
+        f1 = 2 * (w["S"] + w["M"]) * (w["D_in"] + w["D_out"])
+        s1 = w["S"] + w["M"]
+    else:
+        f1 = 2 * w["D_out"] * (w["S"] + w["M"]) * (w["D_in"] + 1)
+        s1 = w["D_out"] * (w["S"] + w["M"])
+    return dict(flops=3 * st * f1, sfu=2 * st * s1, hbm_bytes=3 * w["D_in"] * 4)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-f", self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+        except Exception:
+            return out
+        sm, reasons, mx, pw = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                pw.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if sm:
+            busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw) if pw else None)
+        return out
+
+
+def seeded_draw_patch(seed):
+    """Seed the drop-in's host RNG helpers (same three helpers the reference has)."""
+    from gpode_b200.core import kernels as K
+    from gpode_b200.core import svpy as SV
+    rng = np.random.RandomState(seed)
+    K.sample_normal = lambda shape, seed=None: torch.tensor(rng.normal(size=shape).astype(np.float32))
+    K.sample_uniform = lambda shape, seed=None: torch.tensor(rng.uniform(size=shape).astype(np.float32))
+    SV.sample_normal = lambda shape, seed=None: torch.tensor(rng.normal(size=shape).astype(np.float32))
+
+
+def build_model(w, device, seed):
+    from gpode_b200.core.flow import Flow
+    from gpode_b200.core.svpy import SVGP_Layer
+    from gpode_b200.misc.constraint_utils import invsoftplus
+    np.random.seed(seed)
+    gp = SVGP_Layer(D_in=w["D_in"], D_out=w["D_out"], M=w["M"], S=w["S"], q_diag=False, dimwise=w["variant"] != "rbf_shared",
+                    device=device, kernel=w["kernel"])
+    with torch.no_grad():
+        gp.kern.unconstrained_lengthscales.copy_(invsoftplus(torch.full_like(gp.kern.unconstrained_lengthscales, w["ell"])))
+        gp.kern.unconstrained_variance.copy_(invsoftplus(torch.full_like(gp.kern.unconstrained_variance, w["var"])))
+    flow = Flow(diffeq=gp, order=w["order"], solver=w["method"], use_adjoint=False)
+    return gp, flow
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import gpode_b200  # noqa: F401  (fails loudly if libgpode.so is missing)
+    from gpode_b200.core.svpy import FieldSample
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = dict(WORKLOADS[args.workload])
+    if args.scale != 1.0:
+        w["N"] = max(1, int(w["N"] * args.scale))
+    N, L, T, D = w["N"], w["L"], w["T"], w["D_in"]
+    steps_per_pass = N * L * (T - 1)
+    work = algorithmic_work(w)
+
+    # ---- resident inputs: L function samples (seeds 10..), z0, dL/dtraj ----------------------------------
+    gp, flow = build_model(w, dev, seed=1)
+    samples = []
+    with torch.no_grad():
+        for l in range(L):
+            seeded_draw_patch(10 + l)
+            gp.build_cache()
+            samples.append(gp.field_sample())
+    fs = FieldSample.stack(samples)
+    leaf = lambda v: v.detach().clone().requires_grad_(True)
+    Z, nu, ell, var = leaf(fs.Z), leaf(fs.nu), leaf(fs.ell), leaf(fs.var)
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    z0 = torch.randn(N, D, device=dev, generator=gen).requires_grad_(True)
+    dtraj = torch.randn(L, N, T, D, device=dev, generator=gen)
+    ts = 0.1 * torch.arange(T, dtype=torch.float, device=dev)
+    from gpode_b200 import gp_rollout
+
+    def allreduce_grads(tensors):
+        if world > 1:
+            flat = torch.cat([t_.reshape(-1) for t_ in tensors])
+            dist.all_reduce(flat)
+            return flat
+        return None
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    t_fwd = t_bwd = 0.0
+
+    def kernel_step(record):
+        nonlocal t_fwd, t_bwd
+        for v in (z0, Z, nu, ell, var):
+            v.grad = None
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        traj = gp_rollout(z0, ts, Z, nu, fs.eps, fs.phase, fs.w, ell, var, w["variant"], w["order"], w["method"], fs.B)
+        e1.record()
+        traj.backward(dtraj)
+        allreduce_grads([Z.grad, nu.grad, ell.grad, var.grad])
+        e2.record()
+        if record is not None:
+            record.append((e0, e1, e2))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn(None)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        rec = []
+        s, e = ev(), ev()
+        s.record()
+        for _ in range(steps):
+            fn(rec)
+        e.record()
+        barrier()
+        clocks = sampler.stop()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = tms.item()
+        return ms, rec, clocks
+
+    ms_total, rec, clocks = timed(kernel_step, args.steps, args.warmup)
+    ms_step = ms_total / args.steps
+    fwd_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in rec]))
+    bwd_ms = float(np.mean([b.elapsed_time(c) for _, b, c in rec]))
+    value = world * steps_per_pass / (ms_step * 1e-3)
+
+    # ---- end to end through the drop-in API, host buffers in the timed region --------------------------
+    z0_host = torch.randn(N, D).pin_memory()
+    h2d = [0]
+    d2h = [0]
+    params = [gp.kern.unconstrained_lengthscales, gp.kern.unconstrained_variance, gp.inducing_loc.optvar, gp.Um.optvar,
+              gp.Us_sqrt.optvar]
+    seeded_draw_patch(77 + rank)
+
+    def e2e_step(record):
+        for p_ in params:
+            p_.grad = None
+        z = z0_host.to(dev, non_blocking=True).requires_grad_(True)
+        traj = flow.forward_samples(z, ts, L)                 # build_cache (host draws -> H2D) x L, one rollout launch
+        loss = (traj * dtraj).sum() + flow.kl()
+        loss.backward()
+        flat = allreduce_grads([p_.grad for p_ in params])
+        host = [loss.detach().cpu()] + [(p_.grad if flat is None else p_.grad).cpu() for p_ in params] + [z.grad.cpu()]
+        if record is not None and not h2d[0]:
+            draws = L * (w["S"] * w["D_out"] + w["D_in"] * w["S"] * w["D_out"] + w["S"] * w["D_out"] + w["M"] * w["D_out"]) * 4
+            h2d[0] = z0_host.numel() * 4 + draws
+            d2h[0] = sum(h.numel() * 4 for h in host)
+
+    e2e_warm = min(args.warmup, 3)
+    ms_e2e, _, _ = timed(e2e_step, args.steps, e2e_warm)
+    e2e_value = world * steps_per_pass / (ms_e2e / args.steps * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    fp32_peak = 148 * 128 * 2 * sm_max          # FFMA lanes x 2 flop x max SM clock
+    sfu_peak = 148 * 16 * sm_max
+    per_gpu_rate = steps_per_pass / (ms_step * 1e-3)
+    t_fma = work["flops"] / fp32_peak
+    t_sfu = work["sfu"] / sfu_peak
+    bound_s = max(t_fma, t_sfu) * per_gpu_rate   # fraction of the binding pipe's peak
+    achieved_tflops = work["flops"] * per_gpu_rate / 1e12
+    roof = {"bound": "fp32_fma" if t_fma >= t_sfu else "sfu", "achieved": round(achieved_tflops, 3), "peak": round(fp32_peak / 1e12, 2),
+            "unit": "TFLOP/s", "frac": round(bound_s, 4), "traffic": None,
+            "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json (%s); not an HBM/tensor bound path" % peak_src,
+            "sfu_achieved_tops": round(work["sfu"] * per_gpu_rate / 1e12, 4), "sfu_peak_tops": round(sfu_peak / 1e12, 3),
+            "sfu_frac": round(work["sfu"] * per_gpu_rate / sfu_peak, 4),
+            "hbm_achieved_gbs": round(work["hbm_bytes"] * per_gpu_rate / 1e9, 3), "hbm_peak_gbs": peaks.get("hbm_gbs"),
+            "hbm_frac": round(work["hbm_bytes"] * per_gpu_rate / 1e9 / float(peaks.get("hbm_gbs", 6650.0)), 6),
+            "flops_per_traj_step": work["flops"], "sfu_per_traj_step": work["sfu"], "bytes_per_traj_step": work["hbm_bytes"],
+            "fwd_call_ms": round(fwd_ms, 3), "bwd_call_ms": round(bwd_ms, 3),
+            "fwd_frac": round((work["flops"] / 3) * steps_per_pass / fp32_peak / (fwd_ms * 1e-3), 4),
+            "bwd_frac": round((2 * work["flops"] / 3) * steps_per_pass / fp32_peak / (bwd_ms * 1e-3), 4)}
+    peaks_bin = os.path.join(ROOT, "tools", "peaks")
+    if world == 1 and os.path.exists(peaks_bin) and not args.no_cpu_baseline:
+        try:
+            pk = json.loads(subprocess.check_output([peaks_bin], timeout=120).decode().strip().splitlines()[-1])
+            roof["ffma_measured_tflops"] = pk["ffma_tflops"]
+            roof["mufu_measured_tops"] = pk["ex2_tops"]
+            roof["frac_of_measured_ffma"] = round(achieved_tflops / pk["ffma_tflops"], 4)
+        except Exception as exc:  # the microbenchmark is informative only
+            roof["ffma_measured_tflops"] = "unavailable: %s" % exc
+
+    line = {"metric": "GP-ODE RK4 latent traj-steps/s fwd+bwd", "value": round(value, 1), "unit": "traj-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "per_gpu": {k: w[k] for k in ("N", "L", "T", "D_in", "D_out", "M", "S", "method", "order", "variant")},
+                       "traj_steps_per_gpu_per_step": steps_per_pass, "parallelism": "dp%d (trajectory shards, params replicated)" % world,
+                       "cache": "inputs and saves (%.1f GB) far exceed the 126 MB L2; no flush needed" %
+                                ((T - 1) * STAGES[w["method"]] * (2 * D + w["D_out"]) * N * L * 4 / 1e9)},
+            "roofline": roof,
+            "e2e": {"value": round(e2e_value, 1), "unit": "traj-steps/s", "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": 7 * args.steps, "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(w, reps=3, warmup=1)
+        except Exception as exc:
+            line["cpu_baseline"] = {"value": None, "unit": "traj-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % exc}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(w, reps, warmup):
+    """The reference's CPU path (oracle port with the reference's op sequence) on this box's host cores, on a bounded
+    sample of the workload.  Runs in a subprocess with CUDA hidden, like the reference would on a CPU-only host."""
+    cores = os.cpu_count() or 1
+    s = dict(w)
+    s.update(CPU_SAMPLE)
+    s["N"] = min(s["N"], w["N"])
+    s["T"] = min(s["T"], w["T"])
+    code = ("import sys, json; sys.path.insert(0, %r); import torch; from oracle import port_fp32 as P; "
+            "sec = P.time_rollout(%r, %d, %d, %d, %d, %d, %d, %d, %r, reps=%d, warmup=%d, threads=%d); print(json.dumps(sec))"
+            % (ROOT, s["variant"], s["N"], s["D_in"], s["D_out"], s["M"], s["S"], s["T"], s["order"], s["method"], reps, warmup, cores))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    proc = subprocess.run([sys.executable, "-c", code], env=env, timeout=1200, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    if proc.returncode != 0:
+        raise RuntimeError("cpu baseline subprocess failed: %s" % proc.stderr.decode()[-2000:])
+    sec = json.loads(proc.stdout.decode().strip().splitlines()[-1])
+    n_steps = s["N"] * (s["T"] - 1)
+    return {"value": round(n_steps / sec, 1), "unit": "traj-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d trajectories x 1 MC sample, T=%d, same D=%d M=%d S=%d %s; best of %d after %d warm-up; oracle/port_fp32.py "
+                      "(reference op sequence, torch CPU fp32, %d threads)" % (s["N"], s["T"], s["D_in"], s["M"], s["S"], s["method"],
+                                                                            reps, warmup, cores),
+            "seconds_per_pass": round(sec, 3)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference is Python and
+    /root/reference does not exist on the GPU box), all host threads, same metric / unit / config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = dict(WORKLOADS[args.workload])
+    base = cpu_baseline(w, reps=args.steps, warmup=args.warmup)
+    value = base["value"]
+    line = {"impl": "reference", "metric": "GP-ODE RK4 latent traj-steps/s fwd+bwd", "value": value, "unit": "traj-steps/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", str(args.gpus))), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(base["seconds_per_pass"] * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "per_gpu": {k: w[k] for k in ("N", "L", "T", "D_in", "D_out", "M", "S", "method", "order", "variant")}},
+            "cpu_baseline": base, "e2e": {"value": value, "unit": "traj-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="scale the trajectory count (debugging only; not a valid bench line)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
