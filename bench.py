@@ -42,6 +42,8 @@ WORKLOADS = {
     # smaller shapes for quick looks (not the headline)
     "cfg5_eighth": dict(variant="rbf_dimwise", kernel="RBF", N=8192, L=8, D_in=16, D_out=16, M=512, S=256, T=64, order=1,
                         method="rk4", ell=2.0, var=1.0),
+    "cfg5_t3": dict(variant="rbf_dimwise", kernel="RBF", N=65536, L=8, D_in=16, D_out=16, M=512, S=256, T=3, order=1,
+                    method="rk4", ell=2.0, var=1.0),   # config-5 shapes, 2 grid intervals: short enough for ncu --set full
     "cfg4_rbf_d6_m256_t2_euler": dict(variant="rbf_dimwise", kernel="RBF", N=1048576, L=1, D_in=6, D_out=6, M=256, S=256, T=2,
                                       order=1, method="euler", ell=2.0, var=1.0),
     "cfg1_rbf_d6_m100_t16_rk4": dict(variant="rbf_dimwise", kernel="RBF", N=25, L=1, D_in=6, D_out=6, M=100, S=256, T=16, order=1,

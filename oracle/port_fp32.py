@@ -129,8 +129,11 @@ def time_rollout(variant, N, D_in, D_out, M, S, T, order, method, reps=1, warmup
     ts = 0.1 * torch.arange(T, dtype=torch.float)
     G = torch.randn(N, T, D_in, generator=g)
     best = float("inf")
+    dimwise = variant != "rbf_shared"
     for it in range(warmup + reps):
         t0 = time.perf_counter()
+        # per-rollout part of build_cache that sits in the autograd graph: omega = eps / ell (kernels.py:120-124)
+        c["omega"] = c["eps"] / (c["ell"].t().unsqueeze(1) if dimwise else c["ell"].unsqueeze(1))
         traj = rollout(z0, ts, c, order, method)
         (traj * G).sum().backward()
         dt = time.perf_counter() - t0

@@ -42,16 +42,26 @@ RbfGeom rbf_geom(const GpodeProblem* p, int order) {
   g.S = p->S;
   g.MP2 = (p->M + 1) / 2;
   g.SP2 = (p->S + 1) / 2;
-  g.tile_floats = rbf_tile_floats(g.DP, g.SP2, g.MP2);
+  g.hdr_floats = rbf_hdr_floats(g.DP);
+  g.row_floats = rbf_row_floats(g.DP);
+  const int rc_max = kChunkBytes / (g.row_floats * 4);   // rows per chunk, balanced inside each section
+  g.NCs = (g.SP2 + rc_max - 1) / rc_max;
+  g.RCs = (g.SP2 + g.NCs - 1) / g.NCs;
+  g.NCm = (g.MP2 + rc_max - 1) / rc_max;
+  g.RCm = (g.MP2 + g.NCm - 1) / g.NCm;
+  g.stage_floats = (g.RCs > g.RCm ? g.RCs : g.RCm) * g.row_floats;
   g.order = order;
   g.off = p->D_in - p->D_out;
+  g.cg.stage_floats = g.stage_floats;
+  g.cg.row_floats = g.row_floats;
+  g.cg.SP2 = g.SP2; g.cg.MP2 = g.MP2; g.cg.NCs = g.NCs; g.cg.NCm = g.NCm; g.cg.RCs = g.RCs; g.cg.RCm = g.RCm;
+  g.cg.D_out = g.D_out;
   return g;
 }
 
 size_t packed_floats(const GpodeProblem* p) {
   if (p->variant == GPODE_DF) return df_packed_floats(df_geom(p));
-  const RbfGeom g = rbf_geom(p, 1);
-  return static_cast<size_t>(g.L) * g.D_out * g.tile_floats;
+  return rbf_packed_floats(rbf_geom(p, 1));
 }
 
 size_t acc_floats(const GpodeProblem* p, Ws* w) {
@@ -112,7 +122,7 @@ int check_ws(const void* ws, size_t bytes, size_t need) {
   return GPODE_OK;
 }
 
-int rbf_check_smem(const RbfGeom& g) { return rbf_smem_bytes(g) <= kSmemLimit ? GPODE_OK : GPODE_E_UNSUPPORTED; }
+int rbf_check_smem(const RbfGeom& g) { return rbf_smem_bytes(g, 256, 4, true) <= kSmemLimit ? GPODE_OK : GPODE_E_UNSUPPORTED; }
 
 cudaError_t rbf_pack(const GpodeProblem* p, const RbfGeom& g, float* packed, cudaStream_t st) {
   RbfPackArgs a;
@@ -124,7 +134,7 @@ cudaError_t rbf_pack(const GpodeProblem* p, const RbfGeom& g, float* packed, cud
 }
 
 int pgrad_chunks(long evals_per_sample, int ctas_per_chunk) {
-  const long target = 148L * 8;
+  const long target = 148L * 12;
   long c = (target + ctas_per_chunk - 1) / ctas_per_chunk;
   const long maxc = (evals_per_sample + 127) / 128;
   if (c > maxc) c = maxc;
@@ -140,7 +150,7 @@ cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float
   pa.xsave = xsave;
   pa.gsave = gsave;
   pa.n_te = n_te;
-  pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L);
+  pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * ((g.MP2 + 127) / 128));
   pa.acc = acc;
   cudaError_t e = rbf_launch_pgrad(pa, st);
   if (e != cudaSuccess) return e;

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "chunk_geom.h"
 #include "gpode.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -75,71 +76,91 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-// Streams the per-(sample, output-dim) parameter tiles of one sample through two shared-memory
-// buffers: tile g of the sequence is tile (g mod n_tiles) of the sample.  One elected thread issues
-// the copies; everybody waits on the tile's mbarrier.  release() is a CTA-wide barrier, so every
-// thread of the CTA must walk the same tile sequence.
-struct TilePipe {
-  float* buf0;
-  uint64_t* bar;
-  const float* src;
-  uint32_t tile_bytes;
-  int tile_floats;
-  int n_tiles;
-  long total;
-  long cur;
-  int next_k;  // tile index (mod n_tiles) of the next copy to issue (thread 0 only)
+// ---- packed RBF parameter layout (floats) -------------------------------------------------------
+// per sample l:  headers [D_out][HDR]   : c_kd = -log2(e) / (2 ell_kd^2), d < DP, zero padded to HDR
+//                rows    [D_out][NR][ROW]: NR = SP2 + MP2 rows of (DP+2) float2 = (DP+2)/2 float4
+//                   feature rows  j < SP2 : {omega(2j,d), omega(2j+1,d)}_d<DP, {b, b}, {w', w'}
+//                   inducing rows j >= SP2: {G(2m,d), G(2m+1,d)}_d<DP, {H, H}, {ln2 nu', ln2 nu'}
+// DP = D_in rounded up to even.  Rows stream through shared memory in chunks of <= RC rows that never
+// straddle the feature / inducing boundary.
+__host__ __device__ constexpr int rbf_hdr_floats(int DP) { return ((DP + 3) / 4) * 4; }
+__host__ __device__ constexpr int rbf_row_floats(int DP) { return (DP + 2) * 2; }
+constexpr int kChunkBytes = 12 * 1024;
+constexpr int kPipeStages = 3;
 
-  __device__ __forceinline__ void issue(long g) {
-    if (g < total) {
-      const int b = static_cast<int>(g & 1);
-      mbar_expect_tx(bar + b, tile_bytes);
-      bulk_g2s(buf0 + b * tile_floats, src + static_cast<size_t>(next_k) * tile_floats, tile_bytes, bar + b);
-      next_k = (next_k + 1 == n_tiles) ? 0 : next_k + 1;
+// Streams the row chunks of one sample through a ring of shared-memory stages with 1-D TMA bulk
+// copies (cp.async.bulk -> UBLKCP) completing on mbarriers.  The chunk sequence is cyclic over
+// (k = 0..D_out-1) x (feature chunks, inducing chunks) and repeats for every field evaluation.  One
+// elected thread issues copies; all threads wait.  release() is a CTA-wide barrier, so every thread of
+// the CTA walks the same sequence.
+struct ChunkPipe {
+  float* buf0;
+  uint64_t* bar;       // kPipeStages mbarriers, then 4 ints of producer state (thread 0 only)
+  const float* rows;   // rows region of this sample
+  int stage;           // consumer ring position
+  uint32_t phase;
+
+  __device__ __forceinline__ void issue_next(const ChunkGeom& cg, long total) {
+    int* ps = reinterpret_cast<int*>(bar + kPipeStages);  // {issued_lo.., pk, pc, pstage}
+    long issued = *reinterpret_cast<long*>(ps);
+    if (issued < total) {
+      int pk = ps[2], pc = ps[3], pstage = ps[4];
+      int r0, n;
+      if (pc < cg.NCs) {
+        r0 = pc * cg.RCs;
+        n = min(cg.RCs, cg.SP2 - r0);
+      } else {
+        const int cm = pc - cg.NCs;
+        n = min(cg.RCm, cg.MP2 - cm * cg.RCm);
+        r0 = cg.SP2 + cm * cg.RCm;
+      }
+      const uint32_t bytes = static_cast<uint32_t>(n * cg.row_floats) * 4u;
+      mbar_expect_tx(bar + pstage, bytes);
+      bulk_g2s(buf0 + pstage * cg.stage_floats, rows + (static_cast<size_t>(pk) * (cg.SP2 + cg.MP2) + r0) * cg.row_floats, bytes,
+               bar + pstage);
+      pstage = (pstage + 1 == kPipeStages) ? 0 : pstage + 1;
+      if (++pc == cg.NCs + cg.NCm) {
+        pc = 0;
+        pk = (pk + 1 == cg.D_out) ? 0 : pk + 1;
+      }
+      *reinterpret_cast<long*>(ps) = issued + 1;
+      ps[2] = pk;
+      ps[3] = pc;
+      ps[4] = pstage;
     }
   }
-  __device__ __forceinline__ void init(float* smem_tiles, uint64_t* bars, const float* sample_base, int tile_floats_, int n_tiles_,
-                                       long total_) {
-    buf0 = smem_tiles;
+  __device__ __forceinline__ void init(float* smem_stages, uint64_t* bars, const float* sample_rows, const ChunkGeom& cg, long total) {
+    buf0 = smem_stages;
     bar = bars;
-    src = sample_base;
-    tile_floats = tile_floats_;
-    tile_bytes = static_cast<uint32_t>(tile_floats_) * 4u;
-    n_tiles = n_tiles_;
-    total = total_;
-    cur = 0;
-    next_k = 0;
+    rows = sample_rows;
+    stage = 0;
+    phase = 0;
     if (threadIdx.x == 0) {
-      mbar_init(bar, 1);
-      mbar_init(bar + 1, 1);
+#pragma unroll
+      for (int i = 0; i < kPipeStages; ++i) mbar_init(bar + i, 1);
+      int* ps = reinterpret_cast<int*>(bar + kPipeStages);
+      ps[0] = ps[1] = ps[2] = ps[3] = ps[4] = 0;
       mbar_fence_init();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      issue(0);
-      issue(1);
+#pragma unroll
+      for (int i = 0; i < kPipeStages; ++i) issue_next(cg, total);
     }
   }
-  __device__ __forceinline__ const float* acquire() {
-    const int b = static_cast<int>(cur & 1);
-    mbar_wait(bar + b, static_cast<uint32_t>((cur >> 1) & 1));
-    return buf0 + b * tile_floats;
+  __device__ __forceinline__ const float* acquire(const ChunkGeom& cg) {
+    mbar_wait(bar + stage, phase);
+    return buf0 + stage * cg.stage_floats;
   }
-  __device__ __forceinline__ void release() {
-    __syncthreads();  // every warp is done reading buf[cur & 1]
-    if (threadIdx.x == 0) issue(cur + 2);
-    ++cur;
+  __device__ __forceinline__ void release(const ChunkGeom& cg, long total) {
+    __syncthreads();  // every warp is done reading the stage
+    if (threadIdx.x == 0) issue_next(cg, total);
+    if (++stage == kPipeStages) {
+      stage = 0;
+      phase ^= 1u;
+    }
   }
 };
-
-// ---- packed RBF tile geometry (floats) ----------------------------------------------------------
-// tile(l,k) = [ header: c_kd (DP floats, padded to a multiple of 4) |
-//               S/2 rows: {omega(2j,d),omega(2j+1,d)}_d<DP, {b,b}, {w',w'} |
-//               M/2 rows: {G(2j,d),G(2j+1,d)}_d<DP, {H,H}, {nu',nu'} ]
-// every row is (DP+2) float2 = (DP+2)/2 float4; DP = D_in rounded up to even.
-__host__ __device__ constexpr int rbf_hdr_floats(int DP) { return ((DP + 3) / 4) * 4; }
-__host__ __device__ constexpr int rbf_row_floats(int DP) { return (DP + 2) * 2; }
-__host__ __device__ inline int rbf_tile_floats(int DP, int SP2, int MP2) { return rbf_hdr_floats(DP) + (SP2 + MP2) * rbf_row_floats(DP); }
 
 // Butcher tableaux of the fixed-grid methods (strictly lower A, weights b), see oracle/solvers.py
 struct Tableau {

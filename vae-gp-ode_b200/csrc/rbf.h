@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include "chunk_geom.h"
+
 namespace gpode {
 
 // Save-buffer indexing: entry (te, c, s) with te = t * stages + i (t = 0 when nothing is kept),
@@ -11,9 +13,23 @@ struct RbfGeom {
   int L, N, NL;          // samples, states per sample, L*N
   int D_in, D_out, DP;   // DP = D_in rounded up to even
   int M, S, MP2, SP2;    // pairs (rounded up)
-  int tile_floats;       // floats per packed (l,k) tile
+  int NCs, NCm, RCs, RCm;  // chunks / rows per chunk of the feature and inducing sections
+  int stage_floats;      // floats of one pipeline stage (largest chunk)
+  int hdr_floats;        // floats per (l,k) header
+  int row_floats;        // floats per row
   int order, off;        // ODE order; off = D_in - D_out: where f sits inside the state derivative
+  ChunkGeom cg;          // the same chunking, in the form the pipeline reads
 };
+// packed = [L][D_out][hdr_floats] headers, then [L][D_out][SP2+MP2][row_floats] rows
+inline size_t rbf_packed_floats(const RbfGeom& g) {
+  return static_cast<size_t>(g.L) * g.D_out * (g.hdr_floats + static_cast<size_t>(g.SP2 + g.MP2) * g.row_floats);
+}
+__host__ __device__ inline const float* rbf_hdr_ptr(const float* packed, const RbfGeom& g, int l) {
+  return packed + static_cast<size_t>(l) * g.D_out * g.hdr_floats;
+}
+__host__ __device__ inline const float* rbf_rows_ptr(const float* packed, const RbfGeom& g, int l) {
+  return packed + static_cast<size_t>(g.L) * g.D_out * g.hdr_floats + static_cast<size_t>(l) * g.D_out * (g.SP2 + g.MP2) * g.row_floats;
+}
 
 struct RbfFieldFwdArgs {
   RbfGeom g;
@@ -119,7 +135,7 @@ cudaError_t rbf_launch_rollout_bwd(const RbfRolloutBwdArgs& a, cudaStream_t st);
 cudaError_t rbf_launch_pgrad(const RbfPgradArgs& a, cudaStream_t st);
 cudaError_t rbf_launch_pack(const RbfPackArgs& a, cudaStream_t st);
 cudaError_t rbf_launch_finalize(const RbfFinalizeArgs& a, cudaStream_t st);
-int rbf_smem_bytes(const RbfGeom& g);  // dynamic shared memory of the sweep kernels
+int rbf_smem_bytes(const RbfGeom& g, int threads, int R, bool bwd);  // dynamic shared memory of the sweep kernels
 
 }  // namespace gpode
 

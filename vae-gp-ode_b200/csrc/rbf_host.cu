@@ -4,11 +4,16 @@
 
 namespace gpode {
 
-int rbf_smem_bytes(const RbfGeom& g) { return 128 + 2 * g.tile_floats * 4 + g.D_out * (g.DP + 1) * 4; }
+int rbf_smem_bytes(const RbfGeom& g, int threads, int R, bool bwd) {
+  int floats = 32 + kPipeStages * g.stage_floats + g.D_out * g.hdr_floats + g.DP * R * threads;
+  if (bwd) floats += g.DP * R * threads + g.D_out * (g.DP + 1);
+  return floats * 4;
+}
 
 // ---------------------------------------------------------------------------------------------
-// pack: reference-layout tensors -> per-(sample, output dim) tiles (layout in common.cuh)
-//   omega = eps / ell (kernels.py:120-124), w' = sqrt(var/S) w (kernels.py:149), nu' = var nu (kernels.py:106-107,180)
+// pack: reference-layout tensors -> headers + rows per (sample, output dim) (layout in common.cuh)
+//   omega = eps / ell (kernels.py:120-124), w' = sqrt(var/S) w (kernels.py:149), nu' = var nu (kernels.py:106-107,180);
+//   inducing rows carry ln2 * nu' so that the reverse sweep needs no extra multiply (the forward divides once per output)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_rbf_pack(const RbfPackArgs a) {
   const RbfGeom& g = a.g;
@@ -18,16 +23,16 @@ __global__ void k_rbf_pack(const RbfPackArgs a) {
   if (row > n_rows) return;
   const bool dimwise = a.variant == GPODE_RBF_DIMWISE;
   const int DP = g.DP, D_in = g.D_in, D_out = g.D_out, S = g.S, M = g.M;
-  float* tile = a.packed + (static_cast<size_t>(l) * D_out + k) * g.tile_floats;
-  const int HDR = rbf_hdr_floats(DP);
   const float var_k = dimwise ? a.var[k] : a.var[0];
   auto ell = [&](int d) { return dimwise ? a.ell[k * D_in + d] : a.ell[d]; };
   auto ckd = [&](int d) { const float e = ell(d); return -0.5f * kLog2e / (e * e); };
   if (row == n_rows) {  // header
-    for (int d = 0; d < HDR; ++d) tile[d] = d < D_in ? ckd(d) : 0.f;
+    float* hdr = const_cast<float*>(rbf_hdr_ptr(a.packed, g, l)) + k * g.hdr_floats;
+    for (int d = 0; d < g.hdr_floats; ++d) hdr[d] = d < D_in ? ckd(d) : 0.f;
     return;
   }
-  float2* out = reinterpret_cast<float2*>(tile + HDR) + static_cast<size_t>(row) * (DP + 2);
+  float2* out = reinterpret_cast<float2*>(const_cast<float*>(rbf_rows_ptr(a.packed, g, l)) +
+                                          (static_cast<size_t>(k) * n_rows + row) * g.row_floats);
   if (row < g.SP2) {
     const float amp = sqrtf(var_k / static_cast<float>(S));
     for (int d = 0; d < DP; ++d) {
@@ -68,7 +73,8 @@ __global__ void k_rbf_pack(const RbfPackArgs a) {
     }
     for (int h = 0; h < 2; ++h) {
       const int m = 2 * j + h;
-      if (m < M) nu[h] = var_k * (dimwise ? a.nu[(static_cast<size_t>(l) * D_out + k) * M + m] : a.nu[(static_cast<size_t>(l) * M + m) * D_out + k]);
+      if (m < M)
+        nu[h] = kLn2 * var_k * (dimwise ? a.nu[(static_cast<size_t>(l) * D_out + k) * M + m] : a.nu[(static_cast<size_t>(l) * M + m) * D_out + k]);
     }
     out[DP] = make_float2(H[0], H[1]);
     out[DP + 1] = make_float2(nu[0], nu[1]);

@@ -4,16 +4,21 @@
 //   f_k(x) = sum_s w'_sk cos(x . omega_sk + b_sk)  +  sum_m nu'_km 2^( A_k(x) + x . G_km + H_km )
 //   with w' = sqrt(var_k/S) w, nu' = var_k nu, c_kd = -log2(e)/(2 ell_kd^2), A_k = sum_d c_kd x_d^2,
 //   G_kmd = -2 c_kd Z_md, H_km = sum_d c_kd Z_md^2   (A + x.G + H = sum_d c_kd (x_d - Z_md)^2).
-// Mapping: R states per thread, the output dimension k is the OUTER loop so that only one
-// parameter tile (omega_k, G_k ...) is live; tiles stream through shared memory (TilePipe).  Inside a
-// tile, two features (or two inducing points) are processed per instruction with FFMA2: the state is
-// the scalar-broadcast operand, the parameters come as {even,odd} pairs from broadcast LDS.128.
+//
+// Mapping: R states per thread (register blocking: one broadcast LDS.128 of parameters feeds R states;
+// with R = 1 the kernel is LDS-bound), output dimension k is the OUTER loop so that only
+// the rows of one k are live; rows stream through shared memory in chunks (ChunkPipe, 1-D TMA).  Inside
+// a chunk two features (or two inducing points) are processed per instruction with FFMA2: the state is
+// the scalar-broadcast operand, the parameters come as {even, odd} pairs.
 #pragma once
 
 #include "common.cuh"
 #include "rbf.h"
 
 namespace gpode {
+
+constexpr float kHalfPi = 1.5707963267948966f;
+constexpr float kInvLn2 = 1.4426950408889634f;
 
 // one thread's R states inside sample l
 template <int R>
@@ -36,161 +41,231 @@ __device__ __forceinline__ States<R> map_states(const RbfGeom& g) {
   return st;
 }
 
-// ---------------------------------------------------------------------------------------------
-// forward: prior part fp and update part fu of output k for R states
-// ---------------------------------------------------------------------------------------------
+template <int DP>
+__device__ __forceinline__ void load_row(float4 (&v)[(DP + 2) / 2], const float4* row) {
+#pragma unroll
+  for (int i = 0; i < (DP + 2) / 2; ++i) v[i] = row[i];
+}
+
+// theta pair (two features / inducing points) of one state: row offset term + add + x . row
 template <int DP, int R>
-__device__ __forceinline__ void rbf_tile_fwd(const float* __restrict__ tile, int SP2, int MP2, const float (&x)[R][DP],
-                                             float (&fp)[R], float (&fu)[R]) {
-  constexpr int HDR = rbf_hdr_floats(DP);
-  constexpr int ROW4 = (DP + 2) / 2;  // float4 per row
+__device__ __forceinline__ float2 row_dot(const float4 (&v)[(DP + 2) / 2], const float (&x)[DP], float add) {
+  constexpr int ROW4 = (DP + 2) / 2;
+  float2 t0 = add2(lo(v[ROW4 - 1]), bc(add));
+  if constexpr (R == 1 && DP >= 4) {  // single state per thread: split the dependent chain in two
+    float2 t1 = mul2(bc(x[1]), hi(v[0]));
+    t0 = fma2(bc(x[0]), lo(v[0]), t0);
+#pragma unroll
+    for (int i = 1; i < DP / 2; ++i) {
+      t0 = fma2(bc(x[2 * i]), lo(v[i]), t0);
+      t1 = fma2(bc(x[2 * i + 1]), hi(v[i]), t1);
+    }
+    return add2(t0, t1);
+  } else {
+#pragma unroll
+    for (int i = 0; i < DP / 2; ++i) {
+      t0 = fma2(bc(x[2 * i]), lo(v[i]), t0);
+      t0 = fma2(bc(x[2 * i + 1]), hi(v[i]), t0);
+    }
+    return t0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward over one chunk of n rows: acc += weight * (IS_K ? 2^(theta) : cos(theta)).  Two rows per
+// iteration, all their LDS.128 issued first: 2R independent FFMA2 chains per thread.
+// ---------------------------------------------------------------------------------------------
+template <int DP, int R, bool IS_K>
+__device__ __forceinline__ void rows_fwd(const float* __restrict__ chunk, int n, const float (&x)[R][DP], const float (&A)[R],
+                                         float2 (&acc)[R]) {
+  constexpr int ROW4 = (DP + 2) / 2;
+  const float4* rows = reinterpret_cast<const float4*>(chunk);
+#pragma unroll 1
+  for (int j = 0; j < n; j += 2) {
+    float4 a[ROW4], b[ROW4];
+    const bool two = j + 1 < n;
+    load_row<DP>(a, rows + j * ROW4);
+    load_row<DP>(b, rows + (two ? j + 1 : j) * ROW4);
+    const float2 wb = two ? hi(b[ROW4 - 1]) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float2 ta = row_dot<DP, R>(a, x[r], IS_K ? A[r] : 0.f);
+      const float2 tb = row_dot<DP, R>(b, x[r], IS_K ? A[r] : 0.f);
+      acc[r] = fma2(IS_K ? ex2_2(ta) : cos_2(ta), hi(a[ROW4 - 1]), acc[r]);
+      acc[r] = fma2(IS_K ? ex2_2(tb) : cos_2(tb), wb, acc[r]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward over one chunk: Q_d += t.x row_d.x + t.y row_d.y with
+//   features:  t = w' cos(theta + pi/2) = -w' sin(theta)          (A carries the pi/2)
+//   inducing:  t = ln2 nu' 2^(theta)  (row weight already holds ln2 nu'), Es += t
+// so that  g_k d f_k / d x_d = g_k (Q_d + 2 c_d x_d Es).  Q uses scalar FFMA (same pipe cycles as FFMA2,
+// half the registers).
+// ---------------------------------------------------------------------------------------------
+template <int DP, int R, bool IS_K>
+__device__ __forceinline__ void row_bwd_one(const float4 (&v)[(DP + 2) / 2], float2 wgt, const float (&x)[DP], float add, float (&Q)[DP],
+                                            float& Es) {
+  const float2 th = row_dot<DP, R>(v, x, add);
+  const float2 t = mul2(wgt, IS_K ? ex2_2(th) : cos_2(th));
+  if (IS_K) Es += t.x + t.y;
+#pragma unroll
+  for (int i = 0; i < DP / 2; ++i) {
+    Q[2 * i] = fmaf(t.x, v[i].x, Q[2 * i]);
+    Q[2 * i] = fmaf(t.y, v[i].y, Q[2 * i]);
+    Q[2 * i + 1] = fmaf(t.x, v[i].z, Q[2 * i + 1]);
+    Q[2 * i + 1] = fmaf(t.y, v[i].w, Q[2 * i + 1]);
+  }
+}
+
+template <int DP, int R, bool IS_K>
+__device__ __forceinline__ void rows_bwd(const float* __restrict__ chunk, int n, const float (&x)[R][DP], const float (&A)[R],
+                                         float (&Q)[R][DP], float (&Es)[R]) {
+  constexpr int ROW4 = (DP + 2) / 2;
+  const float4* rows = reinterpret_cast<const float4*>(chunk);
+  if constexpr (DP <= 8) {
+#pragma unroll 1
+    for (int j = 0; j < n; j += 2) {
+      float4 a[ROW4], b[ROW4];
+      const bool two = j + 1 < n;
+      load_row<DP>(a, rows + j * ROW4);
+      load_row<DP>(b, rows + (two ? j + 1 : j) * ROW4);
+      const float2 wb = two ? hi(b[ROW4 - 1]) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        row_bwd_one<DP, R, IS_K>(a, hi(a[ROW4 - 1]), x[r], A[r], Q[r], Es[r]);
+        row_bwd_one<DP, R, IS_K>(b, wb, x[r], A[r], Q[r], Es[r]);
+      }
+    }
+  } else {  // wide rows: one row per iteration keeps the register footprint under the 3-CTA/SM budget
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+      float4 a[ROW4];
+      load_row<DP>(a, rows + j * ROW4);
+#pragma unroll
+      for (int r = 0; r < R; ++r) row_bwd_one<DP, R, IS_K>(a, hi(a[ROW4 - 1]), x[r], A[r], Q[r], Es[r]);
+    }
+  }
+}
+
+// shared-memory carve-up of the sweep kernels:
+//   [mbarriers + producer state (128 B) | kPipeStages x stage | headers D_out x HDR | xs DP x R x threads |
+//    (bwd) dx DP x R x threads | dell D_out x DP | dvar D_out]
+// xs / dx hold per-thread vectors as [d][r][thread] (conflict free); they let the solver glue run as small
+// rolled loops instead of DP x R unrolled register code.
+struct SweepSmem {
+  uint64_t* bars;
+  float* stages;
+  float* hdr;
+  float* xs;
+  float* dx;
+  float* dell;
+  float* dvar;
+};
+template <int DP, int R>
+__device__ __forceinline__ SweepSmem carve_smem(float* smem, const RbfGeom& g) {
+  SweepSmem s;
+  s.bars = reinterpret_cast<uint64_t*>(smem);
+  s.stages = smem + 32;
+  s.hdr = s.stages + kPipeStages * g.stage_floats;
+  s.xs = s.hdr + g.D_out * g.hdr_floats;
+  s.dx = s.xs + DP * R * blockDim.x;
+  s.dell = s.dx + DP * R * blockDim.x;
+  s.dvar = s.dell + g.D_out * DP;
+  return s;
+}
+
+template <int DP, int R>
+__device__ __forceinline__ void sweep_setup(SweepSmem& sm, ChunkPipe& pipe, const RbfGeom& g, const float* packed, long total, bool bwd) {
+  const int l = blockIdx.y;
+  const float* hdr = rbf_hdr_ptr(packed, g, l);
+  for (int i = threadIdx.x; i < g.D_out * g.hdr_floats; i += blockDim.x) sm.hdr[i] = hdr[i];
+  for (int i = threadIdx.x; i < DP * R * blockDim.x; i += blockDim.x) sm.xs[i] = 0.f;  // padded components stay 0
+  if (bwd)
+    for (int i = threadIdx.x; i < g.D_out * (DP + 1); i += blockDim.x) sm.dell[i] = 0.f;
+  // init() contains the __syncthreads that publishes the writes above
+  pipe.init(sm.stages, sm.bars, rbf_rows_ptr(packed, g, l), g.cg, total);
+}
+
+template <int DP, int R>
+__device__ __forceinline__ void load_x(const SweepSmem& sm, float (&x)[R][DP]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int d = 0; d < DP; ++d) x[r][d] = sm.xs[(d * R + r) * blockDim.x + threadIdx.x];
+}
+
+// one full forward evaluation of output k: streams the chunks of k, returns prior and update parts
+template <int DP, int R>
+__device__ __forceinline__ void eval_fwd_k(ChunkPipe& pipe, const RbfGeom& g, long total, const float* hdr_k, const float (&x)[R][DP], float (&fp)[R],
+                                           float (&fu)[R]) {
   float A[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) A[r] = 0.f;
 #pragma unroll
   for (int d = 0; d < DP; ++d) {
-    const float c = tile[d];
+    const float c = hdr_k[d];
 #pragma unroll
     for (int r = 0; r < R; ++r) A[r] = fmaf(c * x[r][d], x[r][d], A[r]);
   }
-  const float4* rows = reinterpret_cast<const float4*>(tile + HDR);
   float2 acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll 2
-  for (int j = 0; j < SP2; ++j) {
-    float4 v[ROW4];
-#pragma unroll
-    for (int i = 0; i < ROW4; ++i) v[i] = rows[j * ROW4 + i];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float2 th = lo(v[ROW4 - 1]);
-#pragma unroll
-      for (int i = 0; i < DP / 2; ++i) {
-        th = fma2(bc(x[r][2 * i]), lo(v[i]), th);
-        th = fma2(bc(x[r][2 * i + 1]), hi(v[i]), th);
-      }
-      acc[r] = fma2(cos_2(th), hi(v[ROW4 - 1]), acc[r]);
-    }
+  for (int c = 0; c < g.NCs; ++c) {
+    const float* chunk = pipe.acquire(g.cg);
+    rows_fwd<DP, R, false>(chunk, min(g.RCs, g.SP2 - c * g.RCs), x, A, acc);
+    pipe.release(g.cg, total);
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     fp[r] = acc[r].x + acc[r].y;
     acc[r] = make_float2(0.f, 0.f);
   }
-  rows += static_cast<size_t>(SP2) * ROW4;
-#pragma unroll 2
-  for (int j = 0; j < MP2; ++j) {
-    float4 v[ROW4];
-#pragma unroll
-    for (int i = 0; i < ROW4; ++i) v[i] = rows[j * ROW4 + i];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float2 ex = add2(lo(v[ROW4 - 1]), bc(A[r]));
-#pragma unroll
-      for (int i = 0; i < DP / 2; ++i) {
-        ex = fma2(bc(x[r][2 * i]), lo(v[i]), ex);
-        ex = fma2(bc(x[r][2 * i + 1]), hi(v[i]), ex);
-      }
-      acc[r] = fma2(ex2_2(ex), hi(v[ROW4 - 1]), acc[r]);
-    }
+  for (int c = 0; c < g.NCm; ++c) {
+    const float* chunk = pipe.acquire(g.cg);
+    rows_fwd<DP, R, true>(chunk, min(g.RCm, g.MP2 - c * g.RCm), x, A, acc);
+    pipe.release(g.cg, total);
   }
 #pragma unroll
-  for (int r = 0; r < R; ++r) fu[r] = acc[r].x + acc[r].y;
+  for (int r = 0; r < R; ++r) fu[r] = (acc[r].x + acc[r].y) * kInvLn2;  // inducing-row weights carry ln2
 }
 
-// ---------------------------------------------------------------------------------------------
-// backward (vector-Jacobian product) of output k: dxk[r][d] = g_k * d f_k / d x_d
-//   rff:  -g sum_s w' sin(theta) omega_d ;  update: g ln2 (2 c_d x_d sum_m e_m + sum_m e_m G_md), e_m = nu'_m E_m
-// ---------------------------------------------------------------------------------------------
+// one VJP of output k: dxk[r][d] = g_k d f_k / d x_d
 template <int DP, int R>
-__device__ __forceinline__ void rbf_tile_bwd(const float* __restrict__ tile, int SP2, int MP2, const float (&x)[R][DP],
-                                             const float (&gk)[R], float (&dxk)[R][DP]) {
-  constexpr int HDR = rbf_hdr_floats(DP);
-  constexpr int ROW4 = (DP + 2) / 2;
-  float A[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) A[r] = 0.f;
-#pragma unroll
-  for (int d = 0; d < DP; ++d) {
-    const float c = tile[d];
-#pragma unroll
-    for (int r = 0; r < R; ++r) A[r] = fmaf(c * x[r][d], x[r][d], A[r]);
-  }
-  const float4* rows = reinterpret_cast<const float4*>(tile + HDR);
-  float2 Q[R][DP];
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int d = 0; d < DP; ++d) Q[r][d] = make_float2(0.f, 0.f);
-#pragma unroll 2
-  for (int j = 0; j < SP2; ++j) {
-    float4 v[ROW4];
-#pragma unroll
-    for (int i = 0; i < ROW4; ++i) v[i] = rows[j * ROW4 + i];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float2 th = lo(v[ROW4 - 1]);
-#pragma unroll
-      for (int i = 0; i < DP / 2; ++i) {
-        th = fma2(bc(x[r][2 * i]), lo(v[i]), th);
-        th = fma2(bc(x[r][2 * i + 1]), hi(v[i]), th);
-      }
-      const float2 t = mul2(hi(v[ROW4 - 1]), sin_2(th));
-#pragma unroll
-      for (int i = 0; i < DP / 2; ++i) {
-        Q[r][2 * i] = fma2(t, lo(v[i]), Q[r][2 * i]);
-        Q[r][2 * i + 1] = fma2(t, hi(v[i]), Q[r][2 * i + 1]);
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      dxk[r][d] = -gk[r] * (Q[r][d].x + Q[r][d].y);
-      Q[r][d] = make_float2(0.f, 0.f);
-    }
-  rows += static_cast<size_t>(SP2) * ROW4;
-  float2 Es[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) Es[r] = make_float2(0.f, 0.f);
-#pragma unroll 2
-  for (int j = 0; j < MP2; ++j) {
-    float4 v[ROW4];
-#pragma unroll
-    for (int i = 0; i < ROW4; ++i) v[i] = rows[j * ROW4 + i];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float2 ex = add2(lo(v[ROW4 - 1]), bc(A[r]));
-#pragma unroll
-      for (int i = 0; i < DP / 2; ++i) {
-        ex = fma2(bc(x[r][2 * i]), lo(v[i]), ex);
-        ex = fma2(bc(x[r][2 * i + 1]), hi(v[i]), ex);
-      }
-      const float2 e = mul2(hi(v[ROW4 - 1]), ex2_2(ex));
-      Es[r] = add2(Es[r], e);
-#pragma unroll
-      for (int i = 0; i < DP / 2; ++i) {
-        Q[r][2 * i] = fma2(e, lo(v[i]), Q[r][2 * i]);
-        Q[r][2 * i + 1] = fma2(e, hi(v[i]), Q[r][2 * i + 1]);
-      }
-    }
-  }
+__device__ __forceinline__ void eval_bwd_k(ChunkPipe& pipe, const RbfGeom& g, long total, const float* hdr_k, const float (&x)[R][DP],
+                                           const float (&gk)[R], float (&dxk)[R][DP]) {
+  float A[R], Ap[R], Es[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const float es = Es[r].x + Es[r].y;
-    const float gl = gk[r] * kLn2;
+    A[r] = 0.f;
+    Ap[r] = kHalfPi;
+    Es[r] = 0.f;
+  }
 #pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      const float c2 = 2.f * tile[d];
-      dxk[r][d] = fmaf(gl, fmaf(c2 * x[r][d], es, Q[r][d].x + Q[r][d].y), dxk[r][d]);
+  for (int d = 0; d < DP; ++d) {
+    const float c = hdr_k[d];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      A[r] = fmaf(c * x[r][d], x[r][d], A[r]);
+      dxk[r][d] = 0.f;
     }
   }
+  for (int c = 0; c < g.NCs; ++c) {
+    const float* chunk = pipe.acquire(g.cg);
+    rows_bwd<DP, R, false>(chunk, min(g.RCs, g.SP2 - c * g.RCs), x, Ap, dxk, Es);
+    pipe.release(g.cg, total);
+  }
+  for (int c = 0; c < g.NCm; ++c) {
+    const float* chunk = pipe.acquire(g.cg);
+    rows_bwd<DP, R, true>(chunk, min(g.RCm, g.MP2 - c * g.RCm), x, A, dxk, Es);
+    pipe.release(g.cg, total);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int d = 0; d < DP; ++d) dxk[r][d] = gk[r] * fmaf(2.f * hdr_k[d] * x[r][d], Es[r], dxk[r][d]);
 }
-
-// shared-memory carve-up of the sweep kernels: [2 mbarriers (pad to 128 B) | tile 0 | tile 1 | dell_x | dvar]
-__device__ __forceinline__ float* smem_tiles(float* smem) { return smem + 32; }
 
 // Folds this thread's contribution to the lengthscale (sum_n x_d dx_kd) and variance (sum_n g (f - fp/2))
 // statistics of output k into the CTA accumulators: one warp reduction per value, lane 0 adds.
@@ -214,27 +289,31 @@ __device__ __forceinline__ void rbf_fold_stats(const float (&x)[R][DP], const fl
   }
 }
 
+#define GPODE_SWEEP_BOUNDS __launch_bounds__((DP <= 8 ? 256 : 128), (DP <= 8 ? 2 : 3))
+
+// smem slot of component d of this thread's r-th state
+#define GPODE_XS(buf, d, r) (buf)[((d) * R + (r)) * blockDim.x + threadIdx.x]
+
 // =============================================================================================
 // field forward: one evaluation, row-major I/O
 // =============================================================================================
 template <int DP, int R>
-__global__ void __launch_bounds__(256, 2) k_rbf_field_fwd(const RbfFieldFwdArgs a) {
+__global__ void GPODE_SWEEP_BOUNDS k_rbf_field_fwd(const RbfFieldFwdArgs a) {
   extern __shared__ __align__(128) float smem[];
   const RbfGeom& g = a.g;
   const States<R> st = map_states<R>(g);
-  TilePipe pipe;
-  pipe.init(smem_tiles(smem), reinterpret_cast<uint64_t*>(smem), a.packed + static_cast<size_t>(blockIdx.y) * g.D_out * g.tile_floats,
-            g.tile_floats, g.D_out, g.D_out);
-  float x[R][DP];
+  SweepSmem sm = carve_smem<DP, R>(smem, g);
+  ChunkPipe pipe;
+  const long total = static_cast<long>(g.D_out) * (g.NCs + g.NCm);
+  sweep_setup<DP, R>(sm, pipe, g, a.packed, total, false);
 #pragma unroll
   for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int d = 0; d < DP; ++d) x[r][d] = d < g.D_in ? a.x[st.s[r] * g.D_in + d] : 0.f;
+    for (int d = 0; d < g.D_in; ++d) GPODE_XS(sm.xs, d, r) = a.x[st.s[r] * g.D_in + d];
+  float x[R][DP];
+  load_x<DP, R>(sm, x);
   for (int k = 0; k < g.D_out; ++k) {
-    const float* tile = pipe.acquire();
     float fp[R], fu[R];
-    rbf_tile_fwd<DP, R>(tile, g.SP2, g.MP2, x, fp, fu);
-    pipe.release();
+    eval_fwd_k<DP, R>(pipe, g, total, sm.hdr + k * g.hdr_floats, x, fp, fu);
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (st.ok[r]) {
@@ -245,32 +324,32 @@ __global__ void __launch_bounds__(256, 2) k_rbf_field_fwd(const RbfFieldFwdArgs 
 }
 
 // =============================================================================================
-// rollout forward: fixed-grid euler / midpoint / rk4(3/8) over ts, all stages, one launch
+// rollout forward: fixed-grid euler / midpoint / rk4(3/8) over ts, all stages, one launch.
+// The state lives in global memory between evaluations (traj / save slabs written by this thread);
+// only the current stage input is register resident.
 // =============================================================================================
 template <int DP, int R>
-__global__ void __launch_bounds__(256, 2) k_rbf_rollout_fwd(const RbfRolloutFwdArgs a) {
+__global__ void GPODE_SWEEP_BOUNDS k_rbf_rollout_fwd(const RbfRolloutFwdArgs a) {
   extern __shared__ __align__(128) float smem[];
   const RbfGeom& g = a.g;
   const States<R> st = map_states<R>(g);
   const int stages = a.method == GPODE_EULER ? 1 : (a.method == GPODE_MIDPOINT ? 2 : 4);
   const long NL = g.NL;
   const int DS = g.D_in;
-  TilePipe pipe;
-  pipe.init(smem_tiles(smem), reinterpret_cast<uint64_t*>(smem), a.packed + static_cast<size_t>(blockIdx.y) * g.D_out * g.tile_floats,
-            g.tile_floats, g.D_out, static_cast<long>(a.T - 1) * stages * g.D_out);
+  SweepSmem sm = carve_smem<DP, R>(smem, g);
+  ChunkPipe pipe;
+  const long total = static_cast<long>(a.T - 1) * stages * g.D_out * (g.NCs + g.NCm);
+  sweep_setup<DP, R>(sm, pipe, g, a.packed, total, false);
 
-  float y0[R][DP], x[R][DP];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const long zrow = a.z0_per_sample ? st.s[r] : (st.s[r] - static_cast<long>(blockIdx.y) * g.N);
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      y0[r][d] = d < DS ? a.z0[zrow * DS + d] : 0.f;
-      if (st.ok[r] && d < DS) a.traj[(st.s[r] * a.T) * DS + d] = y0[r][d];
-    }
+    if (st.ok[r])
+      for (int d = 0; d < DS; ++d) a.traj[(st.s[r] * a.T) * DS + d] = a.z0[zrow * DS + d];
   }
-  // K_j[d] of the current step, re-read from the save slab this thread wrote
-  auto K = [&](long slab, int j, int d, int r) -> float { return a.ksave[((slab + j) * DS + d) * NL + st.s[r]]; };
+  float* ksave = a.ksave;  // plain pointers: values written below are re-read by the same thread
+  float* traj = a.traj;
+  const long ks = static_cast<long>(DS) * NL;  // K_j[d] sits j*ks after K_0[d]
 
 #pragma unroll 1
   for (int t = 0; t < a.T - 1; ++t) {
@@ -278,73 +357,105 @@ __global__ void __launch_bounds__(256, 2) k_rbf_rollout_fwd(const RbfRolloutFwdA
     const long slab = a.keep ? static_cast<long>(t) * stages : 0;
 #pragma unroll 1
     for (int i = 0; i < stages; ++i) {
-      // stage input (operation order of torchdiffeq's fixed-grid step functions)
+      // stage input, in the operation order of torchdiffeq's fixed-grid step functions
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int d = 0; d < DP; ++d) {
-          float v = y0[r][d];
-          if (d < DS && i > 0) {
-            if (a.method == GPODE_MIDPOINT) {
-              v = y0[r][d] + K(slab, 0, d, r) * (0.5f * dt);
-            } else if (i == 1) {
-              v = y0[r][d] + dt * K(slab, 0, d, r) * (1.f / 3.f);
-            } else if (i == 2) {
-              v = y0[r][d] + dt * (K(slab, 1, d, r) - K(slab, 0, d, r) * (1.f / 3.f));
-            } else {
-              v = y0[r][d] + dt * (K(slab, 0, d, r) - K(slab, 1, d, r) + K(slab, 2, d, r));
-            }
+      for (int r = 0; r < R; ++r) {
+        if (!st.ok[r]) continue;  // padded lanes keep whatever finite values the staging buffer holds (zeros)
+#pragma unroll 1
+        for (int d = 0; d < DS; ++d) {
+          const float y0 = traj[(st.s[r] * a.T + t) * DS + d];
+          const long kb = (slab * DS + d) * NL + st.s[r];
+          float v;
+          if (i == 0) {
+            v = y0;
+          } else if (a.method == GPODE_MIDPOINT) {
+            v = y0 + ksave[kb] * (0.5f * dt);
+          } else if (i == 1) {
+            v = y0 + dt * ksave[kb] * (1.f / 3.f);
+          } else if (i == 2) {
+            v = y0 + dt * (ksave[kb + ks] - ksave[kb] * (1.f / 3.f));
+          } else {
+            v = y0 + dt * (ksave[kb] - ksave[kb + ks] + ksave[kb + 2 * ks]);
           }
-          x[r][d] = v;
-          if (st.ok[r] && d < DS) a.xsave[((slab + i) * DS + d) * NL + st.s[r]] = v;
+          a.xsave[((slab + i) * DS + d) * NL + st.s[r]] = v;
+          GPODE_XS(sm.xs, d, r) = v;
+          // order 2: the first q components of the derivative are the velocity part of the state
+          if (g.order == 2 && d >= DP / 2) ksave[((slab + i) * DS + d - DP / 2) * NL + st.s[r]] = v;
         }
-      // order 2: the first q components of the derivative are the velocity part of the state
-      if (g.order == 2) {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int d = 0; d < DP / 2; ++d)
-            if (st.ok[r]) a.ksave[((slab + i) * DS + d) * NL + st.s[r]] = x[r][d + DP / 2];
       }
+      float x[R][DP];
+      load_x<DP, R>(sm, x);
       for (int k = 0; k < g.D_out; ++k) {
-        const float* tile = pipe.acquire();
         float fp[R], fu[R];
-        rbf_tile_fwd<DP, R>(tile, g.SP2, g.MP2, x, fp, fu);
-        pipe.release();
+        eval_fwd_k<DP, R>(pipe, g, total, sm.hdr + k * g.hdr_floats, x, fp, fu);
 #pragma unroll
         for (int r = 0; r < R; ++r)
           if (st.ok[r]) {
-            a.ksave[((slab + i) * DS + g.off + k) * NL + st.s[r]] = fp[r] + fu[r];
+            ksave[((slab + i) * DS + g.off + k) * NL + st.s[r]] = fp[r] + fu[r];
             a.fpsave[((slab + i) * g.D_out + k) * NL + st.s[r]] = fp[r];
           }
       }
     }
     // step update
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int d = 0; d < DP; ++d) {
-        if (d < DS) {
-          float v;
-          if (a.method == GPODE_EULER) {
-            v = y0[r][d] + dt * K(slab, 0, d, r);
-          } else if (a.method == GPODE_MIDPOINT) {
-            v = y0[r][d] + dt * K(slab, 1, d, r);
-          } else {
-            v = y0[r][d] + (K(slab, 0, d, r) + 3.f * (K(slab, 1, d, r) + K(slab, 2, d, r)) + K(slab, 3, d, r)) * dt * 0.125f;
-          }
-          y0[r][d] = v;
-          if (st.ok[r]) a.traj[(st.s[r] * a.T + (t + 1)) * DS + d] = v;
+    for (int r = 0; r < R; ++r) {
+      if (!st.ok[r]) continue;
+#pragma unroll 1
+      for (int d = 0; d < DS; ++d) {
+        const float y0 = traj[(st.s[r] * a.T + t) * DS + d];
+        const long kb = (slab * DS + d) * NL + st.s[r];
+        float v;
+        if (a.method == GPODE_EULER) {
+          v = y0 + dt * ksave[kb];
+        } else if (a.method == GPODE_MIDPOINT) {
+          v = y0 + dt * ksave[kb + ks];
+        } else {
+          v = y0 + (ksave[kb] + 3.f * (ksave[kb + ks] + ksave[kb + 2 * ks]) + ksave[kb + 3 * ks]) * dt * 0.125f;
         }
+        traj[(st.s[r] * a.T + (t + 1)) * DS + d] = v;
       }
+    }
   }
 }
 
 // =============================================================================================
-// rollout backward: reverse sweep through the unrolled solver (stage adjoints via the tableau)
+// all-k VJP at one state evaluation (stage input already staged in sm.xs): element (k, s) of the
+// upstream gradient / f / prior part sits at base[k * kstride + s * sstride].  Leaves sum_k dxk in
+// sm.dx and folds the lengthscale / variance statistics.
 // =============================================================================================
 template <int DP, int R>
-__global__ void __launch_bounds__(256, (DP <= 8 ? 2 : 1)) k_rbf_rollout_bwd(const RbfRolloutBwdArgs a) {
+__device__ __forceinline__ void vjp_all_k(ChunkPipe& pipe, const RbfGeom& g, long total, const SweepSmem& sm, const States<R>& st,
+                                          const float* gvec, const float* fvec, const float* fpvec, long kstride, long sstride) {
+  float x[R][DP];
+  load_x<DP, R>(sm, x);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int d = 0; d < DP; ++d) GPODE_XS(sm.dx, d, r) = 0.f;
+  for (int k = 0; k < g.D_out; ++k) {
+    float gk[R], fk[R], fpk[R], dxk[R][DP];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long at = k * kstride + st.s[r] * sstride;
+      gk[r] = st.ok[r] ? gvec[at] : 0.f;
+      fk[r] = fvec[at];
+      fpk[r] = fpvec[at];
+    }
+    eval_bwd_k<DP, R>(pipe, g, total, sm.hdr + k * g.hdr_floats, x, gk, dxk);
+    rbf_fold_stats<DP, R>(x, dxk, gk, fk, fpk, st.ok, sm.dell, sm.dvar, k);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int d = 0; d < DP; ++d) GPODE_XS(sm.dx, d, r) += dxk[r][d];
+  }
+}
+
+// =============================================================================================
+// rollout backward: reverse sweep through the unrolled solver (stage adjoints via the tableau).
+// Adjoint vectors live in global scratch ([component][state], coalesced).
+// =============================================================================================
+template <int DP, int R>
+__global__ void GPODE_SWEEP_BOUNDS k_rbf_rollout_bwd(const RbfRolloutBwdArgs a) {
   extern __shared__ __align__(128) float smem[];
   const RbfGeom& g = a.g;
   const States<R> st = map_states<R>(g);
@@ -352,19 +463,19 @@ __global__ void __launch_bounds__(256, (DP <= 8 ? 2 : 1)) k_rbf_rollout_bwd(cons
   const int stages = tb.stages;
   const long NL = g.NL;
   const int DS = g.D_in;
-  float* s_dell = smem_tiles(smem) + 2 * g.tile_floats;
-  float* s_dvar = s_dell + g.D_out * DP;
-  for (int i = threadIdx.x; i < g.D_out * (DP + 1); i += blockDim.x) s_dell[i] = 0.f;
-  TilePipe pipe;  // init() contains the __syncthreads that publishes the zeroing above
-  pipe.init(smem_tiles(smem), reinterpret_cast<uint64_t*>(smem), a.packed + static_cast<size_t>(blockIdx.y) * g.D_out * g.tile_floats,
-            g.tile_floats, g.D_out, static_cast<long>(a.T - 1) * stages * g.D_out);
+  SweepSmem sm = carve_smem<DP, R>(smem, g);
+  ChunkPipe pipe;
+  const long total = static_cast<long>(a.T - 1) * stages * g.D_out * (g.NCs + g.NCm);
+  sweep_setup<DP, R>(sm, pipe, g, a.packed, total, true);
+  float* ybar = a.ybar;
+  float* ystage = a.ystage;
+  float* kbar = a.kbar;
 
   // adjoint of z_{T-1}
 #pragma unroll
   for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int d = 0; d < DP; ++d)
-      if (d < DS) a.ybar[d * NL + st.s[r]] = st.ok[r] ? a.dtraj[(st.s[r] * a.T + (a.T - 1)) * DS + d] : 0.f;
+    if (st.ok[r])
+      for (int d = 0; d < DS; ++d) ybar[d * NL + st.s[r]] = a.dtraj[(st.s[r] * a.T + (a.T - 1)) * DS + d];
 
 #pragma unroll 1
   for (int t = a.T - 2; t >= 0; --t) {
@@ -372,126 +483,84 @@ __global__ void __launch_bounds__(256, (DP <= 8 ? 2 : 1)) k_rbf_rollout_bwd(cons
     const long slab = static_cast<long>(t) * stages;
 #pragma unroll 1
     for (int i = stages - 1; i >= 0; --i) {
-      float x[R][DP], dx[R][DP];
-      // kbar_i = dt (b_i ybar + sum_{j>i} a_ji ybar_j)
+      // kbar_i = dt (b_i ybar + sum_{j>i} a_ji ybar_j); stage input back from the forward saves
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int d = 0; d < DP; ++d) {
-          dx[r][d] = 0.f;
-          x[r][d] = 0.f;
-          if (d < DS) {
-            float kb = tb.b[i] * a.ybar[d * NL + st.s[r]];
-            for (int j = i + 1; j < stages; ++j) kb = fmaf(tb.a[j][i], a.ystage[(j * DS + d) * NL + st.s[r]], kb);
-            kb *= dt;
-            if (st.ok[r]) {
-              a.kbar[d * NL + st.s[r]] = kb;
-              if (d >= g.off) a.gsave[((slab + i) * g.D_out + (d - g.off)) * NL + st.s[r]] = kb;
-            }
-            x[r][d] = a.xsave[((slab + i) * DS + d) * NL + st.s[r]];
-          }
+      for (int r = 0; r < R; ++r) {
+        if (!st.ok[r]) continue;
+#pragma unroll 1
+        for (int d = 0; d < DS; ++d) {
+          float kb = tb.b[i] * ybar[d * NL + st.s[r]];
+          for (int j = i + 1; j < stages; ++j) kb = fmaf(tb.a[j][i], ystage[(j * DS + d) * NL + st.s[r]], kb);
+          kb *= dt;
+          kbar[d * NL + st.s[r]] = kb;
+          if (d >= g.off) a.gsave[((slab + i) * g.D_out + (d - g.off)) * NL + st.s[r]] = kb;
+          GPODE_XS(sm.xs, d, r) = a.xsave[((slab + i) * DS + d) * NL + st.s[r]];
         }
-      for (int k = 0; k < g.D_out; ++k) {
-        float gk[R], fk[R], fpk[R], dxk[R][DP];
+      }
+      vjp_all_k<DP, R>(pipe, g, total, sm, st, kbar + g.off * NL, a.ksave + ((slab + i) * DS + g.off) * NL,
+                       a.fpsave + (slab + i) * g.D_out * NL, NL, 1);
+      // ybar_i = J^T kbar_i (+ order 2: d(state derivative)[0:q] = state[q:2q], adjoint flows to the velocity part)
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          gk[r] = st.ok[r] ? a.kbar[(g.off + k) * NL + st.s[r]] : 0.f;
-          fk[r] = a.ksave[((slab + i) * DS + g.off + k) * NL + st.s[r]];
-          fpk[r] = a.fpsave[((slab + i) * g.D_out + k) * NL + st.s[r]];
+      for (int r = 0; r < R; ++r) {
+        if (!st.ok[r]) continue;
+#pragma unroll 1
+        for (int d = 0; d < DS; ++d) {
+          float v = GPODE_XS(sm.dx, d, r);
+          if (g.order == 2 && d >= DP / 2) v += kbar[(d - DP / 2) * NL + st.s[r]];
+          ystage[(i * DS + d) * NL + st.s[r]] = v;
         }
-        const float* tile = pipe.acquire();
-        rbf_tile_bwd<DP, R>(tile, g.SP2, g.MP2, x, gk, dxk);
-        pipe.release();
-        rbf_fold_stats<DP, R>(x, dxk, gk, fk, fpk, st.ok, s_dell, s_dvar, k);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int d = 0; d < DP; ++d) dx[r][d] += dxk[r][d];
       }
-      // order 2: d(state derivative)[0:q] = state[q:2q]  ->  adjoint flows straight to the velocity part
-      if (g.order == 2) {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int d = 0; d < DP / 2; ++d) dx[r][d + DP / 2] += a.kbar[d * NL + st.s[r]];
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int d = 0; d < DP; ++d)
-          if (d < DS && st.ok[r]) a.ystage[(i * DS + d) * NL + st.s[r]] = dx[r][d];
     }
     // ybar_t = ybar_{t+1} + sum_i ybar_i + dL/dz_t
 #pragma unroll
     for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int d = 0; d < DP; ++d)
-        if (d < DS && st.ok[r]) {
-          float v = a.ybar[d * NL + st.s[r]] + a.dtraj[(st.s[r] * a.T + t) * DS + d];
-          for (int j = 0; j < stages; ++j) v += a.ystage[(j * DS + d) * NL + st.s[r]];
-          a.ybar[d * NL + st.s[r]] = v;
+      if (st.ok[r])
+        for (int d = 0; d < DS; ++d) {
+          float v = ybar[d * NL + st.s[r]] + a.dtraj[(st.s[r] * a.T + t) * DS + d];
+          for (int j = 0; j < stages; ++j) v += ystage[(j * DS + d) * NL + st.s[r]];
+          ybar[d * NL + st.s[r]] = v;
         }
   }
 #pragma unroll
   for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int d = 0; d < DP; ++d)
-      if (d < DS && st.ok[r]) a.dz0[st.s[r] * DS + d] = a.ybar[d * NL + st.s[r]];
+    if (st.ok[r])
+      for (int d = 0; d < DS; ++d) a.dz0[st.s[r] * DS + d] = ybar[d * NL + st.s[r]];
   __syncthreads();
-  for (int i = threadIdx.x; i < g.D_out * DP; i += blockDim.x) atomicAdd(&a.acc.dell_x[i], s_dell[i]);
-  for (int i = threadIdx.x; i < g.D_out; i += blockDim.x) atomicAdd(&a.acc.dvar[i], s_dvar[i]);
+  for (int i = threadIdx.x; i < g.D_out * DP; i += blockDim.x) atomicAdd(&a.acc.dell_x[i], sm.dell[i]);
+  for (int i = threadIdx.x; i < g.D_out; i += blockDim.x) atomicAdd(&a.acc.dvar[i], sm.dvar[i]);
 }
 
 // =============================================================================================
 // field backward: one VJP, row-major I/O; leaves transposed x / g for the parameter-gradient kernel
 // =============================================================================================
 template <int DP, int R>
-__global__ void __launch_bounds__(256, (DP <= 8 ? 2 : 1)) k_rbf_field_bwd(const RbfFieldBwdArgs a) {
+__global__ void GPODE_SWEEP_BOUNDS k_rbf_field_bwd(const RbfFieldBwdArgs a) {
   extern __shared__ __align__(128) float smem[];
   const RbfGeom& g = a.g;
   const States<R> st = map_states<R>(g);
   const long NL = g.NL;
-  float* s_dell = smem_tiles(smem) + 2 * g.tile_floats;
-  float* s_dvar = s_dell + g.D_out * DP;
-  for (int i = threadIdx.x; i < g.D_out * (DP + 1); i += blockDim.x) s_dell[i] = 0.f;
-  TilePipe pipe;
-  pipe.init(smem_tiles(smem), reinterpret_cast<uint64_t*>(smem), a.packed + static_cast<size_t>(blockIdx.y) * g.D_out * g.tile_floats,
-            g.tile_floats, g.D_out, g.D_out);
-  float x[R][DP], dx[R][DP];
+  SweepSmem sm = carve_smem<DP, R>(smem, g);
+  ChunkPipe pipe;
+  const long total = static_cast<long>(g.D_out) * (g.NCs + g.NCm);
+  sweep_setup<DP, R>(sm, pipe, g, a.packed, total, true);
 #pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      x[r][d] = d < g.D_in ? a.x[st.s[r] * g.D_in + d] : 0.f;
-      dx[r][d] = 0.f;
-      if (d < g.D_in && st.ok[r]) a.xsave[d * NL + st.s[r]] = x[r][d];
+  for (int r = 0; r < R; ++r) {
+    for (int d = 0; d < g.D_in; ++d) {
+      const float v = a.x[st.s[r] * g.D_in + d];
+      GPODE_XS(sm.xs, d, r) = v;
+      if (st.ok[r]) a.xsave[d * NL + st.s[r]] = v;
     }
-  for (int k = 0; k < g.D_out; ++k) {
-    float gk[R], fk[R], fpk[R], dxk[R][DP];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      gk[r] = st.ok[r] ? a.gout[st.s[r] * g.D_out + k] : 0.f;
-      fk[r] = a.f[st.s[r] * g.D_out + k];
-      fpk[r] = a.f_prior[st.s[r] * g.D_out + k];
-      if (st.ok[r]) a.gsave[k * NL + st.s[r]] = gk[r];
-    }
-    const float* tile = pipe.acquire();
-    rbf_tile_bwd<DP, R>(tile, g.SP2, g.MP2, x, gk, dxk);
-    pipe.release();
-    rbf_fold_stats<DP, R>(x, dxk, gk, fk, fpk, st.ok, s_dell, s_dvar, k);
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int d = 0; d < DP; ++d) dx[r][d] += dxk[r][d];
+    if (st.ok[r])
+      for (int k = 0; k < g.D_out; ++k) a.gsave[k * NL + st.s[r]] = a.gout[st.s[r] * g.D_out + k];
   }
+  vjp_all_k<DP, R>(pipe, g, total, sm, st, a.gout, a.f, a.f_prior, 1, g.D_out);
 #pragma unroll
   for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int d = 0; d < DP; ++d)
-      if (d < g.D_in && st.ok[r]) a.dx[st.s[r] * g.D_in + d] = dx[r][d];
+    if (st.ok[r])
+      for (int d = 0; d < g.D_in; ++d) a.dx[st.s[r] * g.D_in + d] = GPODE_XS(sm.dx, d, r);
   __syncthreads();
-  for (int i = threadIdx.x; i < g.D_out * DP; i += blockDim.x) atomicAdd(&a.acc.dell_x[i], s_dell[i]);
-  for (int i = threadIdx.x; i < g.D_out; i += blockDim.x) atomicAdd(&a.acc.dvar[i], s_dvar[i]);
+  for (int i = threadIdx.x; i < g.D_out * DP; i += blockDim.x) atomicAdd(&a.acc.dell_x[i], sm.dell[i]);
+  for (int i = threadIdx.x; i < g.D_out; i += blockDim.x) atomicAdd(&a.acc.dvar[i], sm.dvar[i]);
 }
 
 // =============================================================================================
@@ -501,25 +570,29 @@ __global__ void __launch_bounds__(256, (DP <= 8 ? 2 : 1)) k_rbf_field_bwd(const 
 // =============================================================================================
 constexpr int kPgBatch = 128;
 
+constexpr int kPgThreads = 128;
+
 template <int DP>
-__global__ void __launch_bounds__(256) k_rbf_pgrad(const RbfPgradArgs a) {
+__global__ void __launch_bounds__(kPgThreads, (DP <= 8 ? 6 : 3)) k_rbf_pgrad(const RbfPgradArgs a) {
   const RbfGeom& g = a.g;
-  constexpr int HDR = rbf_hdr_floats(DP);
   constexpr int ROW4 = (DP + 2) / 2;
   constexpr int SROW = ((DP + 2 + 3) / 4) * 4;  // staged state: x[DP], g, A (+pad), 16-byte rows
   constexpr int NV = SROW / 4;
   __shared__ __align__(16) float stage[kPgBatch * SROW];
   __shared__ float s_c[DP];
   const int k = blockIdx.y, l = blockIdx.z;
-  const float* tile = a.packed + (static_cast<size_t>(l) * g.D_out + k) * g.tile_floats;
-  if (threadIdx.x < DP) s_c[threadIdx.x] = tile[threadIdx.x];
-  const int j = threadIdx.x;  // inducing pair
+  const float* hdr = rbf_hdr_ptr(a.packed, g, l) + k * g.hdr_floats;
+  if (threadIdx.x < DP) s_c[threadIdx.x] = hdr[threadIdx.x];
+  const int n_mblk = (g.MP2 + kPgThreads - 1) / kPgThreads;
+  const int chunk_id = blockIdx.x / n_mblk;
+  const int j = (blockIdx.x - chunk_id * n_mblk) * kPgThreads + threadIdx.x;  // inducing pair
   const bool active = j < g.MP2;
   float2 G[DP], H = make_float2(0.f, 0.f);
 #pragma unroll
   for (int d = 0; d < DP; ++d) G[d] = make_float2(0.f, 0.f);
   if (active) {
-    const float4* row = reinterpret_cast<const float4*>(tile + HDR) + static_cast<size_t>(g.SP2 + j) * ROW4;
+    const float4* row = reinterpret_cast<const float4*>(rbf_rows_ptr(a.packed, g, l) +
+                                                        (static_cast<size_t>(k) * (g.SP2 + g.MP2) + g.SP2 + j) * g.row_floats);
 #pragma unroll
     for (int i = 0; i < DP / 2; ++i) {
       const float4 v = row[i];
@@ -534,7 +607,7 @@ __global__ void __launch_bounds__(256) k_rbf_pgrad(const RbfPgradArgs a) {
 
   const long total = a.n_te * g.N;  // state evaluations of this sample
   const long per = (total + a.chunks - 1) / a.chunks;
-  const long e_lo = static_cast<long>(blockIdx.x) * per;
+  const long e_lo = static_cast<long>(chunk_id) * per;
   const long e_hi = e_lo + per < total ? e_lo + per : total;
   __syncthreads();
   for (long e0 = e_lo; e0 < e_hi; e0 += kPgBatch) {
@@ -597,17 +670,18 @@ __global__ void __launch_bounds__(256) k_rbf_pgrad(const RbfPgradArgs a) {
   }
 }
 
-// launch-shape heuristic of the sweep kernels: states per CTA = threads * R
+// launch-shape heuristic of the sweep kernels: states per CTA = threads * R; prefer deep register
+// blocking (fewer broadcast LDS per FMA) as long as the grid still fills the chip twice over.
 inline void rbf_pick_shape(const RbfGeom& g, int& threads, int& R) {
-  const long states = static_cast<long>(g.N);
-  const long want = 2L * 148;  // CTAs over all samples for a full chip
-  const int cand[5][2] = {{256, 2}, {256, 1}, {128, 1}, {64, 1}, {32, 1}};
-  for (int i = 0; i < 5; ++i) {
+  const long want = 2L * 148;
+  const int tmax = g.DP <= 8 ? 256 : 128;
+  const int rmax = g.DP <= 8 ? 4 : 2;
+  const int cand[7][2] = {{tmax, rmax}, {tmax, rmax / 2}, {128, rmax / 2}, {128, 1}, {64, 1}, {32, 1}, {32, 1}};
+  for (int i = 0; i < 7; ++i) {
     threads = cand[i][0];
     R = cand[i][1];
-    if (R == 2 && g.DP > 8) continue;
     const long per = static_cast<long>(threads) * R;
-    if (((states + per - 1) / per) * g.L >= want) return;
+    if (((static_cast<long>(g.N) + per - 1) / per) * g.L >= want) return;
   }
 }
 
