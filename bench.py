@@ -191,11 +191,13 @@ def run_ours(args):
     ts = 0.1 * torch.arange(T, dtype=torch.float, device=dev)
     from gpode_b200 import gp_rollout
 
+    from gpode_b200.parallel import allreduce_gradients
+
     def allreduce_grads(tensors):
+        """one flat NCCL all-reduce of the gradient buffers (in place); no-op on a single GPU"""
         if world > 1:
-            flat = torch.cat([t_.reshape(-1) for t_ in tensors])
-            dist.all_reduce(flat)
-            return flat
+            allreduce_gradients(tensors)
+            return True
         return None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -263,7 +265,7 @@ def run_ours(args):
         loss = (traj * dtraj).sum() + flow.kl()
         loss.backward()
         flat = allreduce_grads([p_.grad for p_ in params])
-        host = [loss.detach().cpu()] + [(p_.grad if flat is None else p_.grad).cpu() for p_ in params] + [z.grad.cpu()]
+        host = [loss.detach().cpu()] + [p_.grad.cpu() for p_ in params] + [z.grad.cpu()]
         if record is not None and not h2d[0]:
             draws = L * (w["S"] * w["D_out"] + w["D_in"] * w["S"] * w["D_out"] + w["S"] * w["D_out"] + w["M"] * w["D_out"]) * 4
             h2d[0] = z0_host.numel() * 4 + draws
