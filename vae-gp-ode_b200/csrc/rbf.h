@@ -4,11 +4,10 @@
 #include <stddef.h>
 
 #include "chunk_geom.h"
+#include "sweep_args.h"
 
 namespace gpode {
 
-// Save-buffer indexing: entry (te, c, s) with te = t * stages + i (t = 0 when nothing is kept),
-// c a component, s = l * N + n the global state index -> ((te * C + c) * NL + s): coalesced over states.
 struct RbfGeom {
   int L, N, NL;          // samples, states per sample, L*N
   int D_in, D_out, DP;   // DP = D_in rounded up to even
@@ -31,27 +30,6 @@ __host__ __device__ inline const float* rbf_rows_ptr(const float* packed, const 
   return packed + static_cast<size_t>(g.L) * g.D_out * g.hdr_floats + static_cast<size_t>(l) * g.D_out * (g.SP2 + g.MP2) * g.row_floats;
 }
 
-struct RbfFieldFwdArgs {
-  RbfGeom g;
-  const float* packed;
-  const float* x;    // (L,N,D_in)
-  float* f;          // (L,N,D_out)
-  float* f_prior;    // (L,N,D_out) or null
-};
-
-struct RbfRolloutFwdArgs {
-  RbfGeom g;
-  const float* packed;
-  const float* z0;
-  int z0_per_sample;
-  const float* ts;
-  int T, method, keep;   // keep = 1: saves hold every step (backward follows); 0: one step of scratch
-  float* traj;           // (L,N,T,D_in)
-  float* xsave;          // stage inputs      [(T-1)*stages][D_in ][NL]
-  float* ksave;          // stage derivatives [(T-1)*stages][D_in ][NL]
-  float* fpsave;         // prior part        [(T-1)*stages][D_out][NL]
-};
-
 struct RbfAccum {        // fp32 accumulators in the workspace, zeroed before the backward
   float* dnu;            // [L][D_out][2*MP2]          sum_n g E
   float* pg;             // [L][D_out][2*MP2][DP]      sum_n g E x_d
@@ -60,35 +38,10 @@ struct RbfAccum {        // fp32 accumulators in the workspace, zeroed before th
   float* dell_z;         // [D_out][DP]                sum_m z_d * dZ_k,m,d   (filled by the finalize kernel)
 };
 
-struct RbfRolloutBwdArgs {
-  RbfGeom g;
-  const float* packed;
-  const float* ts;
-  int T, method;
-  const float* xsave;
-  const float* ksave;
-  const float* fpsave;
-  const float* dtraj;    // (L,N,T,D_in)
-  float* dz0;            // (L,N,D_in)
-  float* gsave;          // stage adjoints (f part) [(T-1)*stages][D_out][NL]
-  float* ybar;           // scratch [D_in][NL]
-  float* ystage;         // scratch [stages][D_in][NL]
-  float* kbar;           // scratch [D_in][NL]
-  RbfAccum acc;
-};
-
-struct RbfFieldBwdArgs {
-  RbfGeom g;
-  const float* packed;
-  const float* x;        // (L,N,D_in)
-  const float* gout;     // (L,N,D_out)
-  const float* f;        // (L,N,D_out)
-  const float* f_prior;  // (L,N,D_out)
-  float* dx;             // (L,N,D_in)
-  float* xsave;          // [D_in][NL]   transposed copies for the parameter-gradient kernel
-  float* gsave;          // [D_out][NL]
-  RbfAccum acc;
-};
+using RbfFieldFwdArgs = FieldFwdArgsT<RbfGeom>;
+using RbfRolloutFwdArgs = RolloutFwdArgsT<RbfGeom>;
+using RbfRolloutBwdArgs = RolloutBwdArgsT<RbfGeom, RbfAccum>;
+using RbfFieldBwdArgs = FieldBwdArgsT<RbfGeom, RbfAccum>;
 
 struct RbfPgradArgs {
   RbfGeom g;

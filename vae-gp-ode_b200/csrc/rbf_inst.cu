@@ -27,19 +27,19 @@ cudaError_t launch_sweep(Kern kern, const Args& a, int threads, int R, bool bwd,
 #define GPODE_DISPATCH_R(KERNEL, a, bwd, st)                                                         \
   int threads, R;                                                                                    \
   rbf_pick_shape((a).g, threads, R);                                                                 \
-  if (R >= 4) return launch_sweep(KERNEL<DP, RMAX>, a, threads, RMAX, bwd, st);                      \
-  if (R == 2) return launch_sweep(KERNEL<DP, 2>, a, threads, 2, bwd, st);                            \
-  return launch_sweep(KERNEL<DP, 1>, a, threads, 1, bwd, st);
+  if (R >= 4) return launch_sweep(KERNEL<RbfPolicy<DP, RMAX>>, a, threads, RMAX, bwd, st);           \
+  if (R == 2) return launch_sweep(KERNEL<RbfPolicy<DP, 2>>, a, threads, 2, bwd, st);                 \
+  return launch_sweep(KERNEL<RbfPolicy<DP, 1>>, a, threads, 1, bwd, st);
 }  // namespace
 
 template <>
-cudaError_t rbf_field_fwd_dp<DP>(const RbfFieldFwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_rbf_field_fwd, a, false, st) }
+cudaError_t rbf_field_fwd_dp<DP>(const RbfFieldFwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_field_fwd, a, false, st) }
 template <>
-cudaError_t rbf_field_bwd_dp<DP>(const RbfFieldBwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_rbf_field_bwd, a, true, st) }
+cudaError_t rbf_field_bwd_dp<DP>(const RbfFieldBwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_field_bwd, a, true, st) }
 template <>
-cudaError_t rbf_rollout_fwd_dp<DP>(const RbfRolloutFwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_rbf_rollout_fwd, a, false, st) }
+cudaError_t rbf_rollout_fwd_dp<DP>(const RbfRolloutFwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_rollout_fwd, a, false, st) }
 template <>
-cudaError_t rbf_rollout_bwd_dp<DP>(const RbfRolloutBwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_rbf_rollout_bwd, a, true, st) }
+cudaError_t rbf_rollout_bwd_dp<DP>(const RbfRolloutBwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_rollout_bwd, a, true, st) }
 
 template <>
 cudaError_t rbf_pgrad_dp<DP>(const RbfPgradArgs& a, cudaStream_t st) {

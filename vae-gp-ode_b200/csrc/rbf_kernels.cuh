@@ -14,32 +14,12 @@
 
 #include "common.cuh"
 #include "rbf.h"
+#include "sweep.cuh"
 
 namespace gpode {
 
 constexpr float kHalfPi = 1.5707963267948966f;
 constexpr float kInvLn2 = 1.4426950408889634f;
-
-// one thread's R states inside sample l
-template <int R>
-struct States {
-  long s[R];    // global state index l*N + n (clamped for out-of-range lanes)
-  bool ok[R];
-};
-
-template <int R>
-__device__ __forceinline__ States<R> map_states(const RbfGeom& g) {
-  States<R> st;
-  const int l = blockIdx.y;
-  const int n0 = blockIdx.x * (blockDim.x * R) + threadIdx.x;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int n = n0 + r * blockDim.x;
-    st.ok[r] = n < g.N;
-    st.s[r] = static_cast<long>(l) * g.N + (st.ok[r] ? n : g.N - 1);
-  }
-  return st;
-}
 
 template <int DP>
 __device__ __forceinline__ void load_row(float4 (&v)[(DP + 2) / 2], const float4* row) {
@@ -289,135 +269,10 @@ __device__ __forceinline__ void rbf_fold_stats(const float (&x)[R][DP], const fl
   }
 }
 
-#define GPODE_SWEEP_BOUNDS __launch_bounds__((DP <= 8 ? 256 : 128), (DP <= 8 ? 2 : 3))
 
-// smem slot of component d of this thread's r-th state
-#define GPODE_XS(buf, d, r) (buf)[((d) * R + (r)) * blockDim.x + threadIdx.x]
-
-// =============================================================================================
-// field forward: one evaluation, row-major I/O
-// =============================================================================================
-template <int DP, int R>
-__global__ void GPODE_SWEEP_BOUNDS k_rbf_field_fwd(const RbfFieldFwdArgs a) {
-  extern __shared__ __align__(128) float smem[];
-  const RbfGeom& g = a.g;
-  const States<R> st = map_states<R>(g);
-  SweepSmem sm = carve_smem<DP, R>(smem, g);
-  ChunkPipe pipe;
-  const long total = static_cast<long>(g.D_out) * (g.NCs + g.NCm);
-  sweep_setup<DP, R>(sm, pipe, g, a.packed, total, false);
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    for (int d = 0; d < g.D_in; ++d) GPODE_XS(sm.xs, d, r) = a.x[st.s[r] * g.D_in + d];
-  float x[R][DP];
-  load_x<DP, R>(sm, x);
-  for (int k = 0; k < g.D_out; ++k) {
-    float fp[R], fu[R];
-    eval_fwd_k<DP, R>(pipe, g, total, sm.hdr + k * g.hdr_floats, x, fp, fu);
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (st.ok[r]) {
-        a.f[st.s[r] * g.D_out + k] = fp[r] + fu[r];
-        if (a.f_prior) a.f_prior[st.s[r] * g.D_out + k] = fp[r];
-      }
-  }
-}
-
-// =============================================================================================
-// rollout forward: fixed-grid euler / midpoint / rk4(3/8) over ts, all stages, one launch.
-// The state lives in global memory between evaluations (traj / save slabs written by this thread);
-// only the current stage input is register resident.
-// =============================================================================================
-template <int DP, int R>
-__global__ void GPODE_SWEEP_BOUNDS k_rbf_rollout_fwd(const RbfRolloutFwdArgs a) {
-  extern __shared__ __align__(128) float smem[];
-  const RbfGeom& g = a.g;
-  const States<R> st = map_states<R>(g);
-  const int stages = a.method == GPODE_EULER ? 1 : (a.method == GPODE_MIDPOINT ? 2 : 4);
-  const long NL = g.NL;
-  const int DS = g.D_in;
-  SweepSmem sm = carve_smem<DP, R>(smem, g);
-  ChunkPipe pipe;
-  const long total = static_cast<long>(a.T - 1) * stages * g.D_out * (g.NCs + g.NCm);
-  sweep_setup<DP, R>(sm, pipe, g, a.packed, total, false);
-
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const long zrow = a.z0_per_sample ? st.s[r] : (st.s[r] - static_cast<long>(blockIdx.y) * g.N);
-    if (st.ok[r])
-      for (int d = 0; d < DS; ++d) a.traj[(st.s[r] * a.T) * DS + d] = a.z0[zrow * DS + d];
-  }
-  float* ksave = a.ksave;  // plain pointers: values written below are re-read by the same thread
-  float* traj = a.traj;
-  const long ks = static_cast<long>(DS) * NL;  // K_j[d] sits j*ks after K_0[d]
-
-#pragma unroll 1
-  for (int t = 0; t < a.T - 1; ++t) {
-    const float dt = a.ts[t + 1] - a.ts[t];
-    const long slab = a.keep ? static_cast<long>(t) * stages : 0;
-#pragma unroll 1
-    for (int i = 0; i < stages; ++i) {
-      // stage input, in the operation order of torchdiffeq's fixed-grid step functions
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (!st.ok[r]) continue;  // padded lanes keep whatever finite values the staging buffer holds (zeros)
-#pragma unroll 1
-        for (int d = 0; d < DS; ++d) {
-          const float y0 = traj[(st.s[r] * a.T + t) * DS + d];
-          const long kb = (slab * DS + d) * NL + st.s[r];
-          float v;
-          if (i == 0) {
-            v = y0;
-          } else if (a.method == GPODE_MIDPOINT) {
-            v = y0 + ksave[kb] * (0.5f * dt);
-          } else if (i == 1) {
-            v = y0 + dt * ksave[kb] * (1.f / 3.f);
-          } else if (i == 2) {
-            v = y0 + dt * (ksave[kb + ks] - ksave[kb] * (1.f / 3.f));
-          } else {
-            v = y0 + dt * (ksave[kb] - ksave[kb + ks] + ksave[kb + 2 * ks]);
-          }
-          a.xsave[((slab + i) * DS + d) * NL + st.s[r]] = v;
-          GPODE_XS(sm.xs, d, r) = v;
-          // order 2: the first q components of the derivative are the velocity part of the state
-          if (g.order == 2 && d >= DP / 2) ksave[((slab + i) * DS + d - DP / 2) * NL + st.s[r]] = v;
-        }
-      }
-      float x[R][DP];
-      load_x<DP, R>(sm, x);
-      for (int k = 0; k < g.D_out; ++k) {
-        float fp[R], fu[R];
-        eval_fwd_k<DP, R>(pipe, g, total, sm.hdr + k * g.hdr_floats, x, fp, fu);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (st.ok[r]) {
-            ksave[((slab + i) * DS + g.off + k) * NL + st.s[r]] = fp[r] + fu[r];
-            a.fpsave[((slab + i) * g.D_out + k) * NL + st.s[r]] = fp[r];
-          }
-      }
-    }
-    // step update
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (!st.ok[r]) continue;
-#pragma unroll 1
-      for (int d = 0; d < DS; ++d) {
-        const float y0 = traj[(st.s[r] * a.T + t) * DS + d];
-        const long kb = (slab * DS + d) * NL + st.s[r];
-        float v;
-        if (a.method == GPODE_EULER) {
-          v = y0 + dt * ksave[kb];
-        } else if (a.method == GPODE_MIDPOINT) {
-          v = y0 + dt * ksave[kb + ks];
-        } else {
-          v = y0 + (ksave[kb] + 3.f * (ksave[kb + ks] + ksave[kb + 2 * ks]) + ksave[kb + 3 * ks]) * dt * 0.125f;
-        }
-        traj[(st.s[r] * a.T + (t + 1)) * DS + d] = v;
-      }
-    }
-  }
-}
-
+// ---------------------------------------------------------------------------------------------
+// policy glue: what the generic sweep kernels (sweep.cuh) call
+// ---------------------------------------------------------------------------------------------
 // =============================================================================================
 // all-k VJP at one state evaluation (stage input already staged in sm.xs): element (k, s) of the
 // upstream gradient / f / prior part sits at base[k * kstride + s * sstride].  Leaves sum_k dxk in
@@ -450,118 +305,42 @@ __device__ __forceinline__ void vjp_all_k(ChunkPipe& pipe, const RbfGeom& g, lon
   }
 }
 
-// =============================================================================================
-// rollout backward: reverse sweep through the unrolled solver (stage adjoints via the tableau).
-// Adjoint vectors live in global scratch ([component][state], coalesced).
-// =============================================================================================
-template <int DP, int R>
-__global__ void GPODE_SWEEP_BOUNDS k_rbf_rollout_bwd(const RbfRolloutBwdArgs a) {
-  extern __shared__ __align__(128) float smem[];
-  const RbfGeom& g = a.g;
-  const States<R> st = map_states<R>(g);
-  const Tableau tb = make_tableau(a.method);
-  const int stages = tb.stages;
-  const long NL = g.NL;
-  const int DS = g.D_in;
-  SweepSmem sm = carve_smem<DP, R>(smem, g);
-  ChunkPipe pipe;
-  const long total = static_cast<long>(a.T - 1) * stages * g.D_out * (g.NCs + g.NCm);
-  sweep_setup<DP, R>(sm, pipe, g, a.packed, total, true);
-  float* ybar = a.ybar;
-  float* ystage = a.ystage;
-  float* kbar = a.kbar;
 
-  // adjoint of z_{T-1}
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (st.ok[r])
-      for (int d = 0; d < DS; ++d) ybar[d * NL + st.s[r]] = a.dtraj[(st.s[r] * a.T + (a.T - 1)) * DS + d];
+template <int DP_, int R_>
+struct RbfPolicy {
+  static constexpr int DP = DP_;
+  static constexpr int R = R_;
+  static constexpr int kThreads = DP_ <= 8 ? 256 : 128;
+  static constexpr int kMinBlocks = DP_ <= 8 ? 2 : 3;
+  using Geom = RbfGeom;
+  using Accum = RbfAccum;
+  using Smem = SweepSmem;
 
-#pragma unroll 1
-  for (int t = a.T - 2; t >= 0; --t) {
-    const float dt = a.ts[t + 1] - a.ts[t];
-    const long slab = static_cast<long>(t) * stages;
-#pragma unroll 1
-    for (int i = stages - 1; i >= 0; --i) {
-      // kbar_i = dt (b_i ybar + sum_{j>i} a_ji ybar_j); stage input back from the forward saves
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (!st.ok[r]) continue;
-#pragma unroll 1
-        for (int d = 0; d < DS; ++d) {
-          float kb = tb.b[i] * ybar[d * NL + st.s[r]];
-          for (int j = i + 1; j < stages; ++j) kb = fmaf(tb.a[j][i], ystage[(j * DS + d) * NL + st.s[r]], kb);
-          kb *= dt;
-          kbar[d * NL + st.s[r]] = kb;
-          if (d >= g.off) a.gsave[((slab + i) * g.D_out + (d - g.off)) * NL + st.s[r]] = kb;
-          GPODE_XS(sm.xs, d, r) = a.xsave[((slab + i) * DS + d) * NL + st.s[r]];
-        }
-      }
-      vjp_all_k<DP, R>(pipe, g, total, sm, st, kbar + g.off * NL, a.ksave + ((slab + i) * DS + g.off) * NL,
-                       a.fpsave + (slab + i) * g.D_out * NL, NL, 1);
-      // ybar_i = J^T kbar_i (+ order 2: d(state derivative)[0:q] = state[q:2q], adjoint flows to the velocity part)
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (!st.ok[r]) continue;
-#pragma unroll 1
-        for (int d = 0; d < DS; ++d) {
-          float v = GPODE_XS(sm.dx, d, r);
-          if (g.order == 2 && d >= DP / 2) v += kbar[(d - DP / 2) * NL + st.s[r]];
-          ystage[(i * DS + d) * NL + st.s[r]] = v;
-        }
-      }
-    }
-    // ybar_t = ybar_{t+1} + sum_i ybar_i + dL/dz_t
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (st.ok[r])
-        for (int d = 0; d < DS; ++d) {
-          float v = ybar[d * NL + st.s[r]] + a.dtraj[(st.s[r] * a.T + t) * DS + d];
-          for (int j = 0; j < stages; ++j) v += ystage[(j * DS + d) * NL + st.s[r]];
-          ybar[d * NL + st.s[r]] = v;
-        }
+  __device__ static __forceinline__ Smem carve(float* smem, const Geom& g) { return carve_smem<DP, R>(smem, g); }
+  __device__ static __forceinline__ long setup(Smem& sm, ChunkPipe& pipe, const Geom& g, const float* packed, long n_evals, bool bwd) {
+    const long total = n_evals * g.D_out * (g.NCs + g.NCm);
+    sweep_setup<DP, R>(sm, pipe, g, packed, total, bwd);
+    return total;
   }
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (st.ok[r])
-      for (int d = 0; d < DS; ++d) a.dz0[st.s[r] * DS + d] = ybar[d * NL + st.s[r]];
-  __syncthreads();
-  for (int i = threadIdx.x; i < g.D_out * DP; i += blockDim.x) atomicAdd(&a.acc.dell_x[i], sm.dell[i]);
-  for (int i = threadIdx.x; i < g.D_out; i += blockDim.x) atomicAdd(&a.acc.dvar[i], sm.dvar[i]);
-}
-
-// =============================================================================================
-// field backward: one VJP, row-major I/O; leaves transposed x / g for the parameter-gradient kernel
-// =============================================================================================
-template <int DP, int R>
-__global__ void GPODE_SWEEP_BOUNDS k_rbf_field_bwd(const RbfFieldBwdArgs a) {
-  extern __shared__ __align__(128) float smem[];
-  const RbfGeom& g = a.g;
-  const States<R> st = map_states<R>(g);
-  const long NL = g.NL;
-  SweepSmem sm = carve_smem<DP, R>(smem, g);
-  ChunkPipe pipe;
-  const long total = static_cast<long>(g.D_out) * (g.NCs + g.NCm);
-  sweep_setup<DP, R>(sm, pipe, g, a.packed, total, true);
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    for (int d = 0; d < g.D_in; ++d) {
-      const float v = a.x[st.s[r] * g.D_in + d];
-      GPODE_XS(sm.xs, d, r) = v;
-      if (st.ok[r]) a.xsave[d * NL + st.s[r]] = v;
+  template <class Store>
+  __device__ static __forceinline__ void eval_fwd(ChunkPipe& pipe, const Geom& g, long total, const Smem& sm, Store&& store) {
+    float x[R][DP];
+    load_x<DP, R>(sm, x);
+    for (int k = 0; k < g.D_out; ++k) {
+      float fp[R], fu[R];
+      eval_fwd_k<DP, R>(pipe, g, total, sm.hdr + k * g.hdr_floats, x, fp, fu);
+      store(k, fp, fu);
     }
-    if (st.ok[r])
-      for (int k = 0; k < g.D_out; ++k) a.gsave[k * NL + st.s[r]] = a.gout[st.s[r] * g.D_out + k];
   }
-  vjp_all_k<DP, R>(pipe, g, total, sm, st, a.gout, a.f, a.f_prior, 1, g.D_out);
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (st.ok[r])
-      for (int d = 0; d < g.D_in; ++d) a.dx[st.s[r] * g.D_in + d] = GPODE_XS(sm.dx, d, r);
-  __syncthreads();
-  for (int i = threadIdx.x; i < g.D_out * DP; i += blockDim.x) atomicAdd(&a.acc.dell_x[i], sm.dell[i]);
-  for (int i = threadIdx.x; i < g.D_out; i += blockDim.x) atomicAdd(&a.acc.dvar[i], sm.dvar[i]);
-}
+  __device__ static __forceinline__ void vjp(ChunkPipe& pipe, const Geom& g, long total, const Smem& sm, const States<R>& st,
+                                             const float* gvec, const float* fvec, const float* fpvec, long kstride, long sstride) {
+    vjp_all_k<DP, R>(pipe, g, total, sm, st, gvec, fvec, fpvec, kstride, sstride);
+  }
+  __device__ static __forceinline__ void flush(const Smem& sm, const Geom& g, const Accum& acc) {
+    for (int i = threadIdx.x; i < g.D_out * DP; i += blockDim.x) atomicAdd(&acc.dell_x[i], sm.dell[i]);
+    for (int i = threadIdx.x; i < g.D_out; i += blockDim.x) atomicAdd(&acc.dvar[i], sm.dvar[i]);
+  }
+};
 
 // =============================================================================================
 // parameter gradients: threads <-> inducing-point pairs of one (sample, output dim); the CTA walks a
