@@ -47,7 +47,7 @@ def build_flow(g, method, monkeypatch):
     return flow, gp
 
 
-@pytest.mark.parametrize("name", RBF_CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 @pytest.mark.parametrize("method", ["euler", "rk4"])
 def test_flow_end_to_end(name, method, monkeypatch):
     g = load_golden(name)

@@ -53,9 +53,11 @@ RbfGeom rbf_geom(const GpodeProblem* p, int order) {
   g.order = order;
   g.off = p->D_in - p->D_out;
   g.cg.stage_floats = g.stage_floats;
-  g.cg.row_floats = g.row_floats;
+  g.cg.rowf_s = g.cg.rowf_m = g.row_floats;
   g.cg.SP2 = g.SP2; g.cg.MP2 = g.MP2; g.cg.NCs = g.NCs; g.cg.NCm = g.NCm; g.cg.RCs = g.RCs; g.cg.RCm = g.RCm;
-  g.cg.D_out = g.D_out;
+  g.cg.K = g.D_out;
+  g.cg.blk_floats = (g.SP2 + g.MP2) * g.row_floats;
+  g.cg.tail = 0;
   return g;
 }
 
@@ -166,6 +168,40 @@ cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float
   return rbf_launch_finalize(fa, st);
 }
 
+int df_check_smem(const DfGeom& g) { return df_smem_bytes(g, 128, 2, true) <= kSmemLimit ? GPODE_OK : GPODE_E_UNSUPPORTED; }
+
+cudaError_t df_pack(const GpodeProblem* p, const DfGeom& g, float* packed, cudaStream_t st) {
+  DfPackArgs a;
+  a.g = g;
+  a.Z = p->Z; a.ell = p->ell; a.var = p->var; a.eps = p->eps; a.phase = p->phase; a.w = p->w; a.nu = p->nu; a.B = p->B;
+  a.packed = packed;
+  return df_launch_pack(a, st);
+}
+
+cudaError_t df_param_grads(const GpodeProblem* p, const DfGeom& g, const float* packed, const float* xsave, const float* gsave, long n_te,
+                           const DfAccum& acc, const GpodeParamGrads* grads, cudaStream_t st) {
+  DfPgradArgs pa;
+  pa.g = g;
+  pa.packed = packed;
+  pa.xsave = xsave;
+  pa.gsave = gsave;
+  pa.n_te = n_te;
+  pa.chunks = pgrad_chunks(n_te * g.N, g.L * ((g.MP2 + 127) / 128 + (g.D * g.SP2 + 127) / 128));
+  pa.acc = acc;
+  cudaError_t e = df_launch_pgrad(pa, st);
+  if (e != cudaSuccess) return e;
+  DfFinalizeArgs fa;
+  fa.g = g;
+  fa.ell = p->ell; fa.var = p->var; fa.w = p->w;
+  fa.acc = acc;
+  fa.d_Z = grads ? grads->d_Z : nullptr;
+  fa.d_ell = grads ? grads->d_ell : nullptr;
+  fa.d_var = grads ? grads->d_var : nullptr;
+  fa.d_nu = grads ? grads->d_nu : nullptr;
+  fa.d_B = grads ? grads->d_B : nullptr;
+  return df_launch_finalize(fa, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -208,7 +244,19 @@ int gpode_field_fwd(const GpodeProblem* p, const float* x, float* f, float* f_pr
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
   float* packed = reinterpret_cast<float*>(ws + w.packed);
-  if (p->variant == GPODE_DF) return df_field_fwd(p, x, f, f_prior, packed, st);
+  if (p->variant == GPODE_DF) {
+    const DfGeom g = df_geom(p);
+    if ((rc = df_check_smem(g))) return rc;
+    cudaError_t e = df_pack(p, g, packed, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    DfFieldFwdArgs a;
+    a.g = g;
+    a.packed = packed;
+    a.x = x;
+    a.f = f;
+    a.f_prior = f_prior;
+    return static_cast<int>(df_launch_field_fwd(a, st));
+  }
   const RbfGeom g = rbf_geom(p, 1);
   if ((rc = rbf_check_smem(g))) return rc;
   cudaError_t e = rbf_pack(p, g, packed, st);
@@ -234,9 +282,24 @@ int gpode_field_bwd(const GpodeProblem* p, const float* x, const float* g_out, c
   float* packed = reinterpret_cast<float*>(ws + w.packed);
   cudaError_t e = cudaMemsetAsync(ws + w.acc, 0, w.acc_bytes, st);
   if (e != cudaSuccess) return static_cast<int>(e);
-  if (p->variant == GPODE_DF)
-    return df_field_bwd(p, x, g_out, f, f_prior, dx, grads, packed, reinterpret_cast<float*>(ws + w.xs), reinterpret_cast<float*>(ws + w.gsave),
-                        reinterpret_cast<float*>(ws + w.acc), st);
+  if (p->variant == GPODE_DF) {
+    const DfGeom g = df_geom(p);
+    if ((rc = df_check_smem(g))) return rc;
+    if ((e = df_pack(p, g, packed, st)) != cudaSuccess) return static_cast<int>(e);
+    DfFieldBwdArgs a;
+    a.g = g;
+    a.packed = packed;
+    a.x = x;
+    a.gout = g_out;
+    a.f = f;
+    a.f_prior = f_prior;
+    a.dx = dx;
+    a.xsave = reinterpret_cast<float*>(ws + w.xs);
+    a.gsave = reinterpret_cast<float*>(ws + w.gsave);
+    a.acc = df_acc(reinterpret_cast<float*>(ws + w.acc), g);
+    if ((e = df_launch_field_bwd(a, st)) != cudaSuccess) return static_cast<int>(e);
+    return static_cast<int>(df_param_grads(p, g, packed, a.xsave, a.gsave, 1, a.acc, grads, st));
+  }
   const RbfGeom g = rbf_geom(p, 1);
   if ((rc = rbf_check_smem(g))) return rc;
   if ((e = rbf_pack(p, g, packed, st)) != cudaSuccess) return static_cast<int>(e);
@@ -282,7 +345,26 @@ int gpode_rollout_fwd(const GpodeProblem* p, const float* z0, int z0_per_sample,
     ks = reinterpret_cast<float*>(ws + w.ks);
     fps = reinterpret_cast<float*>(ws + w.fps);
   }
-  if (p->variant == GPODE_DF) return df_rollout_fwd(p, z0, z0_per_sample, ts, T, method, traj, xs, ks, fps, save != nullptr, packed, st);
+  if (p->variant == GPODE_DF) {
+    const DfGeom g = df_geom(p);
+    if ((rc = df_check_smem(g))) return rc;
+    cudaError_t e = df_pack(p, g, packed, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    DfRolloutFwdArgs a;
+    a.g = g;
+    a.packed = packed;
+    a.z0 = z0;
+    a.z0_per_sample = z0_per_sample;
+    a.ts = ts;
+    a.T = T;
+    a.method = method;
+    a.keep = save ? 1 : 0;
+    a.traj = traj;
+    a.xsave = xs;
+    a.ksave = ks;
+    a.fpsave = fps;
+    return static_cast<int>(df_launch_rollout_fwd(a, st));
+  }
   const RbfGeom g = rbf_geom(p, order);
   if ((rc = rbf_check_smem(g))) return rc;
   cudaError_t e = rbf_pack(p, g, packed, st);
@@ -327,10 +409,30 @@ int gpode_rollout_bwd(const GpodeProblem* p, const float* ts, int T, int method,
   const float* fps = ks + steps * stages * p->D_in * NL;
   cudaError_t e = cudaMemsetAsync(ws + w.acc, 0, w.acc_bytes, st);
   if (e != cudaSuccess) return static_cast<int>(e);
-  if (p->variant == GPODE_DF)
-    return df_rollout_bwd(p, ts, T, method, xs, ks, fps, dtraj, dz0, grads, packed, reinterpret_cast<float*>(ws + w.gsave),
-                          reinterpret_cast<float*>(ws + w.ybar), reinterpret_cast<float*>(ws + w.ystage),
-                          reinterpret_cast<float*>(ws + w.kbar), reinterpret_cast<float*>(ws + w.acc), st);
+  if (p->variant == GPODE_DF) {
+    const DfGeom g = df_geom(p);
+    if ((rc = df_check_smem(g))) return rc;
+    if ((e = df_pack(p, g, packed, st)) != cudaSuccess) return static_cast<int>(e);
+    DfRolloutBwdArgs a;
+    a.g = g;
+    a.packed = packed;
+    a.ts = ts;
+    a.T = T;
+    a.method = method;
+    a.xsave = xs;
+    a.ksave = ks;
+    a.fpsave = fps;
+    a.dtraj = dtraj;
+    a.dz0 = dz0;
+    a.gsave = reinterpret_cast<float*>(ws + w.gsave);
+    a.ybar = reinterpret_cast<float*>(ws + w.ybar);
+    a.ystage = reinterpret_cast<float*>(ws + w.ystage);
+    a.kbar = reinterpret_cast<float*>(ws + w.kbar);
+    a.acc = df_acc(reinterpret_cast<float*>(ws + w.acc), g);
+    if ((e = df_launch_rollout_bwd(a, st)) != cudaSuccess) return static_cast<int>(e);
+    if (T < 2) return GPODE_OK;
+    return static_cast<int>(df_param_grads(p, g, packed, xs, a.gsave, static_cast<long>(T - 1) * stages, a.acc, grads, st));
+  }
   const RbfGeom g = rbf_geom(p, order);
   if ((rc = rbf_check_smem(g))) return rc;
   if ((e = rbf_pack(p, g, packed, st)) != cudaSuccess) return static_cast<int>(e);

@@ -101,27 +101,34 @@ struct ChunkPipe {
   uint32_t phase;
 
   __device__ __forceinline__ void issue_next(const ChunkGeom& cg, long total) {
-    int* ps = reinterpret_cast<int*>(bar + kPipeStages);  // {issued_lo.., pk, pc, pstage}
+    int* ps = reinterpret_cast<int*>(bar + kPipeStages);  // {issued (long), pk, pc, pstage}
     long issued = *reinterpret_cast<long*>(ps);
     if (issued < total) {
       int pk = ps[2], pc = ps[3], pstage = ps[4];
-      int r0, n;
-      if (pc < cg.NCs) {
-        r0 = pc * cg.RCs;
+      const bool in_m = cg.tail ? (pk == cg.K) : (pc >= cg.NCs);
+      int n, rowf;
+      size_t off;
+      if (!in_m) {
+        const int r0 = pc * cg.RCs;
         n = min(cg.RCs, cg.SP2 - r0);
+        rowf = cg.rowf_s;
+        off = static_cast<size_t>(pk) * cg.blk_floats + static_cast<size_t>(r0) * cg.rowf_s;
       } else {
-        const int cm = pc - cg.NCs;
-        n = min(cg.RCm, cg.MP2 - cm * cg.RCm);
-        r0 = cg.SP2 + cm * cg.RCm;
+        const int r0 = (cg.tail ? pc : pc - cg.NCs) * cg.RCm;
+        n = min(cg.RCm, cg.MP2 - r0);
+        rowf = cg.rowf_m;
+        off = (cg.tail ? static_cast<size_t>(cg.K) * cg.blk_floats : static_cast<size_t>(pk) * cg.blk_floats + static_cast<size_t>(cg.SP2) * cg.rowf_s) +
+              static_cast<size_t>(r0) * cg.rowf_m;
       }
-      const uint32_t bytes = static_cast<uint32_t>(n * cg.row_floats) * 4u;
+      const uint32_t bytes = static_cast<uint32_t>(n * rowf) * 4u;
       mbar_expect_tx(bar + pstage, bytes);
-      bulk_g2s(buf0 + pstage * cg.stage_floats, rows + (static_cast<size_t>(pk) * (cg.SP2 + cg.MP2) + r0) * cg.row_floats, bytes,
-               bar + pstage);
+      bulk_g2s(buf0 + pstage * cg.stage_floats, rows + off, bytes, bar + pstage);
       pstage = (pstage + 1 == kPipeStages) ? 0 : pstage + 1;
-      if (++pc == cg.NCs + cg.NCm) {
+      const int limit = cg.tail ? (pk == cg.K ? cg.NCm : cg.NCs) : cg.NCs + cg.NCm;
+      if (++pc == limit) {
         pc = 0;
-        pk = (pk + 1 == cg.D_out) ? 0 : pk + 1;
+        ++pk;
+        if (pk == (cg.tail ? cg.K + 1 : cg.K)) pk = 0;
       }
       *reinterpret_cast<long*>(ps) = issued + 1;
       ps[2] = pk;

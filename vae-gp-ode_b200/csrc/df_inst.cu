@@ -1,0 +1,50 @@
+// One translation unit per DF dimension GPODE_DF_D (1..8): instantiates the sweep kernels with the DF
+// policy for the register-blocking factors R and wraps their launches.
+#include "df_kernels.cuh"
+
+#ifndef GPODE_DF_D
+#error "compile with -DGPODE_DF_D=<1..8>"
+#endif
+
+namespace gpode {
+
+namespace {
+constexpr int D = GPODE_DF_D;
+
+template <typename Kern, typename Args>
+cudaError_t launch_sweep(Kern kern, const Args& a, int threads, int R, bool bwd, cudaStream_t st) {
+  const int smem = df_smem_bytes(a.g, threads, R, bwd);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  const long per = static_cast<long>(threads) * R;
+  dim3 grid(static_cast<unsigned>((a.g.N + per - 1) / per), static_cast<unsigned>(a.g.L));
+  kern<<<grid, threads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+#define GPODE_DF_DISPATCH_R(KERNEL, a, bwd, st)                                            \
+  int threads, R;                                                                          \
+  df_pick_shape((a).g, bwd, threads, R);                                                   \
+  if (R == 2) return launch_sweep(KERNEL<DfPolicy<D, 2>>, a, threads, 2, bwd, st);         \
+  return launch_sweep(KERNEL<DfPolicy<D, 1>>, a, threads, 1, bwd, st);
+}  // namespace
+
+template <>
+cudaError_t df_field_fwd_d<D>(const DfFieldFwdArgs& a, cudaStream_t st) { GPODE_DF_DISPATCH_R(k_field_fwd, a, false, st) }
+template <>
+cudaError_t df_rollout_fwd_d<D>(const DfRolloutFwdArgs& a, cudaStream_t st) { GPODE_DF_DISPATCH_R(k_rollout_fwd, a, false, st) }
+template <>
+cudaError_t df_field_bwd_d<D>(const DfFieldBwdArgs& a, cudaStream_t st) { return launch_sweep(k_field_bwd<DfPolicy<D, 1>>, a, [&] { int t, r; df_pick_shape(a.g, true, t, r); return t; }(), 1, true, st); }
+template <>
+cudaError_t df_rollout_bwd_d<D>(const DfRolloutBwdArgs& a, cudaStream_t st) { return launch_sweep(k_rollout_bwd<DfPolicy<D, 1>>, a, [&] { int t, r; df_pick_shape(a.g, true, t, r); return t; }(), 1, true, st); }
+
+template <>
+cudaError_t df_pgrad_d<D>(const DfPgradArgs& a, cudaStream_t st) {
+  const int n_mblk = (a.g.MP2 + kDfPgThreads - 1) / kDfPgThreads;
+  const int n_sblk = (a.g.D * a.g.SP2 + kDfPgThreads - 1) / kDfPgThreads;
+  dim3 grid(static_cast<unsigned>(a.chunks), static_cast<unsigned>(n_mblk + n_sblk), static_cast<unsigned>(a.g.L));
+  k_df_pgrad<D><<<grid, kDfPgThreads, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gpode

@@ -1,0 +1,563 @@
+// Divergence-free (DF) sparse-GP vector field: policy for the generic sweep kernels (sweep.cuh) and the
+// parameter-gradient kernels, sm_100a.  Math and packed layout: df.h.
+//
+// Mapping: like the RBF kernels, threads <-> R states, parameter rows stream through shared memory
+// (ChunkPipe, 1-D TMA); every row carries a PAIR of features / inducing points so the inner loops are
+// FFMA2 with the state as the scalar-broadcast operand.  The D x D block of exponentials per
+// (state, inducing point) makes the update part MUFU.EX2-bound (D^2 MUFU against ~5 D^2 FMA-pipe slots),
+// the per-(i,j) constants {k_ij, lc_ij} are broadcast LDS.128 from a shared-memory header.
+#pragma once
+
+#include "common.cuh"
+#include "df.h"
+#include "sweep.cuh"
+
+namespace gpode {
+
+constexpr float kDfHalfPi = 1.5707963267948966f;
+constexpr float kTwoLog2e = 2.8853900817779268f;
+
+template <int N4>
+__device__ __forceinline__ float2 f2at(const float4 (&v)[N4], int q) {
+  return (q & 1) ? hi(v[q >> 1]) : lo(v[q >> 1]);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return fma2(b, bc(-1.f), a); }
+// broadcast load of a per-(i,j) constant; volatile so that the D*D loop-invariant loads are NOT hoisted out of the
+// inducing-point loop into 4 D^2 registers (they are cheaper as LDS.128 than as spills)
+__device__ __forceinline__ float4 lds_const4(const float4* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
+struct DfSmem {
+  uint64_t* bars;
+  float* stages;
+  const float4* kc;   // [D*D] {k,k,lc,lc}
+  const float* h;     // [D]
+  float* xs;
+  float* dx;
+  float* dell;        // [D*D] then dvar [D]
+  float* dvar;
+};
+
+// ---------------------------------------------------------------------------------------------
+// prior part, one chunk of n feature rows of block a:  row = {Om'_d}_d<D, b', {B'_c}_c<D, pad  (float2 pairs)
+// ---------------------------------------------------------------------------------------------
+template <int D, int R>
+__device__ __forceinline__ void df_rows_prior_fwd(const float* __restrict__ chunk, int n, const float (&x)[R][D], float2 (&fp)[R][D]) {
+  constexpr int ROW4 = D + 1;
+  const float4* rows = reinterpret_cast<const float4*>(chunk);
+#pragma unroll 1
+  for (int j = 0; j < n; ++j) {
+    float4 v[ROW4];
+#pragma unroll
+    for (int i = 0; i < ROW4; ++i) v[i] = rows[j * ROW4 + i];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 th = f2at(v, D);
+#pragma unroll
+      for (int d = 0; d < D; ++d) th = fma2(bc(x[r][d]), f2at(v, d), th);
+      const float2 cs = cos_2(th);
+#pragma unroll
+      for (int c = 0; c < D; ++c) fp[r][c] = fma2(cs, f2at(v, D + 1 + c), fp[r][c]);
+    }
+  }
+}
+
+// VJP of the prior part: t = -sin(theta') sum_c g_c B'_c ; Q_d += t Om'_d  (scalar FFMA: half the registers)
+template <int D, int R>
+__device__ __forceinline__ void df_rows_prior_bwd(const float* __restrict__ chunk, int n, const float (&x)[R][D], const float (&g)[R][D],
+                                                  float (&Q)[R][D]) {
+  constexpr int ROW4 = D + 1;
+  const float4* rows = reinterpret_cast<const float4*>(chunk);
+#pragma unroll 1
+  for (int j = 0; j < n; ++j) {
+    float4 v[ROW4];
+#pragma unroll
+    for (int i = 0; i < ROW4; ++i) v[i] = rows[j * ROW4 + i];
+    const float2 b = add2(f2at(v, D), bc(kDfHalfPi));   // cos(th + pi/2) = -sin(th)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 th = b, gc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int d = 0; d < D; ++d) th = fma2(bc(x[r][d]), f2at(v, d), th);
+#pragma unroll
+      for (int c = 0; c < D; ++c) gc = fma2(bc(g[r][c]), f2at(v, D + 1 + c), gc);
+      const float2 t = mul2(cos_2(th), gc);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float2 om = f2at(v, d);
+        Q[r][d] = fmaf(t.x, om.x, Q[r][d]);
+        Q[r][d] = fmaf(t.y, om.y, Q[r][d]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// update part, one chunk of n inducing rows: row = {z_d}_d<D, {nu_i}_i<D  (float2 = two inducing points)
+// ---------------------------------------------------------------------------------------------
+template <int D, int R>
+__device__ __forceinline__ void df_rows_k_fwd(const float* __restrict__ chunk, int n, const DfSmem& sm, const float (&x)[R][D],
+                                              float2 (&F)[R][D]) {
+  const float4* rows = reinterpret_cast<const float4*>(chunk);
+#pragma unroll 1
+  for (int m = 0; m < n; ++m) {
+    float4 v[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = rows[m * D + i];
+    float2 d[R][D], p[R][D], r2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      r2[r] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        d[r][k] = sub2(bc(x[r][k]), f2at(v, k));
+        r2[r] = fma2(d[r][k], d[r][k], r2[r]);
+        p[r][k] = mul2(f2at(v, D + k), d[r][k]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float2 s[R], ejj[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) s[r] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const float4 kc = lds_const4(sm.kc + i * D + j);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float2 e = ex2_2(fma2(r2[r], lo(kc), hi(kc)));
+          s[r] = fma2(p[r][i], e, s[r]);
+          if (i == j) ejj[r] = e;
+        }
+      }
+      const float hj = sm.h[j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        F[r][j] = fma2(d[r][j], s[r], F[r][j]);
+        F[r][j] = fma2(mul2(f2at(v, D + j), ejj[r]), sub2(bc(hj), r2[r]), F[r][j]);
+      }
+    }
+  }
+}
+
+// VJP of the update part (SURVEY.md Appendix A.6 rearranged; checked in tests/test_df_algebra.py):
+//   u_j = g_j d_j, p_i = nu_i d_i, s_j = sum_i p_i e_ij, t_i = sum_j u_j e_ij, W = sum_ij u_j p_i c_ij e_ij,
+//   V = sum_j g_j nu_j e_jj (c_jj (h_j - r2) + 2)   ->   dL/dd_k = g_k s_k + nu_k t_k - d_k (W + V)
+// with c_ij e_ij = -2 ln2 k_ij e_ij (k_ij is already in a register pair).
+template <int D, int R>
+__device__ __forceinline__ void df_rows_k_bwd(const float* __restrict__ chunk, int n, const DfSmem& sm, const float (&x)[R][D],
+                                              const float (&g)[R][D], float2 (&DX)[R][D]) {
+  const float4* rows = reinterpret_cast<const float4*>(chunk);
+#pragma unroll 1
+  for (int m = 0; m < n; ++m) {
+    float4 v[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) v[i] = rows[m * D + i];
+    float2 d[R][D], p[R][D], tt[R][D], r2[R], WV[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      r2[r] = make_float2(0.f, 0.f);
+      WV[r] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        d[r][k] = sub2(bc(x[r][k]), f2at(v, k));
+        r2[r] = fma2(d[r][k], d[r][k], r2[r]);
+        p[r][k] = mul2(f2at(v, D + k), d[r][k]);
+        tt[r][k] = make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float2 s[R], wj[R], ejj[R], u[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        s[r] = make_float2(0.f, 0.f);
+        wj[r] = make_float2(0.f, 0.f);
+        u[r] = mul2(bc(g[r][j]), d[r][j]);
+      }
+      float2 kjj;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const float4 kc = lds_const4(sm.kc + i * D + j);
+        if (i == j) kjj = lo(kc);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float2 e = ex2_2(fma2(r2[r], lo(kc), hi(kc)));
+          const float2 pe = mul2(p[r][i], e);
+          s[r] = add2(s[r], pe);
+          wj[r] = fma2(lo(kc), pe, wj[r]);
+          tt[r][i] = fma2(u[r], e, tt[r][i]);
+          if (i == j) ejj[r] = e;
+        }
+      }
+      const float hj = sm.h[j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        // WV accumulates (W + V) / (-2 ln2):  W = -2 ln2 sum u_j wj ;  V = g_j nu_j e_jj (2 - 2 ln2 k_jj (h_j - r2))
+        WV[r] = fma2(u[r], wj[r], WV[r]);
+        const float2 gne = mul2(mul2(bc(g[r][j]), f2at(v, D + j)), ejj[r]);
+        WV[r] = fma2(gne, fma2(kjj, sub2(bc(hj), r2[r]), bc(-kLog2e)), WV[r]);
+        DX[r][j] = fma2(bc(g[r][j]), s[r], DX[r][j]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float2 wv = mul2(WV[r], bc(2.f * kLn2));   // = -(W + V)
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        DX[r][k] = fma2(f2at(v, D + k), tt[r][k], DX[r][k]);
+        DX[r][k] = fma2(d[r][k], wv, DX[r][k]);
+      }
+    }
+  }
+}
+
+template <int D_, int R_>
+struct DfPolicy {
+  static constexpr int DP = D_;
+  static constexpr int D = D_;
+  static constexpr int R = R_;
+  static constexpr int kThreads = 128;
+  static constexpr int kMinBlocks = 3;
+  using Geom = DfGeom;
+  using Accum = DfAccum;
+  using Smem = DfSmem;
+
+  __device__ static __forceinline__ Smem carve(float* smem, const Geom& g) {
+    Smem s;
+    s.bars = reinterpret_cast<uint64_t*>(smem);
+    s.stages = smem + 32;
+    float* hdr = s.stages + kPipeStages * g.stage_floats;
+    s.kc = reinterpret_cast<const float4*>(hdr);
+    s.h = hdr + 4 * D * D;
+    s.xs = hdr + g.hdr_floats;
+    s.dx = s.xs + D * R * blockDim.x;
+    s.dell = s.dx + D * R * blockDim.x;
+    s.dvar = s.dell + D * D;
+    return s;
+  }
+  __device__ static __forceinline__ long setup(Smem& sm, ChunkPipe& pipe, const Geom& g, const float* packed, long n_evals, bool bwd) {
+    const long total = n_evals * chunks_per_eval(g.cg);
+    float* hdr = sm.stages + kPipeStages * g.stage_floats;
+    for (int i = threadIdx.x; i < g.hdr_floats; i += blockDim.x) hdr[i] = packed[i];
+    for (int i = threadIdx.x; i < D * R * blockDim.x; i += blockDim.x) sm.xs[i] = 0.f;
+    if (bwd)
+      for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) sm.dell[i] = 0.f;
+    pipe.init(sm.stages, sm.bars, df_rows_ptr(packed, g, blockIdx.y), g.cg, total);  // contains the publishing __syncthreads
+    return total;
+  }
+  __device__ static __forceinline__ void load_x(const Smem& sm, float (&x)[R][D]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int d = 0; d < D; ++d) x[r][d] = GPODE_XS(sm.xs, d, r);
+  }
+
+  template <class Store>
+  __device__ static __forceinline__ void eval_fwd(ChunkPipe& pipe, const Geom& g, long total, const Smem& sm, Store&& store) {
+    float x[R][D];
+    load_x(sm, x);
+    float2 acc[R][D];
+    float fpv[D][R];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) acc[r][c] = make_float2(0.f, 0.f);
+    for (int a = 0; a < D; ++a)
+      for (int c = 0; c < g.NCs; ++c) {
+        const float* chunk = pipe.acquire(g.cg);
+        df_rows_prior_fwd<D, R>(chunk, min(g.RCs, g.SP2 - c * g.RCs), x, acc);
+        pipe.release(g.cg, total);
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        fpv[c][r] = acc[r][c].x + acc[r][c].y;
+        acc[r][c] = make_float2(0.f, 0.f);
+      }
+    for (int c = 0; c < g.NCm; ++c) {
+      const float* chunk = pipe.acquire(g.cg);
+      df_rows_k_fwd<D, R>(chunk, min(g.RCm, g.MP2 - c * g.RCm), sm, x, acc);
+      pipe.release(g.cg, total);
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      float fu[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) fu[r] = acc[r][k].x + acc[r][k].y;
+      store(k, fpv[k], fu);
+    }
+  }
+
+  // all-output VJP at one evaluation: leaves dL/dx in sm.dx, folds the lengthscale (theta path) and variance statistics
+  __device__ static __forceinline__ void vjp(ChunkPipe& pipe, const Geom& g, long total, const Smem& sm, const States<R>& st,
+                                             const float* gvec, const float* fvec, const float* fpvec, long kstride, long sstride) {
+    const int lane = threadIdx.x & 31;
+    float x[R][D], gg[R][D], dxs[R][D];
+    load_x(sm, x);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const long at = k * kstride + st.s[r] * sstride;
+        gg[r][k] = st.ok[r] ? gvec[at] : 0.f;
+        v += gg[r][k] * (fvec[at] - 0.5f * fpvec[at]);
+        dxs[r][k] = 0.f;
+      }
+      v = warp_sum(v);
+      if (lane == 0) atomicAdd(&sm.dvar[k], v);
+    }
+    for (int a = 0; a < D; ++a) {
+      float Q[R][D];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int d = 0; d < D; ++d) Q[r][d] = 0.f;
+      for (int c = 0; c < g.NCs; ++c) {
+        const float* chunk = pipe.acquire(g.cg);
+        df_rows_prior_bwd<D, R>(chunk, min(g.RCs, g.SP2 - c * g.RCs), x, gg, Q);
+        pipe.release(g.cg, total);
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float u = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          dxs[r][d] += Q[r][d];
+          u = fmaf(x[r][d], Q[r][d], u);   // padded lanes carry g = 0 -> Q = 0
+        }
+        u = warp_sum(u);
+        if (lane == 0) atomicAdd(&sm.dell[a * D + d], u);
+      }
+    }
+    float2 DX[R][D];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int d = 0; d < D; ++d) DX[r][d] = make_float2(0.f, 0.f);
+    for (int c = 0; c < g.NCm; ++c) {
+      const float* chunk = pipe.acquire(g.cg);
+      df_rows_k_bwd<D, R>(chunk, min(g.RCm, g.MP2 - c * g.RCm), sm, x, gg, DX);
+      pipe.release(g.cg, total);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int d = 0; d < D; ++d) GPODE_XS(sm.dx, d, r) = dxs[r][d] + DX[r][d].x + DX[r][d].y;
+  }
+
+  __device__ static __forceinline__ void flush(const Smem& sm, const Geom& g, const Accum& acc) {
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) atomicAdd(&acc.dell_x[i], sm.dell[i]);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(&acc.dvar[i], sm.dvar[i]);
+  }
+};
+
+// =============================================================================================
+// parameter gradients.  State evaluations (x, g) of one sample stream through shared memory in batches;
+//   role 0 (blockIdx.y <  n_mblk): threads <-> inducing-point pairs: dnu, dZ, dc_ij   (recomputes the D x D exponentials)
+//   role 1 (blockIdx.y >= n_mblk): threads <-> feature-pair rows (a, s): dB'[s,a,c] = sum_n g_c cos(theta')
+// =============================================================================================
+constexpr int kDfPgBatch = 128;
+constexpr int kDfPgThreads = 128;
+
+template <int D>
+__global__ void __launch_bounds__(kDfPgThreads, (D <= 6 ? 3 : 2)) k_df_pgrad(const DfPgradArgs a) {
+  const DfGeom& g = a.g;
+  constexpr int SROW = ((2 * D + 3) / 4) * 4;   // staged evaluation: x[D], g[D] (+pad)
+  constexpr int NV = SROW / 4;
+  __shared__ __align__(16) float stage[kDfPgBatch * SROW];
+  __shared__ __align__(16) float4 s_kc[D * D];
+  __shared__ float s_h[D];
+  __shared__ float s_dc[D * D];
+  const int l = blockIdx.z;
+  const int n_mblk = (g.MP2 + kDfPgThreads - 1) / kDfPgThreads;
+  const bool role_k = static_cast<int>(blockIdx.y) < n_mblk;
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+    s_kc[i] = reinterpret_cast<const float4*>(a.packed)[i];
+    s_dc[i] = 0.f;
+  }
+  if (threadIdx.x < D) s_h[threadIdx.x] = a.packed[4 * D * D + threadIdx.x];
+
+  const float* rows = df_rows_ptr(a.packed, g, l);
+  // this thread's row
+  float2 prm[2 * D + 1];   // role k: z[D], nu[D]; role b: Om'[D], b', then B' unused
+  int row = -1;            // role k: inducing pair index; role b: a * SP2 + s-pair
+  if (role_k) {
+    const int j = blockIdx.y * kDfPgThreads + threadIdx.x;
+    if (j < g.MP2) {
+      row = j;
+      const float2* src = reinterpret_cast<const float2*>(rows + static_cast<size_t>(g.D) * g.SP2 * g.rowf_s + static_cast<size_t>(j) * g.rowf_m);
+#pragma unroll
+      for (int i = 0; i < 2 * D; ++i) prm[i] = src[i];
+    }
+  } else {
+    const int j = (blockIdx.y - n_mblk) * kDfPgThreads + threadIdx.x;
+    if (j < g.D * g.SP2) {
+      row = j;
+      const float2* src = reinterpret_cast<const float2*>(rows + static_cast<size_t>(j) * g.rowf_s);
+#pragma unroll
+      for (int i = 0; i < D + 1; ++i) prm[i] = src[i];
+    }
+  }
+  float2 acc1[D], acc2[D];   // role k: dnu, dz ; role b: dB'_c (acc1)
+  float dc[D * D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    acc1[i] = make_float2(0.f, 0.f);
+    acc2[i] = make_float2(0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) dc[i] = 0.f;
+
+  const long total = a.n_te * g.N;
+  const long per = (total + a.chunks - 1) / a.chunks;
+  const long e_lo = static_cast<long>(blockIdx.x) * per;
+  const long e_hi = e_lo + per < total ? e_lo + per : total;
+  __syncthreads();
+  for (long e0 = e_lo; e0 < e_hi; e0 += kDfPgBatch) {
+    for (int idx = threadIdx.x; idx < kDfPgBatch; idx += blockDim.x) {
+      const long e = e0 + idx;
+      float* srow = stage + idx * SROW;
+      if (e < e_hi) {
+        const long te = e / g.N;
+        const long s = static_cast<long>(l) * g.N + (e - te * g.N);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          srow[d] = a.xsave[(te * D + d) * g.NL + s];
+          srow[D + d] = a.gsave[(te * D + d) * g.NL + s];
+        }
+      }
+    }
+    __syncthreads();
+    if (row >= 0) {
+      const int nb = (e_hi - e0) < kDfPgBatch ? static_cast<int>(e_hi - e0) : kDfPgBatch;
+      if (role_k) {
+#pragma unroll 1
+        for (int idx = 0; idx < nb; ++idx) {
+          const float4* srow = reinterpret_cast<const float4*>(stage + idx * SROW);
+          float xv[SROW];
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const float4 q = srow[i];
+            xv[4 * i] = q.x; xv[4 * i + 1] = q.y; xv[4 * i + 2] = q.z; xv[4 * i + 3] = q.w;
+          }
+          float2 d[D], p[D], tt[D], dd[D], r2 = make_float2(0.f, 0.f), WV = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            d[k] = sub2(bc(xv[k]), prm[k]);
+            r2 = fma2(d[k], d[k], r2);
+            p[k] = mul2(prm[D + k], d[k]);
+            tt[k] = make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const float gj = xv[D + j];
+            const float2 u = mul2(bc(gj), d[j]);
+            float2 s = make_float2(0.f, 0.f), wj = make_float2(0.f, 0.f), ejj, kjj, a2jj;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              const float4 kc = lds_const4(s_kc + i * D + j);
+              const float2 e = ex2_2(fma2(r2, lo(kc), hi(kc)));
+              const float2 pe = mul2(p[i], e);
+              s = add2(s, pe);
+              wj = fma2(lo(kc), pe, wj);
+              tt[i] = fma2(u, e, tt[i]);
+              const float2 a2 = fma2(r2, lo(kc), bc(kTwoLog2e));
+              const float2 upe = mul2(u, pe);
+              dc[i * D + j] = fmaf(upe.x, a2.x, dc[i * D + j]);
+              dc[i * D + j] = fmaf(upe.y, a2.y, dc[i * D + j]);
+              if (i == j) {
+                ejj = e;
+                kjj = lo(kc);
+                a2jj = a2;
+              }
+            }
+            const float2 hr = sub2(bc(s_h[j]), r2);
+            const float2 ge = mul2(bc(gj), ejj);
+            const float2 gne = mul2(ge, prm[D + j]);
+            WV = fma2(u, wj, WV);
+            WV = fma2(gne, fma2(kjj, hr, bc(-kLog2e)), WV);
+            dd[j] = mul2(bc(gj), s);
+            acc1[j] = fma2(ge, hr, acc1[j]);                       // dnu_j += g_j e_jj (h_j - r2)
+            const float2 dg = mul2(gne, fma2(a2jj, hr, bc(-s_h[j] * kLog2e)));
+            dc[j * D + j] += dg.x + dg.y;
+          }
+          const float2 wv = mul2(WV, bc(2.f * kLn2));
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            acc1[k] = fma2(d[k], tt[k], acc1[k]);                  // dnu_k += d_k t_k
+            float2 ddk = fma2(prm[D + k], tt[k], dd[k]);
+            ddk = fma2(d[k], wv, ddk);
+            acc2[k] = sub2(acc2[k], ddk);                          // dZ_k -= dL/dd_k
+          }
+        }
+      } else {
+#pragma unroll 2
+        for (int idx = 0; idx < nb; ++idx) {
+          const float4* srow = reinterpret_cast<const float4*>(stage + idx * SROW);
+          float xv[SROW];
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const float4 q = srow[i];
+            xv[4 * i] = q.x; xv[4 * i + 1] = q.y; xv[4 * i + 2] = q.z; xv[4 * i + 3] = q.w;
+          }
+          float2 th = prm[D];
+#pragma unroll
+          for (int k = 0; k < D; ++k) th = fma2(bc(xv[k]), prm[k], th);
+          const float2 cs = cos_2(th);
+#pragma unroll
+          for (int c = 0; c < D; ++c) acc1[c] = fma2(bc(xv[D + c]), cs, acc1[c]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (row >= 0) {
+    if (role_k) {
+      const size_t m0 = 2 * static_cast<size_t>(row);
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        atomicAdd(&a.acc.dnu[(static_cast<size_t>(l) * 2 * g.MP2 + m0) * D + k], acc1[k].x);
+        atomicAdd(&a.acc.dnu[(static_cast<size_t>(l) * 2 * g.MP2 + m0 + 1) * D + k], acc1[k].y);
+        atomicAdd(&a.acc.dz[m0 * D + k], acc2[k].x);
+        atomicAdd(&a.acc.dz[(m0 + 1) * D + k], acc2[k].y);
+      }
+    } else {
+      const size_t base = (static_cast<size_t>(l) * g.D * g.SP2 + row) * 2 * D;   // [l][a][s-pair][even/odd][c]
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        atomicAdd(&a.acc.dbp[base + c], acc1[c].x);
+        atomicAdd(&a.acc.dbp[base + D + c], acc1[c].y);
+      }
+    }
+  }
+  if (role_k) {   // CTA-uniform branch: every lane takes part in the shuffles (idle lanes hold zeros)
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) {
+      const float v = warp_sum(dc[i]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_dc[i], v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) atomicAdd(&a.acc.dc[i], s_dc[i]);
+  }
+}
+
+// launch-shape heuristic of the DF sweep kernels (states per CTA = 128 * R)
+inline void df_pick_shape(const DfGeom& g, bool bwd, int& threads, int& R) {
+  const long want = 2L * 148;
+  const int rmax = (!bwd && g.D <= 6) ? 2 : 1;
+  const int cand[5][2] = {{128, rmax}, {128, 1}, {64, 1}, {32, 1}, {32, 1}};
+  for (int i = 0; i < 5; ++i) {
+    threads = cand[i][0];
+    R = cand[i][1];
+    const long per = static_cast<long>(threads) * R;
+    if (((static_cast<long>(g.N) + per - 1) / per) * g.L >= want) return;
+  }
+}
+
+}  // namespace gpode
