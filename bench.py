@@ -46,6 +46,12 @@ WORKLOADS = {
                     method="rk4", ell=2.0, var=1.0),   # config-5 shapes, 2 grid intervals: short enough for ncu --set full
     "cfg4_rbf_d6_m256_t2_euler": dict(variant="rbf_dimwise", kernel="RBF", N=1048576, L=1, D_in=6, D_out=6, M=256, S=256, T=2,
                                       order=1, method="euler", ell=2.0, var=1.0),
+    "cfg4_df_d6_m256_t2_euler": dict(variant="df", kernel="DF", N=1048576, L=1, D_in=6, D_out=6, M=256, S=256, T=2,
+                                     order=1, method="euler", ell=2.0, var=1.0),
+    "cfg2_df_d6_m100_t16_rk4": dict(variant="df", kernel="DF", N=256, L=4, D_in=6, D_out=6, M=100, S=256, T=16, order=1,
+                                    method="rk4", ell=2.0, var=1.0),
+    "cfg2x_df_d6_m100_t16_rk4": dict(variant="df", kernel="DF", N=65536, L=4, D_in=6, D_out=6, M=100, S=256, T=16, order=1,
+                                     method="rk4", ell=2.0, var=1.0),   # config-2 shapes with 256x the batch: fills the chip
     "cfg1_rbf_d6_m100_t16_rk4": dict(variant="rbf_dimwise", kernel="RBF", N=25, L=1, D_in=6, D_out=6, M=100, S=256, T=16, order=1,
                                      method="rk4", ell=2.0, var=1.0),
 }

@@ -135,13 +135,26 @@ cudaError_t rbf_pack(const GpodeProblem* p, const RbfGeom& g, float* packed, cud
   return rbf_launch_pack(a, st);
 }
 
-int pgrad_chunks(long evals_per_sample, int ctas_per_chunk) {
-  const long target = 148L * 12;
-  long c = (target + ctas_per_chunk - 1) / ctas_per_chunk;
-  const long maxc = (evals_per_sample + 127) / 128;
-  if (c > maxc) c = maxc;
-  if (c < 1) c = 1;
-  return static_cast<int>(c);
+// CTAs along the state-evaluation axis of a parameter-gradient kernel: the grid (chunks x ctas_per_chunk) should fill
+// the chip's resident-CTA slots a whole number of times (the CTAs do equal work: no tail wave)
+int pgrad_chunks(long evals_per_sample, int ctas_per_chunk, int ctas_per_sm) {
+  const long slots = 148L * ctas_per_sm;
+  long maxc = (evals_per_sample + 255) / 256;
+  if (maxc < 1) maxc = 1;
+  long best = 1;
+  double best_eff = -1.0;
+  for (int w = 2; w <= 8; ++w) {
+    long c = slots * w / ctas_per_chunk;
+    if (c > maxc) c = maxc;
+    if (c < 1) c = 1;
+    const long total = c * ctas_per_chunk, waves = (total + slots - 1) / slots;
+    const double eff = static_cast<double>(total) / static_cast<double>(waves * slots);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = c;
+    }
+  }
+  return static_cast<int>(best);
 }
 
 cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float* packed, const float* xsave, const float* gsave,
@@ -152,7 +165,7 @@ cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float
   pa.xsave = xsave;
   pa.gsave = gsave;
   pa.n_te = n_te;
-  pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * ((g.MP2 + 127) / 128));
+  pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * ((g.MP2 + 127) / 128), g.DP <= 8 ? 6 : 3);
   pa.acc = acc;
   cudaError_t e = rbf_launch_pgrad(pa, st);
   if (e != cudaSuccess) return e;
@@ -186,7 +199,9 @@ cudaError_t df_param_grads(const GpodeProblem* p, const DfGeom& g, const float* 
   pa.xsave = xsave;
   pa.gsave = gsave;
   pa.n_te = n_te;
-  pa.chunks = pgrad_chunks(n_te * g.N, g.L * ((g.MP2 + 127) / 128 + (g.D * g.SP2 + 127) / 128));
+  const int tk = df_pgrad_threads_k(g);
+  pa.chunks = pgrad_chunks(n_te * g.N, g.L * ((g.MP2 + tk - 1) / tk), (g.D <= 6 ? 3 : 2) * 128 / tk);
+  pa.chunks_b = pgrad_chunks(n_te * g.N, g.L * ((g.D * g.SP2 + 127) / 128), 4);
   pa.acc = acc;
   cudaError_t e = df_launch_pgrad(pa, st);
   if (e != cudaSuccess) return e;

@@ -359,14 +359,14 @@ struct DfPolicy {
 
 // =============================================================================================
 // parameter gradients.  State evaluations (x, g) of one sample stream through shared memory in batches;
-//   role 0 (blockIdx.y <  n_mblk): threads <-> inducing-point pairs: dnu, dZ, dc_ij   (recomputes the D x D exponentials)
-//   role 1 (blockIdx.y >= n_mblk): threads <-> feature-pair rows (a, s): dB'[s,a,c] = sum_n g_c cos(theta')
+//   ROLE 0: threads <-> inducing-point pairs: dnu, dZ, dc_ij   (recomputes the D x D exponentials)
+//   ROLE 1: threads <-> feature-pair rows (a, s): dB'[s,a,c] = sum_n g_c cos(theta')
 // =============================================================================================
 constexpr int kDfPgBatch = 128;
 constexpr int kDfPgThreads = 128;
 
-template <int D>
-__global__ void __launch_bounds__(kDfPgThreads, (D <= 6 ? 3 : 2)) k_df_pgrad(const DfPgradArgs a) {
+template <int D, int ROLE>
+__global__ void __launch_bounds__(kDfPgThreads, (ROLE == 1 ? 4 : (D <= 6 ? 3 : 2))) k_df_pgrad(const DfPgradArgs a) {
   const DfGeom& g = a.g;
   constexpr int SROW = ((2 * D + 3) / 4) * 4;   // staged evaluation: x[D], g[D] (+pad)
   constexpr int NV = SROW / 4;
@@ -375,8 +375,7 @@ __global__ void __launch_bounds__(kDfPgThreads, (D <= 6 ? 3 : 2)) k_df_pgrad(con
   __shared__ float s_h[D];
   __shared__ float s_dc[D * D];
   const int l = blockIdx.z;
-  const int n_mblk = (g.MP2 + kDfPgThreads - 1) / kDfPgThreads;
-  const bool role_k = static_cast<int>(blockIdx.y) < n_mblk;
+  constexpr bool role_k = ROLE == 0;
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
     s_kc[i] = reinterpret_cast<const float4*>(a.packed)[i];
     s_dc[i] = 0.f;
@@ -388,7 +387,7 @@ __global__ void __launch_bounds__(kDfPgThreads, (D <= 6 ? 3 : 2)) k_df_pgrad(con
   float2 prm[2 * D + 1];   // role k: z[D], nu[D]; role b: Om'[D], b', then B' unused
   int row = -1;            // role k: inducing pair index; role b: a * SP2 + s-pair
   if (role_k) {
-    const int j = blockIdx.y * kDfPgThreads + threadIdx.x;
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
     if (j < g.MP2) {
       row = j;
       const float2* src = reinterpret_cast<const float2*>(rows + static_cast<size_t>(g.D) * g.SP2 * g.rowf_s + static_cast<size_t>(j) * g.rowf_m);
@@ -396,7 +395,7 @@ __global__ void __launch_bounds__(kDfPgThreads, (D <= 6 ? 3 : 2)) k_df_pgrad(con
       for (int i = 0; i < 2 * D; ++i) prm[i] = src[i];
     }
   } else {
-    const int j = (blockIdx.y - n_mblk) * kDfPgThreads + threadIdx.x;
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
     if (j < g.D * g.SP2) {
       row = j;
       const float2* src = reinterpret_cast<const float2*>(rows + static_cast<size_t>(j) * g.rowf_s);
@@ -415,7 +414,8 @@ __global__ void __launch_bounds__(kDfPgThreads, (D <= 6 ? 3 : 2)) k_df_pgrad(con
   for (int i = 0; i < D * D; ++i) dc[i] = 0.f;
 
   const long total = a.n_te * g.N;
-  const long per = (total + a.chunks - 1) / a.chunks;
+  const int nchunks = role_k ? a.chunks : a.chunks_b;
+  const long per = (total + nchunks - 1) / nchunks;
   const long e_lo = static_cast<long>(blockIdx.x) * per;
   const long e_hi = e_lo + per < total ? e_lo + per : total;
   __syncthreads();
