@@ -68,7 +68,7 @@ DfAccum df_acc(float* base, const DfGeom& g) {
 
 int df_smem_bytes(const DfGeom& g, int threads, int R, bool bwd) {
   int floats = 32 + kPipeStages * g.stage_floats + g.hdr_floats + g.D * R * threads;
-  if (bwd) floats += g.D * R * threads + g.D * g.D + g.D;
+  if (bwd) floats += g.D * R * threads + 2 * g.D * g.D + g.D + g.MP2 * 4 * g.D;
   return floats * 4;
 }
 

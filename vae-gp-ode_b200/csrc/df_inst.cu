@@ -40,11 +40,7 @@ cudaError_t df_rollout_bwd_d<D>(const DfRolloutBwdArgs& a, cudaStream_t st) { re
 
 template <>
 cudaError_t df_pgrad_d<D>(const DfPgradArgs& a, cudaStream_t st) {
-  const int tk = df_pgrad_threads_k(a.g);
-  dim3 gk(static_cast<unsigned>(a.chunks), static_cast<unsigned>((a.g.MP2 + tk - 1) / tk), static_cast<unsigned>(a.g.L));
-  k_df_pgrad<D, 0><<<gk, tk, 0, st>>>(a);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  // the inducing-point gradients (dnu, dZ, dc) come out of the reverse sweep itself; only the feature operator B is left
   dim3 gb(static_cast<unsigned>(a.chunks_b), static_cast<unsigned>((a.g.D * a.g.SP2 + kDfPgThreads - 1) / kDfPgThreads), static_cast<unsigned>(a.g.L));
   k_df_pgrad<D, 1><<<gb, kDfPgThreads, 0, st>>>(a);
   return cudaGetLastError();

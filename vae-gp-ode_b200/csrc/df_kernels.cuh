@@ -37,8 +37,10 @@ struct DfSmem {
   const float* h;     // [D]
   float* xs;
   float* dx;
-  float* dell;        // [D*D] then dvar [D]
+  float* dell;        // [D*D] then dvar [D], then dc [D*D]
   float* dvar;
+  float* dcs;
+  float* pacc;        // [MP2][4D]: per inducing pair {dnu even, dnu odd, dZ even, dZ odd}, summed over this CTA's states
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -143,75 +145,119 @@ __device__ __forceinline__ void df_rows_k_fwd(const float* __restrict__ chunk, i
   }
 }
 
-// VJP of the update part (SURVEY.md Appendix A.6 rearranged; checked in tests/test_df_algebra.py):
+// Cross-lane "transpose reduction": every lane holds K values; afterwards lane q holds the sum over the 32 lanes of value
+// xred_index(q) (K <= 32).  Recursive halving: K + log-many SHFLs instead of 5 K for K independent warp sums.
+template <int K, int OFF>
+struct XRed {
+  static __device__ __forceinline__ float run(const float (&v)[K], int lane) {
+    constexpr int H = (K + 1) / 2;
+    const bool up = (lane & OFF) != 0;
+    float w[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const float a = v[i];
+      const float b = (i + H < K) ? v[i + H] : 0.f;
+      const float send = up ? a : b, keep = up ? b : a;
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+    if constexpr (OFF == 1) {
+      return w[0];
+    } else {
+      return XRed<H, OFF / 2>::run(w, lane);
+    }
+  }
+};
+// which of the K values lane `lane` ends up holding (-1: none)
+__device__ __forceinline__ int xred_index(int K, int lane) {
+  int idx = 0, size = K, valid = K;   // size: (zero-padded) array length at this level, the same in every lane
+  for (int off = 16; off > 0; off >>= 1) {
+    const int h = (size + 1) / 2;
+    if (lane & off) {
+      idx += h;
+      valid -= h;
+    } else {
+      valid = valid < h ? valid : h;
+    }
+    size = h;
+  }
+  return valid >= 1 ? idx : -1;
+}
+
+// VJP of the update part AND its parameter gradients (SURVEY.md Appendix A.6 rearranged; checked in tests/test_df_algebra.py):
 //   u_j = g_j d_j, p_i = nu_i d_i, s_j = sum_i p_i e_ij, t_i = sum_j u_j e_ij, W = sum_ij u_j p_i c_ij e_ij,
 //   V = sum_j g_j nu_j e_jj (c_jj (h_j - r2) + 2)   ->   dL/dd_k = g_k s_k + nu_k t_k - d_k (W + V)
-// with c_ij e_ij = -2 ln2 k_ij e_ij (k_ij is already in a register pair).
-template <int D, int R>
-__device__ __forceinline__ void df_rows_k_bwd(const float* __restrict__ chunk, int n, const DfSmem& sm, const float (&x)[R][D],
-                                              const float (&g)[R][D], float2 (&DX)[R][D]) {
+//   dL/dx_k += dL/dd_k ;  dL/dZ_mk = -sum_n dL/dd_k ;  dL/dnu_mi = sum_n [d_i t_i + g_i e_ii (h_i - r2)]
+//   dc'_ij  = sum_{n,m} u_j p_i e_ij (r2 k_ij + 2 log2e) (+ diagonal term)      (lengthscale gradient, finalize kernel)
+// with c_ij e_ij = -2 ln2 k_ij e_ij (k_ij is already in a register pair).  The per-inducing-point sums over the states
+// of the warp are transpose-reduced with shuffles (4D values per inducing pair) and added to shared-memory accumulators:
+// the D x D exponentials are NOT recomputed by a separate parameter-gradient pass.
+template <int D>
+__device__ __forceinline__ void df_rows_k_bwd(const float* __restrict__ chunk, int n, int row0, const DfSmem& sm, const float (&x)[D],
+                                              const float (&g)[D], float2 (&DX)[D], float (&dc)[D * D], int lane, int my_idx) {
   const float4* rows = reinterpret_cast<const float4*>(chunk);
 #pragma unroll 1
   for (int m = 0; m < n; ++m) {
     float4 v[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) v[i] = rows[m * D + i];
-    float2 d[R][D], p[R][D], tt[R][D], r2[R], WV[R];
+    float2 d[D], p[D], tt[D], gs[D], r2 = make_float2(0.f, 0.f), WV = make_float2(0.f, 0.f);
+    float red[4 * D];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      r2[r] = make_float2(0.f, 0.f);
-      WV[r] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        d[r][k] = sub2(bc(x[r][k]), f2at(v, k));
-        r2[r] = fma2(d[r][k], d[r][k], r2[r]);
-        p[r][k] = mul2(f2at(v, D + k), d[r][k]);
-        tt[r][k] = make_float2(0.f, 0.f);
-      }
+    for (int k = 0; k < D; ++k) {
+      d[k] = sub2(bc(x[k]), f2at(v, k));
+      r2 = fma2(d[k], d[k], r2);
+      p[k] = mul2(f2at(v, D + k), d[k]);
+      tt[k] = make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-      float2 s[R], wj[R], ejj[R], u[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        s[r] = make_float2(0.f, 0.f);
-        wj[r] = make_float2(0.f, 0.f);
-        u[r] = mul2(bc(g[r][j]), d[r][j]);
-      }
-      float2 kjj;
+      const float2 u = mul2(bc(g[j]), d[j]);
+      const float2 ur = mul2(u, r2), u2 = mul2(u, bc(kTwoLog2e));
+      float2 s = make_float2(0.f, 0.f), wj = make_float2(0.f, 0.f), ejj, kjj;
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         const float4 kc = lds_const4(sm.kc + i * D + j);
-        if (i == j) kjj = lo(kc);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float2 e = ex2_2(fma2(r2[r], lo(kc), hi(kc)));
-          const float2 pe = mul2(p[r][i], e);
-          s[r] = add2(s[r], pe);
-          wj[r] = fma2(lo(kc), pe, wj[r]);
-          tt[r][i] = fma2(u[r], e, tt[r][i]);
-          if (i == j) ejj[r] = e;
+        const float2 e = ex2_2(fma2(r2, lo(kc), hi(kc)));
+        const float2 pe = mul2(p[i], e);
+        s = add2(s, pe);
+        wj = fma2(lo(kc), pe, wj);
+        tt[i] = fma2(u, e, tt[i]);
+        const float2 ua = fma2(lo(kc), ur, u2);            // u_j (r2 k_ij + 2 log2e)
+        dc[i * D + j] = fmaf(pe.x, ua.x, dc[i * D + j]);
+        dc[i * D + j] = fmaf(pe.y, ua.y, dc[i * D + j]);
+        if (i == j) {
+          ejj = e;
+          kjj = lo(kc);
         }
       }
       const float hj = sm.h[j];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        // WV accumulates (W + V) / (-2 ln2):  W = -2 ln2 sum u_j wj ;  V = g_j nu_j e_jj (2 - 2 ln2 k_jj (h_j - r2))
-        WV[r] = fma2(u[r], wj[r], WV[r]);
-        const float2 gne = mul2(mul2(bc(g[r][j]), f2at(v, D + j)), ejj[r]);
-        WV[r] = fma2(gne, fma2(kjj, sub2(bc(hj), r2[r]), bc(-kLog2e)), WV[r]);
-        DX[r][j] = fma2(bc(g[r][j]), s[r], DX[r][j]);
-      }
+      const float2 hr = sub2(bc(hj), r2);
+      const float2 ge = mul2(bc(g[j]), ejj);
+      const float2 gne = mul2(ge, f2at(v, D + j));
+      // WV accumulates (W + V) / (-2 ln2):  W = -2 ln2 sum u_j wj ;  V = g_j nu_j e_jj (2 - 2 ln2 k_jj (h_j - r2))
+      WV = fma2(u, wj, WV);
+      WV = fma2(gne, fma2(kjj, hr, bc(-kLog2e)), WV);
+      gs[j] = mul2(bc(g[j]), s);
+      const float2 dnu_diag = mul2(ge, hr);                // g_j e_jj (h_j - r2)
+      red[j] = dnu_diag.x;
+      red[D + j] = dnu_diag.y;
+      const float2 dg = mul2(gne, fma2(fma2(r2, kjj, bc(kTwoLog2e)), hr, bc(-hj * kLog2e)));
+      dc[j * D + j] += dg.x + dg.y;
     }
+    const float2 wv = mul2(WV, bc(2.f * kLn2));            // = -(W + V)
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float2 wv = mul2(WV[r], bc(2.f * kLn2));   // = -(W + V)
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        DX[r][k] = fma2(f2at(v, D + k), tt[r][k], DX[r][k]);
-        DX[r][k] = fma2(d[r][k], wv, DX[r][k]);
-      }
+    for (int k = 0; k < D; ++k) {
+      const float2 dnu = fma2(d[k], tt[k], make_float2(red[k], red[D + k]));
+      float2 ddk = fma2(f2at(v, D + k), tt[k], gs[k]);
+      ddk = fma2(d[k], wv, ddk);
+      DX[k] = add2(DX[k], ddk);
+      red[k] = dnu.x;
+      red[D + k] = dnu.y;
+      red[2 * D + k] = -ddk.x;
+      red[3 * D + k] = -ddk.y;
     }
+    const float tot = XRed<4 * D, 16>::run(red, lane);
+    if (my_idx >= 0) atomicAdd(&sm.pacc[(row0 + m) * 4 * D + my_idx], tot);
   }
 }
 
@@ -222,6 +268,7 @@ struct DfPolicy {
   static constexpr int R = R_;
   static constexpr int kThreads = 128;
   static constexpr int kMinBlocks = 3;
+  static constexpr int kMinBlocksBwd = D_ <= 6 ? 3 : 2;   // the reverse sweep also carries the D x D lengthscale accumulators
   using Geom = DfGeom;
   using Accum = DfAccum;
   using Smem = DfSmem;
@@ -237,6 +284,8 @@ struct DfPolicy {
     s.dx = s.xs + D * R * blockDim.x;
     s.dell = s.dx + D * R * blockDim.x;
     s.dvar = s.dell + D * D;
+    s.dcs = s.dvar + D;
+    s.pacc = s.dcs + D * D;
     return s;
   }
   __device__ static __forceinline__ long setup(Smem& sm, ChunkPipe& pipe, const Geom& g, const float* packed, long n_evals, bool bwd) {
@@ -245,7 +294,7 @@ struct DfPolicy {
     for (int i = threadIdx.x; i < g.hdr_floats; i += blockDim.x) hdr[i] = packed[i];
     for (int i = threadIdx.x; i < D * R * blockDim.x; i += blockDim.x) sm.xs[i] = 0.f;
     if (bwd)
-      for (int i = threadIdx.x; i < D * D + D; i += blockDim.x) sm.dell[i] = 0.f;
+      for (int i = threadIdx.x; i < 2 * D * D + D + g.MP2 * 4 * D; i += blockDim.x) sm.dell[i] = 0.f;
     pipe.init(sm.stages, sm.bars, df_rows_ptr(packed, g, blockIdx.y), g.cg, total);  // contains the publishing __syncthreads
     return total;
   }
@@ -335,25 +384,42 @@ struct DfPolicy {
         if (lane == 0) atomicAdd(&sm.dell[a * D + d], u);
       }
     }
-    float2 DX[R][D];
+    static_assert(R == 1, "the DF reverse sweep runs one state per thread");
+    float2 DX[D];
+    float dc[D * D];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int d = 0; d < D; ++d) DX[d] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int d = 0; d < D; ++d) DX[r][d] = make_float2(0.f, 0.f);
+    for (int i = 0; i < D * D; ++i) dc[i] = 0.f;
+    const int my_idx = xred_index(4 * D, lane);
     for (int c = 0; c < g.NCm; ++c) {
       const float* chunk = pipe.acquire(g.cg);
-      df_rows_k_bwd<D, R>(chunk, min(g.RCm, g.MP2 - c * g.RCm), sm, x, gg, DX);
+      df_rows_k_bwd<D>(chunk, min(g.RCm, g.MP2 - c * g.RCm), c * g.RCm, sm, x[0], gg[0], DX, dc, lane, my_idx);
       pipe.release(g.cg, total);
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int i = 0; i < D * D; ++i) {
+      const float v = warp_sum(dc[i]);
+      if (lane == 0) atomicAdd(&sm.dcs[i], v);
+    }
 #pragma unroll
-      for (int d = 0; d < D; ++d) GPODE_XS(sm.dx, d, r) = dxs[r][d] + DX[r][d].x + DX[r][d].y;
+    for (int d = 0; d < D; ++d) GPODE_XS(sm.dx, d, 0) = dxs[0][d] + DX[d].x + DX[d].y;
   }
 
   __device__ static __forceinline__ void flush(const Smem& sm, const Geom& g, const Accum& acc) {
-    for (int i = threadIdx.x; i < D * D; i += blockDim.x) atomicAdd(&acc.dell_x[i], sm.dell[i]);
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+      atomicAdd(&acc.dell_x[i], sm.dell[i]);
+      atomicAdd(&acc.dc[i], sm.dcs[i]);
+    }
     for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(&acc.dvar[i], sm.dvar[i]);
+    const int l = blockIdx.y;
+    for (int i = threadIdx.x; i < g.MP2 * 4 * D; i += blockDim.x) {
+      const int pair = i / (4 * D), q = i - pair * 4 * D;
+      const int what = q / (2 * D), h = (q / D) & 1, k = q % D;
+      const float v = sm.pacc[i];
+      if (what == 0) atomicAdd(&acc.dnu[(static_cast<size_t>(l) * 2 * g.MP2 + 2 * pair + h) * D + k], v);
+      else atomicAdd(&acc.dz[(2 * static_cast<size_t>(pair) + h) * D + k], v);
+    }
   }
 };
 

@@ -312,6 +312,7 @@ struct RbfPolicy {
   static constexpr int R = R_;
   static constexpr int kThreads = DP_ <= 8 ? 256 : 128;
   static constexpr int kMinBlocks = DP_ <= 8 ? 2 : 3;
+  static constexpr int kMinBlocksBwd = kMinBlocks;
   using Geom = RbfGeom;
   using Accum = RbfAccum;
   using Smem = SweepSmem;

@@ -32,6 +32,7 @@ __device__ __forceinline__ States<R> map_states(const G& g) {
 }
 
 #define GPODE_SWEEP_BOUNDS __launch_bounds__(P::kThreads, P::kMinBlocks)
+#define GPODE_SWEEP_BOUNDS_BWD __launch_bounds__(P::kThreads, P::kMinBlocksBwd)
 
 // smem slot of component d of this thread's r-th state
 #define GPODE_XS(buf, d, r) (buf)[((d) * R + (r)) * blockDim.x + threadIdx.x]
@@ -159,7 +160,7 @@ __global__ void GPODE_SWEEP_BOUNDS k_rollout_fwd(const RolloutFwdArgsT<typename 
 // Adjoint vectors live in global scratch ([component][state], coalesced).
 // =============================================================================================
 template <class P>
-__global__ void GPODE_SWEEP_BOUNDS k_rollout_bwd(const RolloutBwdArgsT<typename P::Geom, typename P::Accum> a) {
+__global__ void GPODE_SWEEP_BOUNDS_BWD k_rollout_bwd(const RolloutBwdArgsT<typename P::Geom, typename P::Accum> a) {
   GPODE_POLICY_CONSTS;
   extern __shared__ __align__(128) float smem[];
   const typename P::Geom& g = a.g;
@@ -237,7 +238,7 @@ __global__ void GPODE_SWEEP_BOUNDS k_rollout_bwd(const RolloutBwdArgsT<typename 
 // field backward: one VJP, row-major I/O; leaves transposed x / g for the parameter-gradient kernel
 // =============================================================================================
 template <class P>
-__global__ void GPODE_SWEEP_BOUNDS k_field_bwd(const FieldBwdArgsT<typename P::Geom, typename P::Accum> a) {
+__global__ void GPODE_SWEEP_BOUNDS_BWD k_field_bwd(const FieldBwdArgsT<typename P::Geom, typename P::Accum> a) {
   GPODE_POLICY_CONSTS;
   extern __shared__ __align__(128) float smem[];
   const typename P::Geom& g = a.g;
