@@ -124,7 +124,7 @@ int check_ws(const void* ws, size_t bytes, size_t need) {
   return GPODE_OK;
 }
 
-int rbf_check_smem(const RbfGeom& g) { return rbf_smem_bytes(g, 256, 4, true) <= kSmemLimit ? GPODE_OK : GPODE_E_UNSUPPORTED; }
+int rbf_check_smem(const RbfGeom& g) { return rbf_smem_bytes(g, 32, 1, true) <= kSmemLimit ? GPODE_OK : GPODE_E_UNSUPPORTED; }
 
 cudaError_t rbf_pack(const GpodeProblem* p, const RbfGeom& g, float* packed, cudaStream_t st) {
   RbfPackArgs a;
@@ -165,7 +165,9 @@ cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float
   pa.xsave = xsave;
   pa.gsave = gsave;
   pa.n_te = n_te;
-  pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * ((g.MP2 + 127) / 128), g.DP <= 8 ? 6 : 3);
+  int pg_threads, pg_pp, pg_mblk;
+  rbf_pgrad_shape(g, pg_threads, pg_pp, pg_mblk);
+  pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * pg_mblk, (g.DP <= 8 ? (pg_pp == 1 ? 6 : 4) : (pg_pp == 1 ? 3 : 2)) * kPgThreads / pg_threads);
   pa.acc = acc;
   cudaError_t e = rbf_launch_pgrad(pa, st);
   if (e != cudaSuccess) return e;

@@ -268,6 +268,7 @@ struct DfPolicy {
   static constexpr int R = R_;
   static constexpr int kThreads = 128;
   static constexpr int kMinBlocks = 3;
+  static constexpr int kThreadsBwd = 128;
   static constexpr int kMinBlocksBwd = D_ <= 6 ? 3 : 2;   // the reverse sweep also carries the D x D lengthscale accumulators
   using Geom = DfGeom;
   using Accum = DfAccum;

@@ -23,11 +23,11 @@ cudaError_t launch_sweep(Kern kern, const Args& a, int threads, int R, bool bwd,
   return cudaGetLastError();
 }
 
-// picks the instantiation for the heuristic's R (R = 4 only exists for DP <= 8)
+// picks the instantiation for the heuristic's R (the reverse sweep with R = 4 only exists for DP <= 8)
 #define GPODE_DISPATCH_R(KERNEL, a, bwd, st)                                                         \
   int threads, R;                                                                                    \
-  rbf_pick_shape((a).g, threads, R);                                                                 \
-  if (R >= 4) return launch_sweep(KERNEL<RbfPolicy<DP, RMAX>>, a, threads, RMAX, bwd, st);           \
+  rbf_pick_shape((a).g, bwd, threads, R);                                                            \
+  if (R >= 4) return launch_sweep(KERNEL<RbfPolicy<DP, ((bwd) ? RMAX : 4)>>, a, threads, ((bwd) ? RMAX : 4), bwd, st); \
   if (R == 2) return launch_sweep(KERNEL<RbfPolicy<DP, 2>>, a, threads, 2, bwd, st);                 \
   return launch_sweep(KERNEL<RbfPolicy<DP, 1>>, a, threads, 1, bwd, st);
 }  // namespace
@@ -43,10 +43,11 @@ cudaError_t rbf_rollout_bwd_dp<DP>(const RbfRolloutBwdArgs& a, cudaStream_t st) 
 
 template <>
 cudaError_t rbf_pgrad_dp<DP>(const RbfPgradArgs& a, cudaStream_t st) {
-  const int n_mblk = (a.g.MP2 + kPgThreads - 1) / kPgThreads;
-  const int threads = n_mblk > 1 ? kPgThreads : ((a.g.MP2 + 31) / 32) * 32;
+  int threads, PP, n_mblk;
+  rbf_pgrad_shape(a.g, threads, PP, n_mblk);
   dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
-  k_rbf_pgrad<DP><<<grid, threads, 0, st>>>(a);
+  if (PP == 2) k_rbf_pgrad<DP, 2><<<grid, threads, 0, st>>>(a);
+  else k_rbf_pgrad<DP, 1><<<grid, threads, 0, st>>>(a);
   return cudaGetLastError();
 }
 

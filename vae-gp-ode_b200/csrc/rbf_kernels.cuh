@@ -32,7 +32,7 @@ template <int DP, int R>
 __device__ __forceinline__ float2 row_dot(const float4 (&v)[(DP + 2) / 2], const float (&x)[DP], float add) {
   constexpr int ROW4 = (DP + 2) / 2;
   float2 t0 = add2(lo(v[ROW4 - 1]), bc(add));
-  if constexpr (R == 1 && DP >= 4) {  // single state per thread: split the dependent chain in two
+  if constexpr (R == 1 && DP >= 4) {  // single state per thread: split the dependent chain in two (measured: hurts at R = 2)
     float2 t1 = mul2(bc(x[1]), hi(v[0]));
     t0 = fma2(bc(x[0]), lo(v[0]), t0);
 #pragma unroll
@@ -310,9 +310,11 @@ template <int DP_, int R_>
 struct RbfPolicy {
   static constexpr int DP = DP_;
   static constexpr int R = R_;
-  static constexpr int kThreads = DP_ <= 8 ? 256 : 128;
-  static constexpr int kMinBlocks = DP_ <= 8 ? 2 : 3;
-  static constexpr int kMinBlocksBwd = kMinBlocks;
+  static constexpr int kThreads = 256;   // compiled for <= 128 registers: 512 resident threads per SM in any block size
+  static constexpr int kMinBlocks = 2;
+  // reverse sweep at D > 8: 128 threads x 3 CTAs (<= 168 registers) -- measured 10% faster than the 128-register build
+  static constexpr int kThreadsBwd = DP_ <= 8 ? 256 : 128;
+  static constexpr int kMinBlocksBwd = DP_ <= 8 ? 2 : 3;
   using Geom = RbfGeom;
   using Accum = RbfAccum;
   using Smem = SweepSmem;
@@ -350,10 +352,10 @@ struct RbfPolicy {
 // =============================================================================================
 constexpr int kPgBatch = 128;
 
-constexpr int kPgThreads = 128;
 
-template <int DP>
-__global__ void __launch_bounds__(kPgThreads, (DP <= 8 ? 6 : 3)) k_rbf_pgrad(const RbfPgradArgs a) {
+// PP inducing-point pairs per thread: one broadcast LDS.128 of a staged state feeds 2 PP inducing points (PP = 1 is LDS-bound)
+template <int DP, int PP>
+__global__ void __launch_bounds__(kPgThreads, (DP <= 8 ? (PP == 1 ? 6 : 4) : (PP == 1 ? 3 : 2))) k_rbf_pgrad(const RbfPgradArgs a) {
   const RbfGeom& g = a.g;
   constexpr int ROW4 = (DP + 2) / 2;
   constexpr int SROW = ((DP + 2 + 3) / 4) * 4;  // staged state: x[DP], g, A (+pad), 16-byte rows
@@ -363,27 +365,35 @@ __global__ void __launch_bounds__(kPgThreads, (DP <= 8 ? 6 : 3)) k_rbf_pgrad(con
   const int k = blockIdx.y, l = blockIdx.z;
   const float* hdr = rbf_hdr_ptr(a.packed, g, l) + k * g.hdr_floats;
   if (threadIdx.x < DP) s_c[threadIdx.x] = hdr[threadIdx.x];
-  const int n_mblk = (g.MP2 + kPgThreads - 1) / kPgThreads;
+  const int per_cta = blockDim.x * PP;
+  const int n_mblk = (g.MP2 + per_cta - 1) / per_cta;
   const int chunk_id = blockIdx.x / n_mblk;
-  const int j = (blockIdx.x - chunk_id * n_mblk) * kPgThreads + threadIdx.x;  // inducing pair
-  const bool active = j < g.MP2;
-  float2 G[DP], H = make_float2(0.f, 0.f);
+  const int j0 = (blockIdx.x - chunk_id * n_mblk) * per_cta + threadIdx.x;  // first inducing pair of this thread
+  float2 G[PP][DP], H[PP], dnu[PP], pg[PP][DP];
+  bool any = false;
 #pragma unroll
-  for (int d = 0; d < DP; ++d) G[d] = make_float2(0.f, 0.f);
-  if (active) {
-    const float4* row = reinterpret_cast<const float4*>(rbf_rows_ptr(a.packed, g, l) +
-                                                        (static_cast<size_t>(k) * (g.SP2 + g.MP2) + g.SP2 + j) * g.row_floats);
+  for (int p = 0; p < PP; ++p) {
+    const int j = j0 + p * blockDim.x;
+    H[p] = make_float2(0.f, 0.f);
+    dnu[p] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < DP / 2; ++i) {
-      const float4 v = row[i];
-      G[2 * i] = lo(v);
-      G[2 * i + 1] = hi(v);
+    for (int d = 0; d < DP; ++d) {
+      G[p][d] = make_float2(0.f, 0.f);
+      pg[p][d] = make_float2(0.f, 0.f);
     }
-    H = lo(row[ROW4 - 1]);
-  }
-  float2 dnu = make_float2(0.f, 0.f), pg[DP];
+    if (j < g.MP2) {
+      any = true;
+      const float4* row = reinterpret_cast<const float4*>(rbf_rows_ptr(a.packed, g, l) +
+                                                          (static_cast<size_t>(k) * (g.SP2 + g.MP2) + g.SP2 + j) * g.row_floats);
 #pragma unroll
-  for (int d = 0; d < DP; ++d) pg[d] = make_float2(0.f, 0.f);
+      for (int i = 0; i < DP / 2; ++i) {
+        const float4 v = row[i];
+        G[p][2 * i] = lo(v);
+        G[p][2 * i + 1] = hi(v);
+      }
+      H[p] = lo(row[ROW4 - 1]);
+    }
+  }
 
   const long total = a.n_te * g.N;  // state evaluations of this sample
   const long per = (total + a.chunks - 1) / a.chunks;
@@ -413,9 +423,9 @@ __global__ void __launch_bounds__(kPgThreads, (DP <= 8 ? 6 : 3)) k_rbf_pgrad(con
       row[DP + 1] = A;
     }
     __syncthreads();
-    if (active) {
+    if (any) {
       const int nb = (e_hi - e0) < kPgBatch ? static_cast<int>(e_hi - e0) : kPgBatch;
-#pragma unroll 2
+#pragma unroll(PP == 1 ? 2 : 1)
       for (int idx = 0; idx < nb; ++idx) {
         const float4* row = reinterpret_cast<const float4*>(stage + idx * SROW);
         float xv[SROW];
@@ -427,41 +437,97 @@ __global__ void __launch_bounds__(kPgThreads, (DP <= 8 ? 6 : 3)) k_rbf_pgrad(con
           xv[4 * i + 2] = q.z;
           xv[4 * i + 3] = q.w;
         }
-        float2 ex = add2(H, bc(xv[DP + 1]));
+        float2 ex[PP];
+        if constexpr (DP >= 8) {   // two partial sums: halves the dependent FFMA2 chain
+          float2 ey[PP];
 #pragma unroll
-        for (int d = 0; d < DP; ++d) ex = fma2(bc(xv[d]), G[d], ex);
-        const float2 ge = mul2(bc(xv[DP]), ex2_2(ex));
-        dnu = add2(dnu, ge);
+          for (int p = 0; p < PP; ++p) {
+            ex[p] = fma2(bc(xv[0]), G[p][0], add2(H[p], bc(xv[DP + 1])));
+            ey[p] = mul2(bc(xv[1]), G[p][1]);
+          }
 #pragma unroll
-        for (int d = 0; d < DP; ++d) pg[d] = fma2(bc(xv[d]), ge, pg[d]);
+          for (int d = 2; d < DP; d += 2)
+#pragma unroll
+            for (int p = 0; p < PP; ++p) {
+              ex[p] = fma2(bc(xv[d]), G[p][d], ex[p]);
+              ey[p] = fma2(bc(xv[d + 1]), G[p][d + 1], ey[p]);
+            }
+#pragma unroll
+          for (int p = 0; p < PP; ++p) ex[p] = add2(ex[p], ey[p]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < PP; ++p) ex[p] = add2(H[p], bc(xv[DP + 1]));
+#pragma unroll
+          for (int d = 0; d < DP; ++d)
+#pragma unroll
+            for (int p = 0; p < PP; ++p) ex[p] = fma2(bc(xv[d]), G[p][d], ex[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+          const float2 ge = mul2(bc(xv[DP]), ex2_2(ex[p]));
+          dnu[p] = add2(dnu[p], ge);
+#pragma unroll
+          for (int d = 0; d < DP; ++d) pg[p][d] = fma2(bc(xv[d]), ge, pg[p][d]);
+        }
       }
     }
     __syncthreads();
   }
-  if (active) {
-    const size_t base = (static_cast<size_t>(l) * g.D_out + k) * (2 * g.MP2) + 2 * j;
-    atomicAdd(&a.acc.dnu[base], dnu.x);
-    atomicAdd(&a.acc.dnu[base + 1], dnu.y);
 #pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      atomicAdd(&a.acc.pg[base * DP + d], pg[d].x);
-      atomicAdd(&a.acc.pg[(base + 1) * DP + d], pg[d].y);
+  for (int p = 0; p < PP; ++p) {
+    const int j = j0 + p * blockDim.x;
+    if (j < g.MP2) {
+      const size_t base = (static_cast<size_t>(l) * g.D_out + k) * (2 * g.MP2) + 2 * j;
+      atomicAdd(&a.acc.dnu[base], dnu[p].x);
+      atomicAdd(&a.acc.dnu[base + 1], dnu[p].y);
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        atomicAdd(&a.acc.pg[base * DP + d], pg[p][d].x);
+        atomicAdd(&a.acc.pg[(base + 1) * DP + d], pg[p][d].y);
+      }
     }
   }
 }
 
-// launch-shape heuristic of the sweep kernels: states per CTA = threads * R; prefer deep register
-// blocking (fewer broadcast LDS per FMA) as long as the grid still fills the chip twice over.
-inline void rbf_pick_shape(const RbfGeom& g, int& threads, int& R) {
-  const long want = 2L * 148;
-  const int tmax = g.DP <= 8 ? 256 : 128;
-  const int rmax = g.DP <= 8 ? 4 : 2;
-  const int cand[7][2] = {{tmax, rmax}, {tmax, rmax / 2}, {128, rmax / 2}, {128, 1}, {64, 1}, {32, 1}, {32, 1}};
-  for (int i = 0; i < 7; ++i) {
-    threads = cand[i][0];
-    R = cand[i][1];
-    const long per = static_cast<long>(threads) * R;
-    if (((static_cast<long>(g.N) + per - 1) / per) * g.L >= want) return;
+// launch-shape heuristic of the sweep kernels.  All sweep kernels are compiled for <= 128 registers (512 resident
+// threads per SM), so any block size up to 256 threads can be launched; states per CTA = threads * R.  The model
+// below estimates the time of a launch as (CTAs the busiest SM runs back to back) x (work per CTA) x (cost per state of
+// the register-blocking factor R: a broadcast LDS.128 feeds R states, small R is LDS-bound) and picks the cheapest shape;
+// for a chip-filling problem this amounts to choosing the shape whose last wave is full.
+inline void rbf_pick_shape(const RbfGeom& g, bool bwd, int& threads, int& R) {
+  const int rc[3] = {4, 2, 1};
+  double best = 1e300;
+  threads = 32;
+  R = 1;
+  for (int ri = 0; ri < 3; ++ri) {
+    const int r = rc[ri];
+    if (bwd && g.DP > 8 && r > 2) continue;   // not compiled: the reverse sweep at D > 8 holds 2 states per thread at most
+    // relative cost per state: forward needs R*2 FMA per parameter float to hide the LDS, the reverse sweep uses each float twice
+    const double cost = bwd ? (r == 1 ? 1.25 : 1.0) : (r == 1 ? (g.DP > 8 ? 2.0 : 1.6) : (r == 2 ? (g.DP > 8 ? 1.2 : 1.05) : 1.0));
+    for (int t = 32; t <= 256; t += 32) {   // ties go to the smaller block
+      const int smem = rbf_smem_bytes(g, t, r, bwd) + 1024;
+      if (bwd && g.DP > 8 && t > 128) continue;
+      int bps = ((bwd && g.DP > 8) ? 384 : 512) / t;
+      const int bps_s = (228 * 1024) / smem;
+      if (bps_s < bps) bps = bps_s;
+      if (bps > 32) bps = 32;
+      if (bps < 1) continue;
+      const long per = static_cast<long>(t) * r;
+      const long ctas = ((static_cast<long>(g.N) + per - 1) / per) * g.L;
+      const long slots = 148L * bps;
+      const long waves = (ctas + slots - 1) / slots;
+      const long rem = ctas - (waves - 1) * slots;
+      const long load = (waves - 1) * bps + (rem + 147) / 148;            // CTAs the busiest SM runs
+      const long resident = load < bps ? load : bps;
+      const double warps = static_cast<double>(resident) * t / 32.0;
+      const double latency = warps >= 12.0 ? 1.0 : (warps >= 8.0 ? 1.08 : 8.0 * 1.08 / warps);   // too few warps: latency bound
+      const double time = static_cast<double>(load) * per * cost * latency;
+      if (time < best * 0.999) {
+        best = time;
+        threads = t;
+        R = r;
+      }
+    }
   }
 }
 

@@ -32,7 +32,7 @@ __device__ __forceinline__ States<R> map_states(const G& g) {
 }
 
 #define GPODE_SWEEP_BOUNDS __launch_bounds__(P::kThreads, P::kMinBlocks)
-#define GPODE_SWEEP_BOUNDS_BWD __launch_bounds__(P::kThreads, P::kMinBlocksBwd)
+#define GPODE_SWEEP_BOUNDS_BWD __launch_bounds__(P::kThreadsBwd, P::kMinBlocksBwd)
 
 // smem slot of component d of this thread's r-th state
 #define GPODE_XS(buf, d, r) (buf)[((d) * R + (r)) * blockDim.x + threadIdx.x]
