@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GPODE_VERSION 100 /* major*100 + minor */
+#define GPODE_VERSION 101 /* major*100 + minor */
 
 /* kernel variants (core/kernels.py: RBF dimwise=False / dimwise=True :29-195, DivergenceFreeKernel :201-393) */
 enum { GPODE_RBF_SHARED = 0, GPODE_RBF_DIMWISE = 1, GPODE_DF = 2 };
@@ -122,6 +122,39 @@ int gpode_rollout_fwd(const GpodeProblem* p, const float* z0, int z0_per_sample,
 int gpode_rollout_bwd(const GpodeProblem* p, const float* ts, int T, int method, int order,
                       const float* traj, const float* save, const float* dtraj, float* dz0,
                       const GpodeParamGrads* grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-rollout setup at the M inducing points (what sits in the autograd graph of SVGP_Layer.build_cache),
+ * batched over output dimensions and MC samples.  RBF variants only: the DF kernel's single (M D x M D)
+ * system is not a small batched problem and stays on cuSOLVER (GPODE_E_UNSUPPORTED here).
+ * ------------------------------------------------------------------------------------------- */
+
+/* scratch bytes / forward->backward save floats of gpode_compute_nu_* (p: variant, L, M, D_in, D_out, Z, ell, var are read) */
+size_t gpode_nu_workspace_bytes(const GpodeProblem* p);
+size_t gpode_nu_save_floats(const GpodeProblem* p);
+
+/* RBF.compute_nu (core/kernels.py:155-172) fused with K(Z,Z) (core/kernels.py:98-110, called at svpy.py:118):
+ *   Lc = chol(K(Z,Z) + 1e-5 I) (lower), nu = Lc^-T (u - Lc^-1 u_prior), one system per output dim (dimwise) or one shared.
+ *   u_prior = rff_forward(Z) and u = sample_inducing() are (L,M,D_out); nu comes out in the GpodeProblem layout.
+ *   save: gpode_nu_save_floats() floats (Cholesky factors + Lc^-1 u_prior) for the backward.
+ *   info (optional, Kc int32): 0, or 1 + index of the first non-positive pivot (torch.linalg.cholesky raises there). */
+int gpode_compute_nu_fwd(const GpodeProblem* p, const float* u_prior, const float* u, float* nu, float* save, int32_t* info,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* autograd backward of the above: d_nu (nu layout) -> d_u_prior, d_u (L,M,D_out) and the direct dependence of K(Z,Z) on
+ * Z (M,D_in), ell, var (layouts of GpodeProblem; written, not accumulated).  Any output may be NULL. */
+int gpode_compute_nu_bwd(const GpodeProblem* p, const float* u, const float* save, const float* d_nu, float* d_u_prior, float* d_u,
+                         float* d_Z, float* d_ell, float* d_var, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SVGP_Layer.sample_inducing (core/svpy.py:88-101, q_diag=False) for L samples on the PACKED lower-triangular parameter
+ * (Us_sqrt.optvar, (D_out, M(M+1)/2) row-major tril order, misc/transforms.py:71-77):
+ *   u[l,n,d] = sum_{m<=n} Lq_d[n,m] eps_u[l,m,d] + Um[n,d];   eps_u, u (L,M,D_out), Um (M,D_out). */
+int gpode_inducing_sample_fwd(int L, int M, int D_out, const float* Lq_packed, const float* Um, const float* eps_u, float* u, void* stream);
+int gpode_inducing_sample_bwd(int L, int M, int D_out, const float* eps_u, const float* d_u, float* d_Lq_packed, float* d_Um, void* stream);
+
+/* SVGP_Layer.kl (core/svpy.py:144-175, q_diag=False) on the packed parameter: kl (1 float on the device)
+ *   = 1/2 sum_d ( -sum_i log Lq_d[i,i]^2 + |Um[:,d]|^2 + |Lq_d|_F^2 - M );  d_kl is a device scalar. */
+int gpode_kl_fwd(int M, int D_out, const float* Lq_packed, const float* Um, float* kl, void* stream);
+int gpode_kl_bwd(int M, int D_out, const float* Lq_packed, const float* Um, const float* d_kl, float* d_Lq_packed, float* d_Um, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,113 @@
+"""GPU parity of the per-rollout setup kernels (csrc/setup_kernels.cu) through the C ABI: compute_nu (K(Z,Z) + blocked
+Cholesky + whitened solves, batched over output dims and MC samples), inducing sample and KL on the packed
+lower-triangular parameter -- against the fp64 oracle (oracle/field.py) and its autograd.
+
+Tolerances: nu goes through a Cholesky of a matrix with cond up to ~1e5, so fp32 nu is compared
+with the fp64 oracle at 1e-3 x cond-aware bars on well-conditioned problems (ell <= 1) and against the fp32 torch result
+on the golden (ell = 2) cases; everything else at 1e-5 / 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import field as OF
+from helpers import load_golden, oracle_cache, rel, t
+
+pytestmark = pytest.mark.gpu
+
+
+def _gp():
+    import gpode_b200
+    return gpode_b200
+
+
+def _problem(variant, M, D_in, D_out, L, seed, ell0=0.7):
+    rs = np.random.RandomState(seed)
+    f64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    dimwise = variant == "rbf_dimwise"
+    Z = f64(rs.normal(size=(M, D_in)))
+    ell = f64(ell0 + 0.3 * rs.uniform(size=(D_out, D_in) if dimwise else (D_in,)))
+    var = f64(0.5 + rs.uniform(size=(D_out,) if dimwise else (1,)))
+    up = f64(rs.normal(size=(L, M, D_out)))
+    u = f64(rs.normal(size=(L, M, D_out)))
+    return Z, ell, var, up, u
+
+
+def _oracle_nu(variant, Z, ell, var, up, u):
+    Ku = OF.rbf_K(Z, None, ell, var, variant == "rbf_dimwise")
+    return torch.stack([OF.compute_nu(Ku, up[l], u[l], variant) for l in range(u.shape[0])])
+
+
+@pytest.mark.parametrize("variant", ["rbf_dimwise", "rbf_shared"])
+@pytest.mark.parametrize("M,D_in,D_out,L", [(100, 6, 6, 1), (33, 3, 2, 3), (256, 6, 3, 2), (512, 16, 16, 4), (70, 16, 5, 8)])
+def test_compute_nu_forward_backward(variant, M, D_in, D_out, L):
+    Z, ell, var, up, u = _problem(variant, M, D_in, D_out, L, seed=M + D_out)
+    leaves = [v.clone().requires_grad_(True) for v in (Z, ell, var, up, u)]
+    nu64 = _oracle_nu(variant, *leaves)
+    G = torch.tensor(np.random.RandomState(1).normal(size=tuple(nu64.shape)), dtype=torch.float64)
+    want = torch.autograd.grad((nu64 * G).sum(), leaves)
+    # the same computation in fp32 torch on the CPU (LAPACK): its distance from the fp64 result is the conditioning noise floor
+    leaves32 = [v.clone().float().requires_grad_(True) for v in (Z, ell, var, up, u)]
+    nu32 = _oracle_nu(variant, *leaves32)
+    floor32 = torch.autograd.grad((nu32 * G.float()).sum(), leaves32)
+    dev = [v.detach().float().cuda().requires_grad_(True) for v in (Z, ell, var, up, u)]
+    nu = _gp().compute_nu(*dev, variant)
+    assert nu.shape == nu64.shape
+    e, e32 = rel(nu, nu64), rel(nu32, nu64)
+    print("%s M=%d nu: %.2e (torch fp32: %.2e)" % (variant, M, e, e32))
+    assert e < max(5 * e32, 2e-5), (e, e32)
+    (nu * G.float().cuda()).sum().backward()
+    for nm, a, b, f in zip(("dZ", "dell", "dvar", "du_prior", "du"), dev, want, floor32):
+        e, e32 = rel(a.grad, b), rel(f, b)
+        print("%s M=%d %s: %.2e (torch fp32: %.2e)" % (variant, M, nm, e, e32))
+        assert e < max(5 * e32, 1e-4), (nm, e, e32)
+
+
+@pytest.mark.parametrize("name", ["rbf_dimwise_o1", "rbf_shared_o1", "rbf_dimwise_d16"])
+def test_compute_nu_matches_reference_golden(name):
+    """reference nu (fp32 LAPACK, ell = 2 -> cond ~1e4..1e6): same inputs through the CUDA kernels; the bar is the
+    reference's own fp32 noise against the fp64 oracle."""
+    g = load_golden(name)
+    m = g["meta"]
+    c64 = oracle_cache(g, shared_nu=False)
+    up64 = OF.prior(c64["Z"], c64)
+    nu = _gp().compute_nu(c64["Z"].float().cuda(), c64["ell"].float().cuda(), c64["var"].float().cuda(), up64.float().cuda()[None],
+                          c64["u"].float().cuda()[None], m["variant"])
+    e_new, e_ref = rel(nu[0], c64["nu"]), rel(g["field_nu"], c64["nu"])
+    print("%s nu: new-vs-fp64 %.2e ref-vs-fp64 %.2e" % (name, e_new, e_ref))
+    assert e_new < max(5 * e_ref, 1e-4)
+
+
+def test_cholesky_failure_is_reported():
+    Z, ell, var, up, u = _problem("rbf_dimwise", 40, 3, 2, 1, seed=0)
+    Z[1] = Z[0]                       # duplicate inducing point: K + 1e-5 I stays SPD (jitter) -> info == 0
+    from gpode_b200 import functional as GF
+    nu = GF.ComputeNu.apply(Z.float().cuda(), ell.float().cuda(), var.float().cuda(), up.float().cuda(), u.float().cuda(), 1)
+    assert torch.isfinite(nu).all()
+    var_bad = -var                    # negative variance: not positive definite -> NaN factor, reported like LAPACK's info
+    nu = _gp().compute_nu(Z.float().cuda(), ell.float().cuda(), var_bad.float().cuda(), up.float().cuda(), u.float().cuda(), "rbf_dimwise")
+    assert not torch.isfinite(nu).all()
+
+
+@pytest.mark.parametrize("M,D,L", [(10, 3, 1), (100, 6, 4), (512, 16, 2), (257, 5, 3)])
+def test_inducing_sample_and_kl(M, D, L):
+    rs = np.random.RandomState(M)
+    P = M * (M + 1) // 2
+    packed = torch.tensor(0.05 * rs.normal(size=(D, P)), dtype=torch.float64)
+    rows, cols = torch.tril_indices(M, M)
+    packed[:, rows == cols] = torch.tensor(0.5 + rs.uniform(size=(D, M)), dtype=torch.float64)
+    Um = torch.tensor(rs.normal(size=(M, D)), dtype=torch.float64)
+    eps = torch.tensor(rs.normal(size=(L, M, D)), dtype=torch.float64)
+    p64, m64 = packed.clone().requires_grad_(True), Um.clone().requires_grad_(True)
+    Lq = OF.tril_from_packed(p64, M)
+    u64 = torch.stack([OF.sample_inducing(Lq, eps[l], m64) for l in range(L)])
+    kl64 = OF.kl_whitened(m64, Lq)
+    G = torch.tensor(rs.normal(size=(L, M, D)), dtype=torch.float64)
+    want = torch.autograd.grad((u64 * G).sum() + 0.7 * kl64, [p64, m64])
+    pc, mc = packed.float().cuda().requires_grad_(True), Um.float().cuda().requires_grad_(True)
+    u = _gp().inducing_sample(pc, mc, eps.float().cuda())
+    kl = _gp().whitened_kl(pc, mc)
+    assert rel(u, u64) < 1e-5
+    assert abs(kl.item() - kl64.item()) < 1e-5 * abs(kl64.item())
+    ((u * G.float().cuda()).sum() + 0.7 * kl).backward()
+    assert rel(pc.grad, want[0]) < 1e-5
+    assert rel(mc.grad, want[1]) < 1e-5

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "df.h"
 #include "rbf.h"
+#include "setup.h"
 
 using namespace gpode;
 
@@ -472,6 +473,79 @@ int gpode_rollout_bwd(const GpodeProblem* p, const float* ts, int T, int method,
   if ((e = rbf_launch_rollout_bwd(a, st)) != cudaSuccess) return static_cast<int>(e);
   if (T < 2) return GPODE_OK;
   return static_cast<int>(rbf_param_grads(p, g, packed, xs, a.gsave, static_cast<long>(T - 1) * stages, a.acc, grads, st));
+}
+
+/* ---- per-rollout setup: compute_nu, inducing sample, KL (setup_kernels.cu) ---- */
+static int nu_geom(const GpodeProblem* p, NuGeom* g) {
+  if (!p) return GPODE_E_NULL;
+  if (p->variant != GPODE_RBF_SHARED && p->variant != GPODE_RBF_DIMWISE) return GPODE_E_UNSUPPORTED;  /* DF: (M D x M D) system, stays on cuSOLVER */
+  if (p->L < 1 || p->D_in < 1 || p->D_out < 1 || p->M < 1) return GPODE_E_SHAPE;
+  if (p->D_in > kMaxD || p->D_out > kMaxD || p->M > 512) return GPODE_E_UNSUPPORTED;
+  if (!p->Z || !p->ell || !p->var) return GPODE_E_NULL;
+  g->L = p->L; g->M = p->M; g->D_in = p->D_in; g->D_out = p->D_out;
+  g->dimwise = p->variant == GPODE_RBF_DIMWISE ? 1 : 0;
+  g->Kc = g->dimwise ? p->D_out : 1;
+  g->NR = g->dimwise ? p->L : p->L * p->D_out;
+  g->jitter = 1e-5f;
+  return GPODE_OK;
+}
+
+size_t gpode_nu_workspace_bytes(const GpodeProblem* p) {
+  NuGeom g;
+  if (nu_geom(p, &g) != GPODE_OK) return 0;
+  return align_up(nu_ws_floats(g) * 4, 256);
+}
+size_t gpode_nu_save_floats(const GpodeProblem* p) {
+  NuGeom g;
+  if (nu_geom(p, &g) != GPODE_OK) return 0;
+  return nu_save_floats(g);
+}
+int gpode_compute_nu_fwd(const GpodeProblem* p, const float* u_prior, const float* u, float* nu, float* save, int32_t* info,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  NuGeom g;
+  int rc = nu_geom(p, &g);
+  if (rc) return rc;
+  if (!u_prior || !u || !nu || !save) return GPODE_E_NULL;
+  if ((rc = check_ws(workspace, workspace_bytes, align_up(nu_ws_floats(g) * 4, 256)))) return rc;
+  return static_cast<int>(nu_forward(g, p->Z, p->ell, p->var, u_prior, u, nu, save, info, static_cast<float*>(workspace),
+                                     static_cast<cudaStream_t>(stream)));
+}
+int gpode_compute_nu_bwd(const GpodeProblem* p, const float* u, const float* save, const float* d_nu, float* d_u_prior, float* d_u,
+                         float* d_Z, float* d_ell, float* d_var, void* workspace, size_t workspace_bytes, void* stream) {
+  NuGeom g;
+  int rc = nu_geom(p, &g);
+  if (rc) return rc;
+  if (!u || !save || !d_nu) return GPODE_E_NULL;
+  if ((rc = check_ws(workspace, workspace_bytes, align_up(nu_ws_floats(g) * 4, 256)))) return rc;
+  return static_cast<int>(nu_backward(g, p->Z, p->ell, p->var, u, save, d_nu, d_u_prior, d_u, d_Z, d_ell, d_var,
+                                      static_cast<float*>(workspace), static_cast<cudaStream_t>(stream)));
+}
+static int check_lq(int L, int M, int D_out, const void* a, const void* b, const void* c, const void* d) {
+  if (L < 1 || M < 1 || D_out < 1) return GPODE_E_SHAPE;
+  if (M > 4096 || D_out > 64) return GPODE_E_UNSUPPORTED;
+  if (!a || !b || !c || !d) return GPODE_E_NULL;
+  return GPODE_OK;
+}
+int gpode_inducing_sample_fwd(int L, int M, int D_out, const float* Lq_packed, const float* Um, const float* eps_u, float* u, void* stream) {
+  int rc = check_lq(L, M, D_out, Lq_packed, Um, eps_u, u);
+  if (rc) return rc;
+  return static_cast<int>(inducing_forward(L, M, D_out, Lq_packed, Um, eps_u, u, static_cast<cudaStream_t>(stream)));
+}
+int gpode_inducing_sample_bwd(int L, int M, int D_out, const float* eps_u, const float* d_u, float* d_Lq_packed, float* d_Um, void* stream) {
+  int rc = check_lq(L, M, D_out, eps_u, d_u, d_Lq_packed, d_Um);
+  if (rc) return rc;
+  return static_cast<int>(inducing_backward(L, M, D_out, eps_u, d_u, d_Lq_packed, d_Um, 0, static_cast<cudaStream_t>(stream)));
+}
+int gpode_kl_fwd(int M, int D_out, const float* Lq_packed, const float* Um, float* kl, void* stream) {
+  int rc = check_lq(1, M, D_out, Lq_packed, Um, kl, kl);
+  if (rc) return rc;
+  return static_cast<int>(kl_forward(M, D_out, Lq_packed, Um, kl, static_cast<cudaStream_t>(stream)));
+}
+int gpode_kl_bwd(int M, int D_out, const float* Lq_packed, const float* Um, const float* d_kl, float* d_Lq_packed, float* d_Um, void* stream) {
+  int rc = check_lq(1, M, D_out, Lq_packed, Um, d_kl, d_Lq_packed);
+  if (rc) return rc;
+  if (!d_Um) return GPODE_E_NULL;
+  return static_cast<int>(kl_backward(M, D_out, Lq_packed, Um, d_kl, d_Lq_packed, d_Um, static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

@@ -5,12 +5,15 @@ Mirrors the reference's module layout for this path only:
     gpode_b200.core.svpy      SVGP_Layer                      (reference: experiments/model/core/svpy.py)
     gpode_b200.core.flow      ODEfunc, Flow                   (reference: experiments/model/core/flow.py)
     gpode_b200.misc.*         Param, transforms, softplus     (reference: experiments/model/misc/*)
-    gpode_b200.functional     GPField / GPRollout autograd Functions over the C ABI (include/gpode.h)
+    gpode_b200.functional     GPField / GPRollout / ComputeNu / InducingSample / WhitenedKL autograd Functions over the
+                              C ABI (include/gpode.h)
 
 There is no CPU path and no fallback: every evaluation goes through libgpode.so on a CUDA device and
 raises if the library or a GPU is missing.
 """
 from . import _lib  # noqa: F401
-from .functional import gp_field, gp_rollout, GPField, GPRollout  # noqa: F401
+from .functional import (gp_field, gp_rollout, GPField, GPRollout, compute_nu, inducing_sample, whitened_kl,  # noqa: F401
+                         ComputeNu, InducingSample, WhitenedKL)
 
-__all__ = ["gp_field", "gp_rollout", "GPField", "GPRollout"]
+__all__ = ["gp_field", "gp_rollout", "GPField", "GPRollout", "compute_nu", "inducing_sample", "whitened_kl", "ComputeNu",
+           "InducingSample", "WhitenedKL"]

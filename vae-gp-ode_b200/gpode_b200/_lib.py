@@ -28,7 +28,9 @@ class GpodeParamGrads(ctypes.Structure):
 
 
 EXPORTS = ["gpode_version", "gpode_error_string", "gpode_workspace_bytes", "gpode_rollout_save_floats",
-           "gpode_field_fwd", "gpode_field_bwd", "gpode_rollout_fwd", "gpode_rollout_bwd"]
+           "gpode_field_fwd", "gpode_field_bwd", "gpode_rollout_fwd", "gpode_rollout_bwd",
+           "gpode_nu_workspace_bytes", "gpode_nu_save_floats", "gpode_compute_nu_fwd", "gpode_compute_nu_bwd",
+           "gpode_inducing_sample_fwd", "gpode_inducing_sample_bwd", "gpode_kl_fwd", "gpode_kl_bwd"]
 
 _lib = None
 
@@ -60,6 +62,22 @@ def load():
     lib.gpode_rollout_fwd.argtypes = [P, _fp, i32, _fp, i32, i32, i32, _fp, _fp, _fp, sz, _fp]
     lib.gpode_rollout_bwd.restype = i32
     lib.gpode_rollout_bwd.argtypes = [P, _fp, i32, i32, i32, _fp, _fp, _fp, _fp, PG, _fp, sz, _fp]
+    lib.gpode_nu_workspace_bytes.restype = sz
+    lib.gpode_nu_workspace_bytes.argtypes = [P]
+    lib.gpode_nu_save_floats.restype = sz
+    lib.gpode_nu_save_floats.argtypes = [P]
+    lib.gpode_compute_nu_fwd.restype = i32
+    lib.gpode_compute_nu_fwd.argtypes = [P, _fp, _fp, _fp, _fp, _fp, _fp, sz, _fp]
+    lib.gpode_compute_nu_bwd.restype = i32
+    lib.gpode_compute_nu_bwd.argtypes = [P, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, sz, _fp]
+    lib.gpode_inducing_sample_fwd.restype = i32
+    lib.gpode_inducing_sample_fwd.argtypes = [i32, i32, i32, _fp, _fp, _fp, _fp, _fp]
+    lib.gpode_inducing_sample_bwd.restype = i32
+    lib.gpode_inducing_sample_bwd.argtypes = [i32, i32, i32, _fp, _fp, _fp, _fp, _fp]
+    lib.gpode_kl_fwd.restype = i32
+    lib.gpode_kl_fwd.argtypes = [i32, i32, _fp, _fp, _fp, _fp]
+    lib.gpode_kl_bwd.restype = i32
+    lib.gpode_kl_bwd.argtypes = [i32, i32, _fp, _fp, _fp, _fp, _fp, _fp]
     _lib = lib
     return lib
 

@@ -78,11 +78,8 @@ class Flow(nn.Module):
 
     def forward_samples(self, z0, ts, L):
         """(N,D_s) -> (L,N,T,D_s): L fresh function samples (caches drawn in order), a single launch."""
-        samples = []
-        for _ in range(L):
-            self.odefunc.before_odeint(rebuild_cache=True)
-            samples.append(self.odefunc.diffeq.field_sample())
-        return self._rollout(z0, ts, FieldSample.stack(samples))
+        self.odefunc.before_odeint(rebuild_cache=False)
+        return self._rollout(z0, ts, self.odefunc.diffeq.build_cache_batched(L))
 
     def num_evals(self):
         return self.odefunc.num_evals()

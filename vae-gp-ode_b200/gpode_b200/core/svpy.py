@@ -63,6 +63,7 @@ class SVGP_Layer(torch.nn.Module):
                                  transform=transforms.LowerTriangular(M, D_out, device=device),
                                  name="Inducing distribution (scale)", device=device)
         self.kern.to(device)
+        self._cache = None
 
     def sample_inducing(self):
         """u = Lq eps + m, eps ~ N(0,I) (M,D_out) (whitened inducing sample, svpy.py:88-101)."""
@@ -71,8 +72,46 @@ class SVGP_Layer(torch.nn.Module):
             return self.Us_sqrt() * eps + self.Um()
         return torch.einsum("dnm,md->nd", self.Us_sqrt(), eps) + self.Um()
 
+    def _fused_setup(self):
+        """RBF kernels with a full (non-diagonal) q(u) on a CUDA device run the per-rollout setup on the kernels of
+        csrc/setup_kernels.cu; DF ((M D x M D) system), q_diag and CPU tensors (host-logic unit tests) use torch ops."""
+        return self.kernel_n == "RBF" and not self.q_diag and self.inducing_loc.optvar.is_cuda and self.M <= 512
+
+    def _draw(self):
+        """host draws of one function sample in the reference's order (kernels.py:126-137, svpy.py:94): w, eps, phase, eps_u."""
+        self.kern.build_cache(self.S, self.device)
+        eps_u = sample_normal(shape=(self.M, self.D_out)).to(self.device)
+        return self.kern.rff_eps, self.kern.rff_phase, self.kern.rff_weights, eps_u
+
+    def build_cache_batched(self, L):
+        """L function samples at once (reference: L serial build_cache calls, odegpvae.py:41-43): draws stay in the
+        reference's order, the GPU work -- inducing sample, prior at Z, K(Z,Z) + Cholesky + whitened solves -- is one
+        batched pass.  Returns a FieldSample with leading axis L."""
+        if not self._fused_setup():
+            samples = []
+            for _ in range(L):
+                self.build_cache()
+                samples.append(self.field_sample())
+            return FieldSample.stack(samples)
+        draws = [self._draw() for _ in range(L)]
+        eps, phase, w, eps_u = (torch.stack([d[i] for d in draws]) for i in range(4))
+        k = self.kern
+        Z, ell, var = self.inducing_loc(), k.lengthscales, k.variance
+        u = GF.inducing_sample(self.Us_sqrt.optvar, self.Um(), eps_u)                      # (L,M,D_out)
+        nu0 = torch.zeros((L, self.D_out, self.M, 1) if k.dimwise else (L, self.M, self.D_out), device=Z.device)
+        u_prior, _ = GF.gp_field(Z[None].expand(L, -1, -1), Z, nu0, eps, phase, w, ell, var, k.variant)   # rff_forward(Z)
+        nu = GF.compute_nu(Z, ell, var, u_prior, u, k.variant)
+        # leave the last sample on the kernel like L serial build_cache calls would
+        k.rff_omega = eps[-1] / (ell.t().unsqueeze(1) if k.dimwise else ell.unsqueeze(1))
+        k.nu = nu[-1]
+        return FieldSample(k.variant, Z, ell, var, eps, phase, w, nu)
+
     def build_cache(self):
         """Fix one function sample: feature draws, inducing sample, nu (svpy.py:103-121; same draw order)."""
+        if self._fused_setup():
+            self._cache = self.build_cache_batched(1)
+            return
+        self._cache = None
         self.kern.build_cache(self.S, self.device)
         u = self.sample_inducing()
         Z = self.inducing_loc()
@@ -85,6 +124,8 @@ class SVGP_Layer(torch.nn.Module):
         k = self.kern
         if k.nu is None:
             raise RuntimeError("build_cache() must run before the layer is evaluated")
+        if getattr(self, "_cache", None) is not None:
+            return self._cache
         B = k.extra_cache()
         return FieldSample(k.variant, self.inducing_loc(), k.lengthscales, k.variance, k.rff_eps[None], k.rff_phase[None],
                            k.rff_weights[None], k.nu[None], None if B is None else B[None])
@@ -98,6 +139,8 @@ class SVGP_Layer(torch.nn.Module):
     def kl(self):
         """whitened KL(q(u) || N(0,I)) = 1/2 sum_d(-log|Lq_d Lq_d^T| + |m_d|^2 + |Lq_d|_F^2 - M) (svpy.py:144-175)."""
         m = self.Um()
+        if not self.q_diag and m.is_cuda:
+            return GF.whitened_kl(self.Us_sqrt.optvar, m)     # packed parameter, no (D_out, M, M) scatter
         if self.q_diag:
             diag = self.Us_sqrt()
             trace = diag.square().sum(0)

@@ -144,3 +144,138 @@ def gp_rollout(z0, ts, Z, nu, eps, phase, w, ell, var, variant, order=1, method=
     v = _lib.VARIANTS[variant] if isinstance(variant, str) else variant
     m = _lib.METHODS[method] if isinstance(method, str) else method
     return GPRollout.apply(z0, ts, Z, nu, eps, phase, w, ell, var, B, v, order, m)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-rollout setup at the inducing points (csrc/setup_kernels.cu)
+# ------------------------------------------------------------------------------------------------
+class ComputeNu(torch.autograd.Function):
+    """nu = Lc^-T (u - Lc^-1 u_prior), Lc = chol(K(Z,Z) + 1e-5 I) for L samples at once -- RBF.compute_nu fused with K(Z)
+    (reference experiments/model/core/kernels.py:98-110,155-172; svpy.py:118-121).  RBF variants only.
+    u_prior, u: (L,M,D_out); returns nu (L,D_out,M,1) [dimwise] or (L,M,D_out) [shared]."""
+
+    @staticmethod
+    def forward(ctx, Z, ell, var, u_prior, u, variant):
+        lib = _lib.load()
+        Z, ell, var, u_prior, u = map(_c, (Z, ell, var, u_prior, u))
+        _lib.require_cuda(Z, ell, var, u_prior, u)
+        M, D_in = Z.shape
+        L, _, D_out = u.shape
+        if u_prior.shape != u.shape or u.shape[1] != M:
+            raise RuntimeError("u_prior and u must both be (L, M=%d, D_out), got %s / %s" % (M, tuple(u_prior.shape), tuple(u.shape)))
+        dev = Z.device
+        with torch.cuda.device(dev):
+            p = _lib.make_problem(variant, L, 1, D_in, D_out, M, 1, Z, ell, var, None, None, None, None, None)
+            nbytes = lib.gpode_nu_workspace_bytes(ctypes.byref(p))
+            nsave = lib.gpode_nu_save_floats(ctypes.byref(p))
+            if nbytes == 0 or nsave == 0:
+                raise RuntimeError("gpode_compute_nu: unsupported problem (RBF variants, M <= 512, D <= 16 only)")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            save = torch.empty(nsave, dtype=torch.float32, device=dev)
+            info = torch.zeros(D_out, dtype=torch.int32, device=dev)
+            nu = torch.empty((L, D_out, M, 1) if variant == _lib.RBF_DIMWISE else (L, M, D_out), dtype=torch.float32, device=dev)
+            rc = lib.gpode_compute_nu_fwd(ctypes.byref(p), _lib.ptr(u_prior), _lib.ptr(u), _lib.ptr(nu), _lib.ptr(save), _lib.ptr(info),
+                                          _lib.ptr(ws), nbytes, _lib.stream_handle(dev))
+        _lib.check(rc, "gpode_compute_nu_fwd")
+        ctx.save_for_backward(Z, ell, var, u, save)
+        ctx.variant = variant
+        ctx.info = info   # non-zero entry: K(Z,Z) + jitter was not positive definite (checked lazily by the caller, no sync here)
+        return nu
+
+    @staticmethod
+    def backward(ctx, dnu):
+        lib = _lib.load()
+        Z, ell, var, u, save = ctx.saved_tensors
+        variant = ctx.variant
+        dnu = dnu.contiguous()
+        M, D_in = Z.shape
+        L, _, D_out = u.shape
+        dev = Z.device
+        with torch.cuda.device(dev):
+            p = _lib.make_problem(variant, L, 1, D_in, D_out, M, 1, Z, ell, var, None, None, None, None, None)
+            nbytes = lib.gpode_nu_workspace_bytes(ctypes.byref(p))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            dup, du = torch.empty_like(u), torch.empty_like(u)
+            dZ, dell, dvar = torch.empty_like(Z), torch.empty_like(ell), torch.empty_like(var)
+            rc = lib.gpode_compute_nu_bwd(ctypes.byref(p), _lib.ptr(u), _lib.ptr(save), _lib.ptr(dnu), _lib.ptr(dup), _lib.ptr(du),
+                                          _lib.ptr(dZ), _lib.ptr(dell), _lib.ptr(dvar), _lib.ptr(ws), nbytes, _lib.stream_handle(dev))
+        _lib.check(rc, "gpode_compute_nu_bwd")
+        return dZ, dell, dvar, dup, du, None
+
+
+class InducingSample(torch.autograd.Function):
+    """u[l] = tril(Lq) eps_u[l] + Um on the packed parameter (reference svpy.py:88-101 + transforms.py:71-77)."""
+
+    @staticmethod
+    def forward(ctx, Lq_packed, Um, eps_u):
+        lib = _lib.load()
+        Lq_packed, Um, eps_u = map(_c, (Lq_packed, Um, eps_u))
+        _lib.require_cuda(Lq_packed, Um, eps_u)
+        L, M, D = eps_u.shape
+        if Lq_packed.shape != (D, M * (M + 1) // 2) or Um.shape != (M, D):
+            raise RuntimeError("Lq_packed must be (D_out, M(M+1)/2) and Um (M, D_out)")
+        u = torch.empty_like(eps_u)
+        with torch.cuda.device(u.device):
+            rc = lib.gpode_inducing_sample_fwd(L, M, D, _lib.ptr(Lq_packed), _lib.ptr(Um), _lib.ptr(eps_u), _lib.ptr(u),
+                                               _lib.stream_handle(u.device))
+        _lib.check(rc, "gpode_inducing_sample_fwd")
+        ctx.save_for_backward(eps_u)
+        ctx.shape = (Lq_packed.shape, Um.shape)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        lib = _lib.load()
+        (eps_u,) = ctx.saved_tensors
+        du = du.contiguous()
+        L, M, D = eps_u.shape
+        dLq = torch.empty(ctx.shape[0], dtype=torch.float32, device=du.device)
+        dUm = torch.empty(ctx.shape[1], dtype=torch.float32, device=du.device)
+        with torch.cuda.device(du.device):
+            rc = lib.gpode_inducing_sample_bwd(L, M, D, _lib.ptr(eps_u), _lib.ptr(du), _lib.ptr(dLq), _lib.ptr(dUm),
+                                               _lib.stream_handle(du.device))
+        _lib.check(rc, "gpode_inducing_sample_bwd")
+        return dLq, dUm, None
+
+
+class WhitenedKL(torch.autograd.Function):
+    """SVGP_Layer.kl (reference svpy.py:144-175, q_diag=False) on the packed lower-triangular parameter."""
+
+    @staticmethod
+    def forward(ctx, Lq_packed, Um):
+        lib = _lib.load()
+        Lq_packed, Um = map(_c, (Lq_packed, Um))
+        _lib.require_cuda(Lq_packed, Um)
+        M, D = Um.shape
+        kl = torch.empty((), dtype=torch.float32, device=Um.device)
+        with torch.cuda.device(Um.device):
+            rc = lib.gpode_kl_fwd(M, D, _lib.ptr(Lq_packed), _lib.ptr(Um), _lib.ptr(kl), _lib.stream_handle(Um.device))
+        _lib.check(rc, "gpode_kl_fwd")
+        ctx.save_for_backward(Lq_packed, Um)
+        return kl
+
+    @staticmethod
+    def backward(ctx, dkl):
+        lib = _lib.load()
+        Lq_packed, Um = ctx.saved_tensors
+        M, D = Um.shape
+        dkl = dkl.contiguous().to(torch.float32)
+        dLq, dUm = torch.empty_like(Lq_packed), torch.empty_like(Um)
+        with torch.cuda.device(Um.device):
+            rc = lib.gpode_kl_bwd(M, D, _lib.ptr(Lq_packed), _lib.ptr(Um), _lib.ptr(dkl), _lib.ptr(dLq), _lib.ptr(dUm),
+                                  _lib.stream_handle(Um.device))
+        _lib.check(rc, "gpode_kl_bwd")
+        return dLq, dUm
+
+
+def compute_nu(Z, ell, var, u_prior, u, variant):
+    v = _lib.VARIANTS[variant] if isinstance(variant, str) else variant
+    return ComputeNu.apply(Z, ell, var, u_prior, u, v)
+
+
+def inducing_sample(Lq_packed, Um, eps_u):
+    return InducingSample.apply(Lq_packed, Um, eps_u)
+
+
+def whitened_kl(Lq_packed, Um):
+    return WhitenedKL.apply(Lq_packed, Um)
