@@ -326,7 +326,7 @@ def run_ours(args):
             "roofline": roof,
             "e2e": {"value": round(e2e_value, 1), "unit": "traj-steps/s", "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "gpu_launches": 7 * args.steps, "clocks": clocks}
+            "gpu_launches": (6 if w["variant"] == "df" else 7) * args.steps, "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(w, reps=3, warmup=1)
