@@ -166,9 +166,15 @@ cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float
   pa.xsave = xsave;
   pa.gsave = gsave;
   pa.n_te = n_te;
-  int pg_threads, pg_pp, pg_mblk;
-  rbf_pgrad_shape(g, pg_threads, pg_pp, pg_mblk);
-  pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * pg_mblk, (g.DP <= 8 ? (pg_pp == 1 ? 6 : 4) : (pg_pp == 1 ? 3 : 2)) * kPgThreads / pg_threads);
+  if (rbf_pgrad_use_mma(g)) {
+    int pg_mt, pg_mblk;
+    rbf_pgrad_mma_shape(g, pg_mt, pg_mblk);
+    pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * pg_mblk, pg_mt == 1 ? 3 : 2);
+  } else {
+    int pg_threads, pg_pp, pg_mblk;
+    rbf_pgrad_shape(g, pg_threads, pg_pp, pg_mblk);
+    pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * pg_mblk, 6 * kPgThreads / pg_threads);
+  }
   pa.acc = acc;
   cudaError_t e = rbf_launch_pgrad(pa, st);
   if (e != cudaSuccess) return e;

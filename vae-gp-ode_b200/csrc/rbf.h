@@ -83,12 +83,21 @@ struct RbfFinalizeArgs {
 constexpr int kPgThreads = 128;
 // block size / pairs per thread / m-blocks of the parameter-gradient kernel
 inline void rbf_pgrad_shape(const RbfGeom& g, int& threads, int& PP, int& n_mblk) {
-  PP = (g.DP > 8 && g.MP2 > 32) ? 2 : 1;   // measured: +4% at D = 16, nothing at D = 6
+  PP = 1;   // 2 pairs per thread only paid at D = 16 (+4 %), where the tensor-path kernel is used instead
   const int want = (g.MP2 + PP - 1) / PP;                       // threads needed to cover all pairs
   threads = want >= kPgThreads ? kPgThreads : (want + 31) / 32 * 32;
   n_mblk = (g.MP2 + threads * PP - 1) / (threads * PP);
 }
 
+// The parameter gradients run on the tensor path (3xTF32 mma.sync, rbf_pgrad_mma.cuh) for D > 8 and on the FFMA path
+// (k_rbf_pgrad) for D <= 8 -- measured on B200: 40.3 vs 42.2 ms at D = 16, 0.97 vs 0.79 ms at D = 6.
+inline bool rbf_pgrad_use_mma(const RbfGeom& g) { return g.DP > 8; }
+// inducing points per CTA of the tensor-path parameter-gradient kernel (8 warps x 16 MT rows)
+inline void rbf_pgrad_mma_shape(const RbfGeom& g, int& MT, int& n_mblk) {
+  MT = 2 * g.MP2 > 128 ? 2 : 1;
+  const int per_cta = 128 * MT;
+  n_mblk = (2 * g.MP2 + per_cta - 1) / per_cta;
+}
 // launchers (one per DP instantiation unit); return cudaGetLastError()
 cudaError_t rbf_launch_field_fwd(const RbfFieldFwdArgs& a, cudaStream_t st);
 cudaError_t rbf_launch_field_bwd(const RbfFieldBwdArgs& a, cudaStream_t st);

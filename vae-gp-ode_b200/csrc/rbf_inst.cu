@@ -1,6 +1,7 @@
 // One translation unit per padded input dimension GPODE_DP (2,4,...,16): instantiates the RBF sweep
 // kernels for the register-blocking factors R (states per thread) and wraps their launches.
 #include "rbf_kernels.cuh"
+#include "rbf_pgrad_mma.cuh"
 
 #ifndef GPODE_DP
 #error "compile with -DGPODE_DP=<even 2..16>"
@@ -41,14 +42,27 @@ cudaError_t rbf_rollout_fwd_dp<DP>(const RbfRolloutFwdArgs& a, cudaStream_t st) 
 template <>
 cudaError_t rbf_rollout_bwd_dp<DP>(const RbfRolloutBwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_rollout_bwd, a, true, st) }
 
-template <>
-cudaError_t rbf_pgrad_dp<DP>(const RbfPgradArgs& a, cudaStream_t st) {
-  int threads, PP, n_mblk;
-  rbf_pgrad_shape(a.g, threads, PP, n_mblk);
-  dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
-  if (PP == 2) k_rbf_pgrad<DP, 2><<<grid, threads, 0, st>>>(a);
-  else k_rbf_pgrad<DP, 1><<<grid, threads, 0, st>>>(a);
+namespace {
+// D > 8: tensor-path kernel (3xTF32 mma.sync): each warp owns 16 * MT inducing points, a CTA 128 * MT;  D <= 8: FFMA kernel
+template <int D>
+cudaError_t launch_pgrad(const RbfPgradArgs& a, cudaStream_t st) {
+  if constexpr (D > 8) {
+    int MT, n_mblk;
+    rbf_pgrad_mma_shape(a.g, MT, n_mblk);
+    dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
+    if (MT == 2) k_rbf_pgrad_mma<2, 2><<<grid, kPgmThreads, 0, st>>>(a);
+    else k_rbf_pgrad_mma<2, 1><<<grid, kPgmThreads, 0, st>>>(a);
+  } else {
+    int threads, PP, n_mblk;
+    rbf_pgrad_shape(a.g, threads, PP, n_mblk);
+    dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
+    k_rbf_pgrad<D, 1><<<grid, threads, 0, st>>>(a);
+  }
   return cudaGetLastError();
 }
+}  // namespace
+
+template <>
+cudaError_t rbf_pgrad_dp<DP>(const RbfPgradArgs& a, cudaStream_t st) { return launch_pgrad<DP>(a, st); }
 
 }  // namespace gpode

@@ -355,7 +355,7 @@ constexpr int kPgBatch = 128;
 
 // PP inducing-point pairs per thread: one broadcast LDS.128 of a staged state feeds 2 PP inducing points (PP = 1 is LDS-bound)
 template <int DP, int PP>
-__global__ void __launch_bounds__(kPgThreads, (DP <= 8 ? (PP == 1 ? 6 : 4) : (PP == 1 ? 3 : 2))) k_rbf_pgrad(const RbfPgradArgs a) {
+__global__ void __launch_bounds__(kPgThreads, (DP <= 8 ? 6 : 3)) k_rbf_pgrad(const RbfPgradArgs a) {
   const RbfGeom& g = a.g;
   constexpr int ROW4 = (DP + 2) / 2;
   constexpr int SROW = ((DP + 2 + 3) / 4) * 4;  // staged state: x[DP], g, A (+pad), 16-byte rows

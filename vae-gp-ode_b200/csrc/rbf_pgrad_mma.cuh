@@ -1,0 +1,225 @@
+// RBF parameter gradients on the warp-level tensor path (mma.sync m16n8k8, 3xTF32), sm_100a.
+//
+//   dnu'_m = sum_e g_e E_em ,   pg_mc = sum_e g_e E_em x_ec ,   E_em = 2^(A_e + H_m + sum_d x_ed G_md)
+// for one (sample l, output k); e runs over every state evaluation of the rollout.  Both contractions are
+// GEMM-shaped (theta^T = G X^T with K = D; PG = GE X with K = evaluations), the exponential sits between them:
+// the structure of a fused attention backward.  Each warp owns 16*MT inducing points (MMA rows); evaluations
+// stream through shared memory in batches and are walked 8 at a time (MMA columns):
+//   1. theta^T (16 m x 8 e) = G (16 x D) X^T (D x 8): 3 MMAs per 8 input dims (hi*hi + hi*lo + lo*hi, "3xTF32":
+//      operands are split into a TF32 head and an fp32 remainder, products accumulate in fp32 -> ~2^-21 relative)
+//   2. GE = g_e 2^(theta + H_m + A_e) on the C fragment (4 values per lane), MUFU.EX2
+//   3. the C fragment IS the A fragment of the second product (rows m, contraction over the 8 evaluations, with
+//      the evaluation order permuted consistently in the B operand -- no shuffles): PG (16 m x 8 c) += GE X.
+// Per (16 m x 8 e) tile at D = 16: 12 HMMA + 4 MUFU per lane + ~25 FMA/ALU-pipe instructions, against 140
+// FMA-pipe cycles for the same tile on the FFMA path (k_rbf_pgrad): the tensor pipe takes the two dot products.
+#pragma once
+
+#include "common.cuh"
+#include "rbf.h"
+
+namespace gpode {
+
+constexpr int kPgmThreads = 256;   // 8 warps
+constexpr int kPgmBatch = 128;     // evaluations per shared-memory batch
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// KS: MMA k-steps over the input dimension (1: DP <= 8, 2: DP <= 16); MT: 16-row inducing tiles per warp
+template <int KS, int MT>
+__global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mma(const RbfPgradArgs a) {
+  const RbfGeom& g = a.g;
+  constexpr int DK = 8 * KS;                 // padded input dimension
+  constexpr int NE = kPgmBatch;
+  constexpr int TS = NE + 8;                 // row stride of the transposed copies (== 8 mod 32: conflict-free LDS.64)
+  // [d][e] TF32 head / remainder of the staged states: B operand of BOTH products (row stride == 8 mod 32 floats makes the
+  // per-lane LDS.32 of product 1 (bank 8 tq + gq) and the LDS.64 of product 2 (bank 8 gq + 2 tq per half warp) conflict free)
+  __shared__ __align__(16) float s_th[DK * TS], s_tl[DK * TS];
+  __shared__ __align__(8) float s_A[NE], s_g[NE];
+  __shared__ float s_c[DK];
+  const int k = blockIdx.y, l = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const float* hdr = rbf_hdr_ptr(a.packed, g, l) + k * g.hdr_floats;
+  if (tid < DK) s_c[tid] = tid < g.DP ? hdr[tid] : 0.f;
+  const int per_cta = (kPgmThreads / 32) * 16 * MT;
+  const int n_mblk = (2 * g.MP2 + per_cta - 1) / per_cta;
+  const int chunk_id = blockIdx.x / n_mblk;
+  const int m_base = (blockIdx.x - chunk_id * n_mblk) * per_cta + warp * 16 * MT;
+
+  // loop-invariant A fragments of product 1: G[m][d] split into head / remainder, and H_m
+  uint32_t Gh[MT][KS][4], Gl[MT][KS][4];
+  float Hm[MT][2];
+  const float* rows = rbf_rows_ptr(a.packed, g, l) + (static_cast<size_t>(k) * (g.SP2 + g.MP2) + g.SP2) * g.row_floats;
+  auto packed_at = [&](int m, int q) -> float {   // q < DP: G_md, q == DP: H_m ; rows hold {even m, odd m} float2 pairs
+    if (m >= 2 * g.MP2) return 0.f;
+    return rows[static_cast<size_t>(m >> 1) * g.row_floats + 2 * q + (m & 1)];
+  };
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = m_base + mt * 16 + gq + 8 * h;
+      Hm[mt][h] = packed_at(m, g.DP);
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int d = 8 * ks + 4 * j + tq;                            // MMA k index (ks, tq + 4 j) <-> input dim d
+          const float v = d < g.DP ? packed_at(m, d) : 0.f;
+          const uint32_t hi_ = tf32_hi(v);
+          Gh[mt][ks][h + 2 * j] = hi_;
+          Gl[mt][ks][h + 2 * j] = __float_as_uint(v - __uint_as_float(hi_));
+        }
+    }
+  }
+  float PG[MT][KS][4], dnu[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    dnu[mt][0] = dnu[mt][1] = 0.f;
+#pragma unroll
+    for (int cb = 0; cb < KS; ++cb)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) PG[mt][cb][i] = 0.f;
+  }
+
+  const long total = a.n_te * g.N;
+  const long per = (total + a.chunks - 1) / a.chunks;
+  const long e_lo = static_cast<long>(chunk_id) * per;
+  const long e_hi = e_lo + per < total ? e_lo + per : total;
+  __syncthreads();
+  for (long e0 = e_lo; e0 < e_hi; e0 += NE) {
+    // ---- stage a batch: thread <-> (evaluation, half of the input dims) ----
+    {
+      const int idx = tid & (NE - 1), half = tid / NE;      // 256 threads: 2 halves of DK / 2 dims each
+      const long e = e0 + idx;
+      const bool ok = e < e_hi;
+      long te = 0, s = 0;
+      if (ok) {
+        te = e / g.N;
+        s = static_cast<long>(l) * g.N + (e - te * g.N);
+      }
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < DK / 2; ++j) {
+        const int d = half * (DK / 2) + j;
+        const float v = (ok && d < g.D_in) ? a.xsave[(te * g.D_in + d) * g.NL + s] : 0.f;
+        part = fmaf(s_c[d] * v, v, part);
+        const float vh = __uint_as_float(tf32_hi(v)), vl = v - vh;
+        s_th[d * TS + idx] = vh;
+        s_tl[d * TS + idx] = vl;
+      }
+      if (half == 0) {
+        s_A[idx] = part;
+        s_g[idx] = ok ? a.gsave[(te * g.D_out + k) * g.NL + s] : 0.f;     // g = 0 switches padded evaluations off
+      }
+      __syncthreads();
+      if (half == 1) s_A[idx] += part;
+    }
+    __syncthreads();
+    const int nblk = static_cast<int>(((e_hi - e0 < NE ? e_hi - e0 : NE) + 7) / 8);
+    // theta^T of block `eb` for every m tile: MMA k index (ks, tq + 4 j) <-> input dim d = 8 ks + 4 j + tq, column n = gq <-> evaluation eb + gq
+    auto theta = [&](int eb, float (&th)[MT][4]) {
+      uint32_t bh[KS][2], bl[KS][2];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          bh[ks][j] = __float_as_uint(s_th[(8 * ks + 4 * j + tq) * TS + eb + gq]);
+          bl[ks][j] = __float_as_uint(s_tl[(8 * ks + 4 * j + tq) * TS + eb + gq]);
+        }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) th[mt][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          mma_tf32(th[mt], Gl[mt][ks], bh[ks][0], bh[ks][1]);
+          mma_tf32(th[mt], Gh[mt][ks], bl[ks][0], bl[ks][1]);
+          mma_tf32(th[mt], Gh[mt][ks], bh[ks][0], bh[ks][1]);
+        }
+      }
+    };
+    float thA[MT][4];
+    theta(0, thA);
+#pragma unroll 1
+    for (int cb8 = 0; cb8 < nblk; ++cb8) {
+      const int eb = cb8 * 8;
+      // software pipeline: the tensor work of the NEXT block is independent of the elementwise work of this one
+      // (block nblk reads the 8 pad columns / stale data: its result is never used)
+      float thB[MT][4];
+      theta(eb + 8, thB);
+      const float2 Ae = *reinterpret_cast<const float2*>(s_A + eb + 2 * tq);      // evaluations eb + 2 tq, + 1 (C columns)
+      const float2 ge = *reinterpret_cast<const float2*>(s_g + eb + 2 * tq);
+      // B fragments of product 2: rows = evaluations (MMA k = tq <-> e = 2 tq, k = tq + 4 <-> e = 2 tq + 1), cols c = gq + 8 cb
+      uint32_t xh2[KS][2], xl2[KS][2];
+#pragma unroll
+      for (int cb = 0; cb < KS; ++cb) {
+        const float2 vh = *reinterpret_cast<const float2*>(s_th + (gq + 8 * cb) * TS + eb + 2 * tq);
+        const float2 vl = *reinterpret_cast<const float2*>(s_tl + (gq + 8 * cb) * TS + eb + 2 * tq);
+        xh2[cb][0] = __float_as_uint(vh.x); xh2[cb][1] = __float_as_uint(vh.y);
+        xl2[cb][0] = __float_as_uint(vl.x); xl2[cb][1] = __float_as_uint(vl.y);
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const float (&th)[4] = thA[mt];
+        // C fragment: th[0] (m = gq, e = 2 tq), th[1] (gq, 2 tq + 1), th[2] (gq + 8, 2 tq), th[3] (gq + 8, 2 tq + 1)
+        const float ge00 = ge.x * ex2_approx(th[0] + (Hm[mt][0] + Ae.x)), ge01 = ge.y * ex2_approx(th[1] + (Hm[mt][0] + Ae.y));
+        const float ge10 = ge.x * ex2_approx(th[2] + (Hm[mt][1] + Ae.x)), ge11 = ge.y * ex2_approx(th[3] + (Hm[mt][1] + Ae.y));
+        dnu[mt][0] += ge00 + ge01;
+        dnu[mt][1] += ge10 + ge11;
+        // A fragment of product 2: a0 (row gq, k tq) = ge00, a1 (row gq + 8, k tq) = ge10, a2 (gq, tq + 4) = ge01, a3 = ge11
+        uint32_t ah[4], al[4];
+        const float v4[4] = {ge00, ge10, ge01, ge11};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ah[i] = tf32_hi(v4[i]);
+          al[i] = __float_as_uint(v4[i] - __uint_as_float(ah[i]));
+        }
+#pragma unroll
+        for (int cb = 0; cb < KS; ++cb) {
+          mma_tf32(PG[mt][cb], al, xh2[cb][0], xh2[cb][1]);
+          mma_tf32(PG[mt][cb], ah, xl2[cb][0], xl2[cb][1]);
+          mma_tf32(PG[mt][cb], ah, xh2[cb][0], xh2[cb][1]);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) thA[mt][i] = thB[mt][i];
+    }
+    __syncthreads();
+  }
+  // ---- flush: PG C fragments (m = gq (+8), c = 2 tq (+1) + 8 cb) and the row sums dnu ----
+  const size_t base = (static_cast<size_t>(l) * g.D_out + k) * (2 * g.MP2);
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = m_base + mt * 16 + gq + 8 * h;
+      float v = dnu[mt][h];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (m < 2 * g.MP2) {
+        if (tq == 0) atomicAdd(&a.acc.dnu[base + m], v);
+#pragma unroll
+        for (int cb = 0; cb < KS; ++cb)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c = 8 * cb + 2 * tq + j;
+            if (c < g.DP) atomicAdd(&a.acc.pg[(base + m) * g.DP + c], PG[mt][cb][2 * h + j]);
+          }
+      }
+    }
+  }
+}
+
+}  // namespace gpode
