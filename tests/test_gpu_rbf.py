@@ -192,3 +192,11 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):  # order 2 needs D_in == 2 D_out
         gp.gp_rollout(t(g["z0"], device="cuda"), t(g["ts"], device="cuda"), s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"],
                       s["var"], "rbf_dimwise", 2, "rk4")
+
+
+def test_tcgen05_parameter_gradient_kernel(monkeypatch):
+    """the opt-in tcgen05 / tensor-memory variant of the D > 8 parameter-gradient kernel (GPODE_PGRAD=tc, csrc/rbf_pgrad_tc.cuh)
+    gives the same kernel-level gradients as the default path, within the same bar against the fp64 oracle."""
+    monkeypatch.setenv("GPODE_PGRAD", "tc")
+    test_rollout_backward_kernel_level("rbf_dimwise_d16", "rk4")
+    test_field_backward_kernel_level("rbf_dimwise_d16")

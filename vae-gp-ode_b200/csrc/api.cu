@@ -1,6 +1,7 @@
 // C ABI of libgpode.so (include/gpode.h): argument checking, workspace carving, kernel sequencing.
 // Nothing here allocates, synchronises or keeps state: every call enqueues on the caller's stream.
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "df.h"
@@ -167,9 +168,13 @@ cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float
   pa.gsave = gsave;
   pa.n_te = n_te;
   if (rbf_pgrad_use_mma(g)) {
-    int pg_mt, pg_mblk;
-    rbf_pgrad_mma_shape(g, pg_mt, pg_mblk);
-    pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * pg_mblk, pg_mt == 1 ? 3 : 2);
+    if (!rbf_pgrad_use_tc()) {
+      int pg_mt, pg_mblk;
+      rbf_pgrad_mma_shape(g, pg_mt, pg_mblk);
+      pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * pg_mblk, pg_mt == 1 ? 3 : 2);
+    } else {
+      pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * ((2 * g.MP2 + 127) / 128), 1);
+    }
   } else {
     int pg_threads, pg_pp, pg_mblk;
     rbf_pgrad_shape(g, pg_threads, pg_pp, pg_mblk);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include "chunk_geom.h"
 #include "sweep_args.h"
@@ -92,6 +93,12 @@ inline void rbf_pgrad_shape(const RbfGeom& g, int& threads, int& PP, int& n_mblk
 // The parameter gradients run on the tensor path (3xTF32 mma.sync, rbf_pgrad_mma.cuh) for D > 8 and on the FFMA path
 // (k_rbf_pgrad) for D <= 8 -- measured on B200: 40.3 vs 42.2 ms at D = 16, 0.97 vs 0.79 ms at D = 6.
 inline bool rbf_pgrad_use_mma(const RbfGeom& g) { return g.DP > 8; }
+// GPODE_PGRAD=tc selects the tcgen05 / tensor-memory variant of the D > 8 kernel (rbf_pgrad_tc.cuh): same results, 42.4 vs
+// 40.3 ms at config-5 shapes today (bound by the per-instruction cost of its skinny N = 32 MMAs)
+inline bool rbf_pgrad_use_tc() {
+  const char* e = getenv("GPODE_PGRAD");
+  return e && e[0] == 't' && e[1] == 'c';
+}
 // inducing points per CTA of the tensor-path parameter-gradient kernel (8 warps x 16 MT rows)
 inline void rbf_pgrad_mma_shape(const RbfGeom& g, int& MT, int& n_mblk) {
   MT = 2 * g.MP2 > 128 ? 2 : 1;

@@ -1,7 +1,10 @@
 // One translation unit per padded input dimension GPODE_DP (2,4,...,16): instantiates the RBF sweep
 // kernels for the register-blocking factors R (states per thread) and wraps their launches.
+#include <cstdlib>
+
 #include "rbf_kernels.cuh"
 #include "rbf_pgrad_mma.cuh"
+#include "rbf_pgrad_tc.cuh"
 
 #ifndef GPODE_DP
 #error "compile with -DGPODE_DP=<even 2..16>"
@@ -43,15 +46,24 @@ template <>
 cudaError_t rbf_rollout_bwd_dp<DP>(const RbfRolloutBwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_rollout_bwd, a, true, st) }
 
 namespace {
-// D > 8: tensor-path kernel (3xTF32 mma.sync): each warp owns 16 * MT inducing points, a CTA 128 * MT;  D <= 8: FFMA kernel
+// D > 8: tensor-path kernels (3xTF32);  D <= 8: FFMA kernel
 template <int D>
 cudaError_t launch_pgrad(const RbfPgradArgs& a, cudaStream_t st) {
   if constexpr (D > 8) {
-    int MT, n_mblk;
-    rbf_pgrad_mma_shape(a.g, MT, n_mblk);
-    dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
-    if (MT == 2) k_rbf_pgrad_mma<2, 2><<<grid, kPgmThreads, 0, st>>>(a);
-    else k_rbf_pgrad_mma<2, 1><<<grid, kPgmThreads, 0, st>>>(a);
+    if (!rbf_pgrad_use_tc()) {   // default: warp-level tensor path (3xTF32 mma.sync): each warp owns 16 * MT inducing points, a CTA 128 * MT
+      int MT, n_mblk;
+      rbf_pgrad_mma_shape(a.g, MT, n_mblk);
+      dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
+      if (MT == 2) k_rbf_pgrad_mma<2, 2><<<grid, kPgmThreads, 0, st>>>(a);
+      else k_rbf_pgrad_mma<2, 1><<<grid, kPgmThreads, 0, st>>>(a);
+    } else {                     // opt-in (GPODE_PGRAD=tc): tcgen05.mma / tensor-memory kernel, one CTA per SM (rbf_pgrad_tc.cuh)
+      const int n_mblk = (2 * a.g.MP2 + 127) / 128;
+      const int smem = rbf_pgrad_tc_smem_bytes();
+      cudaError_t e = cudaFuncSetAttribute(k_rbf_pgrad_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
+      k_rbf_pgrad_tc<0><<<grid, kTcThreads, smem, st>>>(a);
+    }
   } else {
     int threads, PP, n_mblk;
     rbf_pgrad_shape(a.g, threads, PP, n_mblk);
