@@ -22,11 +22,9 @@ namespace gpode {
 constexpr int kPgmThreads = 256;   // 8 warps
 constexpr int kPgmBatch = 128;     // evaluations per shared-memory batch
 
-__device__ __forceinline__ uint32_t tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// TF32 head of x by truncation (one LOP3; cvt.rna.tf32 is emulated with 4 ALU instructions on sm_100a): the remainder
+// x - head is exact in fp32 and < 2^-10 |x|, its own truncation by the tensor core leaves ~2^-20 relative
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -43,7 +41,7 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
   // [d][e] TF32 head / remainder of the staged states: B operand of BOTH products (row stride == 8 mod 32 floats makes the
   // per-lane LDS.32 of product 1 (bank 8 tq + gq) and the LDS.64 of product 2 (bank 8 gq + 2 tq per half warp) conflict free)
   __shared__ __align__(16) float s_th[DK * TS], s_tl[DK * TS];
-  __shared__ __align__(8) float s_A[NE], s_g[NE];
+  __shared__ __align__(8) float s_A[NE + 8], s_g[NE];   // (+8: the software-pipelined theta of the block after the last reads 8 unused offsets)
   __shared__ float s_c[DK];
   const int k = blockIdx.y, l = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -127,7 +125,8 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
     __syncthreads();
     const int nblk = static_cast<int>(((e_hi - e0 < NE ? e_hi - e0 : NE) + 7) / 8);
     // theta^T of block `eb` for every m tile: MMA k index (ks, tq + 4 j) <-> input dim d = 8 ks + 4 j + tq, column n = gq <-> evaluation eb + gq
-    auto theta = [&](int eb, float (&th)[MT][4]) {
+    auto theta = [&](int eb, float (&th)[MT][4]) {   // th = H_m + A_e + G.x (offsets enter as the initial accumulator)
+      const float2 Ae = *reinterpret_cast<const float2*>(s_A + eb + 2 * tq);      // evaluations eb + 2 tq, + 1 (C columns)
       uint32_t bh[KS][2], bl[KS][2];
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks)
@@ -138,8 +137,10 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
         }
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) th[mt][i] = 0.f;
+        th[mt][0] = Hm[mt][0] + Ae.x;
+        th[mt][1] = Hm[mt][0] + Ae.y;
+        th[mt][2] = Hm[mt][1] + Ae.x;
+        th[mt][3] = Hm[mt][1] + Ae.y;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
           mma_tf32(th[mt], Gl[mt][ks], bh[ks][0], bh[ks][1]);
@@ -157,8 +158,7 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
       // (block nblk reads the 8 pad columns / stale data: its result is never used)
       float thB[MT][4];
       theta(eb + 8, thB);
-      const float2 Ae = *reinterpret_cast<const float2*>(s_A + eb + 2 * tq);      // evaluations eb + 2 tq, + 1 (C columns)
-      const float2 ge = *reinterpret_cast<const float2*>(s_g + eb + 2 * tq);
+      const float2 ge = *reinterpret_cast<const float2*>(s_g + eb + 2 * tq);      // evaluations eb + 2 tq, + 1 (C columns)
       // B fragments of product 2: rows = evaluations (MMA k = tq <-> e = 2 tq, k = tq + 4 <-> e = 2 tq + 1), cols c = gq + 8 cb
       uint32_t xh2[KS][2], xl2[KS][2];
 #pragma unroll
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
       for (int mt = 0; mt < MT; ++mt) {
         const float (&th)[4] = thA[mt];
         // C fragment: th[0] (m = gq, e = 2 tq), th[1] (gq, 2 tq + 1), th[2] (gq + 8, 2 tq), th[3] (gq + 8, 2 tq + 1)
-        const float ge00 = ge.x * ex2_approx(th[0] + (Hm[mt][0] + Ae.x)), ge01 = ge.y * ex2_approx(th[1] + (Hm[mt][0] + Ae.y));
-        const float ge10 = ge.x * ex2_approx(th[2] + (Hm[mt][1] + Ae.x)), ge11 = ge.y * ex2_approx(th[3] + (Hm[mt][1] + Ae.y));
+        const float ge00 = ge.x * ex2_approx(th[0]), ge01 = ge.y * ex2_approx(th[1]);
+        const float ge10 = ge.x * ex2_approx(th[2]), ge11 = ge.y * ex2_approx(th[3]);
         dnu[mt][0] += ge00 + ge01;
         dnu[mt][1] += ge10 + ge11;
         // A fragment of product 2: a0 (row gq, k tq) = ge00, a1 (row gq + 8, k tq) = ge10, a2 (gq, tq + 4) = ge01, a3 = ge11
