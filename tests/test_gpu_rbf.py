@@ -200,3 +200,35 @@ def test_tcgen05_parameter_gradient_kernel(monkeypatch):
     monkeypatch.setenv("GPODE_PGRAD", "tc")
     test_rollout_backward_kernel_level("rbf_dimwise_d16", "rk4")
     test_field_backward_kernel_level("rbf_dimwise_d16")
+
+
+@pytest.mark.parametrize("pgrad", ["default", "tc"])
+@pytest.mark.parametrize("D_in,D_out,M,S,N", [(12, 5, 101, 33, 300), (9, 9, 40, 7, 70), (16, 3, 512, 16, 130), (14, 14, 129, 20, 1000)])
+def test_wide_inputs_odd_sizes(pgrad, D_in, D_out, M, S, N, monkeypatch):
+    """D > 8 (tensor-path parameter gradients, padded input dims, odd M / S, ragged N): field + VJP + parameter gradients
+    against the fp64 oracle, for the default (mma.sync) and the opt-in tcgen05 kernel."""
+    if pgrad == "tc":
+        monkeypatch.setenv("GPODE_PGRAD", "tc")
+    rs = np.random.RandomState(D_in * 100 + M)
+    f64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    c = dict(variant="rbf_dimwise", Z=f64(rs.normal(size=(M, D_in))), ell=f64(1.5 + rs.uniform(size=(D_out, D_in))),
+             var=f64(0.5 + rs.uniform(size=D_out)), nu=f64(rs.normal(size=(D_out, M, 1))), eps=f64(rs.normal(size=(D_in, S, D_out))),
+             phase=f64(rs.uniform(size=(1, S, D_out)) * 2 * np.pi), w=f64(rs.normal(size=(S, D_out))))
+    for k in ("Z", "ell", "var", "nu"):
+        c[k].requires_grad_(True)
+    c["omega"] = OF.make_omega(c["eps"], c["ell"], "rbf_dimwise")
+    x64 = f64(1.5 * rs.normal(size=(N, D_in))).requires_grad_(True)
+    gout = f64(rs.normal(size=(N, D_out)))
+    f64v = OF.field(x64, c)
+    want = torch.autograd.grad((f64v * gout).sum(), [x64, c["Z"], c["nu"], c["ell"], c["var"]])
+    s = gpu_sample(c)
+    for k in ("Z", "nu", "ell", "var"):
+        s[k].requires_grad_(True)
+    x = x64.detach().float().cuda()[None].requires_grad_(True)
+    f, _ = _field(s, x, "rbf_dimwise")
+    assert rel(f[0], f64v) < FIELD_TOL
+    (f[0] * gout.float().cuda()).sum().backward()
+    got = [x.grad[0], s["Z"].grad, s["nu"].grad[0], s["ell"].grad, s["var"].grad]
+    for nm, a, b in zip(("dx", "dZ", "dnu", "dell", "dvar"), got, want):
+        e = rel(a, b)
+        assert e < GRAD_TOL, (nm, e)
