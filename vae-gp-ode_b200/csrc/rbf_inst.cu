@@ -54,8 +54,11 @@ cudaError_t launch_pgrad(const RbfPgradArgs& a, cudaStream_t st) {
       int MT, n_mblk;
       rbf_pgrad_mma_shape(a.g, MT, n_mblk);
       dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
-      if (MT == 2) k_rbf_pgrad_mma<2, 2><<<grid, kPgmThreads, 0, st>>>(a);
-      else k_rbf_pgrad_mma<2, 1><<<grid, kPgmThreads, 0, st>>>(a);
+      const int smem = rbf_pgrad_mma_smem_bytes(2);
+      cudaError_t e = cudaFuncSetAttribute(MT == 2 ? k_rbf_pgrad_mma<2, 2> : k_rbf_pgrad_mma<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      if (MT == 2) k_rbf_pgrad_mma<2, 2><<<grid, kPgmThreads, smem, st>>>(a);
+      else k_rbf_pgrad_mma<2, 1><<<grid, kPgmThreads, smem, st>>>(a);
     } else {                     // opt-in (GPODE_PGRAD=tc): tcgen05.mma / tensor-memory kernel, one CTA per SM (rbf_pgrad_tc.cuh)
       const int n_mblk = (2 * a.g.MP2 + 127) / 128;
       const int smem = rbf_pgrad_tc_smem_bytes();

@@ -20,7 +20,8 @@
 namespace gpode {
 
 constexpr int kPgmThreads = 256;   // 8 warps
-constexpr int kPgmBatch = 128;     // evaluations per shared-memory batch
+constexpr int kPgmBatch = 512;     // evaluations per shared-memory batch (dynamic shared memory: 2 x DK x (batch + 8) floats + offsets)
+inline int rbf_pgrad_mma_smem_bytes(int KS) { return (2 * 8 * KS * (kPgmBatch + 8) + (kPgmBatch + 8) + kPgmBatch + 8 * KS) * 4; }
 
 // TF32 head of x by truncation (one LOP3; cvt.rna.tf32 is emulated with 4 ALU instructions on sm_100a): the remainder
 // x - head is exact in fp32 and < 2^-10 |x|, its own truncation by the tensor core leaves ~2^-20 relative
@@ -40,9 +41,12 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
   constexpr int TS = NE + 8;                 // row stride of the transposed copies (== 8 mod 32: conflict-free LDS.64)
   // [d][e] TF32 head / remainder of the staged states: B operand of BOTH products (row stride == 8 mod 32 floats makes the
   // per-lane LDS.32 of product 1 (bank 8 tq + gq) and the LDS.64 of product 2 (bank 8 gq + 2 tq per half warp) conflict free)
-  __shared__ __align__(16) float s_th[DK * TS], s_tl[DK * TS];
-  __shared__ __align__(8) float s_A[NE + 8], s_g[NE];   // (+8: the software-pipelined theta of the block after the last reads 8 unused offsets)
-  __shared__ float s_c[DK];
+  extern __shared__ __align__(16) float pgm_smem[];
+  float* s_th = pgm_smem;
+  float* s_tl = s_th + DK * TS;
+  float* s_A = s_tl + DK * TS;       // [NE + 8]: the software-pipelined theta of the block after the last reads 8 unused offsets
+  float* s_g = s_A + NE + 8;         // [NE]
+  float* s_c = s_g + NE;             // [DK]
   const int k = blockIdx.y, l = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
@@ -95,32 +99,28 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
   const long e_hi = e_lo + per < total ? e_lo + per : total;
   __syncthreads();
   for (long e0 = e_lo; e0 < e_hi; e0 += NE) {
-    // ---- stage a batch: thread <-> (evaluation, half of the input dims) ----
+    // ---- stage a batch: thread <-> evaluation(s) ----
     {
-      const int idx = tid & (NE - 1), half = tid / NE;      // 256 threads: 2 halves of DK / 2 dims each
-      const long e = e0 + idx;
-      const bool ok = e < e_hi;
-      long te = 0, s = 0;
-      if (ok) {
-        te = e / g.N;
-        s = static_cast<long>(l) * g.N + (e - te * g.N);
-      }
-      float part = 0.f;
+      for (int idx = tid; idx < NE; idx += kPgmThreads) {
+        const long e = e0 + idx;
+        const bool ok = e < e_hi;
+        long te = 0, s = 0;
+        if (ok) {
+          te = e / g.N;
+          s = static_cast<long>(l) * g.N + (e - te * g.N);
+        }
+        float part = 0.f;
 #pragma unroll
-      for (int j = 0; j < DK / 2; ++j) {
-        const int d = half * (DK / 2) + j;
-        const float v = (ok && d < g.D_in) ? a.xsave[(te * g.D_in + d) * g.NL + s] : 0.f;
-        part = fmaf(s_c[d] * v, v, part);
-        const float vh = __uint_as_float(tf32_hi(v)), vl = v - vh;
-        s_th[d * TS + idx] = vh;
-        s_tl[d * TS + idx] = vl;
-      }
-      if (half == 0) {
+        for (int d = 0; d < DK; ++d) {
+          const float v = (ok && d < g.D_in) ? a.xsave[(te * g.D_in + d) * g.NL + s] : 0.f;
+          part = fmaf(s_c[d] * v, v, part);
+          const float vh = __uint_as_float(tf32_hi(v)), vl = v - vh;
+          s_th[d * TS + idx] = vh;
+          s_tl[d * TS + idx] = vl;
+        }
         s_A[idx] = part;
         s_g[idx] = ok ? a.gsave[(te * g.D_out + k) * g.NL + s] : 0.f;     // g = 0 switches padded evaluations off
       }
-      __syncthreads();
-      if (half == 1) s_A[idx] += part;
     }
     __syncthreads();
     const int nblk = static_cast<int>(((e_hi - e0 < NE ? e_hi - e0 : NE) + 7) / 8);
