@@ -24,8 +24,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
-import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "vae-gp-ode_b200")):

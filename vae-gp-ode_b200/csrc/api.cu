@@ -213,8 +213,6 @@ cudaError_t df_param_grads(const GpodeProblem* p, const DfGeom& g, const float* 
   pa.xsave = xsave;
   pa.gsave = gsave;
   pa.n_te = n_te;
-  const int tk = df_pgrad_threads_k(g);
-  pa.chunks = pgrad_chunks(n_te * g.N, g.L * ((g.MP2 + tk - 1) / tk), (g.D <= 6 ? 3 : 2) * 128 / tk);
   pa.chunks_b = pgrad_chunks(n_te * g.N, g.L * ((g.D * g.SP2 + 127) / 128), 4);
   pa.acc = acc;
   cudaError_t e = df_launch_pgrad(pa, st);

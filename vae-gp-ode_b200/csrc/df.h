@@ -60,7 +60,7 @@ struct DfPgradArgs {
   const float* xsave;        // [n_te][D][NL]
   const float* gsave;        // [n_te][D][NL]
   long n_te;
-  int chunks, chunks_b;      // CTAs along the state-evaluation axis: inducing-point kernel / feature kernel
+  int chunks_b;              // CTAs along the state-evaluation axis
   DfAccum acc;
 };
 
@@ -91,8 +91,6 @@ struct DfFinalizeArgs {
 };
 
 DfGeom df_geom(const GpodeProblem* p);
-// block size of the inducing-point parameter-gradient kernel (threads <-> inducing pairs)
-inline int df_pgrad_threads_k(const DfGeom& g) { return g.MP2 >= 128 ? 128 : (g.MP2 + 31) / 32 * 32; }
 
 cudaError_t df_launch_field_fwd(const DfFieldFwdArgs& a, cudaStream_t st);
 cudaError_t df_launch_field_bwd(const DfFieldBwdArgs& a, cudaStream_t st);

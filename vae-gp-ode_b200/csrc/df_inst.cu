@@ -42,7 +42,7 @@ template <>
 cudaError_t df_pgrad_d<D>(const DfPgradArgs& a, cudaStream_t st) {
   // the inducing-point gradients (dnu, dZ, dc) come out of the reverse sweep itself; only the feature operator B is left
   dim3 gb(static_cast<unsigned>(a.chunks_b), static_cast<unsigned>((a.g.D * a.g.SP2 + kDfPgThreads - 1) / kDfPgThreads), static_cast<unsigned>(a.g.L));
-  k_df_pgrad<D, 1><<<gb, kDfPgThreads, 0, st>>>(a);
+  k_df_pgrad<D><<<gb, kDfPgThreads, 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -425,67 +425,37 @@ struct DfPolicy {
 };
 
 // =============================================================================================
-// parameter gradients.  State evaluations (x, g) of one sample stream through shared memory in batches;
-//   ROLE 0: threads <-> inducing-point pairs: dnu, dZ, dc_ij   (recomputes the D x D exponentials)
-//   ROLE 1: threads <-> feature-pair rows (a, s): dB'[s,a,c] = sum_n g_c cos(theta')
+// gradient of the feature operator: dB'[s,a,c] = sum_n g_c cos(theta'_sa)  (the inducing-point gradients dnu, dZ and the
+// lengthscale statistics come out of the reverse sweep itself).  Threads <-> feature-pair rows (a, s); state evaluations
+// (x, g) of one sample stream through shared memory in batches.
 // =============================================================================================
 constexpr int kDfPgBatch = 128;
 constexpr int kDfPgThreads = 128;
 
-template <int D, int ROLE>
-__global__ void __launch_bounds__(kDfPgThreads, (ROLE == 1 ? 4 : (D <= 6 ? 3 : 2))) k_df_pgrad(const DfPgradArgs a) {
+template <int D>
+__global__ void __launch_bounds__(kDfPgThreads, 4) k_df_pgrad(const DfPgradArgs a) {
   const DfGeom& g = a.g;
   constexpr int SROW = ((2 * D + 3) / 4) * 4;   // staged evaluation: x[D], g[D] (+pad)
   constexpr int NV = SROW / 4;
   __shared__ __align__(16) float stage[kDfPgBatch * SROW];
-  __shared__ __align__(16) float4 s_kc[D * D];
-  __shared__ float s_h[D];
-  __shared__ float s_dc[D * D];
   const int l = blockIdx.z;
-  constexpr bool role_k = ROLE == 0;
-  for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
-    s_kc[i] = reinterpret_cast<const float4*>(a.packed)[i];
-    s_dc[i] = 0.f;
-  }
-  if (threadIdx.x < D) s_h[threadIdx.x] = a.packed[4 * D * D + threadIdx.x];
-
   const float* rows = df_rows_ptr(a.packed, g, l);
-  // this thread's row
-  float2 prm[2 * D + 1];   // role k: z[D], nu[D]; role b: Om'[D], b', then B' unused
-  int row = -1;            // role k: inducing pair index; role b: a * SP2 + s-pair
-  if (role_k) {
-    const int j = blockIdx.y * blockDim.x + threadIdx.x;
-    if (j < g.MP2) {
-      row = j;
-      const float2* src = reinterpret_cast<const float2*>(rows + static_cast<size_t>(g.D) * g.SP2 * g.rowf_s + static_cast<size_t>(j) * g.rowf_m);
+  float2 prm[D + 1];       // Om'[D], b'
+  const int row = blockIdx.y * blockDim.x + threadIdx.x;   // a * SP2 + s-pair
+  const bool active = row < g.D * g.SP2;
+  if (active) {
+    const float2* src = reinterpret_cast<const float2*>(rows + static_cast<size_t>(row) * g.rowf_s);
 #pragma unroll
-      for (int i = 0; i < 2 * D; ++i) prm[i] = src[i];
-    }
-  } else {
-    const int j = blockIdx.y * blockDim.x + threadIdx.x;
-    if (j < g.D * g.SP2) {
-      row = j;
-      const float2* src = reinterpret_cast<const float2*>(rows + static_cast<size_t>(j) * g.rowf_s);
-#pragma unroll
-      for (int i = 0; i < D + 1; ++i) prm[i] = src[i];
-    }
+    for (int i = 0; i < D + 1; ++i) prm[i] = src[i];
   }
-  float2 acc1[D], acc2[D];   // role k: dnu, dz ; role b: dB'_c (acc1)
-  float dc[D * D];
+  float2 acc[D];
 #pragma unroll
-  for (int i = 0; i < D; ++i) {
-    acc1[i] = make_float2(0.f, 0.f);
-    acc2[i] = make_float2(0.f, 0.f);
-  }
-#pragma unroll
-  for (int i = 0; i < D * D; ++i) dc[i] = 0.f;
+  for (int i = 0; i < D; ++i) acc[i] = make_float2(0.f, 0.f);
 
   const long total = a.n_te * g.N;
-  const int nchunks = role_k ? a.chunks : a.chunks_b;
-  const long per = (total + nchunks - 1) / nchunks;
+  const long per = (total + a.chunks_b - 1) / a.chunks_b;
   const long e_lo = static_cast<long>(blockIdx.x) * per;
   const long e_hi = e_lo + per < total ? e_lo + per : total;
-  __syncthreads();
   for (long e0 = e_lo; e0 < e_hi; e0 += kDfPgBatch) {
     for (int idx = threadIdx.x; idx < kDfPgBatch; idx += blockDim.x) {
       const long e = e0 + idx;
@@ -501,116 +471,34 @@ __global__ void __launch_bounds__(kDfPgThreads, (ROLE == 1 ? 4 : (D <= 6 ? 3 : 2
       }
     }
     __syncthreads();
-    if (row >= 0) {
+    if (active) {
       const int nb = (e_hi - e0) < kDfPgBatch ? static_cast<int>(e_hi - e0) : kDfPgBatch;
-      if (role_k) {
-#pragma unroll 1
-        for (int idx = 0; idx < nb; ++idx) {
-          const float4* srow = reinterpret_cast<const float4*>(stage + idx * SROW);
-          float xv[SROW];
-#pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            const float4 q = srow[i];
-            xv[4 * i] = q.x; xv[4 * i + 1] = q.y; xv[4 * i + 2] = q.z; xv[4 * i + 3] = q.w;
-          }
-          float2 d[D], p[D], tt[D], dd[D], r2 = make_float2(0.f, 0.f), WV = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int k = 0; k < D; ++k) {
-            d[k] = sub2(bc(xv[k]), prm[k]);
-            r2 = fma2(d[k], d[k], r2);
-            p[k] = mul2(prm[D + k], d[k]);
-            tt[k] = make_float2(0.f, 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            const float gj = xv[D + j];
-            const float2 u = mul2(bc(gj), d[j]);
-            float2 s = make_float2(0.f, 0.f), wj = make_float2(0.f, 0.f), ejj, kjj, a2jj;
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-              const float4 kc = lds_const4(s_kc + i * D + j);
-              const float2 e = ex2_2(fma2(r2, lo(kc), hi(kc)));
-              const float2 pe = mul2(p[i], e);
-              s = add2(s, pe);
-              wj = fma2(lo(kc), pe, wj);
-              tt[i] = fma2(u, e, tt[i]);
-              const float2 a2 = fma2(r2, lo(kc), bc(kTwoLog2e));
-              const float2 upe = mul2(u, pe);
-              dc[i * D + j] = fmaf(upe.x, a2.x, dc[i * D + j]);
-              dc[i * D + j] = fmaf(upe.y, a2.y, dc[i * D + j]);
-              if (i == j) {
-                ejj = e;
-                kjj = lo(kc);
-                a2jj = a2;
-              }
-            }
-            const float2 hr = sub2(bc(s_h[j]), r2);
-            const float2 ge = mul2(bc(gj), ejj);
-            const float2 gne = mul2(ge, prm[D + j]);
-            WV = fma2(u, wj, WV);
-            WV = fma2(gne, fma2(kjj, hr, bc(-kLog2e)), WV);
-            dd[j] = mul2(bc(gj), s);
-            acc1[j] = fma2(ge, hr, acc1[j]);                       // dnu_j += g_j e_jj (h_j - r2)
-            const float2 dg = mul2(gne, fma2(a2jj, hr, bc(-s_h[j] * kLog2e)));
-            dc[j * D + j] += dg.x + dg.y;
-          }
-          const float2 wv = mul2(WV, bc(2.f * kLn2));
-#pragma unroll
-          for (int k = 0; k < D; ++k) {
-            acc1[k] = fma2(d[k], tt[k], acc1[k]);                  // dnu_k += d_k t_k
-            float2 ddk = fma2(prm[D + k], tt[k], dd[k]);
-            ddk = fma2(d[k], wv, ddk);
-            acc2[k] = sub2(acc2[k], ddk);                          // dZ_k -= dL/dd_k
-          }
-        }
-      } else {
 #pragma unroll 2
-        for (int idx = 0; idx < nb; ++idx) {
-          const float4* srow = reinterpret_cast<const float4*>(stage + idx * SROW);
-          float xv[SROW];
+      for (int idx = 0; idx < nb; ++idx) {
+        const float4* srow = reinterpret_cast<const float4*>(stage + idx * SROW);
+        float xv[SROW];
 #pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            const float4 q = srow[i];
-            xv[4 * i] = q.x; xv[4 * i + 1] = q.y; xv[4 * i + 2] = q.z; xv[4 * i + 3] = q.w;
-          }
-          float2 th = prm[D];
-#pragma unroll
-          for (int k = 0; k < D; ++k) th = fma2(bc(xv[k]), prm[k], th);
-          const float2 cs = cos_2(th);
-#pragma unroll
-          for (int c = 0; c < D; ++c) acc1[c] = fma2(bc(xv[D + c]), cs, acc1[c]);
+        for (int i = 0; i < NV; ++i) {
+          const float4 q = srow[i];
+          xv[4 * i] = q.x; xv[4 * i + 1] = q.y; xv[4 * i + 2] = q.z; xv[4 * i + 3] = q.w;
         }
+        float2 th = prm[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) th = fma2(bc(xv[k]), prm[k], th);
+        const float2 cs = cos_2(th);
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = fma2(bc(xv[D + c]), cs, acc[c]);
       }
     }
     __syncthreads();
   }
-  if (row >= 0) {
-    if (role_k) {
-      const size_t m0 = 2 * static_cast<size_t>(row);
+  if (active) {
+    const size_t base = (static_cast<size_t>(l) * g.D * g.SP2 + row) * 2 * D;   // [l][a][s-pair][even/odd][c]
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        atomicAdd(&a.acc.dnu[(static_cast<size_t>(l) * 2 * g.MP2 + m0) * D + k], acc1[k].x);
-        atomicAdd(&a.acc.dnu[(static_cast<size_t>(l) * 2 * g.MP2 + m0 + 1) * D + k], acc1[k].y);
-        atomicAdd(&a.acc.dz[m0 * D + k], acc2[k].x);
-        atomicAdd(&a.acc.dz[(m0 + 1) * D + k], acc2[k].y);
-      }
-    } else {
-      const size_t base = (static_cast<size_t>(l) * g.D * g.SP2 + row) * 2 * D;   // [l][a][s-pair][even/odd][c]
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        atomicAdd(&a.acc.dbp[base + c], acc1[c].x);
-        atomicAdd(&a.acc.dbp[base + D + c], acc1[c].y);
-      }
+    for (int c = 0; c < D; ++c) {
+      atomicAdd(&a.acc.dbp[base + c], acc[c].x);
+      atomicAdd(&a.acc.dbp[base + D + c], acc[c].y);
     }
-  }
-  if (role_k) {   // CTA-uniform branch: every lane takes part in the shuffles (idle lanes hold zeros)
-#pragma unroll
-    for (int i = 0; i < D * D; ++i) {
-      const float v = warp_sum(dc[i]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&s_dc[i], v);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < D * D; i += blockDim.x) atomicAdd(&a.acc.dc[i], s_dc[i]);
   }
 }
 
