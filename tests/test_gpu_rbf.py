@@ -232,3 +232,26 @@ def test_wide_inputs_odd_sizes(pgrad, D_in, D_out, M, S, N, monkeypatch):
     for nm, a, b in zip(("dx", "dZ", "dnu", "dell", "dvar"), got, want):
         e = rel(a, b)
         assert e < GRAD_TOL, (nm, e)
+
+
+def test_tensor_path_forward_large_batch():
+    """D > 8 and a chip-filling batch select the tensor-path forward (3xTF32 mma.sync, RbfMmaFwdPolicy): field and RK4
+    trajectories of 40,000 states against the fp64 oracle on a random subset, plus equality of overlapping small/large launches
+    within the field bar (the small launch runs the FFMA kernel)."""
+    g = load_golden("rbf_dimwise_d16")
+    c = oracle_cache(g)
+    s = gpu_sample(c)
+    N, D = 40000, 16
+    rs = np.random.RandomState(5)
+    x = torch.tensor(1.5 * rs.normal(size=(1, N, D)), dtype=torch.float32, device="cuda")
+    f, fp = _field(s, x, "rbf_dimwise")
+    idx = rs.randint(0, N, size=300)
+    truth = OF.field(x[0, idx].double().cpu(), c)
+    assert rel(f[0, idx], truth) < FIELD_TOL
+    assert rel(fp[0, idx], OF.prior(x[0, idx].double().cpu(), c)) < FIELD_TOL
+    f_small, _ = _field(s, x[:, idx].contiguous(), "rbf_dimwise")
+    assert rel(f_small[0], f[0, idx]) < FIELD_TOL
+    ts = 0.1 * torch.arange(6, dtype=torch.float, device="cuda")
+    traj = _gp().gp_rollout(x[0], ts, s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"], "rbf_dimwise", 1, "rk4")
+    truth = OF.rollout(x[0, idx].double().cpu(), ts.double().cpu(), c, 1, "rk4")
+    assert rel(traj[0, idx], truth) < TRAJ_TOL

@@ -346,6 +346,162 @@ struct RbfPolicy {
 };
 
 // =============================================================================================
+// Forward evaluation on the warp-level tensor path for D > 8 (3xTF32 mma.sync m16n8k8, see rbf_pgrad_mma.cuh for the
+// measurements): a warp owns its 64 states (R = 2) as 4 MMA row tiles of 16; the x fragments (TF32 head + remainder) are
+// built once per evaluation from the staged states; every block of 8 features / inducing points (4 pair rows of the
+// streamed chunk) is one B fragment pair, theta = offset (+ A_k(x)) + x . row comes out of 6 MMAs per tile with the
+// offsets as the initial accumulator, the transcendental and the weight multiply run on the C fragment, the sum over the
+// rows is a register accumulator per (tile, row half) that is reduced over the 4 column lanes once per output dimension.
+// =============================================================================================
+__device__ __forceinline__ void mma_tf32_sweep(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int DP_>
+struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
+  static constexpr int DP = DP_;
+  static constexpr int R = 2;
+  static constexpr int NT = 4;   // 16-state tiles per warp (32 lanes x R states)
+  static constexpr int KS = 2;   // MMA k-steps over the (padded to 16) input dimension
+
+  template <bool IS_K>
+  __device__ static __forceinline__ void rows_mma(const float* __restrict__ chunk, int n, int row_floats, const uint32_t (&Ah)[NT][KS][4],
+                                                  const uint32_t (&Al)[NT][KS][4], const float (&Ak)[NT][2], float (&acc)[NT][2], int gq, int tq) {
+#pragma unroll 1
+    for (int blk = 0; blk * 4 < n; ++blk) {
+      // B fragments: column n = gq <-> unit (pair row blk * 4 + gq / 2, parity gq & 1); MMA k index (ks, tq + 4 j) <-> input dim d = 8 ks + 4 j + tq
+      const int pr = blk * 4 + (gq >> 1);
+      const float* rowp = chunk + pr * row_floats + (gq & 1);
+      uint32_t bh[KS][2], bl[KS][2];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int d = 8 * ks + 4 * j + tq;
+          const float v = (pr < n && d < DP) ? rowp[2 * d] : 0.f;
+          const uint32_t h = __float_as_uint(v) & 0xFFFFE000u;
+          bh[ks][j] = h;
+          bl[ks][j] = __float_as_uint(v - __uint_as_float(h));
+        }
+      // offsets and weights of the C columns 2 tq, 2 tq + 1 = both parities of pair row blk * 4 + tq
+      const int pc = blk * 4 + tq;
+      float2 off = make_float2(0.f, 0.f), wgt = make_float2(0.f, 0.f);
+      if (pc < n) {
+        off = *reinterpret_cast<const float2*>(chunk + pc * row_floats + 2 * DP);
+        wgt = *reinterpret_cast<const float2*>(chunk + pc * row_floats + 2 * DP + 2);
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        float th[4];
+        th[0] = IS_K ? Ak[t][0] + off.x : off.x;
+        th[1] = IS_K ? Ak[t][0] + off.y : off.y;
+        th[2] = IS_K ? Ak[t][1] + off.x : off.x;
+        th[3] = IS_K ? Ak[t][1] + off.y : off.y;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          mma_tf32_sweep(th, Al[t][ks], bh[ks][0], bh[ks][1]);
+          mma_tf32_sweep(th, Ah[t][ks], bl[ks][0], bl[ks][1]);
+          mma_tf32_sweep(th, Ah[t][ks], bh[ks][0], bh[ks][1]);
+        }
+        const float v0 = IS_K ? ex2_approx(th[0]) : __cosf(th[0]), v1 = IS_K ? ex2_approx(th[1]) : __cosf(th[1]);
+        const float v2 = IS_K ? ex2_approx(th[2]) : __cosf(th[2]), v3 = IS_K ? ex2_approx(th[3]) : __cosf(th[3]);
+        acc[t][0] = fmaf(v0, wgt.x, acc[t][0]);
+        acc[t][0] = fmaf(v1, wgt.y, acc[t][0]);
+        acc[t][1] = fmaf(v2, wgt.x, acc[t][1]);
+        acc[t][1] = fmaf(v3, wgt.y, acc[t][1]);
+      }
+    }
+  }
+
+  template <class Store>
+  __device__ static __forceinline__ void eval_fwd(ChunkPipe& pipe, const RbfGeom& g, long total, const SweepSmem& sm, Store&& store) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gq = lane >> 2, tq = lane & 3;
+    // x fragments: A (16 states x 8 dims): a[h + 2 j] = x[state row gq + 8 h][dim 8 ks + 4 j + tq]; state jj of the warp = (r = jj / 32, lane jj % 32)
+    uint32_t Ah[NT][KS][4], Al[NT][KS][4];
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int jj = 16 * t + gq + 8 * h;
+        const int r = jj >> 5, src = warp * 32 + (jj & 31);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int d = 8 * ks + 4 * j + tq;
+            const float v = d < DP ? sm.xs[(d * R + r) * blockDim.x + src] : 0.f;
+            const uint32_t hh = __float_as_uint(v) & 0xFFFFE000u;
+            Ah[t][ks][h + 2 * j] = hh;
+            Al[t][ks][h + 2 * j] = __float_as_uint(v - __uint_as_float(hh));
+          }
+      }
+    float* res = sm.dx + warp * 128;   // per-warp scratch [2][64]: prior part / update part of the warp's states
+    for (int k = 0; k < g.D_out; ++k) {
+      const float* hdr_k = sm.hdr + k * g.hdr_floats;
+      float Ak[NT][2], acc[NT][2];
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float s = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int d = 8 * ks + 4 * j + tq;
+              const float xv = __uint_as_float(Ah[t][ks][h + 2 * j]) + __uint_as_float(Al[t][ks][h + 2 * j]);
+              if (d < DP) s = fmaf(hdr_k[d] * xv, xv, s);
+            }
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          Ak[t][h] = s;
+          acc[t][h] = 0.f;
+        }
+      for (int c = 0; c < g.NCs; ++c) {
+        const float* chunk = pipe.acquire(g.cg);
+        rows_mma<false>(chunk, min(g.RCs, g.SP2 - c * g.RCs), g.row_floats, Ah, Al, Ak, acc, gq, tq);
+        pipe.release(g.cg, total);
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float s = acc[t][h];
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          if (tq == 0) res[16 * t + gq + 8 * h] = s;
+          acc[t][h] = 0.f;
+        }
+      for (int c = 0; c < g.NCm; ++c) {
+        const float* chunk = pipe.acquire(g.cg);
+        rows_mma<true>(chunk, min(g.RCm, g.MP2 - c * g.RCm), g.row_floats, Ah, Al, Ak, acc, gq, tq);
+        pipe.release(g.cg, total);
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float s = acc[t][h];
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          if (tq == 0) res[64 + 16 * t + gq + 8 * h] = s * kInvLn2;   // inducing-row weights carry ln2
+        }
+      __syncwarp();
+      float fp[R], fu[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        fp[r] = res[r * 32 + lane];
+        fu[r] = res[64 + r * 32 + lane];
+      }
+      __syncwarp();
+      store(k, fp, fu);
+    }
+  }
+};
+
+// =============================================================================================
 // parameter gradients: threads <-> inducing-point pairs of one (sample, output dim); the CTA walks a
 // chunk of state evaluations staged through shared memory and accumulates in registers:
 //   dnu'_m = sum_n g_n E_nm ,  pg_md = sum_n g_n E_nm x_nd
@@ -494,13 +650,14 @@ __global__ void __launch_bounds__(kPgThreads, (DP <= 8 ? 6 : 3)) k_rbf_pgrad(con
 // below estimates the time of a launch as (CTAs the busiest SM runs back to back) x (work per CTA) x (cost per state of
 // the register-blocking factor R: a broadcast LDS.128 feeds R states, small R is LDS-bound) and picks the cheapest shape;
 // for a chip-filling problem this amounts to choosing the shape whose last wave is full.
-inline void rbf_pick_shape(const RbfGeom& g, bool bwd, int& threads, int& R) {
+inline void rbf_pick_shape(const RbfGeom& g, bool bwd, int& threads, int& R, int force_R = 0) {
   const int rc[3] = {4, 2, 1};
   double best = 1e300;
   threads = 32;
   R = 1;
   for (int ri = 0; ri < 3; ++ri) {
     const int r = rc[ri];
+    if (force_R && r != force_R) continue;
     if (bwd && g.DP > 8 && r > 2) continue;   // not compiled: the reverse sweep at D > 8 holds 2 states per thread at most
     // relative cost per state: forward needs R*2 FMA per parameter float to hide the LDS, the reverse sweep uses each float twice
     const double cost = bwd ? (r == 1 ? 1.25 : 1.0) : (r == 1 ? (g.DP > 8 ? 2.0 : 1.6) : (r == 2 ? (g.DP > 8 ? 1.2 : 1.05) : 1.0));
