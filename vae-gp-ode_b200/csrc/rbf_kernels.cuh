@@ -366,53 +366,61 @@ struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
   static constexpr int NT = 4;   // 16-state tiles per warp (32 lanes x R states)
   static constexpr int KS = 2;   // MMA k-steps over the (padded to 16) input dimension
 
-  template <bool IS_K>
-  __device__ static __forceinline__ void rows_mma(const float* __restrict__ chunk, int n, int row_floats, const uint32_t (&Ah)[NT][KS][4],
-                                                  const uint32_t (&Al)[NT][KS][4], const float (&Ak)[NT][2], float (&acc)[NT][2], int gq, int tq) {
-#pragma unroll 1
-    for (int blk = 0; blk * 4 < n; ++blk) {
-      // B fragments: column n = gq <-> unit (pair row blk * 4 + gq / 2, parity gq & 1); MMA k index (ks, tq + 4 j) <-> input dim d = 8 ks + 4 j + tq
-      const int pr = blk * 4 + (gq >> 1);
-      const float* rowp = chunk + pr * row_floats + (gq & 1);
-      uint32_t bh[KS][2], bl[KS][2];
+  // one block of 8 features / inducing points (4 pair rows starting at `rows`) against the warp's 4 state tiles; CHECK: the
+  // block may run past the n valid pair rows of the chunk (tail block only)
+  template <bool IS_K, bool CHECK>
+  __device__ static __forceinline__ void block_mma(const float* __restrict__ rows, int nvalid, const uint32_t (&Ah)[NT][KS][4],
+                                                   const uint32_t (&Al)[NT][KS][4], const float (&Ak)[NT][2], float (&acc)[NT][2], int gq, int tq) {
+    constexpr int ROWF = rbf_row_floats(DP);
+    // B fragments: column n = gq <-> unit (pair row gq / 2, parity gq & 1); MMA k index (ks, tq + 4 j) <-> input dim d = 8 ks + 4 j + tq
+    const bool okb = !CHECK || (gq >> 1) < nvalid;
+    const float* rowp = rows + (gq >> 1) * ROWF + (gq & 1);
+    uint32_t bh[KS][2], bl[KS][2];
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
+    for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int d = 8 * ks + 4 * j + tq;
-          const float v = (pr < n && d < DP) ? rowp[2 * d] : 0.f;
-          const uint32_t h = __float_as_uint(v) & 0xFFFFE000u;
-          bh[ks][j] = h;
-          bl[ks][j] = __float_as_uint(v - __uint_as_float(h));
-        }
-      // offsets and weights of the C columns 2 tq, 2 tq + 1 = both parities of pair row blk * 4 + tq
-      const int pc = blk * 4 + tq;
-      float2 off = make_float2(0.f, 0.f), wgt = make_float2(0.f, 0.f);
-      if (pc < n) {
-        off = *reinterpret_cast<const float2*>(chunk + pc * row_floats + 2 * DP);
-        wgt = *reinterpret_cast<const float2*>(chunk + pc * row_floats + 2 * DP + 2);
+      for (int j = 0; j < 2; ++j) {
+        const int d = 8 * ks + 4 * j + tq;
+        const float v = (okb && d < DP) ? rowp[2 * d] : 0.f;
+        const uint32_t h = __float_as_uint(v) & 0xFFFFE000u;
+        bh[ks][j] = h;
+        bl[ks][j] = __float_as_uint(v - __uint_as_float(h));
       }
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        float th[4];
-        th[0] = IS_K ? Ak[t][0] + off.x : off.x;
-        th[1] = IS_K ? Ak[t][0] + off.y : off.y;
-        th[2] = IS_K ? Ak[t][1] + off.x : off.x;
-        th[3] = IS_K ? Ak[t][1] + off.y : off.y;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          mma_tf32_sweep(th, Al[t][ks], bh[ks][0], bh[ks][1]);
-          mma_tf32_sweep(th, Ah[t][ks], bl[ks][0], bl[ks][1]);
-          mma_tf32_sweep(th, Ah[t][ks], bh[ks][0], bh[ks][1]);
-        }
-        const float v0 = IS_K ? ex2_approx(th[0]) : __cosf(th[0]), v1 = IS_K ? ex2_approx(th[1]) : __cosf(th[1]);
-        const float v2 = IS_K ? ex2_approx(th[2]) : __cosf(th[2]), v3 = IS_K ? ex2_approx(th[3]) : __cosf(th[3]);
-        acc[t][0] = fmaf(v0, wgt.x, acc[t][0]);
-        acc[t][0] = fmaf(v1, wgt.y, acc[t][0]);
-        acc[t][1] = fmaf(v2, wgt.x, acc[t][1]);
-        acc[t][1] = fmaf(v3, wgt.y, acc[t][1]);
-      }
+    // offsets and weights of the C columns 2 tq, 2 tq + 1 = both parities of pair row tq
+    float2 off = make_float2(0.f, 0.f), wgt = make_float2(0.f, 0.f);
+    if (!CHECK || tq < nvalid) {
+      off = *reinterpret_cast<const float2*>(rows + tq * ROWF + 2 * DP);
+      wgt = *reinterpret_cast<const float2*>(rows + tq * ROWF + 2 * DP + 2);
     }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      float th[4];
+      th[0] = IS_K ? Ak[t][0] + off.x : off.x;
+      th[1] = IS_K ? Ak[t][0] + off.y : off.y;
+      th[2] = IS_K ? Ak[t][1] + off.x : off.x;
+      th[3] = IS_K ? Ak[t][1] + off.y : off.y;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        mma_tf32_sweep(th, Al[t][ks], bh[ks][0], bh[ks][1]);
+        mma_tf32_sweep(th, Ah[t][ks], bl[ks][0], bl[ks][1]);
+        mma_tf32_sweep(th, Ah[t][ks], bh[ks][0], bh[ks][1]);
+      }
+      const float v0 = IS_K ? ex2_approx(th[0]) : __cosf(th[0]), v1 = IS_K ? ex2_approx(th[1]) : __cosf(th[1]);
+      const float v2 = IS_K ? ex2_approx(th[2]) : __cosf(th[2]), v3 = IS_K ? ex2_approx(th[3]) : __cosf(th[3]);
+      acc[t][0] = fmaf(v0, wgt.x, acc[t][0]);
+      acc[t][0] = fmaf(v1, wgt.y, acc[t][0]);
+      acc[t][1] = fmaf(v2, wgt.x, acc[t][1]);
+      acc[t][1] = fmaf(v3, wgt.y, acc[t][1]);
+    }
+  }
+  template <bool IS_K>
+  __device__ static __forceinline__ void rows_mma(const float* __restrict__ chunk, int n, const uint32_t (&Ah)[NT][KS][4],
+                                                  const uint32_t (&Al)[NT][KS][4], const float (&Ak)[NT][2], float (&acc)[NT][2], int gq, int tq) {
+    constexpr int ROWF = rbf_row_floats(DP);
+    const int nfull = n >> 2;
+#pragma unroll 1
+    for (int blk = 0; blk < nfull; ++blk) block_mma<IS_K, false>(chunk + blk * 4 * ROWF, 4, Ah, Al, Ak, acc, gq, tq);
+    if (n & 3) block_mma<IS_K, true>(chunk + nfull * 4 * ROWF, n & 3, Ah, Al, Ak, acc, gq, tq);
   }
 
   template <class Store>
@@ -461,7 +469,7 @@ struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
         }
       for (int c = 0; c < g.NCs; ++c) {
         const float* chunk = pipe.acquire(g.cg);
-        rows_mma<false>(chunk, min(g.RCs, g.SP2 - c * g.RCs), g.row_floats, Ah, Al, Ak, acc, gq, tq);
+        rows_mma<false>(chunk, min(g.RCs, g.SP2 - c * g.RCs), Ah, Al, Ak, acc, gq, tq);
         pipe.release(g.cg, total);
       }
 #pragma unroll
@@ -476,7 +484,7 @@ struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
         }
       for (int c = 0; c < g.NCm; ++c) {
         const float* chunk = pipe.acquire(g.cg);
-        rows_mma<true>(chunk, min(g.RCm, g.MP2 - c * g.RCm), g.row_floats, Ah, Al, Ak, acc, gq, tq);
+        rows_mma<true>(chunk, min(g.RCm, g.MP2 - c * g.RCm), Ah, Al, Ak, acc, gq, tq);
         pipe.release(g.cg, total);
       }
 #pragma unroll
