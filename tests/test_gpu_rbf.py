@@ -255,3 +255,58 @@ def test_tensor_path_forward_large_batch():
     traj = _gp().gp_rollout(x[0], ts, s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"], "rbf_dimwise", 1, "rk4")
     truth = OF.rollout(x[0, idx].double().cpu(), ts.double().cpu(), c, 1, "rk4")
     assert rel(traj[0, idx], truth) < TRAJ_TOL
+
+
+@pytest.mark.parametrize("D_in,D_out,M,S,N", [(12, 5, 101, 33, 40000), (16, 4, 200, 31, 33000)])
+def test_tensor_path_backward_large_batch(D_in, D_out, M, S, N):
+    """chip-filling batches at D > 8 run the tensor-path forward AND reverse sweeps (RbfMmaFwdPolicy / RbfMmaBwdPolicy):
+    field VJP, parameter gradients and a short RK4 rollout backward against autograd through the fp64 oracle."""
+    rs = np.random.RandomState(D_in * 7 + M)
+    f64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    c = dict(variant="rbf_dimwise", Z=f64(rs.normal(size=(M, D_in))), ell=f64(1.5 + rs.uniform(size=(D_out, D_in))),
+             var=f64(0.5 + rs.uniform(size=D_out)), nu=f64(rs.normal(size=(D_out, M, 1))), eps=f64(rs.normal(size=(D_in, S, D_out))),
+             phase=f64(rs.uniform(size=(1, S, D_out)) * 2 * np.pi), w=f64(rs.normal(size=(S, D_out))))
+    for k in ("Z", "ell", "var", "nu"):
+        c[k].requires_grad_(True)
+    c["omega"] = OF.make_omega(c["eps"], c["ell"], "rbf_dimwise")
+    x64 = f64(1.5 * rs.normal(size=(N, D_in))).requires_grad_(True)
+    gout = f64(rs.normal(size=(N, D_out)))
+    want = torch.autograd.grad((OF.field(x64, c) * gout).sum(), [x64, c["Z"], c["nu"], c["ell"], c["var"]])
+    s = gpu_sample(c)
+    for k in ("Z", "nu", "ell", "var"):
+        s[k].requires_grad_(True)
+    x = x64.detach().float().cuda()[None].requires_grad_(True)
+    f, _ = _field(s, x, "rbf_dimwise")
+    (f[0] * gout.float().cuda()).sum().backward()
+    got = [x.grad[0], s["Z"].grad, s["nu"].grad[0], s["ell"].grad, s["var"].grad]
+    for nm, a, b in zip(("dx", "dZ", "dnu", "dell", "dvar"), got, want):
+        e = rel(a, b)
+        print("tensor-path field-bwd D=%d %s: %.2e" % (D_in, nm, e))
+        assert e < GRAD_TOL, (nm, e)
+
+
+def test_tensor_path_rollout_backward_large_batch():
+    D, M, S, N, T = 12, 64, 17, 33000, 3
+    rs = np.random.RandomState(11)
+    f64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    c = dict(variant="rbf_dimwise", Z=f64(rs.normal(size=(M, D))), ell=f64(1.5 + rs.uniform(size=(D, D))), var=f64(0.5 + rs.uniform(size=D)),
+             nu=f64(0.3 * rs.normal(size=(D, M, 1))), eps=f64(rs.normal(size=(D, S, D))), phase=f64(rs.uniform(size=(1, S, D)) * 2 * np.pi),
+             w=f64(rs.normal(size=(S, D))))
+    for k in ("Z", "ell", "var", "nu"):
+        c[k].requires_grad_(True)
+    c["omega"] = OF.make_omega(c["eps"], c["ell"], "rbf_dimwise")
+    z64 = f64(rs.normal(size=(N, D))).requires_grad_(True)
+    ts64 = 0.1 * torch.arange(T, dtype=torch.float64)
+    G = f64(rs.normal(size=(N, T, D)))
+    want = torch.autograd.grad((OF.rollout(z64, ts64, c, 1, "rk4") * G).sum(), [z64, c["Z"], c["nu"], c["ell"], c["var"]])
+    s = gpu_sample(c)
+    for k in ("Z", "nu", "ell", "var"):
+        s[k].requires_grad_(True)
+    z0 = z64.detach().float().cuda().requires_grad_(True)
+    traj = _gp().gp_rollout(z0, ts64.float().cuda(), s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"], "rbf_dimwise", 1, "rk4")
+    (traj[0] * G.float().cuda()).sum().backward()
+    got = [z0.grad, s["Z"].grad, s["nu"].grad[0], s["ell"].grad, s["var"].grad]
+    for nm, a, b in zip(("dz0", "dZ", "dnu", "dell", "dvar"), got, want):
+        e = rel(a, b)
+        print("tensor-path rollout-bwd %s: %.2e" % (nm, e))
+        assert e < GRAD_TOL, (nm, e)

@@ -36,9 +36,9 @@ cudaError_t launch_sweep(Kern kern, const Args& a, int threads, int R, bool bwd,
   return launch_sweep(KERNEL<RbfPolicy<DP, 1>>, a, threads, 1, bwd, st);
 }  // namespace
 
-// forward kernels at D > 8 run on the tensor path (RbfMmaFwdPolicy: R = 2 states per thread) once the batch fills the chip:
-// measured at config-5 shapes 31.5 vs 34.2 ms; a 512-state evaluation (the prior at Z of the setup) is latency bound and
-// stays on the FFMA path (0.34 vs 0.58 ms)
+// sweep kernels at D > 8 run on the tensor path (RbfMmaFwdPolicy / RbfMmaBwdPolicy: R = 2 states per thread) once the batch
+// fills the chip: measured at config-5 shapes forward 24.8 vs 34.2 ms, reverse sweep 48.2 vs 70.5 ms; a 512-state evaluation
+// (the prior at Z of the setup) is latency bound and stays on the FFMA path (0.34 vs 0.58 ms)
 inline bool rbf_fwd_use_mma(const RbfGeom& g) { return static_cast<long>(g.N) * g.L >= 32768; }
 template <typename Args, typename KernMma>
 cudaError_t launch_fwd_mma(KernMma kern, const Args& a, cudaStream_t st) {
@@ -54,8 +54,20 @@ cudaError_t rbf_field_fwd_dp<DP>(const RbfFieldFwdArgs& a, cudaStream_t st) {
   }
   GPODE_DISPATCH_R(k_field_fwd, a, false, st)
 }
+template <typename Args, typename KernMma>
+cudaError_t launch_bwd_mma(KernMma kern, const Args& a, cudaStream_t st) {
+  int threads, R;
+  rbf_pick_shape(a.g, true, threads, R, 2);
+  return launch_sweep(kern, a, threads, 2, true, st);
+}
+
 template <>
-cudaError_t rbf_field_bwd_dp<DP>(const RbfFieldBwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_field_bwd, a, true, st) }
+cudaError_t rbf_field_bwd_dp<DP>(const RbfFieldBwdArgs& a, cudaStream_t st) {
+  if constexpr (DP > 8) {
+    if (rbf_fwd_use_mma(a.g)) return launch_bwd_mma(k_field_bwd<RbfMmaBwdPolicy<DP>>, a, st);
+  }
+  GPODE_DISPATCH_R(k_field_bwd, a, true, st)
+}
 template <>
 cudaError_t rbf_rollout_fwd_dp<DP>(const RbfRolloutFwdArgs& a, cudaStream_t st) {
   if constexpr (DP > 8) {
@@ -64,7 +76,12 @@ cudaError_t rbf_rollout_fwd_dp<DP>(const RbfRolloutFwdArgs& a, cudaStream_t st) 
   GPODE_DISPATCH_R(k_rollout_fwd, a, false, st)
 }
 template <>
-cudaError_t rbf_rollout_bwd_dp<DP>(const RbfRolloutBwdArgs& a, cudaStream_t st) { GPODE_DISPATCH_R(k_rollout_bwd, a, true, st) }
+cudaError_t rbf_rollout_bwd_dp<DP>(const RbfRolloutBwdArgs& a, cudaStream_t st) {
+  if constexpr (DP > 8) {
+    if (rbf_fwd_use_mma(a.g)) return launch_bwd_mma(k_rollout_bwd<RbfMmaBwdPolicy<DP>>, a, st);
+  }
+  GPODE_DISPATCH_R(k_rollout_bwd, a, true, st)
+}
 
 namespace {
 // D > 8: tensor-path kernels (3xTF32);  D <= 8: FFMA kernel
