@@ -364,7 +364,7 @@ struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
   static constexpr int DP = DP_;
   static constexpr int R = 2;
   static constexpr int NT = 4;   // 16-state tiles per warp (32 lanes x R states)
-  static constexpr int KS = 2;   // MMA k-steps over the (padded to 16) input dimension
+  static constexpr int KS = DP_ <= 8 ? 1 : 2;   // MMA k-steps over the (padded to 8 / 16) input dimension
 
   // one block of 8 features / inducing points (4 pair rows starting at `rows`) against the warp's 4 state tiles; CHECK: the
   // block may run past the n valid pair rows of the chunk (tail block only)
@@ -521,8 +521,8 @@ struct RbfMmaBwdPolicy : RbfPolicy<DP_, 2> {
   static constexpr int DP = DP_;
   static constexpr int R = 2;
   static constexpr int NT = 4;
-  static constexpr int KS = 2;
-  static constexpr int NB = 2;   // 8-column blocks of the input dimension in the second product
+  static constexpr int KS = DP_ <= 8 ? 1 : 2;
+  static constexpr int NB = DP_ <= 8 ? 1 : 2;   // 8-column blocks of the input dimension in the second product
 
   template <bool IS_K, bool CHECK>
   __device__ static __forceinline__ void block_bwd(const float* __restrict__ rows, int nvalid, const uint32_t (&Ah)[NT][KS][4],
