@@ -17,6 +17,44 @@ __global__ void k_mma(float* out, int iters) {
   for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) s += c[i][j];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// fp16 / bf16 m16n8k16 (HMMA.16816): twice the K of the TF32 shape per instruction
+template <int KIND>
+__global__ void k_mma16(float* out, int iters) {
+  float c[8][4];
+  for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
+  unsigned a[4] = {0x3c003c00u + threadIdx.x, 0x38003800u, 0x34003400u, 0x3a003a00u}, b[2] = {0x3c003c00u, 0x39003900u + threadIdx.x};
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (KIND == 0)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+  }
+  float s = 0.f;
+  for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) s += c[i][j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int KIND>
+void mma16(float* out) {
+  const int iters = 20000, warps = 16;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_mma16<KIND><<<148, warps * 32>>>(out, 100);
+  cudaEventRecord(e0);
+  k_mma16<KIND><<<148, warps * 32>>>(out, iters);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  const double mmas = 148.0 * warps * 8.0 * iters;
+  printf("{\"shape\": \"m16n8k16 %s\", \"tflops\": %.1f, \"cycles_per_mma_per_smsp\": %.2f}\n", KIND == 0 ? "f16" : "bf16", mmas * 4096 / (ms * 1e-3) / 1e12,
+         (ms * 1e-3 * 1.965e9) / (mmas / (148.0 * 4.0)));
+}
 template <int CH>
 __global__ void k_chain(float* out, int iters) {
   float c[CH][4];
@@ -97,6 +135,7 @@ void chain(float* out, int warps) {
 int main() {
   {
     float* o; cudaMalloc(&o, 148 * 1024 * 4);
+    mma16<0>(o); mma16<1>(o);
     tile<0>(o, 16); tile<64>(o, 16); tile<128>(o, 16); tile<128>(o, 8); tile<256>(o, 16);
     chain<1>(o, 4); chain<2>(o, 4); chain<4>(o, 4); chain<8>(o, 4); chain<1>(o, 16); chain<2>(o, 16); chain<4>(o, 16);
   }

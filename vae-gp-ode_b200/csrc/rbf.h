@@ -20,9 +20,14 @@ struct RbfGeom {
   int order, off;        // ODE order; off = D_in - D_out: where f sits inside the state derivative
   ChunkGeom cg;          // the same chunking, in the form the pipeline reads
 };
-// packed = [L][D_out][hdr_floats] headers, then [L][D_out][SP2+MP2][row_floats] rows
-inline size_t rbf_packed_floats(const RbfGeom& g) {
+// packed = [L][D_out][hdr_floats] headers, [L][D_out][SP2+MP2][row_floats] rows, then [L][D_out] max |row coefficient| (the
+// power-of-two scale of the fp16 tensor-path dot products)
+inline size_t rbf_rows_end_floats(const RbfGeom& g) {
   return static_cast<size_t>(g.L) * g.D_out * (g.hdr_floats + static_cast<size_t>(g.SP2 + g.MP2) * g.row_floats);
+}
+inline size_t rbf_packed_floats(const RbfGeom& g) { return rbf_rows_end_floats(g) + (static_cast<size_t>(g.L) * g.D_out + 3) / 4 * 4; }
+__host__ __device__ inline const float* rbf_maxabs_ptr(const float* packed, const RbfGeom& g, int l) {
+  return packed + static_cast<size_t>(g.L) * g.D_out * (g.hdr_floats + static_cast<size_t>(g.SP2 + g.MP2) * g.row_floats) + static_cast<size_t>(l) * g.D_out;
 }
 __host__ __device__ inline const float* rbf_hdr_ptr(const float* packed, const RbfGeom& g, int l) {
   return packed + static_cast<size_t>(l) * g.D_out * g.hdr_floats;

@@ -5,7 +5,7 @@
 namespace gpode {
 
 int rbf_smem_bytes(const RbfGeom& g, int threads, int R, bool bwd) {
-  int floats = 32 + kPipeStages * g.stage_floats + g.D_out * g.hdr_floats + g.DP * R * threads;
+  int floats = 32 + kPipeStages * g.stage_floats + g.D_out * g.hdr_floats + (g.D_out + 3) / 4 * 4 + g.DP * R * threads;
   if (bwd) floats += g.DP * R * threads + g.D_out * (g.DP + 1) + 2 * threads;   // + per-warp scratch (64 floats) of the tensor-path reverse sweep
   else floats += 4 * threads;   // per-warp result scratch (128 floats) of the tensor-path forward
   return floats * 4;
@@ -57,6 +57,9 @@ __global__ void k_rbf_pack(const RbfPackArgs a) {
     }
     out[DP] = make_float2(b[0], b[1]);
     out[DP + 1] = make_float2(w[0], w[1]);
+    float mx = 0.f;
+    for (int d = 0; d < DP; ++d) mx = fmaxf(mx, fmaxf(fabsf(out[d].x), fabsf(out[d].y)));
+    atomicMax(reinterpret_cast<unsigned int*>(const_cast<float*>(rbf_maxabs_ptr(a.packed, g, l)) + k), __float_as_uint(mx));
   } else {
     const int j = row - g.SP2;
     float H[2] = {0.f, 0.f}, nu[2] = {0.f, 0.f};
@@ -79,10 +82,15 @@ __global__ void k_rbf_pack(const RbfPackArgs a) {
     }
     out[DP] = make_float2(H[0], H[1]);
     out[DP + 1] = make_float2(nu[0], nu[1]);
+    float mx = 0.f;
+    for (int d = 0; d < DP; ++d) mx = fmaxf(mx, fmaxf(fabsf(out[d].x), fabsf(out[d].y)));
+    atomicMax(reinterpret_cast<unsigned int*>(const_cast<float*>(rbf_maxabs_ptr(a.packed, g, l)) + k), __float_as_uint(mx));
   }
 }
 
 cudaError_t rbf_launch_pack(const RbfPackArgs& a, cudaStream_t st) {
+  cudaError_t e0 = cudaMemsetAsync(const_cast<float*>(rbf_maxabs_ptr(a.packed, a.g, 0)), 0, static_cast<size_t>(a.g.L) * a.g.D_out * 4, st);
+  if (e0 != cudaSuccess) return e0;
   const int rows = a.g.SP2 + a.g.MP2 + 1;
   dim3 grid((rows + 127) / 128, a.g.D_out, a.g.L);
   k_rbf_pack<<<grid, 128, 0, st>>>(a);

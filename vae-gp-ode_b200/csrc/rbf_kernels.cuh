@@ -12,6 +12,8 @@
 // the scalar-broadcast operand, the parameters come as {even, odd} pairs.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "rbf.h"
 #include "sweep.cuh"
@@ -138,6 +140,7 @@ struct SweepSmem {
   uint64_t* bars;
   float* stages;
   float* hdr;
+  float* pmax;   // [D_out] max |row coefficient| of this sample's rows (scale of the fp16 dot products)
   float* xs;
   float* dx;
   float* dell;
@@ -149,7 +152,8 @@ __device__ __forceinline__ SweepSmem carve_smem(float* smem, const RbfGeom& g) {
   s.bars = reinterpret_cast<uint64_t*>(smem);
   s.stages = smem + 32;
   s.hdr = s.stages + kPipeStages * g.stage_floats;
-  s.xs = s.hdr + g.D_out * g.hdr_floats;
+  s.pmax = s.hdr + g.D_out * g.hdr_floats;
+  s.xs = s.pmax + (g.D_out + 3) / 4 * 4;
   s.dx = s.xs + DP * R * blockDim.x;
   s.dell = s.dx + DP * R * blockDim.x;
   s.dvar = s.dell + g.D_out * DP;
@@ -161,6 +165,7 @@ __device__ __forceinline__ void sweep_setup(SweepSmem& sm, ChunkPipe& pipe, cons
   const int l = blockIdx.y;
   const float* hdr = rbf_hdr_ptr(packed, g, l);
   for (int i = threadIdx.x; i < g.D_out * g.hdr_floats; i += blockDim.x) sm.hdr[i] = hdr[i];
+  for (int i = threadIdx.x; i < g.D_out; i += blockDim.x) sm.pmax[i] = rbf_maxabs_ptr(packed, g, l)[i];
   for (int i = threadIdx.x; i < DP * R * blockDim.x; i += blockDim.x) sm.xs[i] = 0.f;  // padded components stay 0
   if (bwd)
     for (int i = threadIdx.x; i < g.D_out * (DP + 1); i += blockDim.x) sm.dell[i] = 0.f;
@@ -346,46 +351,162 @@ struct RbfPolicy {
 };
 
 // =============================================================================================
-// Forward evaluation on the warp-level tensor path for D > 8 (3xTF32 mma.sync m16n8k8, see rbf_pgrad_mma.cuh for the
-// measurements): a warp owns its 64 states (R = 2) as 4 MMA row tiles of 16; the x fragments (TF32 head + remainder) are
-// built once per evaluation from the staged states; every block of 8 features / inducing points (4 pair rows of the
-// streamed chunk) is one B fragment pair, theta = offset (+ A_k(x)) + x . row comes out of 6 MMAs per tile with the
-// offsets as the initial accumulator, the transcendental and the weight multiply run on the C fragment, the sum over the
-// rows is a register accumulator per (tile, row half) that is reduced over the 4 column lanes once per output dimension.
+// Forward evaluation on the warp-level tensor path for D > 8 (measurements: rbf_pgrad_mma.cuh).
+// A warp owns its 64 states (R = 2) as 4 MMA row tiles of 16.  theta = offset (+ A_k(x)) + x . row is ONE k-step of
+// mma.sync m16n8k16 with a two-way fp16 split (head + remainder: 22 bits, three products lo*hi + hi*lo + hi*hi, fp32
+// accumulate) -- half the tensor instructions of the 3xTF32 form (6 x m16n8k8), measured 18.8 vs 24.8 ms.  fp16 has no
+// exponent headroom, so both operands are scaled by exact powers of two first: every state row by 2^-a (a from its largest
+// |x_d|), the rows of output k by 2^-b (b from the largest |coefficient| of that k, found by the pack kernel); the product
+// is un-scaled and the offsets added by one FFMA on the C fragment.  Overflow cannot occur, small values degrade like
+// block floating point (absolute, not relative, to the row maximum).  The transcendental and the weight run on the C
+// fragment; the sum over the rows is a register accumulator per (tile, row half), reduced over the 4 column lanes per k.
 // =============================================================================================
 __device__ __forceinline__ void mma_tf32_sweep(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16_sweep(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (v0, v1) -> packed fp16 heads and packed fp16 remainders.  The remainders are stored scaled by 2^11 (exact) so that they stay
+// fp16-normal wherever the head is; the cross products are accumulated separately and folded in with 2^-11 (kLoScale).
+constexpr float kLoUp = 2048.f, kLoScale = 1.f / 2048.f;
+__device__ __forceinline__ void split_h2(float v0, float v1, uint32_t& hi_, uint32_t& lo_) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const __half2 l = __floats2half2_rn((v0 - __low2float(h)) * kLoUp, (v1 - __high2float(h)) * kLoUp);
+  hi_ = *reinterpret_cast<const uint32_t*>(&h);
+  lo_ = *reinterpret_cast<const uint32_t*>(&l);
+}
+// exact power-of-two scale s (and 1 / s): 1 while 2^-6 <= m < 2^6 (the common case: fp16 heads + remainders then carry
+// >= 21 bits of every element above 2^-11 of the maximum), otherwise the scale that brings m into [1/2, 1) -- block floating
+// point: no overflow for large operands, no loss of the remainders for small ones
+__device__ __forceinline__ void pow2_scales(float m, float& s, float& inv) {
+  unsigned be = (__float_as_uint(m) >> 23) & 255u;
+  be = be > 252u ? 252u : be;
+  const unsigned bs = (be >= 121u && be < 133u) || be == 0u ? 127u : 253u - be;
+  s = __uint_as_float(bs << 23);
+  inv = __uint_as_float((254u - bs) << 23);
+}
+
+// pieces shared by the forward and reverse tensor-path policies
+template <int DP>
+struct RbfMmaCommon {
+  static constexpr int R = 2;
+  static constexpr int NT = 4;   // 16-state tiles per warp (32 lanes x R states)
+
+  // A (16 states x 16 dims as fp16 pairs): a[h + 2 j] = s_row x[row gq + 8 h][dims 2 tq + 8 j, 2 tq + 8 j + 1]; state jj of the warp =
+  // (r = jj / 32, lane jj % 32).  inv[t][h] = 1 / s_row.
+  __device__ static __forceinline__ void build_A(const SweepSmem& sm, int warp, int gq, int tq, uint32_t (&Ah)[NT][4], uint32_t (&Al)[NT][4],
+                                                 float (&inv)[NT][2]) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int jj = 16 * t + gq + 8 * h;
+        const int r = jj >> 5, src = warp * 32 + (jj & 31);
+        float v[4], mx = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int d = 2 * tq + 8 * j + i;
+            v[2 * j + i] = d < DP ? sm.xs[(d * R + r) * blockDim.x + src] : 0.f;
+            mx = fmaxf(mx, fabsf(v[2 * j + i]));
+          }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float sa;
+        pow2_scales(mx, sa, inv[t][h]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) split_h2(v[2 * j] * sa, v[2 * j + 1] * sa, Ah[t][h + 2 * j], Al[t][h + 2 * j]);
+      }
+  }
+  // A_k(x) = sum_d c_kd x_d^2 of every state row: computed thread <-> state from the staged states, handed to the row lanes
+  // through a 64-float per-warp scratch
+  __device__ static __forceinline__ void quad_A(const SweepSmem& sm, const float* hdr_k, float* scratch, int lane, int gq, float (&Ak)[NT][2]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const float xv = GPODE_XS(sm.xs, d, r);
+        s = fmaf(hdr_k[d] * xv, xv, s);
+      }
+      scratch[r * 32 + lane] = s;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) Ak[t][h] = scratch[16 * t + gq + 8 * h];
+    __syncwarp();
+  }
+  // B fragments of one block of 8 rows (4 pair rows at `rows`), scaled by sb: column n = gq <-> unit (pair row gq / 2, parity gq & 1);
+  // b[j] holds dims 2 tq + 8 j, 2 tq + 8 j + 1
+  template <bool CHECK, bool SCALED>
+  __device__ static __forceinline__ void build_B(const float* __restrict__ rows, int nvalid, float sb, int gq, int tq, uint32_t (&bh)[2], uint32_t (&bl)[2]) {
+    constexpr int ROWF = rbf_row_floats(DP);
+    const bool okb = !CHECK || (gq >> 1) < nvalid;
+    const float* rowp = rows + (gq >> 1) * ROWF + (gq & 1);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int d = 2 * tq + 8 * j;
+      const float v0 = (okb && d < DP) ? rowp[2 * d] : 0.f, v1 = (okb && d + 1 < DP) ? rowp[2 * d + 2] : 0.f;
+      if constexpr (SCALED) split_h2(v0 * sb, v1 * sb, bh[j], bl[j]);
+      else split_h2(v0, v1, bh[j], bl[j]);
+    }
+  }
+  // theta of one tile: init + u_row (x' . row').  SCALED = false (every scale of this warp and output is 1, the common case): the
+  // offsets are simply the initial accumulator
+  template <bool SCALED>
+  __device__ static __forceinline__ void theta_tile(const uint32_t (&Ah)[4], const uint32_t (&Al)[4], const uint32_t (&bh)[2], const uint32_t (&bl)[2],
+                                                    float u0, float u1, const float (&init)[4], float (&th)[4]) {
+    float x2[4] = {0.f, 0.f, 0.f, 0.f};   // cross terms lo' * hi + hi * lo' (x 2^11)
+    mma_f16_sweep(x2, Al, bh[0], bh[1]);
+    mma_f16_sweep(x2, Ah, bl[0], bl[1]);
+    if constexpr (SCALED) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_f16_sweep(c, Ah, bh[0], bh[1]);
+      th[0] = fmaf(x2[0], u0 * kLoScale, fmaf(c[0], u0, init[0]));
+      th[1] = fmaf(x2[1], u0 * kLoScale, fmaf(c[1], u0, init[1]));
+      th[2] = fmaf(x2[2], u1 * kLoScale, fmaf(c[2], u1, init[2]));
+      th[3] = fmaf(x2[3], u1 * kLoScale, fmaf(c[3], u1, init[3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) th[i] = init[i];
+      mma_f16_sweep(th, Ah, bh[0], bh[1]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) th[i] = fmaf(x2[i], kLoScale, th[i]);
+    }
+  }
+  // true when every un-scaling factor of this warp is exactly 1 (warp uniform)
+  __device__ static __forceinline__ bool all_unit(const float (&u)[NT][2]) {
+    bool one = true;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) one = one && u[t][0] == 1.f && u[t][1] == 1.f;
+    return __all_sync(0xffffffffu, one);
+  }
+};
 
 template <int DP_>
 struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
   static constexpr int DP = DP_;
   static constexpr int R = 2;
-  static constexpr int NT = 4;   // 16-state tiles per warp (32 lanes x R states)
-  static constexpr int KS = DP_ <= 8 ? 1 : 2;   // MMA k-steps over the (padded to 8 / 16) input dimension
+  static constexpr int NT = 4;
+  using C = RbfMmaCommon<DP_>;
 
-  // one block of 8 features / inducing points (4 pair rows starting at `rows`) against the warp's 4 state tiles; CHECK: the
-  // block may run past the n valid pair rows of the chunk (tail block only)
-  template <bool IS_K, bool CHECK>
-  __device__ static __forceinline__ void block_mma(const float* __restrict__ rows, int nvalid, const uint32_t (&Ah)[NT][KS][4],
-                                                   const uint32_t (&Al)[NT][KS][4], const float (&Ak)[NT][2], float (&acc)[NT][2], int gq, int tq) {
+  // one block of 8 features / inducing points against the warp's 4 state tiles; CHECK: the block may run past the n valid pair
+  // rows of the chunk (tail block only)
+  template <bool IS_K, bool CHECK, bool SCALED>
+  __device__ static __forceinline__ void block_mma(const float* __restrict__ rows, int nvalid, float sb, const uint32_t (&Ah)[NT][4],
+                                                   const uint32_t (&Al)[NT][4], const float (&u)[NT][2], const float (&Ak)[NT][2], float (&acc)[NT][2],
+                                                   int gq, int tq) {
     constexpr int ROWF = rbf_row_floats(DP);
-    // B fragments: column n = gq <-> unit (pair row gq / 2, parity gq & 1); MMA k index (ks, tq + 4 j) <-> input dim d = 8 ks + 4 j + tq
-    const bool okb = !CHECK || (gq >> 1) < nvalid;
-    const float* rowp = rows + (gq >> 1) * ROWF + (gq & 1);
-    uint32_t bh[KS][2], bl[KS][2];
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int d = 8 * ks + 4 * j + tq;
-        const float v = (okb && d < DP) ? rowp[2 * d] : 0.f;
-        const uint32_t h = __float_as_uint(v) & 0xFFFFE000u;
-        bh[ks][j] = h;
-        bl[ks][j] = __float_as_uint(v - __uint_as_float(h));
-      }
+    uint32_t bh[2], bl[2];
+    C::template build_B<CHECK, SCALED>(rows, nvalid, sb, gq, tq, bh, bl);
     // offsets and weights of the C columns 2 tq, 2 tq + 1 = both parities of pair row tq
     float2 off = make_float2(0.f, 0.f), wgt = make_float2(0.f, 0.f);
     if (!CHECK || tq < nvalid) {
@@ -394,17 +515,12 @@ struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
     }
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      float th[4];
-      th[0] = IS_K ? Ak[t][0] + off.x : off.x;
-      th[1] = IS_K ? Ak[t][0] + off.y : off.y;
-      th[2] = IS_K ? Ak[t][1] + off.x : off.x;
-      th[3] = IS_K ? Ak[t][1] + off.y : off.y;
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        mma_tf32_sweep(th, Al[t][ks], bh[ks][0], bh[ks][1]);
-        mma_tf32_sweep(th, Ah[t][ks], bl[ks][0], bl[ks][1]);
-        mma_tf32_sweep(th, Ah[t][ks], bh[ks][0], bh[ks][1]);
-      }
+      float init[4], th[4];
+      init[0] = IS_K ? Ak[t][0] + off.x : off.x;
+      init[1] = IS_K ? Ak[t][0] + off.y : off.y;
+      init[2] = IS_K ? Ak[t][1] + off.x : off.x;
+      init[3] = IS_K ? Ak[t][1] + off.y : off.y;
+      C::template theta_tile<SCALED>(Ah[t], Al[t], bh, bl, u[t][0], u[t][1], init, th);
       const float v0 = IS_K ? ex2_approx(th[0]) : __cosf(th[0]), v1 = IS_K ? ex2_approx(th[1]) : __cosf(th[1]);
       const float v2 = IS_K ? ex2_approx(th[2]) : __cosf(th[2]), v3 = IS_K ? ex2_approx(th[3]) : __cosf(th[3]);
       acc[t][0] = fmaf(v0, wgt.x, acc[t][0]);
@@ -414,62 +530,44 @@ struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
     }
   }
   template <bool IS_K>
-  __device__ static __forceinline__ void rows_mma(const float* __restrict__ chunk, int n, const uint32_t (&Ah)[NT][KS][4],
-                                                  const uint32_t (&Al)[NT][KS][4], const float (&Ak)[NT][2], float (&acc)[NT][2], int gq, int tq) {
+  __device__ static __forceinline__ void rows_mma(const float* __restrict__ chunk, int n, bool plain, float sb, const uint32_t (&Ah)[NT][4],
+                                                  const uint32_t (&Al)[NT][4], const float (&u)[NT][2], const float (&Ak)[NT][2], float (&acc)[NT][2], int gq,
+                                                  int tq) {
     constexpr int ROWF = rbf_row_floats(DP);
     const int nfull = n >> 2;
+    if (plain) {
 #pragma unroll 1
-    for (int blk = 0; blk < nfull; ++blk) block_mma<IS_K, false>(chunk + blk * 4 * ROWF, 4, Ah, Al, Ak, acc, gq, tq);
-    if (n & 3) block_mma<IS_K, true>(chunk + nfull * 4 * ROWF, n & 3, Ah, Al, Ak, acc, gq, tq);
+      for (int blk = 0; blk < nfull; ++blk) block_mma<IS_K, false, false>(chunk + blk * 4 * ROWF, 4, sb, Ah, Al, u, Ak, acc, gq, tq);
+      if (n & 3) block_mma<IS_K, true, false>(chunk + nfull * 4 * ROWF, n & 3, sb, Ah, Al, u, Ak, acc, gq, tq);
+    } else {
+#pragma unroll 1
+      for (int blk = 0; blk < nfull; ++blk) block_mma<IS_K, false, true>(chunk + blk * 4 * ROWF, 4, sb, Ah, Al, u, Ak, acc, gq, tq);
+      if (n & 3) block_mma<IS_K, true, true>(chunk + nfull * 4 * ROWF, n & 3, sb, Ah, Al, u, Ak, acc, gq, tq);
+    }
   }
 
   template <class Store>
   __device__ static __forceinline__ void eval_fwd(ChunkPipe& pipe, const RbfGeom& g, long total, const SweepSmem& sm, Store&& store) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gq = lane >> 2, tq = lane & 3;
-    // x fragments: A (16 states x 8 dims): a[h + 2 j] = x[state row gq + 8 h][dim 8 ks + 4 j + tq]; state jj of the warp = (r = jj / 32, lane jj % 32)
-    uint32_t Ah[NT][KS][4], Al[NT][KS][4];
-#pragma unroll
-    for (int t = 0; t < NT; ++t)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int jj = 16 * t + gq + 8 * h;
-        const int r = jj >> 5, src = warp * 32 + (jj & 31);
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int d = 8 * ks + 4 * j + tq;
-            const float v = d < DP ? sm.xs[(d * R + r) * blockDim.x + src] : 0.f;
-            const uint32_t hh = __float_as_uint(v) & 0xFFFFE000u;
-            Ah[t][ks][h + 2 * j] = hh;
-            Al[t][ks][h + 2 * j] = __float_as_uint(v - __uint_as_float(hh));
-          }
-      }
+    uint32_t Ah[NT][4], Al[NT][4];
+    float inv[NT][2];
+    C::build_A(sm, warp, gq, tq, Ah, Al, inv);
     float* res = sm.dx + warp * 128;   // per-warp scratch [2][64]: prior part / update part of the warp's states
     for (int k = 0; k < g.D_out; ++k) {
-      const float* hdr_k = sm.hdr + k * g.hdr_floats;
-      float Ak[NT][2], acc[NT][2];
+      float sb, isb, Ak[NT][2], u[NT][2], acc[NT][2];
+      pow2_scales(sm.pmax[k], sb, isb);
+      C::quad_A(sm, sm.hdr + k * g.hdr_floats, res, lane, gq, Ak);
 #pragma unroll
       for (int t = 0; t < NT; ++t)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          float s = 0.f;
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int d = 8 * ks + 4 * j + tq;
-              const float xv = __uint_as_float(Ah[t][ks][h + 2 * j]) + __uint_as_float(Al[t][ks][h + 2 * j]);
-              if (d < DP) s = fmaf(hdr_k[d] * xv, xv, s);
-            }
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          Ak[t][h] = s;
+          u[t][h] = inv[t][h] * isb;
           acc[t][h] = 0.f;
         }
+      const bool plain = C::all_unit(u);
       for (int c = 0; c < g.NCs; ++c) {
         const float* chunk = pipe.acquire(g.cg);
-        rows_mma<false>(chunk, min(g.RCs, g.SP2 - c * g.RCs), Ah, Al, Ak, acc, gq, tq);
+        rows_mma<false>(chunk, min(g.RCs, g.SP2 - c * g.RCs), plain, sb, Ah, Al, u, Ak, acc, gq, tq);
         pipe.release(g.cg, total);
       }
 #pragma unroll
@@ -484,7 +582,7 @@ struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
         }
       for (int c = 0; c < g.NCm; ++c) {
         const float* chunk = pipe.acquire(g.cg);
-        rows_mma<true>(chunk, min(g.RCm, g.MP2 - c * g.RCm), Ah, Al, Ak, acc, gq, tq);
+        rows_mma<true>(chunk, min(g.RCm, g.MP2 - c * g.RCm), plain, sb, Ah, Al, u, Ak, acc, gq, tq);
         pipe.release(g.cg, total);
       }
 #pragma unroll
