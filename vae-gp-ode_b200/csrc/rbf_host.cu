@@ -6,7 +6,7 @@ namespace gpode {
 
 int rbf_smem_bytes(const RbfGeom& g, int threads, int R, bool bwd) {
   int floats = 32 + kPipeStages * g.stage_floats + g.D_out * g.hdr_floats + (g.D_out + 3) / 4 * 4 + g.DP * R * threads;
-  if (bwd) floats += g.DP * R * threads + g.D_out * (g.DP + 1) + 2 * threads;   // + per-warp scratch (64 floats) of the tensor-path reverse sweep
+  if (bwd) floats += g.DP * R * threads + g.D_out * (g.DP + 1) + 4 * threads;   // + per-warp scratch (128 floats) of the tensor-path reverse sweep
   else floats += 4 * threads;   // per-warp result scratch (128 floats) of the tensor-path forward
   return floats * 4;
 }

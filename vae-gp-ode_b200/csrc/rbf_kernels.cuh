@@ -609,8 +609,9 @@ struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
 
 // =============================================================================================
 // Reverse-sweep VJP on the warp-level tensor path for D > 8: same tiling as RbfMmaFwdPolicy.  Per block of 8 rows and state
-// tile: theta (6 MMAs), t = weight * (-sin | 2^theta) on the C fragment, and the second product Q[state, d] += t P[row, d]
-// (6 MMAs) with the C fragment reused as the A fragment (row order permuted consistently in B, no shuffles) -- the two
+// tile: theta (3 fp16 MMAs, as in the forward), t = weight * (-sin | 2^theta) on the C fragment, and the second product
+// Q[state, d] += t P[row, d] (6 MMAs, 3xTF32 m16n8k8: t spans the dynamic range of the exponentials, so it keeps the fp32
+// exponent) with the C fragment reused as the A fragment (row order permuted consistently in B, no shuffles) -- the two
 // D-length contractions of the FFMA kernel.  dx_k = g_k (Q + 2 c_k x Es) is folded into the shared dx / lengthscale
 // statistics once per output dimension.
 // =============================================================================================
@@ -619,34 +620,24 @@ struct RbfMmaBwdPolicy : RbfPolicy<DP_, 2> {
   static constexpr int DP = DP_;
   static constexpr int R = 2;
   static constexpr int NT = 4;
-  static constexpr int KS = DP_ <= 8 ? 1 : 2;
-  static constexpr int NB = DP_ <= 8 ? 1 : 2;   // 8-column blocks of the input dimension in the second product
+  static constexpr int NB = 2;   // 8-column blocks of the input dimension in the second product
+  using C = RbfMmaCommon<DP_>;
 
-  template <bool IS_K, bool CHECK>
-  __device__ static __forceinline__ void block_bwd(const float* __restrict__ rows, int nvalid, const uint32_t (&Ah)[NT][KS][4],
-                                                   const uint32_t (&Al)[NT][KS][4], const float (&Ak)[NT][2], float (&Q)[NT][NB][4], float (&Es)[NT][2],
-                                                   int gq, int tq) {
+  template <bool IS_K, bool CHECK, bool SCALED>
+  __device__ static __forceinline__ void block_bwd(const float* __restrict__ rows, int nvalid, float sb, const uint32_t (&Ah)[NT][4],
+                                                   const uint32_t (&Al)[NT][4], const float (&u)[NT][2], const float (&Ak)[NT][2], float (&Q)[NT][NB][4],
+                                                   float (&Es)[NT][2], int gq, int tq) {
     constexpr int ROWF = rbf_row_floats(DP);
-    const bool okb = !CHECK || (gq >> 1) < nvalid;
     const bool okc = !CHECK || tq < nvalid;
-    const float* rowp = rows + (gq >> 1) * ROWF + (gq & 1);
-    uint32_t bh[KS][2], bl[KS][2];
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int d = 8 * ks + 4 * j + tq;
-        const float v = (okb && d < DP) ? rowp[2 * d] : 0.f;
-        const uint32_t h = __float_as_uint(v) & 0xFFFFE000u;
-        bh[ks][j] = h;
-        bl[ks][j] = __float_as_uint(v - __uint_as_float(h));
-      }
+    uint32_t bh[2], bl[2];
+    C::template build_B<CHECK, SCALED>(rows, nvalid, sb, gq, tq, bh, bl);
     float2 off = make_float2(0.f, 0.f), wgt = make_float2(0.f, 0.f);
     if (okc) {
       off = *reinterpret_cast<const float2*>(rows + tq * ROWF + 2 * DP);
       wgt = *reinterpret_cast<const float2*>(rows + tq * ROWF + 2 * DP + 2);
     }
-    // B of the second product: MMA k index tq <-> row unit 2 tq, k = tq + 4 <-> unit 2 tq + 1 (both parities of pair row tq); column gq <-> dim gq + 8 nb
+    // B of the second product (3xTF32: t has the dynamic range of the exponentials): MMA k index tq <-> row unit 2 tq, k = tq + 4 <-> unit
+    // 2 tq + 1 (both parities of pair row tq); column gq <-> dim gq + 8 nb
     uint32_t ph[NB][2], pl[NB][2];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
@@ -660,17 +651,12 @@ struct RbfMmaBwdPolicy : RbfPolicy<DP_, 2> {
     }
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      float th[4];
-      th[0] = IS_K ? Ak[t][0] + off.x : off.x + kHalfPi;    // cos(theta + pi/2) = -sin(theta)
-      th[1] = IS_K ? Ak[t][0] + off.y : off.y + kHalfPi;
-      th[2] = IS_K ? Ak[t][1] + off.x : off.x + kHalfPi;
-      th[3] = IS_K ? Ak[t][1] + off.y : off.y + kHalfPi;
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        mma_tf32_sweep(th, Al[t][ks], bh[ks][0], bh[ks][1]);
-        mma_tf32_sweep(th, Ah[t][ks], bl[ks][0], bl[ks][1]);
-        mma_tf32_sweep(th, Ah[t][ks], bh[ks][0], bh[ks][1]);
-      }
+      float init[4], th[4];
+      init[0] = IS_K ? Ak[t][0] + off.x : off.x + kHalfPi;    // cos(theta + pi/2) = -sin(theta)
+      init[1] = IS_K ? Ak[t][0] + off.y : off.y + kHalfPi;
+      init[2] = IS_K ? Ak[t][1] + off.x : off.x + kHalfPi;
+      init[3] = IS_K ? Ak[t][1] + off.y : off.y + kHalfPi;
+      C::template theta_tile<SCALED>(Ah[t], Al[t], bh, bl, u[t][0], u[t][1], init, th);
       // C fragment: [0] (row gq, unit 2 tq), [1] (gq, 2 tq + 1), [2] (gq + 8, 2 tq), [3] (gq + 8, 2 tq + 1)
       const float t0 = wgt.x * (IS_K ? ex2_approx(th[0]) : __cosf(th[0])), t1 = wgt.y * (IS_K ? ex2_approx(th[1]) : __cosf(th[1]));
       const float t2 = wgt.x * (IS_K ? ex2_approx(th[2]) : __cosf(th[2])), t3 = wgt.y * (IS_K ? ex2_approx(th[3]) : __cosf(th[3]));
@@ -695,42 +681,33 @@ struct RbfMmaBwdPolicy : RbfPolicy<DP_, 2> {
     }
   }
   template <bool IS_K>
-  __device__ static __forceinline__ void rows_bwd_mma(const float* __restrict__ chunk, int n, const uint32_t (&Ah)[NT][KS][4],
-                                                      const uint32_t (&Al)[NT][KS][4], const float (&Ak)[NT][2], float (&Q)[NT][NB][4], float (&Es)[NT][2],
-                                                      int gq, int tq) {
+  __device__ static __forceinline__ void rows_bwd_mma(const float* __restrict__ chunk, int n, bool plain, float sb, const uint32_t (&Ah)[NT][4],
+                                                      const uint32_t (&Al)[NT][4], const float (&u)[NT][2], const float (&Ak)[NT][2], float (&Q)[NT][NB][4],
+                                                      float (&Es)[NT][2], int gq, int tq) {
     constexpr int ROWF = rbf_row_floats(DP);
     const int nfull = n >> 2;
+    if (plain) {
 #pragma unroll 1
-    for (int blk = 0; blk < nfull; ++blk) block_bwd<IS_K, false>(chunk + blk * 4 * ROWF, 4, Ah, Al, Ak, Q, Es, gq, tq);
-    if (n & 3) block_bwd<IS_K, true>(chunk + nfull * 4 * ROWF, n & 3, Ah, Al, Ak, Q, Es, gq, tq);
+      for (int blk = 0; blk < nfull; ++blk) block_bwd<IS_K, false, false>(chunk + blk * 4 * ROWF, 4, sb, Ah, Al, u, Ak, Q, Es, gq, tq);
+      if (n & 3) block_bwd<IS_K, true, false>(chunk + nfull * 4 * ROWF, n & 3, sb, Ah, Al, u, Ak, Q, Es, gq, tq);
+    } else {
+#pragma unroll 1
+      for (int blk = 0; blk < nfull; ++blk) block_bwd<IS_K, false, true>(chunk + blk * 4 * ROWF, 4, sb, Ah, Al, u, Ak, Q, Es, gq, tq);
+      if (n & 3) block_bwd<IS_K, true, true>(chunk + nfull * 4 * ROWF, n & 3, sb, Ah, Al, u, Ak, Q, Es, gq, tq);
+    }
   }
 
   __device__ static __forceinline__ void vjp(ChunkPipe& pipe, const RbfGeom& g, long total, const SweepSmem& sm, const States<R>& st,
                                              const float* gvec, const float* fvec, const float* fpvec, long kstride, long sstride) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gq = lane >> 2, tq = lane & 3;
-    uint32_t Ah[NT][KS][4], Al[NT][KS][4];
-#pragma unroll
-    for (int t = 0; t < NT; ++t)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int jj = 16 * t + gq + 8 * h;
-        const int r = jj >> 5, src = warp * 32 + (jj & 31);
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int d = 8 * ks + 4 * j + tq;
-            const float v = d < DP ? sm.xs[(d * R + r) * blockDim.x + src] : 0.f;
-            const uint32_t hh = __float_as_uint(v) & 0xFFFFE000u;
-            Ah[t][ks][h + 2 * j] = hh;
-            Al[t][ks][h + 2 * j] = __float_as_uint(v - __uint_as_float(hh));
-          }
-      }
+    uint32_t Ah[NT][4], Al[NT][4];
+    float inv[NT][2];
+    C::build_A(sm, warp, gq, tq, Ah, Al, inv);
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int d = 0; d < DP; ++d) GPODE_XS(sm.dx, d, r) = 0.f;
-    float* gs = sm.dvar + g.D_out + warp * 64;   // per-warp scratch: upstream gradient of the warp's 64 states
+    float* gs = sm.dvar + g.D_out + warp * 128;   // per-warp scratch: [64] upstream gradient of the warp's states, [64] A_k hand-over
     for (int k = 0; k < g.D_out; ++k) {
       const float* hdr_k = sm.hdr + k * g.hdr_floats;
       // thread <-> state part: upstream gradient, variance statistic
@@ -746,24 +723,14 @@ struct RbfMmaBwdPolicy : RbfPolicy<DP_, 2> {
         v = warp_sum(v);
         if (lane == 0) atomicAdd(&sm.dvar[k], v);
       }
-      __syncwarp();
-      float Ak[NT][2], Es[NT][2], Q[NT][NB][4];
+      float sb, isb, Ak[NT][2], u[NT][2], Es[NT][2], Q[NT][NB][4];
+      pow2_scales(sm.pmax[k], sb, isb);
+      C::quad_A(sm, hdr_k, gs + 64, lane, gq, Ak);     // (contains the __syncwarp that publishes gs)
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          float s = 0.f;
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int d = 8 * ks + 4 * j + tq;
-              const float xv = __uint_as_float(Ah[t][ks][h + 2 * j]) + __uint_as_float(Al[t][ks][h + 2 * j]);
-              if (d < DP) s = fmaf(hdr_k[d] * xv, xv, s);
-            }
-          s += __shfl_xor_sync(0xffffffffu, s, 1);
-          s += __shfl_xor_sync(0xffffffffu, s, 2);
-          Ak[t][h] = s;
+          u[t][h] = inv[t][h] * isb;
           Es[t][h] = 0.f;
         }
 #pragma unroll
@@ -771,14 +738,15 @@ struct RbfMmaBwdPolicy : RbfPolicy<DP_, 2> {
 #pragma unroll
           for (int i = 0; i < 4; ++i) Q[t][nb][i] = 0.f;
       }
+      const bool plain = C::all_unit(u);
       for (int c = 0; c < g.NCs; ++c) {
         const float* chunk = pipe.acquire(g.cg);
-        rows_bwd_mma<false>(chunk, min(g.RCs, g.SP2 - c * g.RCs), Ah, Al, Ak, Q, Es, gq, tq);
+        rows_bwd_mma<false>(chunk, min(g.RCs, g.SP2 - c * g.RCs), plain, sb, Ah, Al, u, Ak, Q, Es, gq, tq);
         pipe.release(g.cg, total);
       }
       for (int c = 0; c < g.NCm; ++c) {
         const float* chunk = pipe.acquire(g.cg);
-        rows_bwd_mma<true>(chunk, min(g.RCm, g.MP2 - c * g.RCm), Ah, Al, Ak, Q, Es, gq, tq);
+        rows_bwd_mma<true>(chunk, min(g.RCm, g.MP2 - c * g.RCm), plain, sb, Ah, Al, u, Ak, Q, Es, gq, tq);
         pipe.release(g.cg, total);
       }
       // dx_k[state][d] = g_k (Q + 2 c_d x_d Es) in the C layout (rows gq + 8 h, dims 8 nb + 2 tq + j); fold into dx and the lengthscale statistic
