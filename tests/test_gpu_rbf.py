@@ -325,20 +325,27 @@ def test_tensor_path_extreme_magnitudes(scale_x, scale_ell):
              phase=f64(rs.uniform(size=(1, S, D)) * 2 * np.pi), w=f64(rs.normal(size=(S, D))))
     c["omega"] = OF.make_omega(c["eps"], c["ell"], "rbf_dimwise")
     x64 = f64(scale_x * rs.normal(size=(N, D)))
-    idx = rs.choice(N, size=400, replace=False)
+    for k in ("Z", "nu", "ell", "var"):
+        c[k].requires_grad_(True)
+    c["omega"] = OF.make_omega(c["eps"], c["ell"], "rbf_dimwise")
     s = gpu_sample(c)
+    for k in ("Z", "nu", "ell", "var"):
+        s[k].requires_grad_(True)
     x = x64.float().cuda()[None].requires_grad_(True)
     f, _ = _field(s, x, "rbf_dimwise")
     assert torch.isfinite(f).all()
-    xs = x64[idx].clone().requires_grad_(True)
+    xs = x64.clone().requires_grad_(True)
     truth = OF.field(xs, c)
     # the phase of the features is |x . omega| ~ 4 / scale_ell: fp32 itself resolves cos only to ~1e-7 x that
     tol = max(FIELD_TOL, 3e-6 / scale_ell)
-    assert rel(f[0, idx], truth) < tol, (rel(f[0, idx], truth), tol)
-    gout = torch.zeros(1, N, D, device="cuda")
-    gsel = torch.tensor(rs.normal(size=(400, D)), dtype=torch.float32)
-    gout[0, idx] = gsel.cuda()
-    f.backward(gout)
-    (want,) = torch.autograd.grad((truth * gsel.double()).sum(), xs)
-    assert torch.isfinite(x.grad).all()
-    assert rel(x.grad[0, idx], want) < max(GRAD_TOL, 3e-5 / scale_ell)
+    assert rel(f[0], truth) < tol, (rel(f[0], truth), tol)
+    gsel = torch.tensor(rs.normal(size=(N, D)), dtype=torch.float32)
+    f.backward(gsel.cuda()[None])
+    want = torch.autograd.grad((truth * gsel.double()).sum(), [xs, c["Z"], c["nu"], c["ell"], c["var"]])
+    got = [x.grad[0], s["Z"].grad, s["nu"].grad[0], s["ell"].grad, s["var"].grad]
+    gtol = max(GRAD_TOL, 3e-5 / scale_ell)
+    for nm, a, b in zip(("dx", "dZ", "dnu", "dell", "dvar"), got, want):
+        assert torch.isfinite(a).all(), nm
+        e = rel(a, b)
+        print("extreme (%g, %g) %s: %.2e (tol %.1e)" % (scale_x, scale_ell, nm, e, gtol))
+        assert e < gtol, (nm, e, gtol)

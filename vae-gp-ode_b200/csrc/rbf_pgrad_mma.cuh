@@ -21,7 +21,7 @@ namespace gpode {
 
 constexpr int kPgmThreads = 256;   // 8 warps
 constexpr int kPgmBatch = 512;     // evaluations per shared-memory batch (dynamic shared memory: 2 x DK x (batch + 8) floats + offsets)
-inline int rbf_pgrad_mma_smem_bytes(int KS) { return (2 * 8 * KS * (kPgmBatch + 8) + (kPgmBatch + 8) + kPgmBatch + 8 * KS) * 4; }
+inline int rbf_pgrad_mma_smem_bytes(int KS) { return (3 * 8 * KS * (kPgmBatch + 8) + 2 * (kPgmBatch + 8) + kPgmBatch + 8 * KS) * 4; }
 
 // TF32 head of x by truncation (one LOP3; cvt.rna.tf32 is emulated with 4 ALU instructions on sm_100a): the remainder
 // x - head is exact in fp32 and < 2^-10 |x|, its own truncation by the tensor core leaves ~2^-20 relative
@@ -47,6 +47,11 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
   float* s_A = s_tl + DK * TS;       // [NE + 8]: the software-pipelined theta of the block after the last reads 8 unused offsets
   float* s_g = s_A + NE + 8;         // [NE]
   float* s_c = s_g + NE;             // [DK]
+  // product 1 runs as fp16 m16n8k16 (two-way split, see rbf_kernels.cuh): the staged states once more as packed fp16 pairs
+  // [dim pair][e] (head / 2^11-scaled remainder) of x scaled by a power of two per evaluation, and the un-scaling factor per evaluation
+  uint32_t* s_xh2 = reinterpret_cast<uint32_t*>(s_c + DK);
+  uint32_t* s_xl2 = s_xh2 + (DK / 2) * TS;
+  float* s_u = reinterpret_cast<float*>(s_xl2 + (DK / 2) * TS);   // [NE + 8]
   const int k = blockIdx.y, l = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
@@ -57,9 +62,12 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
   const int chunk_id = blockIdx.x / n_mblk;
   const int m_base = (blockIdx.x - chunk_id * n_mblk) * per_cta + warp * 16 * MT;
 
-  // loop-invariant A fragments of product 1: G[m][d] split into head / remainder, and H_m
-  uint32_t Gh[MT][KS][4], Gl[MT][KS][4];
+  // loop-invariant A fragments of product 1 (fp16 pairs): a[h + 2 j] = sb G[m = gq + 8 h][dims 2 tq + 8 j, + 1], and H_m
+  static_assert(KS == 2, "the fp16 form of product 1 covers the 16 padded input dims in one m16n8k16 k-step");
+  uint32_t Gh[MT][4], Gl[MT][4];
   float Hm[MT][2];
+  float sb, isb;
+  pow2_scales(rbf_maxabs_ptr(a.packed, g, l)[k], sb, isb);
   const float* rows = rbf_rows_ptr(a.packed, g, l) + (static_cast<size_t>(k) * (g.SP2 + g.MP2) + g.SP2) * g.row_floats;
   auto packed_at = [&](int m, int q) -> float {   // q < DP: G_md, q == DP: H_m ; rows hold {even m, odd m} float2 pairs
     if (m >= 2 * g.MP2) return 0.f;
@@ -72,15 +80,11 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
       const int m = m_base + mt * 16 + gq + 8 * h;
       Hm[mt][h] = packed_at(m, g.DP);
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int d = 8 * ks + 4 * j + tq;                            // MMA k index (ks, tq + 4 j) <-> input dim d
-          const float v = d < g.DP ? packed_at(m, d) : 0.f;
-          const uint32_t hi_ = tf32_hi(v);
-          Gh[mt][ks][h + 2 * j] = hi_;
-          Gl[mt][ks][h + 2 * j] = __float_as_uint(v - __uint_as_float(hi_));
-        }
+      for (int j = 0; j < 2; ++j) {
+        const int d = 2 * tq + 8 * j;
+        const float v0 = d < g.DP ? packed_at(m, d) : 0.f, v1 = d + 1 < g.DP ? packed_at(m, d + 1) : 0.f;
+        split_h2(v0 * sb, v1 * sb, Gh[mt][h + 2 * j], Gl[mt][h + 2 * j]);
+      }
     }
   }
   float PG[MT][KS][4], dnu[MT][2];
@@ -100,6 +104,7 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
   __syncthreads();
   for (long e0 = e_lo; e0 < e_hi; e0 += NE) {
     // ---- stage a batch: thread <-> evaluation(s) ----
+    int plain_here = 1;
     {
       for (int idx = tid; idx < NE; idx += kPgmThreads) {
         const long e = e0 + idx;
@@ -109,43 +114,64 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
           te = e / g.N;
           s = static_cast<long>(l) * g.N + (e - te * g.N);
         }
-        float part = 0.f;
+        float part = 0.f, xv[DK], mx = 0.f;
 #pragma unroll
         for (int d = 0; d < DK; ++d) {
           const float v = (ok && d < g.D_in) ? a.xsave[(te * g.D_in + d) * g.NL + s] : 0.f;
+          xv[d] = v;
+          mx = fmaxf(mx, fabsf(v));
           part = fmaf(s_c[d] * v, v, part);
           const float vh = __uint_as_float(tf32_hi(v)), vl = v - vh;
           s_th[d * TS + idx] = vh;
           s_tl[d * TS + idx] = vl;
         }
+        float sa, isa;
+        pow2_scales(mx, sa, isa);
+#pragma unroll
+        for (int dp = 0; dp < DK / 2; ++dp) split_h2(xv[2 * dp] * sa, xv[2 * dp + 1] * sa, s_xh2[dp * TS + idx], s_xl2[dp * TS + idx]);
+        s_u[idx] = isa * isb;
+        plain_here = plain_here && (isa * isb == 1.f);
         s_A[idx] = part;
         s_g[idx] = ok ? a.gsave[(te * g.D_out + k) * g.NL + s] : 0.f;     // g = 0 switches padded evaluations off
       }
     }
-    __syncthreads();
+    const int plain = __syncthreads_and(plain_here);   // every scale of this batch is 1 (CTA uniform): offsets as accumulator init
     const int nblk = static_cast<int>(((e_hi - e0 < NE ? e_hi - e0 : NE) + 7) / 8);
-    // theta^T of block `eb` for every m tile: MMA k index (ks, tq + 4 j) <-> input dim d = 8 ks + 4 j + tq, column n = gq <-> evaluation eb + gq
-    auto theta = [&](int eb, float (&th)[MT][4]) {   // th = H_m + A_e + G.x (offsets enter as the initial accumulator)
+    // theta^T of block `eb` for every m tile (3 fp16 MMAs each): th = H_m + A_e + u_e (G' . x'), column n = gq <-> evaluation eb + gq
+    auto theta = [&](int eb, float (&th)[MT][4]) {
       const float2 Ae = *reinterpret_cast<const float2*>(s_A + eb + 2 * tq);      // evaluations eb + 2 tq, + 1 (C columns)
-      uint32_t bh[KS][2], bl[KS][2];
+      uint32_t bh[2], bl[2];
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
+      for (int j = 0; j < 2; ++j) {
+        bh[j] = s_xh2[(tq + 4 * j) * TS + eb + gq];     // dims 2 tq + 8 j, + 1 of evaluation eb + gq
+        bl[j] = s_xl2[(tq + 4 * j) * TS + eb + gq];
+      }
+      if (plain) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          bh[ks][j] = __float_as_uint(s_th[(8 * ks + 4 * j + tq) * TS + eb + gq]);
-          bl[ks][j] = __float_as_uint(s_tl[(8 * ks + 4 * j + tq) * TS + eb + gq]);
+        for (int mt = 0; mt < MT; ++mt) {
+          float x2[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_f16_sweep(x2, Gl[mt], bh[0], bh[1]);
+          mma_f16_sweep(x2, Gh[mt], bl[0], bl[1]);
+          th[mt][0] = Hm[mt][0] + Ae.x;
+          th[mt][1] = Hm[mt][0] + Ae.y;
+          th[mt][2] = Hm[mt][1] + Ae.x;
+          th[mt][3] = Hm[mt][1] + Ae.y;
+          mma_f16_sweep(th[mt], Gh[mt], bh[0], bh[1]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) th[mt][i] = fmaf(x2[i], kLoScale, th[mt][i]);
         }
+      } else {
+        const float2 ue = *reinterpret_cast<const float2*>(s_u + eb + 2 * tq);
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        th[mt][0] = Hm[mt][0] + Ae.x;
-        th[mt][1] = Hm[mt][0] + Ae.y;
-        th[mt][2] = Hm[mt][1] + Ae.x;
-        th[mt][3] = Hm[mt][1] + Ae.y;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          mma_tf32(th[mt], Gl[mt][ks], bh[ks][0], bh[ks][1]);
-          mma_tf32(th[mt], Gh[mt][ks], bl[ks][0], bl[ks][1]);
-          mma_tf32(th[mt], Gh[mt][ks], bh[ks][0], bh[ks][1]);
+        for (int mt = 0; mt < MT; ++mt) {
+          float x2[4] = {0.f, 0.f, 0.f, 0.f}, c[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_f16_sweep(x2, Gl[mt], bh[0], bh[1]);
+          mma_f16_sweep(x2, Gh[mt], bl[0], bl[1]);
+          mma_f16_sweep(c, Gh[mt], bh[0], bh[1]);
+          th[mt][0] = fmaf(x2[0], ue.x * kLoScale, fmaf(c[0], ue.x, Hm[mt][0] + Ae.x));
+          th[mt][1] = fmaf(x2[1], ue.y * kLoScale, fmaf(c[1], ue.y, Hm[mt][0] + Ae.y));
+          th[mt][2] = fmaf(x2[2], ue.x * kLoScale, fmaf(c[2], ue.x, Hm[mt][1] + Ae.x));
+          th[mt][3] = fmaf(x2[3], ue.y * kLoScale, fmaf(c[3], ue.y, Hm[mt][1] + Ae.y));
         }
       }
     };
