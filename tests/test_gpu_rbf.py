@@ -346,6 +346,9 @@ def test_tensor_path_extreme_magnitudes(scale_x, scale_ell):
     gtol = max(GRAD_TOL, 3e-5 / scale_ell)
     for nm, a, b in zip(("dx", "dZ", "dnu", "dell", "dvar"), got, want):
         assert torch.isfinite(a).all(), nm
+        if b.norm() < 1e-30:      # K(x, Z) underflows fp32 at this lengthscale: the gradient through it is zero to fp32
+            assert a.norm() < 1e-30, nm
+            continue
         e = rel(a, b)
         print("extreme (%g, %g) %s: %.2e (tol %.1e)" % (scale_x, scale_ell, nm, e, gtol))
         assert e < gtol, (nm, e, gtol)
