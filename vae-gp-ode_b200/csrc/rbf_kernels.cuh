@@ -12,6 +12,7 @@
 // the scalar-broadcast operand, the parameters come as {even, odd} pairs.
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -371,6 +372,15 @@ __device__ __forceinline__ void mma_f16_sweep(float (&c)[4], const uint32_t (&a)
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_bf16_sweep(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo_, float hi_) {   // lo_ -> bits 0..15 (the even k index)
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo_, hi_);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 // (v0, v1) -> packed fp16 heads and packed fp16 remainders.  The remainders are stored scaled by 2^11 (exact) so that they stay
 // fp16-normal wherever the head is; the cross products are accumulated separately and folded in with 2^-11 (kLoScale).
 constexpr float kLoUp = 2048.f, kLoScale = 1.f / 2048.f;
@@ -610,9 +620,11 @@ struct RbfMmaFwdPolicy : RbfPolicy<DP_, 2> {
 // =============================================================================================
 // Reverse-sweep VJP on the warp-level tensor path for D > 8: same tiling as RbfMmaFwdPolicy.  Per block of 8 rows and state
 // tile: theta (3 fp16 MMAs, as in the forward), t = weight * (-sin | 2^theta) on the C fragment, and the second product
-// Q[state, d] += t P[row, d] (6 MMAs, 3xTF32 m16n8k8: t spans the dynamic range of the exponentials, so it keeps the fp32
-// exponent) with the C fragment reused as the A fragment (row order permuted consistently in B, no shuffles) -- the two
-// D-length contractions of the FFMA kernel.  dx_k = g_k (Q + 2 c_k x Es) is folded into the shared dx / lengthscale
+// Q[state, d] += t P[row, d] with the C fragment reused as the A fragment (row order permuted consistently in B, no shuffles):
+// t spans the dynamic range of the exponentials, so it keeps the fp32 exponent -- head x head is one TF32 m16n8k8, the two
+// cross terms rem(t) P + t rem(P) share ONE bf16 m16n8k16 (k = 8 rows x {remainder, value}; bf16 has the fp32 exponent and
+// the cross terms only need 8 of their bits: 2^-19 relative overall) -- 4 MMAs per tile instead of the 6 of 3xTF32.  These
+// are the two D-length contractions of the FFMA kernel.  dx_k = g_k (Q + 2 c_k x Es) is folded into the shared dx / lengthscale
 // statistics once per output dimension.
 // =============================================================================================
 template <int DP_>
@@ -638,7 +650,7 @@ struct RbfMmaBwdPolicy : RbfPolicy<DP_, 2> {
     }
     // B of the second product (3xTF32: t has the dynamic range of the exponentials): MMA k index tq <-> row unit 2 tq, k = tq + 4 <-> unit
     // 2 tq + 1 (both parities of pair row tq); column gq <-> dim gq + 8 nb
-    uint32_t ph[NB][2], pl[NB][2];
+    uint32_t ph[NB][2], pc[NB][2];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
       const int d = gq + 8 * nb;
@@ -646,8 +658,9 @@ struct RbfMmaBwdPolicy : RbfPolicy<DP_, 2> {
       if (okc && d < DP) pv = *reinterpret_cast<const float2*>(rows + tq * ROWF + 2 * d);
       ph[nb][0] = __float_as_uint(pv.x) & 0xFFFFE000u;
       ph[nb][1] = __float_as_uint(pv.y) & 0xFFFFE000u;
-      pl[nb][0] = __float_as_uint(pv.x - __uint_as_float(ph[nb][0]));
-      pl[nb][1] = __float_as_uint(pv.y - __uint_as_float(ph[nb][1]));
+      // correction operand (bf16 k16): k 2 tq, 2 tq + 1 <-> P of units 2 tq, 2 tq + 1; k + 8 <-> their TF32 remainders
+      pc[nb][0] = pack_bf16(pv.x, pv.y);
+      pc[nb][1] = pack_bf16(pv.x - __uint_as_float(ph[nb][0]), pv.y - __uint_as_float(ph[nb][1]));
     }
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
@@ -666,16 +679,21 @@ struct RbfMmaBwdPolicy : RbfPolicy<DP_, 2> {
       }
       // A fragment of the second product: a0 (row gq, k tq) = t0, a1 (row gq + 8, k tq) = t2, a2 (gq, tq + 4) = t1, a3 = t3
       const float v4[4] = {t0, t2, t1, t3};
-      uint32_t ah[4], al[4];
+      uint32_t ah[4], ac[4];
+      float al[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         ah[i] = __float_as_uint(v4[i]) & 0xFFFFE000u;
-        al[i] = __float_as_uint(v4[i] - __uint_as_float(ah[i]));
+        al[i] = v4[i] - __uint_as_float(ah[i]);
       }
+      // correction fragment: (row gq | gq + 8, k 2 tq, 2 tq + 1) = remainders of t, (k + 8) = t itself
+      ac[0] = pack_bf16(al[0], al[2]);
+      ac[1] = pack_bf16(al[1], al[3]);
+      ac[2] = pack_bf16(t0, t1);
+      ac[3] = pack_bf16(t2, t3);
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
-        mma_tf32_sweep(Q[t][nb], al, ph[nb][0], ph[nb][1]);
-        mma_tf32_sweep(Q[t][nb], ah, pl[nb][0], pl[nb][1]);
+        mma_bf16_sweep(Q[t][nb], ac, pc[nb][0], pc[nb][1]);
         mma_tf32_sweep(Q[t][nb], ah, ph[nb][0], ph[nb][1]);
       }
     }

@@ -42,9 +42,12 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
   // [d][e] TF32 head / remainder of the staged states: B operand of BOTH products (row stride == 8 mod 32 floats makes the
   // per-lane LDS.32 of product 1 (bank 8 tq + gq) and the LDS.64 of product 2 (bank 8 gq + 2 tq per half warp) conflict free)
   extern __shared__ __align__(16) float pgm_smem[];
+  constexpr int TSH = NE / 2 + 4;            // row stride of the evaluation-pair copies (== 4 mod 32: conflict-free LDS.32 at gq * TSH + tq)
   float* s_th = pgm_smem;
-  float* s_tl = s_th + DK * TS;
-  float* s_A = s_tl + DK * TS;       // [NE + 8]: the software-pipelined theta of the block after the last reads 8 unused offsets
+  // cross-term operand of product 2 (bf16 m16n8k16): [d][evaluation pair] packed bf16 of the states / of their TF32 remainders
+  uint32_t* s_pc0 = reinterpret_cast<uint32_t*>(s_th + DK * TS);
+  uint32_t* s_pc1 = s_pc0 + DK * TSH;
+  float* s_A = reinterpret_cast<float*>(s_pc1 + DK * TSH);   // [NE + 8]: the software-pipelined theta of the block after the last reads 8 unused offsets
   float* s_g = s_A + NE + 8;         // [NE]
   float* s_c = s_g + NE;             // [DK]
   // product 1 runs as fp16 m16n8k16 (two-way split, see rbf_kernels.cuh): the staged states once more as packed fp16 pairs
@@ -123,7 +126,11 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
           part = fmaf(s_c[d] * v, v, part);
           const float vh = __uint_as_float(tf32_hi(v)), vl = v - vh;
           s_th[d * TS + idx] = vh;
-          s_tl[d * TS + idx] = vl;
+          const float vn = __shfl_xor_sync(0xffffffffu, v, 1), vln = __shfl_xor_sync(0xffffffffu, vl, 1);   // evaluation idx + 1 (NE % 256 == 0: full warps)
+          if (!(idx & 1)) {
+            s_pc0[d * TSH + (idx >> 1)] = pack_bf16(v, vn);
+            s_pc1[d * TSH + (idx >> 1)] = pack_bf16(vl, vln);
+          }
         }
         float sa, isa;
         pow2_scales(mx, sa, isa);
@@ -186,13 +193,14 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
       theta(eb + 8, thB);
       const float2 ge = *reinterpret_cast<const float2*>(s_g + eb + 2 * tq);      // evaluations eb + 2 tq, + 1 (C columns)
       // B fragments of product 2: rows = evaluations (MMA k = tq <-> e = 2 tq, k = tq + 4 <-> e = 2 tq + 1), cols c = gq + 8 cb
-      uint32_t xh2[KS][2], xl2[KS][2];
+      // cross terms (bf16 k16): k = 2 tq, 2 tq + 1 <-> x of those evaluations (times the remainders of GE), k + 8 <-> the TF32 remainders of x
+      uint32_t xh2[KS][2], xc[KS][2];
 #pragma unroll
       for (int cb = 0; cb < KS; ++cb) {
         const float2 vh = *reinterpret_cast<const float2*>(s_th + (gq + 8 * cb) * TS + eb + 2 * tq);
-        const float2 vl = *reinterpret_cast<const float2*>(s_tl + (gq + 8 * cb) * TS + eb + 2 * tq);
         xh2[cb][0] = __float_as_uint(vh.x); xh2[cb][1] = __float_as_uint(vh.y);
-        xl2[cb][0] = __float_as_uint(vl.x); xl2[cb][1] = __float_as_uint(vl.y);
+        xc[cb][0] = s_pc0[(gq + 8 * cb) * TSH + (eb >> 1) + tq];
+        xc[cb][1] = s_pc1[(gq + 8 * cb) * TSH + (eb >> 1) + tq];
       }
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
@@ -203,17 +211,22 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
         dnu[mt][0] += ge00 + ge01;
         dnu[mt][1] += ge10 + ge11;
         // A fragment of product 2: a0 (row gq, k tq) = ge00, a1 (row gq + 8, k tq) = ge10, a2 (gq, tq + 4) = ge01, a3 = ge11
-        uint32_t ah[4], al[4];
+        uint32_t ah[4], ac[4];
+        float al[4];
         const float v4[4] = {ge00, ge10, ge01, ge11};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           ah[i] = tf32_hi(v4[i]);
-          al[i] = __float_as_uint(v4[i] - __uint_as_float(ah[i]));
+          al[i] = v4[i] - __uint_as_float(ah[i]);
         }
+        // cross-term fragment: (row gq | gq + 8, k 2 tq, 2 tq + 1) = remainders of GE, (k + 8) = GE
+        ac[0] = pack_bf16(al[0], al[2]);
+        ac[1] = pack_bf16(al[1], al[3]);
+        ac[2] = pack_bf16(ge00, ge01);
+        ac[3] = pack_bf16(ge10, ge11);
 #pragma unroll
         for (int cb = 0; cb < KS; ++cb) {
-          mma_tf32(PG[mt][cb], al, xh2[cb][0], xh2[cb][1]);
-          mma_tf32(PG[mt][cb], ah, xl2[cb][0], xl2[cb][1]);
+          mma_bf16_sweep(PG[mt][cb], ac, xc[cb][0], xc[cb][1]);
           mma_tf32(PG[mt][cb], ah, xh2[cb][0], xh2[cb][1]);
         }
       }
