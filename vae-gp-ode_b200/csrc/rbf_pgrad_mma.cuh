@@ -106,27 +106,41 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
   const long e_hi = e_lo + per < total ? e_lo + per : total;
   __syncthreads();
   for (long e0 = e_lo; e0 < e_hi; e0 += NE) {
-    // ---- stage a batch: thread <-> evaluation(s) ----
+    // ---- stage a batch: thread <-> evaluations tid, tid + 256 (all global loads first, then the splits) ----
     int plain_here = 1;
     {
-      for (int idx = tid; idx < NE; idx += kPgmThreads) {
-        const long e = e0 + idx;
-        const bool ok = e < e_hi;
-        long te = 0, s = 0;
-        if (ok) {
-          te = e / g.N;
-          s = static_cast<long>(l) * g.N + (e - te * g.N);
+      constexpr int PER = NE / kPgmThreads;
+      static_assert(NE % kPgmThreads == 0, "full warps in the staging shuffles");
+      float xv[PER][DK], gv[PER];
+      // (te, n) of the first evaluation of the batch by one division; the threads step from there
+      const long te0 = e0 / g.N;
+      const long n0 = e0 - te0 * g.N;
+#pragma unroll
+      for (int p = 0; p < PER; ++p) {
+        const int idx = tid + p * kPgmThreads;
+        const bool ok = e0 + idx < e_hi;
+        long te = te0, n = n0 + idx;
+        while (n >= g.N) {
+          n -= g.N;
+          ++te;
         }
-        float part = 0.f, xv[DK], mx = 0.f;
+        const float* xp = a.xsave + (te * g.D_in) * g.NL + static_cast<long>(l) * g.N + n;
+#pragma unroll
+        for (int d = 0; d < DK; ++d) xv[p][d] = (ok && d < g.D_in) ? xp[static_cast<long>(d) * g.NL] : 0.f;
+        gv[p] = ok ? a.gsave[(te * g.D_out + k) * g.NL + static_cast<long>(l) * g.N + n] : 0.f;     // g = 0 switches padded evaluations off
+      }
+#pragma unroll
+      for (int p = 0; p < PER; ++p) {
+        const int idx = tid + p * kPgmThreads;
+        float part = 0.f, mx = 0.f;
 #pragma unroll
         for (int d = 0; d < DK; ++d) {
-          const float v = (ok && d < g.D_in) ? a.xsave[(te * g.D_in + d) * g.NL + s] : 0.f;
-          xv[d] = v;
+          const float v = xv[p][d];
           mx = fmaxf(mx, fabsf(v));
           part = fmaf(s_c[d] * v, v, part);
           const float vh = __uint_as_float(tf32_hi(v)), vl = v - vh;
           s_th[d * TS + idx] = vh;
-          const float vn = __shfl_xor_sync(0xffffffffu, v, 1), vln = __shfl_xor_sync(0xffffffffu, vl, 1);   // evaluation idx + 1 (NE % 256 == 0: full warps)
+          const float vn = __shfl_xor_sync(0xffffffffu, v, 1), vln = __shfl_xor_sync(0xffffffffu, vl, 1);   // evaluation idx + 1
           if (!(idx & 1)) {
             s_pc0[d * TSH + (idx >> 1)] = pack_bf16(v, vn);
             s_pc1[d * TSH + (idx >> 1)] = pack_bf16(vl, vln);
@@ -135,11 +149,11 @@ __global__ void __launch_bounds__(kPgmThreads, (MT == 1 ? 3 : 2)) k_rbf_pgrad_mm
         float sa, isa;
         pow2_scales(mx, sa, isa);
 #pragma unroll
-        for (int dp = 0; dp < DK / 2; ++dp) split_h2(xv[2 * dp] * sa, xv[2 * dp + 1] * sa, s_xh2[dp * TS + idx], s_xl2[dp * TS + idx]);
+        for (int dp = 0; dp < DK / 2; ++dp) split_h2(xv[p][2 * dp] * sa, xv[p][2 * dp + 1] * sa, s_xh2[dp * TS + idx], s_xl2[dp * TS + idx]);
         s_u[idx] = isa * isb;
         plain_here = plain_here && (isa * isb == 1.f);
         s_A[idx] = part;
-        s_g[idx] = ok ? a.gsave[(te * g.D_out + k) * g.NL + s] : 0.f;     // g = 0 switches padded evaluations off
+        s_g[idx] = gv[p];
       }
     }
     const int plain = __syncthreads_and(plain_here);   // every scale of this batch is 1 (CTA uniform): offsets as accumulator init
