@@ -296,8 +296,9 @@ def run_ours(args):
     roof = {"bound": "fp32_fma" if t_fma >= t_sfu else "sfu", "achieved": round(achieved_tflops, 3), "peak": round(fp32_peak / 1e12, 2),
             "unit": "TFLOP/s", "frac": round(bound_s, 4), "traffic": None,
             "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json (%s); not an HBM-bound path" % peak_src,
-            "note": ("D > 8: the D-length dot products run on the warp-level tensor path (3xTF32 mma.sync, fp32 accumulate, 278 TFLOP/s "
-                     "measured peak); frac is still the ALGORITHMIC fp32 work over the FP32-pipe peak" if w["D_in"] > 8 and w["variant"] != "df"
+            "note": ("D > 8: the D-length dot products run on the warp-level tensor path (mma.sync: two-way fp16 split for theta, TF32 head + "
+                     "bf16 cross terms for the second products, fp32 accumulate); frac is still the ALGORITHMIC fp32 work over the FP32-pipe "
+                     "peak, so a call can exceed 1" if w["D_in"] > 8 and w["variant"] != "df"
                      else "FP32 / MUFU pipes only"),
             "sfu_achieved_tops": round(work["sfu"] * per_gpu_rate / 1e12, 4), "sfu_peak_tops": round(sfu_peak / 1e12, 3),
             "sfu_frac": round(work["sfu"] * per_gpu_rate / sfu_peak, 4),
