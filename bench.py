@@ -33,6 +33,12 @@ for p in (ROOT, os.path.join(ROOT, "vae-gp-ode_b200")):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (the reverse sweep), per launch, from the ncu capture named here
+# (one B200; the stage saves make it ~9x the algorithmic 192 B per trajectory-step, and still < 1 % of the HBM peak)
+TRAFFIC = {
+    "cfg5_rbf_d16_m512_t64_rk4": (54192663552, "k_rollout_bwd<RbfMmaBwdPolicy<16>>, profiles/traffic_r01_cfg5_default.txt"),
+}
+
 WORKLOADS = {
     # BASELINE.json configs[4]; per GPU
     "cfg5_rbf_d16_m512_t64_rk4": dict(variant="rbf_dimwise", kernel="RBF", N=65536, L=8, D_in=16, D_out=16, M=512, S=256, T=64,
@@ -294,7 +300,8 @@ def run_ours(args):
     bound_s = max(t_fma, t_sfu) * per_gpu_rate   # fraction of the binding pipe's peak
     achieved_tflops = work["flops"] * per_gpu_rate / 1e12
     roof = {"bound": "fp32_fma" if t_fma >= t_sfu else "sfu", "achieved": round(achieved_tflops, 3), "peak": round(fp32_peak / 1e12, 2),
-            "unit": "TFLOP/s", "frac": round(bound_s, 4), "traffic": None,
+            "unit": "TFLOP/s", "frac": round(bound_s, 4), "traffic": TRAFFIC.get(args.workload, (None, None))[0],
+            "traffic_source": TRAFFIC.get(args.workload, (None, None))[1],
             "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json (%s); not an HBM-bound path" % peak_src,
             "note": ("D > 8: the D-length dot products run on the warp-level tensor path (mma.sync: two-way fp16 split for theta, TF32 head + "
                      "bf16 cross terms for the second products, fp32 accumulate); frac is still the ALGORITHMIC fp32 work over the FP32-pipe "

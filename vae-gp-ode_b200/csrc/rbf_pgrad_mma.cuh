@@ -1,16 +1,17 @@
-// RBF parameter gradients on the warp-level tensor path (mma.sync m16n8k8, 3xTF32), sm_100a.
+// RBF parameter gradients on the warp-level tensor path (mma.sync), sm_100a.
 //
 //   dnu'_m = sum_e g_e E_em ,   pg_mc = sum_e g_e E_em x_ec ,   E_em = 2^(A_e + H_m + sum_d x_ed G_md)
 // for one (sample l, output k); e runs over every state evaluation of the rollout.  Both contractions are
 // GEMM-shaped (theta^T = G X^T with K = D; PG = GE X with K = evaluations), the exponential sits between them:
 // the structure of a fused attention backward.  Each warp owns 16*MT inducing points (MMA rows); evaluations
 // stream through shared memory in batches and are walked 8 at a time (MMA columns):
-//   1. theta^T (16 m x 8 e) = G (16 x D) X^T (D x 8): 3 MMAs per 8 input dims (hi*hi + hi*lo + lo*hi, "3xTF32":
-//      operands are split into a TF32 head and an fp32 remainder, products accumulate in fp32 -> ~2^-21 relative)
+//   1. theta^T (16 m x 8 e) = G (16 x D) X^T (D x 8): ONE k-step of m16n8k16 with a two-way fp16 split (head + 2^11-scaled
+//      remainder, power-of-two block scales per evaluation and per output dimension, see rbf_kernels.cuh): 3 MMAs
 //   2. GE = g_e 2^(theta + H_m + A_e) on the C fragment (4 values per lane), MUFU.EX2
 //   3. the C fragment IS the A fragment of the second product (rows m, contraction over the 8 evaluations, with
-//      the evaluation order permuted consistently in the B operand -- no shuffles): PG (16 m x 8 c) += GE X.
-// Per (16 m x 8 e) tile at D = 16: 12 HMMA + 4 MUFU per lane + ~25 FMA/ALU-pipe instructions, against 140
+//      the evaluation order permuted consistently in the B operand -- no shuffles): PG (16 m x 8 c) += GE X as
+//      TF32 head x head (m16n8k8) + ONE bf16 m16n8k16 for both cross terms rem(GE) X + GE rem(X): GE keeps the fp32 exponent
+// Per (16 m x 8 e) tile at D = 16: 7 HMMA + 4 MUFU per lane + ~40 FMA/ALU-pipe instructions, against 140
 // FMA-pipe cycles for the same tile on the FFMA path (k_rbf_pgrad): the tensor pipe takes the two dot products.
 #pragma once
 
@@ -24,7 +25,7 @@ constexpr int kPgmBatch = 512;     // evaluations per shared-memory batch (dynam
 inline int rbf_pgrad_mma_smem_bytes(int KS) { return (3 * 8 * KS * (kPgmBatch + 8) + 2 * (kPgmBatch + 8) + kPgmBatch + 8 * KS) * 4; }
 
 // TF32 head of x by truncation (one LOP3; cvt.rna.tf32 is emulated with 4 ALU instructions on sm_100a): the remainder
-// x - head is exact in fp32 and < 2^-10 |x|, its own truncation by the tensor core leaves ~2^-20 relative
+// x - head is exact in fp32 and < 2^-10 |x|; it enters the cross-term MMA rounded to bf16 (~2^-19 relative overall)
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
