@@ -234,8 +234,45 @@ def test_wide_inputs_odd_sizes(pgrad, D_in, D_out, M, S, N, monkeypatch):
         assert e < GRAD_TOL, (nm, e)
 
 
-def test_tensor_path_forward_large_batch():
-    """D > 8 and a chip-filling batch select the tensor-path forward (3xTF32 mma.sync, RbfMmaFwdPolicy): field and RK4
+@pytest.fixture(params=["mma", "tc"])
+def fwd_kernel(request, monkeypatch):
+    """the two forward kernels of the D > 8 tensor path: mma.sync (RbfMmaFwdPolicy) and tcgen05 / tensor memory (RbfTcFwdPolicy,
+    the default when its 256-unit operand tiles are < 15 % padding); libgpode reads GPODE_FWD at every call"""
+    monkeypatch.setenv("GPODE_FWD", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("order,D_out,M,S,L", [(1, 16, 300, 260, 1), (2, 8, 512, 256, 2), (1, 16, 97, 513, 1)])
+def test_forward_kernels_ragged_tiles(fwd_kernel, order, D_out, M, S, L):
+    """both forward kernels on shapes whose feature / inducing sections do not fill the 256-unit operand tiles (and one that does),
+    first and second order, several samples per launch, N not a multiple of the CTA: field, prior part and an RK4 rollout against
+    the fp64 oracle on a random subset of a chip-filling batch"""
+    D_in, N = 16, 33001
+    rs = np.random.RandomState(M + S)
+    f64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    Z, ell, var = f64(rs.normal(size=(M, D_in))), f64(1.5 + rs.uniform(size=(D_out, D_in))), f64(0.5 + rs.uniform(size=D_out))
+    caches = []
+    for l in range(L):
+        c = dict(variant="rbf_dimwise", Z=Z, ell=ell, var=var, nu=f64(rs.normal(size=(D_out, M, 1))), eps=f64(rs.normal(size=(D_in, S, D_out))),
+                 phase=f64(rs.uniform(size=(1, S, D_out)) * 2 * np.pi), w=f64(rs.normal(size=(S, D_out))))
+        c["omega"] = OF.make_omega(c["eps"], c["ell"], "rbf_dimwise")
+        caches.append(c)
+    ss = [gpu_sample(c) for c in caches]
+    s = {k: (ss[0][k] if k in ("Z", "ell", "var", "B") else torch.cat([q[k] for q in ss], 0)) for k in ss[0]}
+    x = torch.tensor(1.2 * rs.normal(size=(L, N, D_in)), dtype=torch.float32, device="cuda")
+    f, fp = _field(s, x, "rbf_dimwise")
+    idx = rs.choice(N, size=200, replace=False)
+    ts = 0.1 * torch.arange(4, dtype=torch.float, device="cuda")
+    traj = _gp().gp_rollout(x, ts, s["Z"], s["nu"], s["eps"], s["phase"], s["w"], s["ell"], s["var"], "rbf_dimwise", order, "rk4")
+    for l, c in enumerate(caches):
+        xs = x[l, idx].double().cpu()
+        assert rel(f[l, idx], OF.field(xs, c)) < FIELD_TOL, (fwd_kernel, l)
+        assert rel(fp[l, idx], OF.prior(xs, c)) < FIELD_TOL, (fwd_kernel, l)
+        assert rel(traj[l, idx], OF.rollout(xs, ts.double().cpu(), c, order, "rk4")) < TRAJ_TOL, (fwd_kernel, l)
+
+
+def test_tensor_path_forward_large_batch(fwd_kernel):
+    """D > 8 and a chip-filling batch select the tensor-path forward (RbfMmaFwdPolicy / RbfTcFwdPolicy): field and RK4
     trajectories of 40,000 states against the fp64 oracle on a random subset, plus equality of overlapping small/large launches
     within the field bar (the small launch runs the FFMA kernel)."""
     g = load_golden("rbf_dimwise_d16")
@@ -313,7 +350,7 @@ def test_tensor_path_rollout_backward_large_batch():
 
 
 @pytest.mark.parametrize("scale_x,scale_ell", [(300.0, 60.0), (0.002, 0.02), (30.0, 0.3), (1.0, 0.05)])
-def test_tensor_path_extreme_magnitudes(scale_x, scale_ell):
+def test_tensor_path_extreme_magnitudes(fwd_kernel, scale_x, scale_ell):
     """the fp16 tensor-path dot products are scaled by exact powers of two per state and per output dimension: states and
     lengthscales far from O(1) (row coefficients from 1e-5 to 1e3, |x| up to ~1e3) must neither overflow nor lose the field bar
     where the field is well conditioned; checked against the fp64 oracle on a chip-filling batch (forward and VJP)."""

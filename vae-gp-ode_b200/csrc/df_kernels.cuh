@@ -268,12 +268,14 @@ struct DfPolicy {
   static constexpr int R = R_;
   static constexpr int kThreads = 128;
   static constexpr int kMinBlocks = 3;
+  static constexpr int kStateThreads = 0;
   static constexpr int kThreadsBwd = 128;
   static constexpr int kMinBlocksBwd = D_ <= 6 ? 3 : 2;   // the reverse sweep also carries the D x D lengthscale accumulators
   using Geom = DfGeom;
   using Accum = DfAccum;
   using Smem = DfSmem;
 
+  __device__ static __forceinline__ void finish(Smem&) {}
   __device__ static __forceinline__ Smem carve(float* smem, const Geom& g) {
     Smem s;
     s.bars = reinterpret_cast<uint64_t*>(smem);

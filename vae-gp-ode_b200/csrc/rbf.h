@@ -25,7 +25,23 @@ struct RbfGeom {
 inline size_t rbf_rows_end_floats(const RbfGeom& g) {
   return static_cast<size_t>(g.L) * g.D_out * (g.hdr_floats + static_cast<size_t>(g.SP2 + g.MP2) * g.row_floats);
 }
-inline size_t rbf_packed_floats(const RbfGeom& g) { return rbf_rows_end_floats(g) + (static_cast<size_t>(g.L) * g.D_out + 3) / 4 * 4; }
+// D > 8 only: behind the maxima, the operand tiles of the tcgen05 forward sweep (rbf_fwd_tc.cuh), [L][D_out][blocks] tiles of
+// kTcfRows units: B operand as no-swizzle K-major core matrices (16-byte chunks of 4 consecutive k; chunk c of row r at
+// c * rows * 4 + (r / 8) * 32 + (r % 8) * 4 floats): chunks 0-3 TF32 heads of the 16 coefficients, 4-7 their remainders,
+// 8 = (offset head, offset remainder, 0, 0), 9 = 0; then the kTcfRows weights.  Feature units first, inducing units after.
+constexpr int kTcfRows = 256;
+constexpr int kTcfChunks = 10;
+constexpr int kTcfBFloats = kTcfChunks * kTcfRows * 4;
+constexpr int kTcfTileFloats = kTcfBFloats + kTcfRows;
+__host__ __device__ inline int rbf_tc_blocks_s(const RbfGeom& g) { return (g.S + kTcfRows - 1) / kTcfRows; }
+__host__ __device__ inline int rbf_tc_blocks(const RbfGeom& g) { return rbf_tc_blocks_s(g) + (g.M + kTcfRows - 1) / kTcfRows; }
+inline size_t rbf_tc_floats(const RbfGeom& g) { return g.DP > 8 ? static_cast<size_t>(g.L) * g.D_out * rbf_tc_blocks(g) * kTcfTileFloats : 0; }
+inline size_t rbf_maxabs_floats(const RbfGeom& g) { return (static_cast<size_t>(g.L) * g.D_out + 3) / 4 * 4; }
+inline size_t rbf_packed_floats(const RbfGeom& g) { return rbf_rows_end_floats(g) + rbf_maxabs_floats(g) + rbf_tc_floats(g); }
+__host__ __device__ inline const float* rbf_tc_tiles_ptr(const float* packed, const RbfGeom& g, int l) {
+  return packed + static_cast<size_t>(g.L) * g.D_out * (g.hdr_floats + static_cast<size_t>(g.SP2 + g.MP2) * g.row_floats) +
+         (static_cast<size_t>(g.L) * g.D_out + 3) / 4 * 4 + static_cast<size_t>(l) * g.D_out * rbf_tc_blocks(g) * kTcfTileFloats;
+}
 __host__ __device__ inline const float* rbf_maxabs_ptr(const float* packed, const RbfGeom& g, int l) {
   return packed + static_cast<size_t>(g.L) * g.D_out * (g.hdr_floats + static_cast<size_t>(g.SP2 + g.MP2) * g.row_floats) + static_cast<size_t>(l) * g.D_out;
 }
@@ -103,6 +119,16 @@ inline bool rbf_pgrad_use_mma(const RbfGeom& g) { return g.DP > 8; }
 inline bool rbf_pgrad_use_tc() {
   const char* e = getenv("GPODE_PGRAD");
   return e && e[0] == 't' && e[1] == 'c';
+}
+// Forward sweep at D > 8 once the batch fills the chip: tcgen05 / tensor-memory kernel (rbf_fwd_tc.cuh; 17.8 vs 19.0 ms at config-5
+// shapes) unless its 256-unit operand tiles would be more than 15 % padding, in which case (or with GPODE_FWD=mma) the mma.sync
+// kernel (RbfMmaFwdPolicy) runs.  Both are parity-tested against the oracle; the choice depends on shapes only.
+inline bool rbf_fwd_use_tc(const RbfGeom& g) {
+  if (g.DP <= 8 || static_cast<long>(g.N) * g.L < 32768) return false;
+  const char* e = getenv("GPODE_FWD");
+  if (e && e[0] == 'm') return false;
+  if (e && e[0] == 't') return true;    // (tests: force the tensor-memory kernel whatever the padding)
+  return static_cast<long>(rbf_tc_blocks(g)) * kTcfRows * 100 <= static_cast<long>(g.S + g.M) * 115;
 }
 // inducing points per CTA of the tensor-path parameter-gradient kernel (8 warps x 16 MT rows)
 inline void rbf_pgrad_mma_shape(const RbfGeom& g, int& MT, int& n_mblk) {

@@ -88,12 +88,44 @@ __global__ void k_rbf_pack(const RbfPackArgs a) {
   }
 }
 
+// operand tiles of the tcgen05 forward sweep from the packed rows (layout: rbf.h); thread <-> unit of the tile
+__global__ void k_rbf_pack_tc(const RbfPackArgs a) {
+  const RbfGeom& g = a.g;
+  const int blk = blockIdx.x, k = blockIdx.y, l = blockIdx.z, r = threadIdx.x;
+  const int nbs = rbf_tc_blocks_s(g), nb = rbf_tc_blocks(g);
+  const bool is_m = blk >= nbs;
+  const int unit = (is_m ? blk - nbs : blk) * kTcfRows + r;
+  const bool real = unit < (is_m ? g.M : g.S);
+  const float* row = rbf_rows_ptr(a.packed, g, l) + (static_cast<size_t>(k) * (g.SP2 + g.MP2) + (is_m ? g.SP2 : 0) + (unit >> 1)) * g.row_floats + (unit & 1);
+  float* tile = const_cast<float*>(rbf_tc_tiles_ptr(a.packed, g, l)) + (static_cast<size_t>(k) * nb + blk) * kTcfTileFloats;
+  auto at = [&](int c) { return tile + c * kTcfRows * 4 + (r >> 3) * 32 + (r & 7) * 4; };
+  auto head = [](float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+  for (int c = 0; c < 4; ++c) {
+    float v[4], h[4];
+    for (int i = 0; i < 4; ++i) {
+      const int d = 4 * c + i;
+      v[i] = (real && d < g.DP) ? row[2 * d] : 0.f;
+      h[i] = head(v[i]);
+    }
+    *reinterpret_cast<float4*>(at(c)) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(at(4 + c)) = make_float4(v[0] - h[0], v[1] - h[1], v[2] - h[2], v[3] - h[3]);
+  }
+  const float off = real ? row[2 * g.DP] : 0.f, oh = head(off);
+  *reinterpret_cast<float4*>(at(8)) = make_float4(oh, off - oh, 0.f, 0.f);
+  *reinterpret_cast<float4*>(at(9)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  tile[kTcfBFloats + r] = real ? row[2 * g.DP + 2] : 0.f;
+}
+
 cudaError_t rbf_launch_pack(const RbfPackArgs& a, cudaStream_t st) {
   cudaError_t e0 = cudaMemsetAsync(const_cast<float*>(rbf_maxabs_ptr(a.packed, a.g, 0)), 0, static_cast<size_t>(a.g.L) * a.g.D_out * 4, st);
   if (e0 != cudaSuccess) return e0;
   const int rows = a.g.SP2 + a.g.MP2 + 1;
   dim3 grid((rows + 127) / 128, a.g.D_out, a.g.L);
   k_rbf_pack<<<grid, 128, 0, st>>>(a);
+  if (rbf_fwd_use_tc(a.g)) {
+    dim3 gt(rbf_tc_blocks(a.g), a.g.D_out, a.g.L);
+    k_rbf_pack_tc<<<gt, kTcfRows, 0, st>>>(a);
+  }
   return cudaGetLastError();
 }
 

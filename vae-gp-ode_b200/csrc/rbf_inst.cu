@@ -5,6 +5,7 @@
 #include "rbf_kernels.cuh"
 #include "rbf_pgrad_mma.cuh"
 #include "rbf_pgrad_tc.cuh"
+#include "rbf_fwd_tc.cuh"
 
 #ifndef GPODE_DP
 #error "compile with -DGPODE_DP=<even 2..16>"
@@ -47,9 +48,21 @@ cudaError_t launch_fwd_mma(KernMma kern, const Args& a, cudaStream_t st) {
   return launch_sweep(kern, a, threads, 2, false, st);
 }
 
+// tcgen05 forward sweep (rbf_fwd_tc.cuh): 256 states per CTA, one CTA per SM (all 512 tensor-memory columns)
+template <typename Args, typename KernTc>
+cudaError_t launch_fwd_tc(KernTc kern, const Args& a, cudaStream_t st) {
+  const int smem = rbf_fwd_tc_smem_bytes(a.g);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(static_cast<unsigned>((a.g.N + kFtStates - 1) / kFtStates), static_cast<unsigned>(a.g.L));
+  kern<<<grid, kFtThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 template <>
 cudaError_t rbf_field_fwd_dp<DP>(const RbfFieldFwdArgs& a, cudaStream_t st) {
   if constexpr (DP > 8) {   // (measured at D = 6: 1.17 vs 1.22 ms forward, 2.12 vs 2.10 ms reverse -- no gain below D = 9)
+    if (rbf_fwd_use_tc(a.g)) return launch_fwd_tc(k_field_fwd<RbfTcFwdPolicy<DP>>, a, st);
     if (rbf_fwd_use_mma(a.g)) return launch_fwd_mma(k_field_fwd<RbfMmaFwdPolicy<DP>>, a, st);
   }
   GPODE_DISPATCH_R(k_field_fwd, a, false, st)
@@ -71,6 +84,7 @@ cudaError_t rbf_field_bwd_dp<DP>(const RbfFieldBwdArgs& a, cudaStream_t st) {
 template <>
 cudaError_t rbf_rollout_fwd_dp<DP>(const RbfRolloutFwdArgs& a, cudaStream_t st) {
   if constexpr (DP > 8) {   // (measured at D = 6: 1.17 vs 1.22 ms forward, 2.12 vs 2.10 ms reverse -- no gain below D = 9)
+    if (rbf_fwd_use_tc(a.g)) return launch_fwd_tc(k_rollout_fwd<RbfTcFwdPolicy<DP>>, a, st);
     if (rbf_fwd_use_mma(a.g)) return launch_fwd_mma(k_rollout_fwd<RbfMmaFwdPolicy<DP>>, a, st);
   }
   GPODE_DISPATCH_R(k_rollout_fwd, a, false, st)

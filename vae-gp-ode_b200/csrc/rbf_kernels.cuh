@@ -318,6 +318,7 @@ struct RbfPolicy {
   static constexpr int R = R_;
   static constexpr int kThreads = 256;   // compiled for <= 128 registers: 512 resident threads per SM in any block size
   static constexpr int kMinBlocks = 2;
+  static constexpr int kStateThreads = 0;   // every thread of the CTA owns states
   // reverse sweep at D > 8: 128 threads x 3 CTAs (<= 168 registers) -- measured 10% faster than the 128-register build
   static constexpr int kThreadsBwd = DP_ <= 8 ? 256 : 128;
   static constexpr int kMinBlocksBwd = DP_ <= 8 ? 2 : 3;
@@ -326,6 +327,7 @@ struct RbfPolicy {
   using Smem = SweepSmem;
 
   __device__ static __forceinline__ Smem carve(float* smem, const Geom& g) { return carve_smem<DP, R>(smem, g); }
+  __device__ static __forceinline__ void finish(Smem&) {}
   __device__ static __forceinline__ long setup(Smem& sm, ChunkPipe& pipe, const Geom& g, const float* packed, long n_evals, bool bwd) {
     const long total = n_evals * g.D_out * (g.NCs + g.NCm);
     sweep_setup<DP, R>(sm, pipe, g, packed, total, bwd);

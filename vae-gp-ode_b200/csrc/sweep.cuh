@@ -2,7 +2,7 @@
 //   k_field_fwd / k_field_bwd      one evaluation / one VJP, row-major I/O (SVGP_Layer.forward, torchdiffeq RHS)
 //   k_rollout_fwd / k_rollout_bwd  whole fixed-grid solve / reverse sweep in ONE launch
 // A policy supplies: Geom, Accum, Smem (with xs / dx staging buffers), DP, R, kThreads, kMinBlocks and
-//   carve(), setup() -> total chunks, eval_fwd(store(k, fp, fu)), vjp() -> sum_k dx in sm.dx, flush().
+//   carve(), setup() -> total chunks, eval_fwd(store(k, fp, fu)), finish() (forward teardown), vjp() -> sum_k dx in sm.dx, flush().
 #pragma once
 
 #include "common.cuh"
@@ -17,15 +17,17 @@ struct States {
   bool ok[R];
 };
 
+// state_threads > 0: only the first `state_threads` threads of the CTA own states (the rest are helper warps of the policy)
 template <int R, class G>
-__device__ __forceinline__ States<R> map_states(const G& g) {
+__device__ __forceinline__ States<R> map_states(const G& g, int state_threads = 0) {
   States<R> st;
   const int l = blockIdx.y;
-  const int n0 = blockIdx.x * (blockDim.x * R) + threadIdx.x;
+  const int nthr = state_threads > 0 ? state_threads : static_cast<int>(blockDim.x);
+  const int n0 = blockIdx.x * (nthr * R) + threadIdx.x;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int n = n0 + r * blockDim.x;
-    st.ok[r] = n < g.N;
+    const int n = n0 + r * nthr;
+    st.ok[r] = n < g.N && static_cast<int>(threadIdx.x) < nthr;
     st.s[r] = static_cast<long>(l) * g.N + (st.ok[r] ? n : g.N - 1);
   }
   return st;
@@ -47,7 +49,7 @@ __global__ void GPODE_SWEEP_BOUNDS k_field_fwd(const FieldFwdArgsT<typename P::G
   GPODE_POLICY_CONSTS;
   extern __shared__ __align__(128) float smem[];
   const typename P::Geom& g = a.g;
-  const States<R> st = map_states<R>(g);
+  const States<R> st = map_states<R>(g, P::kStateThreads);
   typename P::Smem sm = P::carve(smem, g);
   ChunkPipe pipe;
   const long total = P::setup(sm, pipe, g, a.packed, 1, false);
@@ -62,6 +64,7 @@ __global__ void GPODE_SWEEP_BOUNDS k_field_fwd(const FieldFwdArgsT<typename P::G
         if (a.f_prior) a.f_prior[st.s[r] * g.D_out + k] = fp[r];
       }
   });
+  P::finish(sm);
 }
 
 // =============================================================================================
@@ -74,7 +77,7 @@ __global__ void GPODE_SWEEP_BOUNDS k_rollout_fwd(const RolloutFwdArgsT<typename 
   GPODE_POLICY_CONSTS;
   extern __shared__ __align__(128) float smem[];
   const typename P::Geom& g = a.g;
-  const States<R> st = map_states<R>(g);
+  const States<R> st = map_states<R>(g, P::kStateThreads);
   const int stages = a.method == GPODE_EULER ? 1 : (a.method == GPODE_MIDPOINT ? 2 : 4);
   const long NL = g.NL;
   const int DS = g.D_in;
@@ -153,6 +156,7 @@ __global__ void GPODE_SWEEP_BOUNDS k_rollout_fwd(const RolloutFwdArgsT<typename 
       }
     }
   }
+  P::finish(sm);
 }
 
 // =============================================================================================
