@@ -164,6 +164,16 @@ def build_model(w, device, seed):
     return gp, flow
 
 
+def tc_forward(w):
+    """mirrors rbf_fwd_use_tc (csrc/rbf.h): the tensor-memory forward adds one launch (its operand-tile pack) per step"""
+    if w["variant"] == "df" or w["D_in"] <= 8 or w["N"] * w["L"] < 32768 or os.environ.get("GPODE_FWD", "")[:1] == "m":
+        return False
+    if os.environ.get("GPODE_FWD", "")[:1] == "t":
+        return True
+    units = (-(-w["S"] // 256) + -(-w["M"] // 256)) * 256
+    return units * 100 <= (w["S"] + w["M"]) * 115
+
+
 def run_ours(args):
     import torch.distributed as dist
     import gpode_b200  # noqa: F401  (fails loudly if libgpode.so is missing)
@@ -304,7 +314,7 @@ def run_ours(args):
             "traffic_source": TRAFFIC.get(args.workload, (None, None))[1],
             "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json (%s); not an HBM-bound path" % peak_src,
             "note": ("D > 8: the D-length dot products run on the warp-level tensor path (mma.sync: two-way fp16 split for theta, TF32 head + "
-                     "bf16 cross terms for the second products, fp32 accumulate); frac is still the ALGORITHMIC fp32 work over the FP32-pipe "
+                     "bf16 cross terms for the second products, fp32 accumulate; forward sweep: tcgen05.mma 3xTF32 into tensor memory); frac is still the ALGORITHMIC fp32 work over the FP32-pipe "
                      "peak, so a call can exceed 1" if w["D_in"] > 8 and w["variant"] != "df"
                      else "FP32 / MUFU pipes only"),
             "sfu_achieved_tops": round(work["sfu"] * per_gpu_rate / 1e12, 4), "sfu_peak_tops": round(sfu_peak / 1e12, 3),
@@ -335,7 +345,7 @@ def run_ours(args):
             "roofline": roof,
             "e2e": {"value": round(e2e_value, 1), "unit": "traj-steps/s", "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "gpu_launches": (6 if w["variant"] == "df" else 7) * args.steps, "clocks": clocks}
+            "gpu_launches": (6 if w["variant"] == "df" else (8 if tc_forward(w) else 7)) * args.steps, "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(w, reps=3, warmup=1)

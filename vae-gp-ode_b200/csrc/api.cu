@@ -128,9 +128,10 @@ int check_ws(const void* ws, size_t bytes, size_t need) {
 
 int rbf_check_smem(const RbfGeom& g) { return rbf_smem_bytes(g, 32, 1, true) <= kSmemLimit ? GPODE_OK : GPODE_E_UNSUPPORTED; }
 
-cudaError_t rbf_pack(const GpodeProblem* p, const RbfGeom& g, float* packed, cudaStream_t st) {
+cudaError_t rbf_pack(const GpodeProblem* p, const RbfGeom& g, float* packed, cudaStream_t st, bool fwd) {
   RbfPackArgs a;
   a.g = g;
+  a.with_tc = fwd ? 1 : 0;
   a.variant = p->variant;
   a.Z = p->Z; a.ell = p->ell; a.var = p->var; a.eps = p->eps; a.phase = p->phase; a.w = p->w; a.nu = p->nu;
   a.packed = packed;
@@ -286,7 +287,7 @@ int gpode_field_fwd(const GpodeProblem* p, const float* x, float* f, float* f_pr
   }
   const RbfGeom g = rbf_geom(p, 1);
   if ((rc = rbf_check_smem(g))) return rc;
-  cudaError_t e = rbf_pack(p, g, packed, st);
+  cudaError_t e = rbf_pack(p, g, packed, st, true);
   if (e != cudaSuccess) return static_cast<int>(e);
   RbfFieldFwdArgs a;
   a.g = g;
@@ -329,7 +330,7 @@ int gpode_field_bwd(const GpodeProblem* p, const float* x, const float* g_out, c
   }
   const RbfGeom g = rbf_geom(p, 1);
   if ((rc = rbf_check_smem(g))) return rc;
-  if ((e = rbf_pack(p, g, packed, st)) != cudaSuccess) return static_cast<int>(e);
+  if ((e = rbf_pack(p, g, packed, st, false)) != cudaSuccess) return static_cast<int>(e);
   RbfFieldBwdArgs a;
   a.g = g;
   a.packed = packed;
@@ -394,7 +395,7 @@ int gpode_rollout_fwd(const GpodeProblem* p, const float* z0, int z0_per_sample,
   }
   const RbfGeom g = rbf_geom(p, order);
   if ((rc = rbf_check_smem(g))) return rc;
-  cudaError_t e = rbf_pack(p, g, packed, st);
+  cudaError_t e = rbf_pack(p, g, packed, st, true);
   if (e != cudaSuccess) return static_cast<int>(e);
   RbfRolloutFwdArgs a;
   a.g = g;
@@ -462,7 +463,7 @@ int gpode_rollout_bwd(const GpodeProblem* p, const float* ts, int T, int method,
   }
   const RbfGeom g = rbf_geom(p, order);
   if ((rc = rbf_check_smem(g))) return rc;
-  if ((e = rbf_pack(p, g, packed, st)) != cudaSuccess) return static_cast<int>(e);
+  if ((e = rbf_pack(p, g, packed, st, false)) != cudaSuccess) return static_cast<int>(e);
   RbfRolloutBwdArgs a;
   a.g = g;
   a.packed = packed;

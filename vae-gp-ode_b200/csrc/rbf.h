@@ -86,6 +86,7 @@ struct RbfPackArgs {
   const float* w;
   const float* nu;
   float* packed;
+  int with_tc;           // also lay out the operand tiles of the tensor-memory forward (forward entry points only)
 };
 
 struct RbfFinalizeArgs {

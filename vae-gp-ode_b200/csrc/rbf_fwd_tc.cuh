@@ -59,12 +59,13 @@ struct FwdTcSmem {
   uint32_t* tmem_slot;
   const float* tiles; // operand tiles of this sample (global)
   uint32_t tmem;
+  uint32_t pair_par;  // phase bits of this warp pair's two hand-over barriers
   long blk;           // running tile counter of this CTA
   long total;
 };
 
 inline int rbf_fwd_tc_smem_bytes(const RbfGeom& g) {
-  return (16 * kFtThreads + 4 * kFtStates + g.D_out * g.hdr_floats + 2 * kFtAFloats + kFtStages * kTcfTileFloats) * 4 + 128 + 1024;
+  return (16 * kFtThreads + 4 * kFtStates + g.D_out * g.hdr_floats + 2 * kFtAFloats + kFtStages * kTcfTileFloats) * 4 + 384 + 1024;
 }
 
 template <int DP_>
@@ -85,6 +86,7 @@ struct RbfTcFwdPolicy {
   __device__ static __forceinline__ uint64_t* empty(const Smem& sm, int s) { return sm.bars + kFtStages + s; }
   __device__ static __forceinline__ uint64_t* acc_full(const Smem& sm, int t, int h) { return sm.bars + 2 * kFtStages + 2 * t + h; }
   __device__ static __forceinline__ uint64_t* acc_empty(const Smem& sm, int t, int h) { return sm.bars + 2 * kFtStages + 4 + 2 * t + h; }
+  __device__ static __forceinline__ uint64_t* pair(const Smem& sm, int w, int par) { return sm.bars + 2 * kFtStages + 8 + 2 * w + par; }
 
   __device__ static __forceinline__ Smem carve(float* smem, const Geom& g) {
     Smem s;
@@ -95,8 +97,9 @@ struct RbfTcFwdPolicy {
     s.part = s.xs + 16 * kFtThreads;
     s.hdr = s.part + 4 * kFtStates;
     s.bars = reinterpret_cast<uint64_t*>(s.hdr + g.D_out * g.hdr_floats + ((g.D_out * g.hdr_floats) & 1));
-    s.tmem_slot = reinterpret_cast<uint32_t*>(s.bars + 2 * kFtStages + 8);
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.bars + 2 * kFtStages + 8 + 16);
     s.blk = 0;
+    s.pair_par = 0;
     return s;
   }
 
@@ -133,6 +136,7 @@ struct RbfTcFwdPolicy {
           mbar_init(acc_full(sm, t, h), 1);
           mbar_init(acc_empty(sm, t, h), 4);
         }
+      for (int i = 0; i < 16; ++i) mbar_init(sm.bars + 2 * kFtStages + 8 + i, 1);
       mbar_fence_init();
     }
     if (tid < 32) {
@@ -303,14 +307,18 @@ struct RbfTcFwdPolicy {
           acc0 = acc1 = 0.f;
         }
         fu[0] = acc0 + acc1;
-        // the second-half warps hand their partial sums to the state threads (double-buffered over k: one barrier per k)
+        // the second-half warps hand their partial sums to the state threads: warp w + 8 -> warp w through an mbarrier per
+        // (warp pair, k parity); the buffers are double-buffered over k and the accumulator flow control keeps the pair within
+        // one output dimension of each other
         float* part = sm.part + (k & 1) * 2 * kFtStates;
         if (h == 1) {
           part[sidx] = fp[0];
           part[kFtStates + sidx] = fu[0];
-        }
-        asm volatile("bar.sync 1, %0;" ::"r"(kFtEpi) : "memory");
-        if (h == 0) {
+          __syncwarp();
+          if (lane == 0) tc_arrive(pair(sm, warp & 7, k & 1));
+        } else {
+          tc_wait(pair(sm, warp & 7, k & 1), (sm.pair_par >> (k & 1)) & 1u);
+          sm.pair_par ^= 1u << (k & 1);
           fp[0] += part[sidx];
           fu[0] = (fu[0] + part[kFtStates + sidx]) * kInvLn2;   // inducing-row weights carry ln2
           store(k, fp, fu);

@@ -122,7 +122,7 @@ cudaError_t rbf_launch_pack(const RbfPackArgs& a, cudaStream_t st) {
   const int rows = a.g.SP2 + a.g.MP2 + 1;
   dim3 grid((rows + 127) / 128, a.g.D_out, a.g.L);
   k_rbf_pack<<<grid, 128, 0, st>>>(a);
-  if (rbf_fwd_use_tc(a.g)) {
+  if (a.with_tc && rbf_fwd_use_tc(a.g)) {
     dim3 gt(rbf_tc_blocks(a.g), a.g.D_out, a.g.L);
     k_rbf_pack_tc<<<gt, kTcfRows, 0, st>>>(a);
   }
