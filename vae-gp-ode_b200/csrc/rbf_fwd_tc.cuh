@@ -3,14 +3,18 @@
 // A CTA owns 256 states = two 128-row MMA tiles (row = TMEM lane = one thread's state).  Per evaluation and output k the
 // parameter rows arrive as pre-laid operand tiles of 256 units (k_rbf_pack_tc: no-swizzle K-major core matrices, TF32 head /
 // remainder / offset columns, then the 256 weights), one 42 KB bulk copy each, 3-stage ring:
-//   theta (128 states x 256 units) = A B^T over K = 56 in seven kind::tf32 k-steps (3xTF32 along K, fp32 accumulate in TMEM):
+//   theta (128 states x 128 units per MMA) = A B^T over K = 56 in seven kind::tf32 k-steps (3xTF32 along K, fp32 accumulate in TMEM):
 //       X_h G_h (2) + X_l G_h (2) + X_h G_l (2) + [1 1 0 0 ..][off_h off_l 0 0 ..] (1)      ~2^-21 relative, fp32 exponent range
-//   every thread then reads ITS state's 256 thetas from tensor memory (tcgen05.ld, 16 at a time) and accumulates
+//   the epilogue threads then read THEIR state's thetas from tensor memory (tcgen05.ld, 16 columns at a time, the next load in
+//   flight) and accumulate
 //       f_prior += w cos(theta)      |      f_update += nu' 2^(theta + A_k(x))
 // in registers: no operand splits, no fragment shuffles, no cross-lane reduction -- the instruction stream is MUFU + FFMA
-// (+ one FADD for A_k), which makes the sweep MUFU-bound.  The two tiles alternate: while one is in its epilogue the MMAs of the
-// other run (two accumulators of 256 columns fill the tensor memory; 128-column double buffers were measured slower: the
-// cost of a tcgen05.mma does not shrink with N).  A ninth warp is producer (bulk copies) and MMA issuer; completion is tracked with
+// (+ one FADD for A_k), which makes the sweep MUFU-bound.  Tensor memory holds four accumulators of 128 columns (2 state tiles x
+// 2 unit halves of a block): the MMAs of one half run under the epilogue of the other (the cost of a tcgen05.mma scales with N
+// down to 128 -- 139 -> 69 cycles -- but not to 64).  16 epilogue warps: warp w and warp w + 8 share 32 states, each takes 64 of
+// the 128 columns of every accumulator (4 warps per scheduler; with 2 the MUFU pipe stalls at 65 %); the pair's partial sums meet
+// through shared memory and an mbarrier once per output dimension.  A 17th warp is producer (bulk copies) and MMA issuer: a
+// tcgen05.mma blocks its issuing thread for its duration, so it must not sit inside an epilogue warp.  Completion is tracked with
 // tcgen05.commit -> mbarrier, every wait is bounded (a lost arrival traps instead of hanging the GPU).
 #pragma once
 
@@ -20,12 +24,13 @@
 namespace gpode {
 
 constexpr int kFtStates = 256;                 // states per CTA: threads 0..255 own one state each (solver glue, stores)
-constexpr int kFtEpi = 2 * kFtStates;          // epilogue threads: warp w and warp w + 8 share the states of warp w -- w takes the first 128 units
-                                               // of every block, w + 8 the second 128 (4 warps per scheduler keep the MUFU pipe fed; 2 reach 65 %)
+constexpr int kFtEpi = 2 * kFtStates;          // epilogue threads: warp w and warp w + 8 share the states of warp w -- of every 128-unit accumulator
+                                               // w takes the first 64 columns, w + 8 the second 64 (4 warps per scheduler keep the MUFU pipe fed; 2 reach 65 %)
 constexpr int kFtThreads = kFtEpi + 32;        // + one producer / MMA-issuer warp (a tcgen05.mma blocks its issuing thread ~140 cycles)
 constexpr int kFtStages = 3;
 constexpr int kFtAFloats = kTcfChunks * 128 * 4;     // operand tile of 128 states
-constexpr int kFtHalf = 128;                         // units per MMA (N): every state tile has two accumulator halves of 128 columns
+constexpr int kFtHalf = 128;                         // units per MMA (N): every state tile has two accumulators of 128 columns -- the MMAs of one
+                                                     // run under the epilogue of the other
 
 // tensor-memory load without the wait (16 consecutive columns of this thread's lane) / the wait, which hands the registers over
 __device__ __forceinline__ void tc_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
@@ -134,7 +139,7 @@ struct RbfTcFwdPolicy {
       for (int t = 0; t < 2; ++t)
         for (int h = 0; h < 2; ++h) {
           mbar_init(acc_full(sm, t, h), 1);
-          mbar_init(acc_empty(sm, t, h), 4);
+          mbar_init(acc_empty(sm, t, h), 8);
         }
       for (int i = 0; i < 16; ++i) mbar_init(sm.bars + 2 * kFtStages + 8 + i, 1);
       mbar_fence_init();
@@ -173,7 +178,7 @@ struct RbfTcFwdPolicy {
   __device__ static __forceinline__ void eval_fwd(ChunkPipe&, const Geom& g, long, Smem& sm, Store&& store) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sidx = tid & (kFtStates - 1);          // state slot of this epilogue thread
-    const int tile = sidx >> 7, row = sidx & 127, h = (tid >> 8) & 1;   // h: which 128 units of every block this warp takes
+    const int tile = sidx >> 7, row = sidx & 127, h = (tid >> 8) & 1;   // h: which 64 columns of every accumulator this warp takes
     const int nbs = rbf_tc_blocks_s(g), nb = rbf_tc_blocks(g);
     const int n = g.D_out * nb;   // blocks of one evaluation
     const long b0 = sm.blk;
@@ -246,8 +251,8 @@ struct RbfTcFwdPolicy {
         }
       }
     } else {
-      // =============== epilogue warps: thread <-> (state, half of the units) ===============
-      const uint32_t ta = sm.tmem + tile * kTcfRows + h * kFtHalf + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+      // =============== epilogue warps: thread <-> (state, 64-column share of both accumulators) ===============
+      const uint32_t ta0 = sm.tmem + tile * kTcfRows + h * (kFtHalf / 2) + (static_cast<uint32_t>((warp & 3) * 32) << 16);
       int slot = static_cast<int>(b0 % kFtStages);
       uint32_t par = static_cast<uint32_t>(b0 & 1);
       for (int k = 0; k < g.D_out; ++k) {
@@ -266,19 +271,22 @@ struct RbfTcFwdPolicy {
             fp[0] = acc0 + acc1;
             acc0 = acc1 = 0.f;
           }
-          tc_wait(acc_full(sm, tile, h), par);
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {
+          tc_wait(acc_full(sm, tile, hh), par);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t wa = smem_u32(sm.B + slot * kTcfTileFloats + kTcfBFloats + h * kFtHalf);
+          const uint32_t wa = smem_u32(sm.B + slot * kTcfTileFloats + kTcfBFloats + hh * kFtHalf + h * (kFtHalf / 2));
+          const uint32_t ta = ta0 + hh * kFtHalf;
           // 16 columns at a time; the tensor-memory load of the next 16 is in flight while these are processed
           uint32_t r[2][16];
           tc_ld16_async(ta, r[0]);
 #pragma unroll
-          for (int s = 0; s < kFtHalf / 16; ++s) {
+          for (int s = 0; s < kFtHalf / 32; ++s) {
             float w[16];
 #pragma unroll
             for (int v = 0; v < 4; ++v) lds128(wa + (16 * s + 4 * v) * 4, w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
             tc_ld_wait(r[s & 1]);
-            if (s + 1 < kFtHalf / 16) tc_ld16_async(ta + 16 * (s + 1), r[(s + 1) & 1]);
+            if (s + 1 < kFtHalf / 32) tc_ld16_async(ta + 16 * (s + 1), r[(s + 1) & 1]);
             if (is_k) {
 #pragma unroll
               for (int v = 0; v < 16; v += 2) {
@@ -296,8 +304,9 @@ struct RbfTcFwdPolicy {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            tc_arrive(acc_empty(sm, tile, h));
-            tc_arrive(empty(sm, slot));
+            tc_arrive(acc_empty(sm, tile, hh));
+            if (hh == 1) tc_arrive(empty(sm, slot));
+          }
           }
           par ^= 1u;
           if (++slot == kFtStages) slot = 0;
