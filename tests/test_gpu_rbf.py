@@ -242,12 +242,14 @@ def fwd_kernel(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("order,D_out,M,S,L", [(1, 16, 300, 260, 1), (2, 8, 512, 256, 2), (1, 16, 97, 513, 1)])
-def test_forward_kernels_ragged_tiles(fwd_kernel, order, D_out, M, S, L):
+@pytest.mark.parametrize("order,D_in,D_out,M,S,L", [(1, 16, 16, 300, 260, 1), (2, 16, 8, 512, 256, 2), (1, 16, 16, 97, 513, 1), (1, 11, 11, 260, 130, 1),
+                                                    (2, 14, 7, 130, 250, 1)])
+def test_forward_kernels_ragged_tiles(fwd_kernel, order, D_in, D_out, M, S, L):
     """both forward kernels on shapes whose feature / inducing sections do not fill the 256-unit operand tiles (and one that does),
-    first and second order, several samples per launch, N not a multiple of the CTA: field, prior part and an RK4 rollout against
+    first and second order, odd and even input dimensions 11..16, several samples per launch, N not a multiple of the CTA: field, prior
+    part and an RK4 rollout against
     the fp64 oracle on a random subset of a chip-filling batch"""
-    D_in, N = 16, 33001
+    N = 33001
     rs = np.random.RandomState(M + S)
     f64 = lambda a: torch.tensor(a, dtype=torch.float64)
     Z, ell, var = f64(rs.normal(size=(M, D_in))), f64(1.5 + rs.uniform(size=(D_out, D_in))), f64(0.5 + rs.uniform(size=D_out))
