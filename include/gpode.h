@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GPODE_VERSION 101 /* major*100 + minor */
+#define GPODE_VERSION 102 /* major*100 + minor */
 
 /* kernel variants (core/kernels.py: RBF dimwise=False / dimwise=True :29-195, DivergenceFreeKernel :201-393) */
 enum { GPODE_RBF_SHARED = 0, GPODE_RBF_DIMWISE = 1, GPODE_DF = 2 };
@@ -88,6 +88,12 @@ typedef struct GpodeParamGrads {
 
 int gpode_version(void);
 const char* gpode_error_string(int code);
+/* Which forward-sweep kernel family gpode_field_fwd / gpode_rollout_fwd will launch for this problem (shapes and, for the
+ * RBF variants at D_in > 8, the GPODE_FWD environment switch decide; no CUDA call is made): */
+#define GPODE_FWD_FFMA 0   /* FP32 / MUFU pipes (every D_in <= 8, small batches, the divergence-free kernel) */
+#define GPODE_FWD_MMA 1    /* warp-level tensor path (mma.sync) */
+#define GPODE_FWD_TCGEN05 2 /* tcgen05.mma with the accumulators in tensor memory */
+int gpode_forward_kernel(const GpodeProblem* p);
 
 /* bytes of scratch the calls below need for this problem (T, method only matter for the rollout).
  * `workspace` must be 256-byte aligned and is clobbered by every call. */

@@ -236,6 +236,14 @@ extern "C" {
 
 int gpode_version(void) { return GPODE_VERSION; }
 
+int gpode_forward_kernel(const GpodeProblem* p) {
+  if (!p) return GPODE_E_NULL;
+  if (p->variant == GPODE_DF) return GPODE_FWD_FFMA;
+  const RbfGeom g = rbf_geom(p, 1);
+  if (rbf_fwd_use_tc(g)) return GPODE_FWD_TCGEN05;
+  return (g.DP > 8 && rbf_fwd_use_mma(g)) ? GPODE_FWD_MMA : GPODE_FWD_FFMA;
+}
+
 const char* gpode_error_string(int code) {
   switch (code) {
     case GPODE_OK: return "ok";

@@ -121,6 +121,8 @@ inline bool rbf_pgrad_use_tc() {
   const char* e = getenv("GPODE_PGRAD");
   return e && e[0] == 't' && e[1] == 'c';
 }
+// the tensor-path sweep kernels (D > 8) need a chip-filling batch; below it the FFMA kernels run (latency bound there)
+inline bool rbf_fwd_use_mma(const RbfGeom& g) { return static_cast<long>(g.N) * g.L >= 32768; }
 // Forward sweep at D > 8 once the batch fills the chip: tcgen05 / tensor-memory kernel (rbf_fwd_tc.cuh; 17.1 vs 19.0 ms at config-5
 // shapes) unless its 256-unit operand tiles would be more than 15 % padding, in which case (or with GPODE_FWD=mma) the mma.sync
 // kernel (RbfMmaFwdPolicy) runs.  Both are parity-tested against the oracle; the choice depends on shapes only.

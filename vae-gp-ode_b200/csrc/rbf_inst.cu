@@ -40,7 +40,6 @@ cudaError_t launch_sweep(Kern kern, const Args& a, int threads, int R, bool bwd,
 // sweep kernels at D > 8 run on the tensor path (RbfMmaFwdPolicy / RbfMmaBwdPolicy: R = 2 states per thread) once the batch
 // fills the chip: measured at config-5 shapes forward 24.8 vs 34.2 ms, reverse sweep 48.2 vs 70.5 ms; a 512-state evaluation
 // (the prior at Z of the setup) is latency bound and stays on the FFMA path (0.34 vs 0.58 ms)
-inline bool rbf_fwd_use_mma(const RbfGeom& g) { return static_cast<long>(g.N) * g.L >= 32768; }
 template <typename Args, typename KernMma>
 cudaError_t launch_fwd_mma(KernMma kern, const Args& a, cudaStream_t st) {
   int threads, R;
