@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GPODE_VERSION 102 /* major*100 + minor */
+#define GPODE_VERSION 200 /* major*100 + minor */
 
 /* kernel variants (core/kernels.py: RBF dimwise=False / dimwise=True :29-195, DivergenceFreeKernel :201-393) */
 enum { GPODE_RBF_SHARED = 0, GPODE_RBF_DIMWISE = 1, GPODE_DF = 2 };
@@ -63,7 +63,7 @@ typedef struct GpodeProblem {
   int32_t D_out;  /* GP output dim */
   int32_t M;      /* inducing points */
   int32_t S;      /* random Fourier features */
-  int32_t reserved;
+  int32_t flags;  /* GPODE_FLAG_* (0 = defaults); replaces the environment switches of ABI 1.x */
   const float* Z;     /* (M,D_in) */
   const float* ell;
   const float* var;
@@ -88,8 +88,16 @@ typedef struct GpodeParamGrads {
 
 int gpode_version(void);
 const char* gpode_error_string(int code);
-/* Which forward-sweep kernel family gpode_field_fwd / gpode_rollout_fwd will launch for this problem (shapes and, for the
- * RBF variants at D_in > 8, the GPODE_FWD environment switch decide; no CUDA call is made): */
+/* Kernel-selection flags (GpodeProblem.flags).  Shapes alone pick the kernels (each shape has exactly one default); these
+ * flags exist for the parity tests and for A/B measurements and never change results beyond rounding:
+ *   RBF variants at D_in > 8 and >= 32,768 states: */
+#define GPODE_FLAG_FWD_MMA 1      /* forward sweep on the warp-level tensor path (mma.sync) instead of tcgen05 */
+#define GPODE_FLAG_FWD_TCGEN05 2  /* forward sweep on tcgen05 even when its 256-unit operand tiles are > 15 % padding */
+#define GPODE_FLAG_BWD_MMA 4      /* reverse sweep + parameter gradients on the warp-level tensor path instead of tcgen05 */
+#define GPODE_FLAG_DETERMINISTIC 8 /* parameter-gradient partial sums are reduced in a fixed order (no float atomics on the
+                                      shared accumulators): bit-identical gradients run to run, slightly slower */
+/* Which forward-sweep kernel family gpode_field_fwd / gpode_rollout_fwd will launch for this problem (shapes and the flags
+ * above decide; no CUDA call is made): */
 #define GPODE_FWD_FFMA 0   /* FP32 / MUFU pipes (every D_in <= 8, small batches, the divergence-free kernel) */
 #define GPODE_FWD_MMA 1    /* warp-level tensor path (mma.sync) */
 #define GPODE_FWD_TCGEN05 2 /* tcgen05.mma with the accumulators in tensor memory */

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert sorted(_lib.EXPORTS) == declared
     L = _lib.load()
-    assert L.gpode_version() == 102
+    assert L.gpode_version() == 200
     assert b"NULL" in L.gpode_error_string(-1)
     # argument checking happens before any CUDA call: NULL problem -> 0 bytes / error code
     assert L.gpode_workspace_bytes(None, 16, 2) == 0
@@ -32,26 +32,25 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_forward_kernel_selection(monkeypatch):
-    """which forward kernel family a problem gets depends on shapes only (plus the GPODE_FWD switch): no CUDA call involved"""
+    """which forward kernel family a problem gets depends on shapes only (plus GpodeProblem.flags): no CUDA call involved, and no
+    environment variable is read"""
     from gpode_b200 import _lib
     L = _lib.load()
 
-    def kind(variant, N, Lm, D, M, S):
+    def kind(variant, N, Lm, D, M, S, flags=0):
         p = _lib.GpodeProblem()
-        p.variant, p.L, p.N, p.D_in, p.D_out, p.M, p.S = _lib.VARIANTS[variant], Lm, N, D, D, M, S
+        p.variant, p.L, p.N, p.D_in, p.D_out, p.M, p.S, p.flags = _lib.VARIANTS[variant], Lm, N, D, D, M, S, flags
         return L.gpode_forward_kernel(ctypes.byref(p))
 
-    monkeypatch.delenv("GPODE_FWD", raising=False)
+    monkeypatch.setenv("GPODE_FWD", "mma")      # ABI 1.x switch: must be ignored now
     assert L.gpode_forward_kernel(None) < 0
     assert kind("rbf_dimwise", 65536, 8, 16, 512, 256) == 2      # config 5: tensor memory
     assert kind("rbf_dimwise", 65536, 8, 16, 300, 100) == 1      # 400 units would pad to 768: mma.sync
     assert kind("rbf_dimwise", 1024, 8, 16, 512, 256) == 0       # small batch: FFMA
     assert kind("rbf_dimwise", 1048576, 1, 6, 256, 256) == 0     # D <= 8: FFMA
     assert kind("df", 1048576, 1, 6, 256, 256) == 0
-    monkeypatch.setenv("GPODE_FWD", "mma")
-    assert kind("rbf_dimwise", 65536, 8, 16, 512, 256) == 1
-    monkeypatch.setenv("GPODE_FWD", "tc")
-    assert kind("rbf_dimwise", 65536, 8, 16, 300, 100) == 2
+    assert kind("rbf_dimwise", 65536, 8, 16, 512, 256, _lib.FLAG_FWD_MMA) == 1
+    assert kind("rbf_dimwise", 65536, 8, 16, 300, 100, _lib.FLAG_FWD_TCGEN05) == 2
 
 
 def test_state_dict_keys_match_reference():

@@ -98,3 +98,53 @@ def test_unsupported_solver_raises(monkeypatch):
     flow, _ = build_flow(g, "dopri5", monkeypatch)
     with pytest.raises(NotImplementedError):
         flow(t(g["z0"], device="cuda"), t(g["ts"], device="cuda"))
+
+
+@pytest.mark.parametrize("name", ["rbf_dimwise_o1", "df_o1"])
+def test_single_time_point_rollout_has_zero_parameter_gradients(name, monkeypatch):
+    """T = 1 (e.g. T_custom = 1): no step is taken, traj == z0, dz0 == dtraj and every parameter gradient is exactly zero --
+    written by the library, not left as uninitialised memory (round-1 advisor finding)."""
+    g = load_golden(name)
+    flow, gp = build_flow(g, "rk4", monkeypatch)
+    z0 = t(g["z0"], device="cuda").requires_grad_(True)
+    traj = flow(z0, t(g["ts"][:1], device="cuda"))
+    assert traj.shape[1] == 1 and torch.equal(traj[:, 0], z0.detach())
+    G = torch.randn_like(traj)
+    (traj * G).sum().backward()
+    assert torch.equal(z0.grad, G[:, 0])
+    for p in (gp.kern.unconstrained_lengthscales, gp.kern.unconstrained_variance, gp.inducing_loc.optvar, gp.Um.optvar, gp.Us_sqrt.optvar):
+        assert p.grad is None or (torch.isfinite(p.grad).all() and p.grad.abs().max().item() == 0.0)
+
+
+def test_non_positive_definite_gram_raises_like_the_reference(monkeypatch):
+    """torch.linalg.cholesky raises in the reference (kernels.py:163); the fused setup reports the failed pivot in a device flag that
+    SVGP_Layer checks after build_cache (check_cholesky=True) or on request (cholesky_ok())."""
+    g = load_golden("rbf_dimwise_o1")
+    flow, gp = build_flow(g, "rk4", monkeypatch)
+    with torch.no_grad():
+        gp.inducing_loc.optvar[3, 2] = float("nan")
+    with pytest.raises(torch.linalg.LinAlgError):
+        gp.build_cache()
+    gp.check_cholesky = False
+    gp.build_cache()                      # no host sync, no exception ...
+    assert gp.cholesky_ok() is False      # ... but the status is there to be asked for
+
+
+def test_stale_cache_is_not_served_after_batched_samples(monkeypatch):
+    """SVGP_Layer.forward after Flow.forward_samples must evaluate the LAST batched sample (what the kernel attributes hold), not a
+    cache left behind by an earlier build_cache() (round-1 advisor finding)."""
+    g = load_golden("rbf_dimwise_o1")
+    flow, gp = build_flow(g, "rk4", monkeypatch)
+    x = t(g["x"], device="cuda")
+    gp.build_cache()
+    f_first = gp(x).detach().clone()
+    assert rel(f_first, g["field_f"]) < 5e-5
+    # a different sample: scale the inducing means, then draw batched samples (same host draws)
+    with torch.no_grad():
+        gp.Um.optvar.mul_(3.0)
+    flow.forward_samples(t(g["z0"], device="cuda"), t(g["ts"], device="cuda"), 2)
+    assert gp._cache is None
+    f_after = gp(x).detach()
+    assert rel(f_after, f_first) > 1e-2                      # not the stale sample
+    gp.build_cache()
+    assert rel(gp(x), f_after) < 1e-5                        # the same draws and parameters reproduce it

@@ -194,21 +194,10 @@ def test_errors_are_loud():
                       s["var"], "rbf_dimwise", 2, "rk4")
 
 
-def test_tcgen05_parameter_gradient_kernel(monkeypatch):
-    """the opt-in tcgen05 / tensor-memory variant of the D > 8 parameter-gradient kernel (GPODE_PGRAD=tc, csrc/rbf_pgrad_tc.cuh)
-    gives the same kernel-level gradients as the default path, within the same bar against the fp64 oracle."""
-    monkeypatch.setenv("GPODE_PGRAD", "tc")
-    test_rollout_backward_kernel_level("rbf_dimwise_d16", "rk4")
-    test_field_backward_kernel_level("rbf_dimwise_d16")
-
-
-@pytest.mark.parametrize("pgrad", ["default", "tc"])
 @pytest.mark.parametrize("D_in,D_out,M,S,N", [(12, 5, 101, 33, 300), (9, 9, 40, 7, 70), (16, 3, 512, 16, 130), (14, 14, 129, 20, 1000)])
-def test_wide_inputs_odd_sizes(pgrad, D_in, D_out, M, S, N, monkeypatch):
+def test_wide_inputs_odd_sizes(D_in, D_out, M, S, N):
     """D > 8 (tensor-path parameter gradients, padded input dims, odd M / S, ragged N): field + VJP + parameter gradients
-    against the fp64 oracle, for the default (mma.sync) and the opt-in tcgen05 kernel."""
-    if pgrad == "tc":
-        monkeypatch.setenv("GPODE_PGRAD", "tc")
+    against the fp64 oracle."""
     rs = np.random.RandomState(D_in * 100 + M)
     f64 = lambda a: torch.tensor(a, dtype=torch.float64)
     c = dict(variant="rbf_dimwise", Z=f64(rs.normal(size=(M, D_in))), ell=f64(1.5 + rs.uniform(size=(D_out, D_in))),
@@ -235,11 +224,11 @@ def test_wide_inputs_odd_sizes(pgrad, D_in, D_out, M, S, N, monkeypatch):
 
 
 @pytest.fixture(params=["mma", "tc"])
-def fwd_kernel(request, monkeypatch):
+def fwd_kernel(request):
     """the two forward kernels of the D > 8 tensor path: mma.sync (RbfMmaFwdPolicy) and tcgen05 / tensor memory (RbfTcFwdPolicy,
-    the default when its 256-unit operand tiles are < 15 % padding); libgpode reads GPODE_FWD at every call"""
-    monkeypatch.setenv("GPODE_FWD", request.param)
-    return request.param
+    the default when its 256-unit operand tiles are < 15 % padding), selected through GpodeProblem.flags"""
+    with _gp().kernel_flags(_gp().FLAG_FWD_MMA if request.param == "mma" else _gp().FLAG_FWD_TCGEN05):
+        yield request.param
 
 
 @pytest.mark.parametrize("order,D_in,D_out,M,S,L", [(1, 16, 16, 300, 260, 1), (2, 16, 8, 512, 256, 2), (1, 16, 16, 97, 513, 1), (1, 11, 11, 260, 130, 1),

@@ -54,6 +54,7 @@ RbfGeom rbf_geom(const GpodeProblem* p, int order) {
   g.stage_floats = (g.RCs > g.RCm ? g.RCs : g.RCm) * g.row_floats;
   g.order = order;
   g.off = p->D_in - p->D_out;
+  g.flags = p->flags;
   g.cg.stage_floats = g.stage_floats;
   g.cg.rowf_s = g.cg.rowf_m = g.row_floats;
   g.cg.SP2 = g.SP2; g.cg.MP2 = g.MP2; g.cg.NCs = g.NCs; g.cg.NCm = g.NCm; g.cg.RCs = g.RCs; g.cg.RCm = g.RCm;
@@ -169,13 +170,9 @@ cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float
   pa.gsave = gsave;
   pa.n_te = n_te;
   if (rbf_pgrad_use_mma(g)) {
-    if (!rbf_pgrad_use_tc()) {
-      int pg_mt, pg_mblk;
-      rbf_pgrad_mma_shape(g, pg_mt, pg_mblk);
-      pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * pg_mblk, pg_mt == 1 ? 3 : 2);
-    } else {
-      pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * ((2 * g.MP2 + 127) / 128), 1);
-    }
+    int pg_mt, pg_mblk;
+    rbf_pgrad_mma_shape(g, pg_mt, pg_mblk);
+    pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * pg_mblk, pg_mt == 1 ? 3 : 2);
   } else {
     int pg_threads, pg_pp, pg_mblk;
     rbf_pgrad_shape(g, pg_threads, pg_pp, pg_mblk);
@@ -228,6 +225,23 @@ cudaError_t df_param_grads(const GpodeProblem* p, const DfGeom& g, const float* 
   fa.d_nu = grads ? grads->d_nu : nullptr;
   fa.d_B = grads ? grads->d_B : nullptr;
   return df_launch_finalize(fa, st);
+}
+
+// T == 1: no step is taken, every parameter gradient is exactly zero (outputs are written, never left uninitialised)
+cudaError_t zero_param_grads(const GpodeProblem* p, const GpodeParamGrads* grads, cudaStream_t st) {
+  if (!grads) return cudaSuccess;
+  const size_t D_in = p->D_in, D_out = p->D_out, M = p->M, L = p->L, S = p->S;
+  const bool df = p->variant == GPODE_DF, dimwise = p->variant == GPODE_RBF_DIMWISE;
+  const size_t n_ell = (df || dimwise) ? D_out * D_in : D_in, n_var = (df || dimwise) ? D_out : 1;
+  const size_t n_nu = L * M * D_out;   // (L,D_out,M,1) / (L,M,D_out) / (L,M*D,1)
+  struct { float* ptr; size_t n; } outs[5] = {{grads->d_Z, M * D_in}, {grads->d_ell, n_ell}, {grads->d_var, n_var}, {grads->d_nu, n_nu},
+                                              {df ? grads->d_B : nullptr, L * S * D_in * D_in}};
+  for (auto& o : outs)
+    if (o.ptr) {
+      cudaError_t e = cudaMemsetAsync(o.ptr, 0, o.n * sizeof(float), st);
+      if (e != cudaSuccess) return e;
+    }
+  return cudaSuccess;
 }
 
 }  // namespace
@@ -466,7 +480,7 @@ int gpode_rollout_bwd(const GpodeProblem* p, const float* ts, int T, int method,
     a.kbar = reinterpret_cast<float*>(ws + w.kbar);
     a.acc = df_acc(reinterpret_cast<float*>(ws + w.acc), g);
     if ((e = df_launch_rollout_bwd(a, st)) != cudaSuccess) return static_cast<int>(e);
-    if (T < 2) return GPODE_OK;
+    if (T < 2) return static_cast<int>(zero_param_grads(p, grads, st));
     return static_cast<int>(df_param_grads(p, g, packed, xs, a.gsave, static_cast<long>(T - 1) * stages, a.acc, grads, st));
   }
   const RbfGeom g = rbf_geom(p, order);
@@ -489,7 +503,7 @@ int gpode_rollout_bwd(const GpodeProblem* p, const float* ts, int T, int method,
   a.kbar = reinterpret_cast<float*>(ws + w.kbar);
   a.acc = rbf_acc(ws, w);
   if ((e = rbf_launch_rollout_bwd(a, st)) != cudaSuccess) return static_cast<int>(e);
-  if (T < 2) return GPODE_OK;
+  if (T < 2) return static_cast<int>(zero_param_grads(p, grads, st));
   return static_cast<int>(rbf_param_grads(p, g, packed, xs, a.gsave, static_cast<long>(T - 1) * stages, a.acc, grads, st));
 }
 

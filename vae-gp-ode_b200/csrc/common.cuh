@@ -56,18 +56,34 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Every mbarrier wait in the library is bounded in TIME, not in polls: a lost arrival (a bug) traps after kWaitTimeoutNs of no
+// progress instead of hanging the GPU, while slow progress (compute-sanitizer, cuda-gdb, a shared SM) never reaches the bound.
+// -DGPODE_WAIT_TIMEOUT_NS=0 compiles the bound out.
+#ifndef GPODE_WAIT_TIMEOUT_NS
+#define GPODE_WAIT_TIMEOUT_NS 20000000000ull   /* 20 s */
+#endif
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {   // non-blocking phase test
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+  const unsigned long long t0 = global_ns();
+  while (!mbar_try(bar, parity)) {
+    __nanosleep(128);
+    if (GPODE_WAIT_TIMEOUT_NS != 0ull && global_ns() - t0 > GPODE_WAIT_TIMEOUT_NS) __trap();
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+#pragma unroll 1
+  for (int i = 0; i < 4096; ++i)
+    if (mbar_try(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 // global -> shared bulk copy, completion counted in bytes on `bar`; bytes % 16 == 0, both 16-B aligned
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

@@ -2,9 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
-#include <stdlib.h>
 
 #include "chunk_geom.h"
+#include "gpode.h"
 #include "sweep_args.h"
 
 namespace gpode {
@@ -18,6 +18,7 @@ struct RbfGeom {
   int hdr_floats;        // floats per (l,k) header
   int row_floats;        // floats per row
   int order, off;        // ODE order; off = D_in - D_out: where f sits inside the state derivative
+  int flags;             // GPODE_FLAG_* of the problem (kernel selection for tests / A-B runs)
   ChunkGeom cg;          // the same chunking, in the form the pipeline reads
 };
 // packed = [L][D_out][hdr_floats] headers, [L][D_out][SP2+MP2][row_floats] rows, then [L][D_out] max |row coefficient| (the
@@ -115,22 +116,15 @@ inline void rbf_pgrad_shape(const RbfGeom& g, int& threads, int& PP, int& n_mblk
 // The parameter gradients run on the tensor path (3xTF32 mma.sync, rbf_pgrad_mma.cuh) for D > 8 and on the FFMA path
 // (k_rbf_pgrad) for D <= 8 -- measured on B200: 40.3 vs 42.2 ms at D = 16, 0.97 vs 0.79 ms at D = 6.
 inline bool rbf_pgrad_use_mma(const RbfGeom& g) { return g.DP > 8; }
-// GPODE_PGRAD=tc selects the tcgen05 / tensor-memory variant of the D > 8 kernel (rbf_pgrad_tc.cuh): same results, 42.4 vs
-// 40.3 ms at config-5 shapes today (bound by the per-instruction cost of its skinny N = 32 MMAs)
-inline bool rbf_pgrad_use_tc() {
-  const char* e = getenv("GPODE_PGRAD");
-  return e && e[0] == 't' && e[1] == 'c';
-}
 // the tensor-path sweep kernels (D > 8) need a chip-filling batch; below it the FFMA kernels run (latency bound there)
 inline bool rbf_fwd_use_mma(const RbfGeom& g) { return static_cast<long>(g.N) * g.L >= 32768; }
 // Forward sweep at D > 8 once the batch fills the chip: tcgen05 / tensor-memory kernel (rbf_fwd_tc.cuh; 17.1 vs 19.0 ms at config-5
-// shapes) unless its 256-unit operand tiles would be more than 15 % padding, in which case (or with GPODE_FWD=mma) the mma.sync
-// kernel (RbfMmaFwdPolicy) runs.  Both are parity-tested against the oracle; the choice depends on shapes only.
+// shapes) unless its 256-unit operand tiles would be more than 15 % padding, in which case (or with GPODE_FLAG_FWD_MMA) the mma.sync
+// kernel (RbfMmaFwdPolicy) runs.  Both are parity-tested against the oracle; the choice depends on shapes and the caller's flags only.
 inline bool rbf_fwd_use_tc(const RbfGeom& g) {
   if (g.DP <= 8 || static_cast<long>(g.N) * g.L < 32768) return false;
-  const char* e = getenv("GPODE_FWD");
-  if (e && e[0] == 'm') return false;
-  if (e && e[0] == 't') return true;    // (tests: force the tensor-memory kernel whatever the padding)
+  if (g.flags & GPODE_FLAG_FWD_MMA) return false;
+  if (g.flags & GPODE_FLAG_FWD_TCGEN05) return true;    // (tests: force the tensor-memory kernel whatever the padding)
   return static_cast<long>(rbf_tc_blocks(g)) * kTcfRows * 100 <= static_cast<long>(g.S + g.M) * 115;
 }
 // inducing points per CTA of the tensor-path parameter-gradient kernel (8 warps x 16 MT rows)

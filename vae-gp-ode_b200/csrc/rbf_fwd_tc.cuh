@@ -19,7 +19,7 @@
 #pragma once
 
 #include "rbf_kernels.cuh"
-#include "rbf_pgrad_tc.cuh"   // descriptor / tcgen05 helpers
+#include "tc_common.cuh"   // descriptor / tcgen05 helpers
 
 namespace gpode {
 
@@ -45,11 +45,7 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[16]) {
                  "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :: "memory");
 }
-__device__ __forceinline__ bool tc_try(uint64_t* bar, uint32_t parity) {   // non-blocking phase test
-  uint32_t ok;
-  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
+__device__ __forceinline__ bool tc_try(uint64_t* bar, uint32_t parity) { return mbar_try(bar, parity); }
 __device__ __forceinline__ void lds128(uint32_t saddr, float& a, float& b, float& c, float& d) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(saddr));
 }
@@ -214,6 +210,7 @@ struct RbfTcFwdPolicy {
           rpar[q] = static_cast<uint32_t>((b0 / kFtStages) & 1);
         }
         int done = 0, cnt = 0, spins = 0;   // cnt: 4-bit counters of the accumulators issued per ring slot
+        unsigned long long idle_t0 = 0;
         while (done < 4) {
           bool any = false;
 #pragma unroll
@@ -247,7 +244,11 @@ struct RbfTcFwdPolicy {
             }
           }
           if (any) spins = 0;
-          else if (++spins > (1 << 24)) __trap();
+          else if (++spins > 4096) {   // time-bounded like every other wait (common.cuh)
+            if (spins == 4097) idle_t0 = global_ns();
+            __nanosleep(128);
+            if (GPODE_WAIT_TIMEOUT_NS != 0ull && global_ns() - idle_t0 > GPODE_WAIT_TIMEOUT_NS) __trap();
+          }
         }
       }
     } else {

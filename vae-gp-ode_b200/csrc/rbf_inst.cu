@@ -4,7 +4,6 @@
 
 #include "rbf_kernels.cuh"
 #include "rbf_pgrad_mma.cuh"
-#include "rbf_pgrad_tc.cuh"
 #include "rbf_fwd_tc.cuh"
 
 #ifndef GPODE_DP
@@ -101,23 +100,15 @@ namespace {
 template <int D>
 cudaError_t launch_pgrad(const RbfPgradArgs& a, cudaStream_t st) {
   if constexpr (D > 8) {
-    if (!rbf_pgrad_use_tc()) {   // default: warp-level tensor path (3xTF32 mma.sync): each warp owns 16 * MT inducing points, a CTA 128 * MT
-      int MT, n_mblk;
-      rbf_pgrad_mma_shape(a.g, MT, n_mblk);
-      dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
-      const int smem = rbf_pgrad_mma_smem_bytes(2);
-      cudaError_t e = cudaFuncSetAttribute(MT == 2 ? k_rbf_pgrad_mma<2, 2> : k_rbf_pgrad_mma<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      if (MT == 2) k_rbf_pgrad_mma<2, 2><<<grid, kPgmThreads, smem, st>>>(a);
-      else k_rbf_pgrad_mma<2, 1><<<grid, kPgmThreads, smem, st>>>(a);
-    } else {                     // opt-in (GPODE_PGRAD=tc): tcgen05.mma / tensor-memory kernel, one CTA per SM (rbf_pgrad_tc.cuh)
-      const int n_mblk = (2 * a.g.MP2 + 127) / 128;
-      const int smem = rbf_pgrad_tc_smem_bytes();
-      cudaError_t e = cudaFuncSetAttribute(k_rbf_pgrad_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
-      k_rbf_pgrad_tc<0><<<grid, kTcThreads, smem, st>>>(a);
-    }
+    // warp-level tensor path (mma.sync): each warp owns 16 * MT inducing points, a CTA 128 * MT
+    int MT, n_mblk;
+    rbf_pgrad_mma_shape(a.g, MT, n_mblk);
+    dim3 grid(static_cast<unsigned>(a.chunks * n_mblk), static_cast<unsigned>(a.g.D_out), static_cast<unsigned>(a.g.L));
+    const int smem = rbf_pgrad_mma_smem_bytes(2);
+    cudaError_t e = cudaFuncSetAttribute(MT == 2 ? k_rbf_pgrad_mma<2, 2> : k_rbf_pgrad_mma<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    if (MT == 2) k_rbf_pgrad_mma<2, 2><<<grid, kPgmThreads, smem, st>>>(a);
+    else k_rbf_pgrad_mma<2, 1><<<grid, kPgmThreads, smem, st>>>(a);
   } else {
     int threads, PP, n_mblk;
     rbf_pgrad_shape(a.g, threads, PP, n_mblk);

@@ -19,7 +19,7 @@ _fp = ctypes.c_void_p
 
 class GpodeProblem(ctypes.Structure):
     _fields_ = [("variant", ctypes.c_int32), ("L", ctypes.c_int32), ("N", ctypes.c_int32), ("D_in", ctypes.c_int32),
-                ("D_out", ctypes.c_int32), ("M", ctypes.c_int32), ("S", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("D_out", ctypes.c_int32), ("M", ctypes.c_int32), ("S", ctypes.c_int32), ("flags", ctypes.c_int32),
                 ("Z", _fp), ("ell", _fp), ("var", _fp), ("eps", _fp), ("phase", _fp), ("w", _fp), ("nu", _fp), ("B", _fp)]
 
 
@@ -108,9 +108,33 @@ def require_cuda(*tensors):
             raise RuntimeError("gpode_b200 computes in fp32 (got %s)" % t.dtype)
 
 
-def make_problem(variant, L, N, D_in, D_out, M, S, Z, ell, var, eps, phase, w, nu, B=None):
+# GpodeProblem.flags (include/gpode.h): kernel selection for the parity tests / A-B measurements; 0 = shape-driven defaults
+FLAG_FWD_MMA, FLAG_FWD_TCGEN05, FLAG_BWD_MMA, FLAG_DETERMINISTIC = 1, 2, 4, 8
+_flags = 0
+
+
+class kernel_flags:
+    """``with kernel_flags(FLAG_FWD_MMA): ...`` -- every problem built inside the block carries these flags (an explicit field
+    of the C ABI; the library itself reads no environment variable and keeps no state)."""
+
+    def __init__(self, flags):
+        self.flags = int(flags)
+
+    def __enter__(self):
+        global _flags
+        self.prev, _flags = _flags, self.flags
+        return self
+
+    def __exit__(self, *exc):
+        global _flags
+        _flags = self.prev
+        return False
+
+
+def make_problem(variant, L, N, D_in, D_out, M, S, Z, ell, var, eps, phase, w, nu, B=None, flags=None):
     p = GpodeProblem()
-    p.variant, p.L, p.N, p.D_in, p.D_out, p.M, p.S, p.reserved = variant, L, N, D_in, D_out, M, S, 0
+    p.variant, p.L, p.N, p.D_in, p.D_out, p.M, p.S = variant, L, N, D_in, D_out, M, S
+    p.flags = _flags if flags is None else int(flags)
     p.Z, p.ell, p.var, p.eps, p.phase, p.w, p.nu = ptr(Z), ptr(ell), ptr(var), ptr(eps), ptr(phase), ptr(w), ptr(nu)
     p.B = ptr(B)
     return p

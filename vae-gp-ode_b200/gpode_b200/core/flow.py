@@ -74,7 +74,10 @@ class Flow(nn.Module):
     def forward(self, z0, ts):
         """(N,D_s), (T,) -> (N,T,D_s) for one fresh function sample."""
         self.odefunc.before_odeint(rebuild_cache=True)
-        return self._rollout(z0, ts, self.odefunc.diffeq.field_sample())[0]
+        gp = self.odefunc.diffeq
+        sample = gp.field_sample()
+        gp._cache = None    # consumed: later SVGP_Layer.forward calls read the sample from the kernel attributes, and the
+        return self._rollout(z0, ts, sample)[0]   # layer does not keep this iteration's autograd graph alive
 
     def forward_samples(self, z0, ts, L):
         """(N,D_s) -> (L,N,T,D_s): L fresh function samples (caches drawn in order), a single launch."""

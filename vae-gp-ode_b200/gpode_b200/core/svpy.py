@@ -64,6 +64,11 @@ class SVGP_Layer(torch.nn.Module):
                                  name="Inducing distribution (scale)", device=device)
         self.kern.to(device)
         self._cache = None
+        # torch.linalg.cholesky raises in the reference when K(Z,Z) + jitter is not positive definite (kernels.py:163); the fused
+        # setup reports it in a device flag instead.  True: read the flag after every build_cache (one 4-byte D2H, the same host
+        # sync torch.linalg.cholesky performs) and raise torch.linalg.LinAlgError; False: no sync, call cholesky_ok() when wanted.
+        self.check_cholesky = True
+        self.chol_info = None
 
     def sample_inducing(self):
         """u = Lq eps + m, eps ~ N(0,I) (M,D_out) (whitened inducing sample, svpy.py:88-101)."""
@@ -87,6 +92,7 @@ class SVGP_Layer(torch.nn.Module):
         """L function samples at once (reference: L serial build_cache calls, odegpvae.py:41-43): draws stay in the
         reference's order, the GPU work -- inducing sample, prior at Z, K(Z,Z) + Cholesky + whitened solves -- is one
         batched pass.  Returns a FieldSample with leading axis L."""
+        self._cache = None      # a cache left by an earlier build_cache() is stale from here on
         if not self._fused_setup():
             samples = []
             for _ in range(L):
@@ -100,11 +106,27 @@ class SVGP_Layer(torch.nn.Module):
         u = GF.inducing_sample(self.Us_sqrt.optvar, self.Um(), eps_u)                      # (L,M,D_out)
         nu0 = torch.zeros((L, self.D_out, self.M, 1) if k.dimwise else (L, self.M, self.D_out), device=Z.device)
         u_prior, _ = GF.gp_field(Z[None].expand(L, -1, -1), Z, nu0, eps, phase, w, ell, var, k.variant)   # rff_forward(Z)
-        nu = GF.compute_nu(Z, ell, var, u_prior, u, k.variant)
+        nu, self.chol_info = GF.compute_nu(Z, ell, var, u_prior, u, k.variant, return_info=True)
+        if self.check_cholesky:
+            self.cholesky_ok(raise_error=True)
         # leave the last sample on the kernel like L serial build_cache calls would
         k.rff_omega = eps[-1] / (ell.t().unsqueeze(1) if k.dimwise else ell.unsqueeze(1))
         k.nu = nu[-1]
         return FieldSample(k.variant, Z, ell, var, eps, phase, w, nu)
+
+    def cholesky_ok(self, raise_error=False):
+        """Status of the last fused setup's Cholesky factorisations (host sync).  The reference raises from
+        torch.linalg.cholesky (kernels.py:163) -- with raise_error the same exception type is raised here."""
+        if self.chol_info is None:
+            return True
+        bad = self.chol_info.nonzero()
+        if bad.numel() == 0:
+            return True
+        if raise_error:
+            k = int(bad[0, 0])
+            raise torch.linalg.LinAlgError("gpode_b200 compute_nu: K(Z,Z) + jitter of output dimension %d is not positive definite "
+                                           "(leading minor of order %d)" % (k, int(self.chol_info[k])))
+        return False
 
     def build_cache(self):
         """Fix one function sample: feature draws, inducing sample, nu (svpy.py:103-121; same draw order)."""

@@ -48,6 +48,7 @@ class GPField(torch.autograd.Function):
         ctx.save_for_backward(x, Z, nu, eps, phase, w, ell, var, B if B is not None else x.new_empty(0), f, fp)
         ctx.variant = variant
         ctx.has_B = B is not None
+        ctx.flags = p.flags
         ctx.mark_non_differentiable(fp)
         return f, fp
 
@@ -61,7 +62,7 @@ class GPField(torch.autograd.Function):
         L, M, D_in, D_out, S = _dims(variant, Z, w, nu, eps)
         N = x.shape[1]
         with torch.cuda.device(x.device):
-            p = _lib.make_problem(variant, L, N, D_in, D_out, M, S, Z, ell, var, eps, phase, w, nu, B)
+            p = _lib.make_problem(variant, L, N, D_in, D_out, M, S, Z, ell, var, eps, phase, w, nu, B, flags=ctx.flags)
             ws, nbytes = _lib.workspace(p, 2, _lib.EULER, x.device)
             dx = torch.empty_like(x)
             dZ, dnu, dell, dvar = torch.empty_like(Z), torch.empty_like(nu), torch.empty_like(ell), torch.empty_like(var)
@@ -104,6 +105,7 @@ class GPRollout(torch.autograd.Function):
         ctx.save_for_backward(ts, Z, nu, eps, phase, w, ell, var, B if B is not None else ts.new_empty(0),
                               save if save is not None else ts.new_empty(0))
         ctx.cfg = (variant, order, method, per_sample, N, B is not None)
+        ctx.flags = p.flags
         return traj
 
     @staticmethod
@@ -119,7 +121,7 @@ class GPRollout(torch.autograd.Function):
         T = ts.shape[0]
         dev = dtraj.device
         with torch.cuda.device(dev):
-            p = _lib.make_problem(variant, L, N, D_in, D_out, M, S, Z, ell, var, eps, phase, w, nu, B)
+            p = _lib.make_problem(variant, L, N, D_in, D_out, M, S, Z, ell, var, eps, phase, w, nu, B, flags=ctx.flags)
             ws, nbytes = _lib.workspace(p, T, method, dev)
             dz0 = torch.empty((L, N, D_in), dtype=torch.float32, device=dev)
             dZ, dnu, dell, dvar = torch.empty_like(Z), torch.empty_like(nu), torch.empty_like(ell), torch.empty_like(var)
@@ -152,7 +154,9 @@ def gp_rollout(z0, ts, Z, nu, eps, phase, w, ell, var, variant, order=1, method=
 class ComputeNu(torch.autograd.Function):
     """nu = Lc^-T (u - Lc^-1 u_prior), Lc = chol(K(Z,Z) + 1e-5 I) for L samples at once -- RBF.compute_nu fused with K(Z)
     (reference experiments/model/core/kernels.py:98-110,155-172; svpy.py:118-121).  RBF variants only.
-    u_prior, u: (L,M,D_out); returns nu (L,D_out,M,1) [dimwise] or (L,M,D_out) [shared]."""
+    u_prior, u: (L,M,D_out); returns (nu, info): nu (L,D_out,M,1) [dimwise] or (L,M,D_out) [shared]; info (Kc,) int32 on the device,
+    0 or 1 + the index of the first non-positive pivot of K(Z,Z) + jitter -- where torch.linalg.cholesky raises in the reference.
+    No host synchronisation happens here; SVGP_Layer reads info (one 4-byte D2H) when its check_cholesky attribute is set."""
 
     @staticmethod
     def forward(ctx, Z, ell, var, u_prior, u, variant):
@@ -172,18 +176,18 @@ class ComputeNu(torch.autograd.Function):
                 raise RuntimeError("gpode_compute_nu: unsupported problem (RBF variants, M <= 512, D <= 16 only)")
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             save = torch.empty(nsave, dtype=torch.float32, device=dev)
-            info = torch.zeros(D_out, dtype=torch.int32, device=dev)
+            info = torch.zeros(D_out if variant == _lib.RBF_DIMWISE else 1, dtype=torch.int32, device=dev)
             nu = torch.empty((L, D_out, M, 1) if variant == _lib.RBF_DIMWISE else (L, M, D_out), dtype=torch.float32, device=dev)
             rc = lib.gpode_compute_nu_fwd(ctypes.byref(p), _lib.ptr(u_prior), _lib.ptr(u), _lib.ptr(nu), _lib.ptr(save), _lib.ptr(info),
                                           _lib.ptr(ws), nbytes, _lib.stream_handle(dev))
         _lib.check(rc, "gpode_compute_nu_fwd")
         ctx.save_for_backward(Z, ell, var, u, save)
         ctx.variant = variant
-        ctx.info = info   # non-zero entry: K(Z,Z) + jitter was not positive definite (checked lazily by the caller, no sync here)
-        return nu
+        ctx.mark_non_differentiable(info)
+        return nu, info
 
     @staticmethod
-    def backward(ctx, dnu):
+    def backward(ctx, dnu, _dinfo=None):
         lib = _lib.load()
         Z, ell, var, u, save = ctx.saved_tensors
         variant = ctx.variant
@@ -268,9 +272,11 @@ class WhitenedKL(torch.autograd.Function):
         return dLq, dUm
 
 
-def compute_nu(Z, ell, var, u_prior, u, variant):
+def compute_nu(Z, ell, var, u_prior, u, variant, return_info=False):
+    """nu for L samples; with return_info also the Cholesky status vector (see ComputeNu)."""
     v = _lib.VARIANTS[variant] if isinstance(variant, str) else variant
-    return ComputeNu.apply(Z, ell, var, u_prior, u, v)
+    nu, info = ComputeNu.apply(Z, ell, var, u_prior, u, v)
+    return (nu, info) if return_info else nu
 
 
 def inducing_sample(Lq_packed, Um, eps_u):

@@ -22,6 +22,10 @@ def shard_trajectories(z0, rank=None, world=None):
     """Slice the trajectory axis (dim -2) of z0 (N,D) or (L,N,D) for this rank."""
     rank = dist.get_rank() if rank is None else rank
     world = dist.get_world_size() if world is None else world
+    if z0.shape[-2] < world:
+        # an empty shard would make this rank raise inside the rollout (N < 1 is a shape error) while the others block in the
+        # all-reduce: fail on EVERY rank, before any collective
+        raise ValueError("cannot shard %d trajectories over %d ranks: every rank needs at least one" % (z0.shape[-2], world))
     lo, hi = shard_bounds(z0.shape[-2], rank, world)
     return z0[..., lo:hi, :]
 
