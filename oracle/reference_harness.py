@@ -19,7 +19,10 @@ import types
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("GPODE_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the live tree in the build container; elsewhere (GPU box) the verbatim copy made by oracle/fetch_ref.py (git-ignored oracle/_ref)
+REFERENCE_ROOT = os.environ.get("GPODE_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/experiments/model/core")
+                                                             else os.path.join(_HERE, "_ref"))
 
 
 def reference_available():
@@ -82,9 +85,10 @@ def load_reference():
     import model.core.odegpvae as odegpvae
     import model.create_model as create_model
     import model.core.initialization as initialization
+    import model.core.vae as vae
 
     _loaded.update(kernels=kernels, svpy=svpy, flow=flow, odegpvae=odegpvae,
-                   create_model=create_model, initialization=initialization)
+                   create_model=create_model, initialization=initialization, vae=vae)
     return _loaded
 
 

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from helpers import ALL_CASES, RBF_CASES, load_golden, rel, t
+from oracle import field as OF
 
 pytestmark = pytest.mark.gpu
 
@@ -47,6 +48,25 @@ def build_flow(g, method, monkeypatch):
     return flow, gp
 
 
+LEAVES = ("raw_ell", "raw_var", "Z", "Um", "Us_sqrt")
+
+
+def fp64_truth(g, method):
+    """The whole path in float64 with its OWN nu (fp64 K(Z,Z), Cholesky, solves -- oracle.field.build_cache without nu_override), the
+    rollout, the KL and autograd down to the leaf parameters: the truth both fp32 implementations are measured against."""
+    m = g["meta"]
+    f64 = torch.float64
+    leaves = {k: t(g["p_" + k], f64).requires_grad_(True) for k in LEAVES}
+    Lq = OF.tril_from_packed(leaves["Us_sqrt"], m["M"])
+    draws = dict(w=t(g["draw_w"], f64), eps=t(g["draw_eps"], f64), phase01=t(g["draw_phase01"], f64), eps_u=t(g["draw_eps_u"], f64))
+    c = OF.build_cache(m["variant"], leaves["Z"], leaves["raw_ell"], leaves["raw_var"], leaves["Um"], Lq, draws)
+    z0 = t(g["z0"], f64).requires_grad_(True)
+    traj = OF.rollout(z0, t(g["ts"], f64), c, m["order"], method)
+    loss = (traj * t(g["G"], f64)).sum() + OF.kl_whitened(leaves["Um"], Lq)
+    grads = torch.autograd.grad(loss, [z0] + [leaves[k] for k in LEAVES])
+    return traj.detach(), dict(zip(("z0",) + LEAVES, grads))
+
+
 @pytest.mark.parametrize("name", ALL_CASES)
 @pytest.mark.parametrize("method", ["euler", "rk4"])
 def test_flow_end_to_end(name, method, monkeypatch):
@@ -67,12 +87,20 @@ def test_flow_end_to_end(name, method, monkeypatch):
     loss.backward()
     got = {"z0": z0.grad, "raw_ell": gp.kern.unconstrained_lengthscales.grad, "raw_var": gp.kern.unconstrained_variance.grad,
            "Z": gp.inducing_loc.optvar.grad, "Um": gp.Um.optvar.grad, "Us_sqrt": gp.Us_sqrt.optvar.grad}
+    # north_star bar 3 (parameter gradients to rel 1e-4) as three numbers per leaf: the reference's own fp32
+    # gradients carry the noise of its fp32 Cholesky of an ill-conditioned K(Z,Z) (cond 1e4..1e6), so "equal to
+    # the reference to 1e-4" is only meaningful where the reference itself is that close to the truth.  Required of the new path:
+    # at least as close to the fp64 truth as 1e-4, or as the reference is.
+    traj64, want = fp64_truth(g, method)
+    e_new, e_ref = rel(traj, traj64), rel(g["traj_" + method], traj64)
+    print("%s %s traj: new-vs-fp64 %.2e  ref-vs-fp64 %.2e  new-vs-ref %.2e" % (name, method, e_new, e_ref, rel(traj, g["traj_" + method])))
+    assert e_new <= max(1e-4, e_ref)
     for k, v in got.items():
-        e = rel(v, g["roll_%s_d%s" % (method, k)])
-        print("%s %s d%s: %.2e" % (name, method, k, e))
-        # the reference's own fp32 gradients carry the noise of an ill-conditioned Cholesky (cond ~1e4..1e6);
-        # kernel-level gradients are held to 1e-4 in test_gpu_rbf.py, here the bar is the reference's noise
-        assert e < 2e-3, (k, e)
+        ref = g["roll_%s_d%s" % (method, k)]
+        e_new, e_ref, e_nr = rel(v, want[k]), rel(ref, want[k]), rel(v, ref)
+        print("%s %s d%s: new-vs-fp64 %.2e  ref-vs-fp64 %.2e  new-vs-ref %.2e" % (name, method, k, e_new, e_ref, e_nr))
+        assert e_new <= max(1e-4, e_ref), (k, e_new, e_ref)
+        assert e_nr <= max(1e-4, 2.0 * (e_new + e_ref)), (k, e_nr)      # and the two fp32 paths differ by no more than their noise
 
 
 @pytest.mark.parametrize("name", ["rbf_dimwise_o1", "rbf_dimwise_o2"])

@@ -22,6 +22,11 @@ namespace {
 
 constexpr int NB = 32;            // block size of the blocked factorisation / substitutions
 constexpr int kSetupThreads = 256;
+// The factorisation, the substitutions and the contraction of the backward run in double precision: K(Z,Z) + jitter has
+// cond 1e4..1e6 at the reference's settings and an fp32 Cholesky is the largest single error of the reference's own
+// nu and leaf gradients; the systems are tiny (M <= 512) next to the rollout, B200 has full-rate FP64 FMA units, and inputs / outputs
+// stay fp32 at the ABI.  (tests/test_gpu_setup.py: nu and its gradients against the fp64 oracle.)
+using real = double;
 
 // element (k, i, r) of a reference-layout (L, M, D_out) tensor seen as the (Kc, M, NR) right-hand-side array
 __device__ __forceinline__ size_t lmd_index(const NuGeom& g, int k, int i, int r) {
@@ -34,24 +39,29 @@ __device__ __forceinline__ size_t nu_index(const NuGeom& g, int k, int i, int r)
   if (g.dimwise) return (static_cast<size_t>(r) * g.D_out + k) * g.M + i;
   return lmd_index(g, k, i, r);
 }
+__device__ __forceinline__ real warp_sum_real(real v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ float ell_of(const NuGeom& g, const float* ell, int k, int d) { return g.dimwise ? ell[k * g.D_in + d] : ell[d]; }
 
 // ---------------------------------------------------------------------------------------------
 // K(Z,Z) + jitter I  (core/kernels.py:98-110 evaluated with direct differences)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_kzz_build(const NuGeom g, const float* __restrict__ Z, const float* __restrict__ ell, const float* __restrict__ var,
-                            float* __restrict__ A) {
+                            real* __restrict__ A) {
   const int k = blockIdx.y;
   const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long>(g.M) * g.M) return;
   const int i = static_cast<int>(idx / g.M), j = static_cast<int>(idx - static_cast<long>(i) * g.M);
-  float sq = 0.f;
+  real sq = 0;
   for (int d = 0; d < g.D_in; ++d) {
-    const float t = (Z[i * g.D_in + d] - Z[j * g.D_in + d]) / ell_of(g, ell, k, d);
-    sq = fmaf(t, t, sq);
+    const real t = (static_cast<real>(Z[i * g.D_in + d]) - static_cast<real>(Z[j * g.D_in + d])) / static_cast<real>(ell_of(g, ell, k, d));
+    sq = fma(t, t, sq);
   }
-  float v = var[g.dimwise ? k : 0] * expf(-0.5f * sq);
-  if (i == j) v += g.jitter;
+  real v = static_cast<real>(var[g.dimwise ? k : 0]) * exp(-0.5 * sq);
+  if (i == j) v += static_cast<real>(g.jitter);
   A[(static_cast<size_t>(k) * g.M + i) * g.M + j] = v;
 }
 
@@ -60,12 +70,13 @@ __global__ void k_kzz_build(const NuGeom g, const float* __restrict__ Z, const f
 // the current 32-column panel transposed in shared memory for the trailing update.
 // info[k] = 1 + index of the first non-positive pivot (0 = ok), like LAPACK potrf.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSetupThreads) k_chol(const int M, float* __restrict__ Aall, int* __restrict__ info) {
-  extern __shared__ __align__(16) float sm[];
-  float* Dg = sm;                       // [NB][NB+1] diagonal block
-  float* Pt = sm + NB * (NB + 1);       // [NB][Mp] panel, transposed: Pt[c][row - row0]
+__global__ void __launch_bounds__(kSetupThreads) k_chol(const int M, real* __restrict__ Aall, int* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  real* sm = reinterpret_cast<real*>(sm_raw);
+  real* Dg = sm;                       // [NB][NB+1] diagonal block
+  real* Pt = sm + NB * (NB + 1);       // [NB][Mp] panel, transposed: Pt[c][row - row0]
   const int Mp = (M + NB - 1) / NB * NB;
-  float* A = Aall + static_cast<size_t>(blockIdx.x) * M * M;
+  real* A = Aall + static_cast<size_t>(blockIdx.x) * M * M;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int s_bad;
   if (tid == 0) s_bad = 0;
@@ -74,20 +85,20 @@ __global__ void __launch_bounds__(kSetupThreads) k_chol(const int M, float* __re
     // (a) diagonal block -> shared, factor with warp 0 (rows >= nbk act as identity)
     for (int e = tid; e < NB * NB; e += blockDim.x) {
       const int r = e / NB, c = e - r * NB;
-      Dg[r * (NB + 1) + c] = (r < nbk && c < nbk) ? A[static_cast<size_t>(j0 + r) * M + j0 + c] : (r == c ? 1.f : 0.f);
+      Dg[r * (NB + 1) + c] = (r < nbk && c < nbk) ? A[static_cast<size_t>(j0 + r) * M + j0 + c] : (r == c ? real(1) : real(0));
     }
     __syncthreads();
     if (warp == 0) {
       for (int c = 0; c < NB; ++c) {
-        float piv = Dg[c * (NB + 1) + c];
-        if (!(piv > 0.f) && c < nbk && lane == 0 && s_bad == 0) s_bad = j0 + c + 1;
-        piv = sqrtf(piv);
+        real piv = Dg[c * (NB + 1) + c];
+        if (!(piv > real(0)) && c < nbk && lane == 0 && s_bad == 0) s_bad = j0 + c + 1;
+        piv = sqrt(piv);
         __syncwarp();
         if (lane == c) Dg[c * (NB + 1) + c] = piv;
         if (lane > c) Dg[lane * (NB + 1) + c] /= piv;
         __syncwarp();
         if (lane > c) {
-          const float lrc = Dg[lane * (NB + 1) + c];
+          const real lrc = Dg[lane * (NB + 1) + c];
           for (int cc = c + 1; cc <= lane; ++cc) Dg[lane * (NB + 1) + cc] -= lrc * Dg[cc * (NB + 1) + c];
         }
         __syncwarp();
@@ -103,15 +114,15 @@ __global__ void __launch_bounds__(kSetupThreads) k_chol(const int M, float* __re
     if (nrows <= 0) break;
     // (b) panel: X Lbb^T = A[r0:, j0:j0+nb]  -> one thread per row, forward substitution over the 32 columns
     for (int rr = tid; rr < nrows; rr += blockDim.x) {
-      float x[NB];
-      float* arow = A + static_cast<size_t>(r0 + rr) * M + j0;
+      real x[NB];
+      real* arow = A + static_cast<size_t>(r0 + rr) * M + j0;
 #pragma unroll
-      for (int c = 0; c < NB; ++c) x[c] = c < nbk ? arow[c] : 0.f;
+      for (int c = 0; c < NB; ++c) x[c] = c < nbk ? arow[c] : real(0);
 #pragma unroll
       for (int c = 0; c < NB; ++c) {
-        float v = x[c];
+        real v = x[c];
 #pragma unroll
-        for (int cc = 0; cc < c; ++cc) v = fmaf(-x[cc], Dg[c * (NB + 1) + cc], v);
+        for (int cc = 0; cc < c; ++cc) v = fma(-x[cc], Dg[c * (NB + 1) + cc], v);
         x[c] = v / Dg[c * (NB + 1) + c];
       }
 #pragma unroll
@@ -126,20 +137,20 @@ __global__ void __launch_bounds__(kSetupThreads) k_chol(const int M, float* __re
     for (long t = tid; t < static_cast<long>(nt) * nt; t += blockDim.x) {
       const int ti = static_cast<int>(t / nt), tj = static_cast<int>(t - static_cast<long>(ti) * nt);
       if (tj > ti) continue;
-      float acc[4][4];
+      real acc[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        for (int b = 0; b < 4; ++b) acc[a][b] = real(0);
 #pragma unroll 4
       for (int c = 0; c < NB; ++c) {
-        const float4 pi = *reinterpret_cast<const float4*>(Pt + c * Mp + 4 * ti);
-        const float4 pj = *reinterpret_cast<const float4*>(Pt + c * Mp + 4 * tj);
-        const float vi[4] = {pi.x, pi.y, pi.z, pi.w}, vj[4] = {pj.x, pj.y, pj.z, pj.w};
+        const double4 pi = *reinterpret_cast<const double4*>(Pt + c * Mp + 4 * ti);
+        const double4 pj = *reinterpret_cast<const double4*>(Pt + c * Mp + 4 * tj);
+        const real vi[4] = {pi.x, pi.y, pi.z, pi.w}, vj[4] = {pj.x, pj.y, pj.z, pj.w};
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(vi[a], vj[b], acc[a][b]);
+          for (int b = 0; b < 4; ++b) acc[a][b] = fma(vi[a], vj[b], acc[a][b]);
       }
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
@@ -163,28 +174,29 @@ __global__ void __launch_bounds__(kSetupThreads) k_chol(const int M, float* __re
 // src / dst are (Kc, M, NR) arrays (dst may alias src); src_t: read the source transposed ((Kc, NR, M), NR == M).
 // ---------------------------------------------------------------------------------------------
 template <bool TRANS>
-__global__ void __launch_bounds__(kSetupThreads) k_trsm(const int M, const int NR, const float* __restrict__ Lall, const float* src,
-                                                        float* dst, const int src_t) {
-  extern __shared__ __align__(16) float sm[];
+__global__ void __launch_bounds__(kSetupThreads) k_trsm(const int M, const int NR, const real* __restrict__ Lall, const real* src,
+                                                        real* dst, const int src_t) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  real* sm = reinterpret_cast<real*>(sm_raw);
   const int Mp = (M + NB - 1) / NB * NB;
-  float* Xs = sm;                          // [Mp][NB+1]
-  float* Lb = Xs + Mp * (NB + 1);          // [NB][NB+1] diagonal block
-  float* Ls = Lb + NB * (NB + 1);          // [64][NB+1] rows of the off-diagonal strip
+  real* Xs = sm;                          // [Mp][NB+1]
+  real* Lb = Xs + Mp * (NB + 1);          // [NB][NB+1] diagonal block
+  real* Ls = Lb + NB * (NB + 1);          // [64][NB+1] rows of the off-diagonal strip
   const int k = blockIdx.y, c0 = blockIdx.x * NB;
   const int ncol = min(NB, NR - c0);
-  const float* Lc = Lall + static_cast<size_t>(k) * M * M;
-  const float* S = src + static_cast<size_t>(k) * M * NR;
-  float* Dd = dst + static_cast<size_t>(k) * M * NR;
+  const real* Lc = Lall + static_cast<size_t>(k) * M * M;
+  const real* S = src + static_cast<size_t>(k) * M * NR;
+  real* Dd = dst + static_cast<size_t>(k) * M * NR;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   if (src_t) {
     for (int e = tid; e < Mp * NB; e += blockDim.x) {
       const int c = e / Mp, i = e - c * Mp;                        // consecutive threads walk i: coalesced rows of the source
-      Xs[i * (NB + 1) + c] = (i < M && c < ncol) ? S[static_cast<size_t>(c0 + c) * M + i] : 0.f;
+      Xs[i * (NB + 1) + c] = (i < M && c < ncol) ? S[static_cast<size_t>(c0 + c) * M + i] : real(0);
     }
   } else {
     for (int e = tid; e < Mp * NB; e += blockDim.x) {
       const int i = e / NB, c = e - i * NB;
-      Xs[i * (NB + 1) + c] = (i < M && c < ncol) ? S[static_cast<size_t>(i) * NR + c0 + c] : 0.f;
+      Xs[i * (NB + 1) + c] = (i < M && c < ncol) ? S[static_cast<size_t>(i) * NR + c0 + c] : real(0);
     }
   }
   const int nblk = Mp / NB;
@@ -195,27 +207,27 @@ __global__ void __launch_bounds__(kSetupThreads) k_trsm(const int M, const int N
     for (int e = tid; e < NB * NB; e += blockDim.x) {
       const int r = e / NB, c = e - r * NB;
       const int gr = j0 + r, gc = j0 + c;
-      Lb[r * (NB + 1) + c] = (gr < M && gc < M && gc <= gr) ? Lc[static_cast<size_t>(gr) * M + gc] : (r == c ? 1.f : 0.f);
+      Lb[r * (NB + 1) + c] = (gr < M && gc < M && gc <= gr) ? Lc[static_cast<size_t>(gr) * M + gc] : (r == c ? real(1) : real(0));
     }
     __syncthreads();
     if (warp == 0) {                       // lane = column: 32-step substitution on the diagonal block
-      float x[NB];
+      real x[NB];
 #pragma unroll
       for (int r = 0; r < NB; ++r) x[r] = Xs[(j0 + r) * (NB + 1) + lane];
       if (!TRANS) {
 #pragma unroll
         for (int r = 0; r < NB; ++r) {
-          float v = x[r];
+          real v = x[r];
 #pragma unroll
-          for (int c = 0; c < r; ++c) v = fmaf(-Lb[r * (NB + 1) + c], x[c], v);
+          for (int c = 0; c < r; ++c) v = fma(-Lb[r * (NB + 1) + c], x[c], v);
           x[r] = v / Lb[r * (NB + 1) + r];
         }
       } else {
 #pragma unroll
         for (int r = NB - 1; r >= 0; --r) {
-          float v = x[r];
+          real v = x[r];
 #pragma unroll
-          for (int c = r + 1; c < NB; ++c) v = fmaf(-Lb[c * (NB + 1) + r], x[c], v);
+          for (int c = r + 1; c < NB; ++c) v = fma(-Lb[c * (NB + 1) + r], x[c], v);
           x[r] = v / Lb[r * (NB + 1) + r];
         }
       }
@@ -231,20 +243,20 @@ __global__ void __launch_bounds__(kSetupThreads) k_trsm(const int M, const int N
         for (int e = tid; e < ns * NB; e += blockDim.x) {
           const int rr = e / NB, c = e - rr * NB;
           const int gi = s0 + rr, gc = j0 + c;
-          Ls[rr * (NB + 1) + c] = (gi < M && gc < M) ? Lc[static_cast<size_t>(gi) * M + gc] : 0.f;
+          Ls[rr * (NB + 1) + c] = (gi < M && gc < M) ? Lc[static_cast<size_t>(gi) * M + gc] : real(0);
         }
       } else {
         for (int e = tid; e < ns * NB; e += blockDim.x) {
           const int c = e / ns, rr = e - c * ns;                    // consecutive threads walk the row of Lc: coalesced
           const int gj = s0 + rr, gc = j0 + c;
-          Ls[rr * (NB + 1) + c] = (gc < M && gj < M) ? Lc[static_cast<size_t>(gc) * M + gj] : 0.f;
+          Ls[rr * (NB + 1) + c] = (gc < M && gj < M) ? Lc[static_cast<size_t>(gc) * M + gj] : real(0);
         }
       }
       __syncthreads();
       for (int rr = warp; rr < ns; rr += nwarp) {
-        float acc = 0.f;
+        real acc = 0;
 #pragma unroll
-        for (int c = 0; c < NB; ++c) acc = fmaf(Ls[rr * (NB + 1) + c], Xs[(j0 + c) * (NB + 1) + lane], acc);
+        for (int c = 0; c < NB; ++c) acc = fma(Ls[rr * (NB + 1) + c], Xs[(j0 + c) * (NB + 1) + lane], acc);
         Xs[(s0 + rr) * (NB + 1) + lane] -= acc;
       }
       __syncthreads();
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(kSetupThreads) k_trsm(const int M, const int N
 // small glue kernels (all elementwise over (k, i, r) or (k, i, j))
 // ---------------------------------------------------------------------------------------------
 // rhs[k][i][r] = reference-layout (L, M, D_out) tensor
-__global__ void k_gather_lmd(const NuGeom g, const float* __restrict__ src, float* __restrict__ rhs) {
+__global__ void k_gather_lmd(const NuGeom g, const float* __restrict__ src, real* __restrict__ rhs) {
   const long n = static_cast<long>(g.Kc) * g.M * g.NR;
   for (long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.M), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.M));
@@ -269,23 +281,23 @@ __global__ void k_gather_lmd(const NuGeom g, const float* __restrict__ src, floa
   }
 }
 // b = u - a  (u in reference layout), in place on the a array
-__global__ void k_u_minus_a(const NuGeom g, const float* __restrict__ u, float* __restrict__ a_then_b) {
+__global__ void k_u_minus_a(const NuGeom g, const float* __restrict__ u, real* __restrict__ a_then_b) {
   const long n = static_cast<long>(g.Kc) * g.M * g.NR;
   for (long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.M), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.M));
-    a_then_b[e] = u[lmd_index(g, k, i, r)] - a_then_b[e];
+    a_then_b[e] = static_cast<real>(u[lmd_index(g, k, i, r)]) - a_then_b[e];
   }
 }
 // scatter (Kc, M, NR) -> nu layout (mode 0) or (L, M, D_out) layout with a sign (mode 1)
-__global__ void k_scatter(const NuGeom g, const float* __restrict__ rhs, float* __restrict__ out, const int mode, const float scale) {
+__global__ void k_scatter(const NuGeom g, const real* __restrict__ rhs, float* __restrict__ out, const int mode, const float scale) {
   const long n = static_cast<long>(g.Kc) * g.M * g.NR;
   for (long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.M), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.M));
-    out[mode == 0 ? nu_index(g, k, i, r) : lmd_index(g, k, i, r)] = scale * rhs[e];
+    out[mode == 0 ? nu_index(g, k, i, r) : lmd_index(g, k, i, r)] = static_cast<float>(scale * rhs[e]);
   }
 }
 // gather nu-layout tensor into (Kc, M, NR)
-__global__ void k_gather_nu(const NuGeom g, const float* __restrict__ src, float* __restrict__ rhs) {
+__global__ void k_gather_nu(const NuGeom g, const float* __restrict__ src, real* __restrict__ rhs) {
   const long n = static_cast<long>(g.Kc) * g.M * g.NR;
   for (long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.M), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.M));
@@ -293,62 +305,62 @@ __global__ void k_gather_nu(const NuGeom g, const float* __restrict__ src, float
   }
 }
 // S[k][i][j] = -1/2 sum_r u[k][max(i,j)][r] bb[k][min(i,j)][r]
-__global__ void k_build_S(const NuGeom g, const float* __restrict__ u, const float* __restrict__ bb, float* __restrict__ S) {
+__global__ void k_build_S(const NuGeom g, const float* __restrict__ u, const real* __restrict__ bb, real* __restrict__ S) {
   const int k = blockIdx.y;
   const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long>(g.M) * g.M) return;
   const int i = static_cast<int>(idx / g.M), j = static_cast<int>(idx - static_cast<long>(i) * g.M);
   const int hi_ = i > j ? i : j, lo_ = i > j ? j : i;
-  float acc = 0.f;
-  for (int r = 0; r < g.NR; ++r) acc = fmaf(u[lmd_index(g, k, hi_, r)], bb[(static_cast<size_t>(k) * g.M + lo_) * g.NR + r], acc);
-  S[(static_cast<size_t>(k) * g.M + i) * g.M + j] = -0.5f * acc;
+  real acc = 0;
+  for (int r = 0; r < g.NR; ++r) acc = fma(static_cast<real>(u[lmd_index(g, k, hi_, r)]), bb[(static_cast<size_t>(k) * g.M + lo_) * g.NR + r], acc);
+  S[(static_cast<size_t>(k) * g.M + i) * g.M + j] = -0.5 * acc;
 }
 // A_bar = X + 1/2 sum_r (r_i q_j + q_i r_j) contracted with dK/d(var, ell, Z); one warp per (k, i) row
 __global__ void k_kzz_bwd(const NuGeom g, const float* __restrict__ Z, const float* __restrict__ ell, const float* __restrict__ var,
-                          const float* __restrict__ X, const float* __restrict__ rr_, const float* __restrict__ qq_, float* __restrict__ d_Z,
+                          const real* __restrict__ X, const real* __restrict__ rr_, const real* __restrict__ qq_, float* __restrict__ d_Z,
                           float* __restrict__ d_ell, float* __restrict__ d_var) {
   const int k = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= g.M) return;
-  const float vk = var[g.dimwise ? k : 0];
-  float zi[kMaxD], inv2[kMaxD], dz[kMaxD], dl[kMaxD], dv = 0.f;
+  const real vk = var[g.dimwise ? k : 0];
+  real zi[kMaxD], inv2[kMaxD], dz[kMaxD], dl[kMaxD], dv = 0;
   for (int d = 0; d < g.D_in; ++d) {
     zi[d] = Z[i * g.D_in + d];
-    const float e = ell_of(g, ell, k, d);
-    inv2[d] = 1.f / (e * e);
-    dz[d] = 0.f;
-    dl[d] = 0.f;
+    const real e = ell_of(g, ell, k, d);
+    inv2[d] = 1.0 / (e * e);
+    dz[d] = 0;
+    dl[d] = 0;
   }
-  const float* ri = rr_ + (static_cast<size_t>(k) * g.M + i) * g.NR;
-  const float* qi = qq_ + (static_cast<size_t>(k) * g.M + i) * g.NR;
+  const real* ri = rr_ + (static_cast<size_t>(k) * g.M + i) * g.NR;
+  const real* qi = qq_ + (static_cast<size_t>(k) * g.M + i) * g.NR;
   for (int j = lane; j < g.M; j += 32) {
-    float ab = X[(static_cast<size_t>(k) * g.M + i) * g.M + j];
-    const float* rj = rr_ + (static_cast<size_t>(k) * g.M + j) * g.NR;
-    const float* qj = qq_ + (static_cast<size_t>(k) * g.M + j) * g.NR;
-    float rk = 0.f;
+    real ab = X[(static_cast<size_t>(k) * g.M + i) * g.M + j];
+    const real* rj = rr_ + (static_cast<size_t>(k) * g.M + j) * g.NR;
+    const real* qj = qq_ + (static_cast<size_t>(k) * g.M + j) * g.NR;
+    real rk = 0;
     for (int r = 0; r < g.NR; ++r) rk += ri[r] * qj[r] + qi[r] * rj[r];
-    ab = fmaf(0.5f, rk, ab);
-    float diff[kMaxD], sq = 0.f;
+    ab = fma(0.5, rk, ab);
+    real diff[kMaxD], sq = 0;
     for (int d = 0; d < g.D_in; ++d) {
-      diff[d] = zi[d] - Z[j * g.D_in + d];
-      sq = fmaf(diff[d] * diff[d], inv2[d], sq);
+      diff[d] = zi[d] - static_cast<real>(Z[j * g.D_in + d]);
+      sq = fma(diff[d] * diff[d], inv2[d], sq);
     }
-    const float E = expf(-0.5f * sq);
-    const float G = ab * vk * E;                 // A_bar_ij K_ij
-    dv = fmaf(ab, E, dv);                        // dK/dvar = E
+    const real E = exp(-0.5 * sq);
+    const real G = ab * vk * E;                 // A_bar_ij K_ij
+    dv = fma(ab, E, dv);                        // dK/dvar = E
     for (int d = 0; d < g.D_in; ++d) {
-      dl[d] = fmaf(G * diff[d] * diff[d], inv2[d], dl[d]);      // x 1/ell below
-      dz[d] = fmaf(-2.f * G * diff[d], inv2[d], dz[d]);         // both (i,j) and (j,i) entries depend on Z_i (A_bar symmetric)
+      dl[d] = fma(G * diff[d] * diff[d], inv2[d], dl[d]);      // x 1/ell below
+      dz[d] = fma(-2.0 * G * diff[d], inv2[d], dz[d]);         // both (i,j) and (j,i) entries depend on Z_i (A_bar symmetric)
     }
   }
-  dv = warp_sum(dv);
-  if (lane == 0 && d_var) atomicAdd(&d_var[g.dimwise ? k : 0], dv);
+  dv = warp_sum_real(dv);
+  if (lane == 0 && d_var) atomicAdd(&d_var[g.dimwise ? k : 0], static_cast<float>(dv));
   for (int d = 0; d < g.D_in; ++d) {
-    const float a = warp_sum(dl[d]), b = warp_sum(dz[d]);
+    const real a = warp_sum_real(dl[d]), b = warp_sum_real(dz[d]);
     if (lane == 0) {
-      if (d_ell) atomicAdd(&d_ell[g.dimwise ? k * g.D_in + d : d], a / ell_of(g, ell, k, d));
-      if (d_Z) atomicAdd(&d_Z[i * g.D_in + d], b);
+      if (d_ell) atomicAdd(&d_ell[g.dimwise ? k * g.D_in + d : d], static_cast<float>(a / static_cast<real>(ell_of(g, ell, k, d))));
+      if (d_Z) atomicAdd(&d_Z[i * g.D_in + d], static_cast<float>(b));
     }
   }
 }
@@ -436,15 +448,15 @@ inline int blocks_for(long n, int threads, int cap = 148 * 8) {
 }
 inline size_t trsm_smem(int M) {
   const int Mp = (M + NB - 1) / NB * NB;
-  return (static_cast<size_t>(Mp) * (NB + 1) + NB * (NB + 1) + 64 * (NB + 1)) * 4;
+  return (static_cast<size_t>(Mp) * (NB + 1) + NB * (NB + 1) + 64 * (NB + 1)) * sizeof(real);
 }
 inline size_t chol_smem(int M) {
   const int Mp = (M + NB - 1) / NB * NB;
-  return (static_cast<size_t>(NB) * (NB + 1) + static_cast<size_t>(NB) * Mp) * 4;
+  return (static_cast<size_t>(NB) * (NB + 1) + static_cast<size_t>(NB) * Mp) * sizeof(real);
 }
 
 template <bool TRANS>
-cudaError_t trsm(const NuGeom& g, int NR, const float* Lc, const float* src, float* dst, int src_t, cudaStream_t st) {
+cudaError_t trsm(const NuGeom& g, int NR, const real* Lc, const real* src, real* dst, int src_t, cudaStream_t st) {
   const size_t smem = trsm_smem(g.M);
   cudaError_t e = cudaFuncSetAttribute(k_trsm<TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
@@ -461,16 +473,18 @@ cudaError_t trsm(const NuGeom& g, int NR, const float* Lc, const float* src, flo
     if (e_ != cudaSuccess) return e_;    \
   } while (0)
 
-size_t nu_save_floats(const NuGeom& g) { return static_cast<size_t>(g.Kc) * g.M * g.M + static_cast<size_t>(g.Kc) * g.M * g.NR; }
+// (sizes in FLOATS of the caller's buffers: the factors and right-hand sides are stored in `real` = double)
+size_t nu_save_floats(const NuGeom& g) { return (sizeof(real) / 4) * (static_cast<size_t>(g.Kc) * g.M * g.M + static_cast<size_t>(g.Kc) * g.M * g.NR); }
 size_t nu_ws_floats(const NuGeom& g) {
-  return 2 * static_cast<size_t>(g.Kc) * g.M * g.M + 4 * static_cast<size_t>(g.Kc) * g.M * g.NR + 64;
+  return (sizeof(real) / 4) * (2 * static_cast<size_t>(g.Kc) * g.M * g.M + 4 * static_cast<size_t>(g.Kc) * g.M * g.NR) + 64;
 }
 
 cudaError_t nu_forward(const NuGeom& g, const float* Z, const float* ell, const float* var, const float* u_prior, const float* u, float* nu,
-                       float* save, int* info, float* ws, cudaStream_t st) {
-  float* Lc = save;                                                  // (Kc, M, M)
-  float* a = save + static_cast<size_t>(g.Kc) * g.M * g.M;           // (Kc, M, NR): Lc^-1 u_prior
-  float* b = ws;                                                     // (Kc, M, NR)
+                       float* save_f, int* info, float* ws_f, cudaStream_t st) {
+  real* save = reinterpret_cast<real*>(save_f);
+  real* Lc = save;                                                   // (Kc, M, M)
+  real* a = save + static_cast<size_t>(g.Kc) * g.M * g.M;            // (Kc, M, NR): Lc^-1 u_prior
+  real* b = reinterpret_cast<real*>(ws_f);                           // (Kc, M, NR)
   const long mm = static_cast<long>(g.M) * g.M, rhs = static_cast<long>(g.Kc) * g.M * g.NR;
   k_kzz_build<<<dim3(static_cast<unsigned>((mm + 255) / 256), g.Kc), 256, 0, st>>>(g, Z, ell, var, Lc);
   GPODE_CK(cudaGetLastError());
@@ -481,7 +495,7 @@ cudaError_t nu_forward(const NuGeom& g, const float* Z, const float* ell, const 
   k_gather_lmd<<<blocks_for(rhs, 256), 256, 0, st>>>(g, u_prior, a);
   GPODE_CK(cudaGetLastError());
   GPODE_CK(trsm<false>(g, g.NR, Lc, a, a, 0, st));
-  GPODE_CK(cudaMemcpyAsync(b, a, rhs * 4, cudaMemcpyDeviceToDevice, st));
+  GPODE_CK(cudaMemcpyAsync(b, a, rhs * sizeof(real), cudaMemcpyDeviceToDevice, st));
   k_u_minus_a<<<blocks_for(rhs, 256), 256, 0, st>>>(g, u, b);
   GPODE_CK(cudaGetLastError());
   GPODE_CK(trsm<true>(g, g.NR, Lc, b, b, 0, st));
@@ -489,16 +503,17 @@ cudaError_t nu_forward(const NuGeom& g, const float* Z, const float* ell, const 
   return cudaGetLastError();
 }
 
-cudaError_t nu_backward(const NuGeom& g, const float* Z, const float* ell, const float* var, const float* u, const float* save, const float* dnu,
-                        float* d_uprior, float* d_u, float* d_Z, float* d_ell, float* d_var, float* ws, cudaStream_t st) {
-  const float* Lc = save;
-  const float* a = save + static_cast<size_t>(g.Kc) * g.M * g.M;
+cudaError_t nu_backward(const NuGeom& g, const float* Z, const float* ell, const float* var, const float* u, const float* save_f, const float* dnu,
+                        float* d_uprior, float* d_u, float* d_Z, float* d_ell, float* d_var, float* ws_f, cudaStream_t st) {
+  const real* save = reinterpret_cast<const real*>(save_f);
+  const real* Lc = save;
+  const real* a = save + static_cast<size_t>(g.Kc) * g.M * g.M;
   const size_t mm = static_cast<size_t>(g.Kc) * g.M * g.M, rhs = static_cast<size_t>(g.Kc) * g.M * g.NR;
-  float* S = ws;                 // (Kc, M, M)
-  float* Y = S + mm;             // (Kc, M, M)
-  float* bb = Y + mm;            // (Kc, M, NR)
-  float* rr = bb + rhs;
-  float* qq = rr + rhs;
+  real* S = reinterpret_cast<real*>(ws_f);   // (Kc, M, M)
+  real* Y = S + mm;              // (Kc, M, M)
+  real* bb = Y + mm;             // (Kc, M, NR)
+  real* rr = bb + rhs;
+  real* qq = rr + rhs;
   k_gather_nu<<<blocks_for(static_cast<long>(rhs), 256), 256, 0, st>>>(g, dnu, bb);
   GPODE_CK(cudaGetLastError());
   GPODE_CK(trsm<false>(g, g.NR, Lc, bb, bb, 0, st));                 // bb = Lc^-1 nu_bar   (= u_bar)

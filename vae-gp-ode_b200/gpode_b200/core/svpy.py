@@ -79,8 +79,44 @@ class SVGP_Layer(torch.nn.Module):
 
     def _fused_setup(self):
         """RBF kernels with a full (non-diagonal) q(u) on a CUDA device run the per-rollout setup on the kernels of
-        csrc/setup_kernels.cu; DF ((M D x M D) system), q_diag and CPU tensors (host-logic unit tests) use torch ops."""
+        csrc/setup_kernels.cu; q_diag and CPU tensors (host-logic unit tests) use torch ops; DF see _df_batched_setup."""
         return self.kernel_n == "RBF" and not self.q_diag and self.inducing_loc.optvar.is_cuda and self.M <= 512
+
+    def _df_batched_setup(self, L):
+        """DF kernel on a CUDA device: the L function samples of a rollout share Z, lengthscales and variance, hence ONE
+        (M D x M D) Gram matrix and ONE Cholesky factor (the reference rebuilds and refactors it for every sample,
+        kernels.py:376-387 called from svpy.py:118-121 inside the serial MC loop); the L right-hand sides are solved together.
+        The factorisation and the two triangular solves run in float64 (cuSOLVER / cuBLAS through torch.linalg): K(Z,Z) has
+        cond 1e4..1e6 and the fp32 factorisation is the largest single error of the reference's own
+        gradients -- here nu is exact to fp32 rounding.  Inducing sample, prior at Z (CUDA field kernel with nu = 0) and
+        B(omega) are batched over L as well."""
+        k = self.kern
+        draws = [self._draw() for _ in range(L)]
+        eps, phase, w, eps_u = (torch.stack([d[i] for d in draws]) for i in range(4))
+        Z, ell, var = self.inducing_loc(), k.lengthscales, k.variance
+        u = GF.inducing_sample(self.Us_sqrt.optvar, self.Um(), eps_u)                      # (L,M,D)
+        omega = eps / ell.t()[None, :, None, :]                                            # (L,D,S,D)  sample_freq, kernels.py:120-124
+        B = torch.stack([k.operator_B(omega[l]) for l in range(L)])                        # (L,S,D,D)
+        n = self.M * self.D_out
+        nu0 = torch.zeros((L, n, 1), device=Z.device)
+        u_prior, _ = GF.gp_field(Z[None].expand(L, -1, -1), Z, nu0, eps, phase, w, ell, var, k.variant, B)   # rff_forward(Z), (L,M,D)
+        f64 = torch.float64
+        X = Z.to(f64)
+        d = X[None, :, :] - X[:, None, :]
+        r2 = d.square().sum(-1)[:, :, None, None]
+        c = ell.to(f64).pow(-2)
+        H = d[:, :, :, None] * d[:, :, None, :] * c + torch.eye(self.D_in, device=Z.device, dtype=f64) * ((self.D_in - 1.0) - r2 * c)
+        Ku = (var.to(f64) * torch.exp(-0.5 * r2 * c) * H * c).permute(0, 2, 1, 3).reshape(n, n)    # kernels.py:289-303
+        Lc, info = torch.linalg.cholesky_ex(Ku + jitter * torch.eye(n, device=Z.device, dtype=f64))   # lower triangle only, like the reference
+        self.chol_info = info.reshape(1)
+        if self.check_cholesky:
+            self.cholesky_ok(raise_error=True)
+        rhs_p = u_prior.reshape(L, n).t().to(f64)                                           # vec layout m*D+i (kernels.py:384-386)
+        rhs_u = u.reshape(L, n).t().to(f64)
+        a = torch.linalg.solve_triangular(Lc, rhs_p, upper=False)
+        nu = torch.linalg.solve_triangular(Lc.t(), rhs_u - a, upper=True).t().to(torch.float32).reshape(L, n, 1)
+        k.rff_omega, k.rff_B, k.nu = omega[-1], B[-1], nu[-1]                               # the last sample stays on the kernel
+        return FieldSample(k.variant, Z, ell, var, eps, phase, w, nu, B)
 
     def _draw(self):
         """host draws of one function sample in the reference's order (kernels.py:126-137, svpy.py:94): w, eps, phase, eps_u."""
@@ -93,6 +129,8 @@ class SVGP_Layer(torch.nn.Module):
         reference's order, the GPU work -- inducing sample, prior at Z, K(Z,Z) + Cholesky + whitened solves -- is one
         batched pass.  Returns a FieldSample with leading axis L."""
         self._cache = None      # a cache left by an earlier build_cache() is stale from here on
+        if self.kernel_n == "DF" and not self.q_diag and self.inducing_loc.optvar.is_cuda:
+            return self._df_batched_setup(L)
         if not self._fused_setup():
             samples = []
             for _ in range(L):
@@ -130,7 +168,7 @@ class SVGP_Layer(torch.nn.Module):
 
     def build_cache(self):
         """Fix one function sample: feature draws, inducing sample, nu (svpy.py:103-121; same draw order)."""
-        if self._fused_setup():
+        if self._fused_setup() or (self.kernel_n == "DF" and not self.q_diag and self.inducing_loc.optvar.is_cuda):
             self._cache = self.build_cache_batched(1)
             return
         self._cache = None
