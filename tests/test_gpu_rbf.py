@@ -231,6 +231,14 @@ def fwd_kernel(request):
         yield request.param
 
 
+@pytest.fixture(params=["mma", "tc"])
+def bwd_kernel(request):
+    """the two reverse-sweep / parameter-gradient kernel families of the D > 8 tensor path: mma.sync (RbfMmaBwdPolicy, k_rbf_pgrad_mma) and
+    tcgen05 / tensor memory (RbfTcBwdPolicy, rbf_bwd_tc.cuh), selected through GpodeProblem.flags"""
+    with _gp().kernel_flags(_gp().FLAG_BWD_MMA if request.param == "mma" else _gp().FLAG_BWD_TCGEN05):
+        yield request.param
+
+
 @pytest.mark.parametrize("order,D_in,D_out,M,S,L", [(1, 16, 16, 300, 260, 1), (2, 16, 8, 512, 256, 2), (1, 16, 16, 97, 513, 1), (1, 11, 11, 260, 130, 1),
                                                     (2, 14, 7, 130, 250, 1)])
 def test_forward_kernels_ragged_tiles(fwd_kernel, order, D_in, D_out, M, S, L):
@@ -286,7 +294,7 @@ def test_tensor_path_forward_large_batch(fwd_kernel):
 
 
 @pytest.mark.parametrize("D_in,D_out,M,S,N", [(12, 5, 101, 33, 40000), (16, 4, 200, 31, 33000)])
-def test_tensor_path_backward_large_batch(D_in, D_out, M, S, N):
+def test_tensor_path_backward_large_batch(bwd_kernel, D_in, D_out, M, S, N):
     """chip-filling batches at D > 8 run the tensor-path forward AND reverse sweeps (RbfMmaFwdPolicy / RbfMmaBwdPolicy):
     field VJP, parameter gradients and a short RK4 rollout backward against autograd through the fp64 oracle."""
     rs = np.random.RandomState(D_in * 7 + M)
@@ -309,11 +317,11 @@ def test_tensor_path_backward_large_batch(D_in, D_out, M, S, N):
     got = [x.grad[0], s["Z"].grad, s["nu"].grad[0], s["ell"].grad, s["var"].grad]
     for nm, a, b in zip(("dx", "dZ", "dnu", "dell", "dvar"), got, want):
         e = rel(a, b)
-        print("tensor-path field-bwd D=%d %s: %.2e" % (D_in, nm, e))
+        print("tensor-path [%s] field-bwd D=%d %s: %.2e" % (bwd_kernel, D_in, nm, e))
         assert e < GRAD_TOL, (nm, e)
 
 
-def test_tensor_path_rollout_backward_large_batch():
+def test_tensor_path_rollout_backward_large_batch(bwd_kernel):
     D, M, S, N, T = 12, 64, 17, 33000, 3
     rs = np.random.RandomState(11)
     f64 = lambda a: torch.tensor(a, dtype=torch.float64)
@@ -336,12 +344,12 @@ def test_tensor_path_rollout_backward_large_batch():
     got = [z0.grad, s["Z"].grad, s["nu"].grad[0], s["ell"].grad, s["var"].grad]
     for nm, a, b in zip(("dz0", "dZ", "dnu", "dell", "dvar"), got, want):
         e = rel(a, b)
-        print("tensor-path rollout-bwd %s: %.2e" % (nm, e))
+        print("tensor-path [%s] rollout-bwd %s: %.2e" % (bwd_kernel, nm, e))
         assert e < GRAD_TOL, (nm, e)
 
 
 @pytest.mark.parametrize("scale_x,scale_ell", [(300.0, 60.0), (0.002, 0.02), (30.0, 0.3), (1.0, 0.05)])
-def test_tensor_path_extreme_magnitudes(fwd_kernel, scale_x, scale_ell):
+def test_tensor_path_extreme_magnitudes(fwd_kernel, bwd_kernel, scale_x, scale_ell):
     """the fp16 tensor-path dot products are scaled by exact powers of two per state and per output dimension: states and
     lengthscales far from O(1) (row coefficients from 1e-5 to 1e3, |x| up to ~1e3) must neither overflow nor lose the field bar
     where the field is well conditioned; checked against the fp64 oracle on a chip-filling batch (forward and VJP)."""

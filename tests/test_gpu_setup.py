@@ -81,11 +81,12 @@ def test_cholesky_failure_is_reported():
     Z, ell, var, up, u = _problem("rbf_dimwise", 40, 3, 2, 1, seed=0)
     Z[1] = Z[0]                       # duplicate inducing point: K + 1e-5 I stays SPD (jitter) -> info == 0
     from gpode_b200 import functional as GF
-    nu = GF.ComputeNu.apply(Z.float().cuda(), ell.float().cuda(), var.float().cuda(), up.float().cuda(), u.float().cuda(), 1)
-    assert torch.isfinite(nu).all()
+    nu, info = GF.ComputeNu.apply(Z.float().cuda(), ell.float().cuda(), var.float().cuda(), up.float().cuda(), u.float().cuda(), 1)
+    assert torch.isfinite(nu).all() and int(info.abs().max()) == 0
     var_bad = -var                    # negative variance: not positive definite -> NaN factor, reported like LAPACK's info
-    nu = _gp().compute_nu(Z.float().cuda(), ell.float().cuda(), var_bad.float().cuda(), up.float().cuda(), u.float().cuda(), "rbf_dimwise")
-    assert not torch.isfinite(nu).all()
+    nu, info = _gp().compute_nu(Z.float().cuda(), ell.float().cuda(), var_bad.float().cuda(), up.float().cuda(), u.float().cuda(), "rbf_dimwise",
+                                return_info=True)
+    assert not torch.isfinite(nu).all() and int(info.min()) >= 1      # 1 + index of the first non-positive pivot, per matrix
 
 
 @pytest.mark.parametrize("M,D,L", [(10, 3, 1), (100, 6, 4), (512, 16, 2), (257, 5, 3)])

@@ -132,7 +132,7 @@ int rbf_check_smem(const RbfGeom& g) { return rbf_smem_bytes(g, 32, 1, true) <= 
 cudaError_t rbf_pack(const GpodeProblem* p, const RbfGeom& g, float* packed, cudaStream_t st, bool fwd) {
   RbfPackArgs a;
   a.g = g;
-  a.with_tc = fwd ? 1 : 0;
+  a.with_tc = fwd ? 1 : 2;
   a.variant = p->variant;
   a.Z = p->Z; a.ell = p->ell; a.var = p->var; a.eps = p->eps; a.phase = p->phase; a.w = p->w; a.nu = p->nu;
   a.packed = packed;

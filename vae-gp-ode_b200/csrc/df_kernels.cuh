@@ -269,6 +269,7 @@ struct DfPolicy {
   static constexpr int kThreads = 128;
   static constexpr int kMinBlocks = 3;
   static constexpr int kStateThreads = 0;
+  static constexpr int kXsStride = 0;       // staging buffers xs / dx are strided by the block size
   static constexpr int kThreadsBwd = 128;
   static constexpr int kMinBlocksBwd = D_ <= 6 ? 3 : 2;   // the reverse sweep also carries the D x D lengthscale accumulators
   using Geom = DfGeom;

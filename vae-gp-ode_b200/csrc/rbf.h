@@ -34,14 +34,33 @@ constexpr int kTcfRows = 256;
 constexpr int kTcfChunks = 10;
 constexpr int kTcfBFloats = kTcfChunks * kTcfRows * 4;
 constexpr int kTcfTileFloats = kTcfBFloats + kTcfRows;
+// Reverse sweep / parameter gradients on tcgen05 (rbf_bwd_tc.cuh, rbf_pgrad_tc.cuh): behind the forward tiles, [L][D_out][items] tiles of kTcbUnits
+// units ("items": feature units first, inducing units after, each section padded to whole items):
+//   theta operand  : kTcfChunks x kTcbUnits x 16 B, the layout of the forward tiles (feature offsets carry + pi/2: cos(theta + pi/2) = -sin theta)
+//   second operand : B (N = kTcbQN columns x K = 2 kTcbUnits) of Q[state][n] = sum_r (tau_h[r] B[n][2r] + tau_l[r] B[n][2r+1]) in bf16, K-major core
+//                    matrices (8 columns x 8 k): 16-byte chunk c of column n at c * kTcbQN * 16 + (n / 8) * 128 + (n % 8) * 16 bytes.  Columns
+//                    n < 24: head part -- n = d < DP: P_h[r][d] on both k rows, n = 16: the weight's head (inducing units only: the A_k(x) term);
+//                    n >= 24: remainder part -- n = 24 + d: (P_l[r][d], 0), n = 40: (w_l, 0).  P[r][d] = weight_r x coefficient_rd.
+constexpr int kTcbUnits = 128;
+constexpr int kTcbQN = 48;
+constexpr int kTcbThFloats = kTcfChunks * kTcbUnits * 4;            // 20,480 B
+constexpr int kTcbPFloats = kTcbQN * 2 * kTcbUnits * 2 / 4;         // 24,576 B
+constexpr int kTcbTileFloats = kTcbThFloats + kTcbPFloats;
 __host__ __device__ inline int rbf_tc_blocks_s(const RbfGeom& g) { return (g.S + kTcfRows - 1) / kTcfRows; }
 __host__ __device__ inline int rbf_tc_blocks(const RbfGeom& g) { return rbf_tc_blocks_s(g) + (g.M + kTcfRows - 1) / kTcfRows; }
 inline size_t rbf_tc_floats(const RbfGeom& g) { return g.DP > 8 ? static_cast<size_t>(g.L) * g.D_out * rbf_tc_blocks(g) * kTcfTileFloats : 0; }
+__host__ __device__ inline int rbf_tcb_items_s(const RbfGeom& g) { return (g.S + kTcbUnits - 1) / kTcbUnits; }
+__host__ __device__ inline int rbf_tcb_items(const RbfGeom& g) { return rbf_tcb_items_s(g) + (g.M + kTcbUnits - 1) / kTcbUnits; }
+inline size_t rbf_tcb_floats(const RbfGeom& g) { return g.DP > 8 ? static_cast<size_t>(g.L) * g.D_out * rbf_tcb_items(g) * kTcbTileFloats : 0; }
 inline size_t rbf_maxabs_floats(const RbfGeom& g) { return (static_cast<size_t>(g.L) * g.D_out + 3) / 4 * 4; }
-inline size_t rbf_packed_floats(const RbfGeom& g) { return rbf_rows_end_floats(g) + rbf_maxabs_floats(g) + rbf_tc_floats(g); }
+inline size_t rbf_packed_floats(const RbfGeom& g) { return rbf_rows_end_floats(g) + rbf_maxabs_floats(g) + rbf_tc_floats(g) + rbf_tcb_floats(g); }
 __host__ __device__ inline const float* rbf_tc_tiles_ptr(const float* packed, const RbfGeom& g, int l) {
   return packed + static_cast<size_t>(g.L) * g.D_out * (g.hdr_floats + static_cast<size_t>(g.SP2 + g.MP2) * g.row_floats) +
          (static_cast<size_t>(g.L) * g.D_out + 3) / 4 * 4 + static_cast<size_t>(l) * g.D_out * rbf_tc_blocks(g) * kTcfTileFloats;
+}
+__host__ __device__ inline const float* rbf_tcb_tiles_ptr(const float* packed, const RbfGeom& g, int l) {
+  return rbf_tc_tiles_ptr(packed, g, 0) + static_cast<size_t>(g.L) * g.D_out * rbf_tc_blocks(g) * kTcfTileFloats +
+         static_cast<size_t>(l) * g.D_out * rbf_tcb_items(g) * kTcbTileFloats;
 }
 __host__ __device__ inline const float* rbf_maxabs_ptr(const float* packed, const RbfGeom& g, int l) {
   return packed + static_cast<size_t>(g.L) * g.D_out * (g.hdr_floats + static_cast<size_t>(g.SP2 + g.MP2) * g.row_floats) + static_cast<size_t>(l) * g.D_out;
@@ -87,7 +106,8 @@ struct RbfPackArgs {
   const float* w;
   const float* nu;
   float* packed;
-  int with_tc;           // also lay out the operand tiles of the tensor-memory forward (forward entry points only)
+  int with_tc;           // bit 0: also lay out the operand tiles of the tensor-memory forward (forward entry points); bit 1: those of the
+                         // tensor-memory reverse sweep / parameter gradients (backward entry points)
 };
 
 struct RbfFinalizeArgs {
@@ -126,6 +146,16 @@ inline bool rbf_fwd_use_tc(const RbfGeom& g) {
   if (g.flags & GPODE_FLAG_FWD_MMA) return false;
   if (g.flags & GPODE_FLAG_FWD_TCGEN05) return true;    // (tests: force the tensor-memory kernel whatever the padding)
   return static_cast<long>(rbf_tc_blocks(g)) * kTcfRows * 100 <= static_cast<long>(g.S + g.M) * 115;
+}
+// Reverse sweep at D > 8 on a chip-filling batch: the mma.sync kernel (RbfMmaBwdPolicy) is the default; the tcgen05 / tensor-memory
+// kernel (rbf_bwd_tc.cuh) is selected with GPODE_FLAG_BWD_TCGEN05.  Measured at config-5 shapes: the tensor-memory
+// port serialises accumulator updates, the A-operand reads of the second product and the epilogue's tcgen05.ld / .st, which puts the
+// tensor-memory kernel at ~2,500 cycles per (128 states x 128 units) against ~3,100 for the mma.sync kernel on paper and behind it in
+// practice (41 vs 37.5 ms at T = 3) -- parity-tested, kept as the measured alternative, not the default.
+inline bool rbf_bwd_use_tc(const RbfGeom& g) {
+  if (g.DP <= 8 || static_cast<long>(g.N) * g.L < 32768) return false;
+  if (g.flags & GPODE_FLAG_BWD_MMA) return false;
+  return (g.flags & GPODE_FLAG_BWD_TCGEN05) != 0;
 }
 // inducing points per CTA of the tensor-path parameter-gradient kernel (8 warps x 16 MT rows)
 inline void rbf_pgrad_mma_shape(const RbfGeom& g, int& MT, int& n_mblk) {

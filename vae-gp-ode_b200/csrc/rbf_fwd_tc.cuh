@@ -76,6 +76,7 @@ struct RbfTcFwdPolicy {
   static constexpr int kThreads = kFtThreads;
   static constexpr int kMinBlocks = 1;
   static constexpr int kStateThreads = kFtStates;
+  static constexpr int kXsStride = 0;       // staging buffers xs / dx are strided by the block size
   static constexpr int kThreadsBwd = kFtThreads;
   static constexpr int kMinBlocksBwd = 1;
   using Geom = RbfGeom;

@@ -5,6 +5,7 @@
 #include "rbf_kernels.cuh"
 #include "rbf_pgrad_mma.cuh"
 #include "rbf_fwd_tc.cuh"
+#include "rbf_bwd_tc.cuh"
 
 #ifndef GPODE_DP
 #error "compile with -DGPODE_DP=<even 2..16>"
@@ -72,9 +73,21 @@ cudaError_t launch_bwd_mma(KernMma kern, const Args& a, cudaStream_t st) {
   return launch_sweep(kern, a, threads, 2, true, st);
 }
 
+// tcgen05 reverse sweep (rbf_bwd_tc.cuh): 128 states per CTA, one CTA per SM (all 512 tensor-memory columns)
+template <typename Args, typename KernTc>
+cudaError_t launch_bwd_tc(KernTc kern, const Args& a, cudaStream_t st) {
+  const int smem = rbf_bwd_tc_smem_bytes(a.g);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(static_cast<unsigned>((a.g.N + kBtStates - 1) / kBtStates), static_cast<unsigned>(a.g.L));
+  kern<<<grid, kBtThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 template <>
 cudaError_t rbf_field_bwd_dp<DP>(const RbfFieldBwdArgs& a, cudaStream_t st) {
   if constexpr (DP > 8) {   // (measured at D = 6: 1.17 vs 1.22 ms forward, 2.12 vs 2.10 ms reverse -- no gain below D = 9)
+    if (rbf_bwd_use_tc(a.g)) return launch_bwd_tc(k_field_bwd<RbfTcBwdPolicy<DP>>, a, st);
     if (rbf_fwd_use_mma(a.g)) return launch_bwd_mma(k_field_bwd<RbfMmaBwdPolicy<DP>>, a, st);
   }
   GPODE_DISPATCH_R(k_field_bwd, a, true, st)
@@ -90,6 +103,7 @@ cudaError_t rbf_rollout_fwd_dp<DP>(const RbfRolloutFwdArgs& a, cudaStream_t st) 
 template <>
 cudaError_t rbf_rollout_bwd_dp<DP>(const RbfRolloutBwdArgs& a, cudaStream_t st) {
   if constexpr (DP > 8) {   // (measured at D = 6: 1.17 vs 1.22 ms forward, 2.12 vs 2.10 ms reverse -- no gain below D = 9)
+    if (rbf_bwd_use_tc(a.g)) return launch_bwd_tc(k_rollout_bwd<RbfTcBwdPolicy<DP>>, a, st);
     if (rbf_fwd_use_mma(a.g)) return launch_bwd_mma(k_rollout_bwd<RbfMmaBwdPolicy<DP>>, a, st);
   }
   GPODE_DISPATCH_R(k_rollout_bwd, a, true, st)

@@ -319,6 +319,7 @@ struct RbfPolicy {
   static constexpr int kThreads = 256;   // compiled for <= 128 registers: 512 resident threads per SM in any block size
   static constexpr int kMinBlocks = 2;
   static constexpr int kStateThreads = 0;   // every thread of the CTA owns states
+  static constexpr int kXsStride = 0;       // staging buffers xs / dx are strided by the block size
   // reverse sweep at D > 8: 128 threads x 3 CTAs (<= 168 registers) -- measured 10% faster than the 128-register build
   static constexpr int kThreadsBwd = DP_ <= 8 ? 256 : 128;
   static constexpr int kMinBlocksBwd = DP_ <= 8 ? 2 : 3;

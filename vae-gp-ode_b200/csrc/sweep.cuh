@@ -36,8 +36,9 @@ __device__ __forceinline__ States<R> map_states(const G& g, int state_threads = 
 #define GPODE_SWEEP_BOUNDS __launch_bounds__(P::kThreads, P::kMinBlocks)
 #define GPODE_SWEEP_BOUNDS_BWD __launch_bounds__(P::kThreadsBwd, P::kMinBlocksBwd)
 
-// smem slot of component d of this thread's r-th state
+// smem slot of component d of this thread's r-th state (policies whose helper warps own no state may use a tighter stride: kXsStride)
 #define GPODE_XS(buf, d, r) (buf)[((d) * R + (r)) * blockDim.x + threadIdx.x]
+#define GPODE_XSG(buf, d, r) (buf)[((d) * R + (r)) * (P::kXsStride ? P::kXsStride : static_cast<int>(blockDim.x)) + threadIdx.x]
 
 #define GPODE_POLICY_CONSTS constexpr int DP = P::DP; constexpr int R = P::R; (void)DP
 
@@ -55,7 +56,7 @@ __global__ void GPODE_SWEEP_BOUNDS k_field_fwd(const FieldFwdArgsT<typename P::G
   const long total = P::setup(sm, pipe, g, a.packed, 1, false);
 #pragma unroll
   for (int r = 0; r < R; ++r)
-    for (int d = 0; d < g.D_in; ++d) GPODE_XS(sm.xs, d, r) = a.x[st.s[r] * g.D_in + d];
+    for (int d = 0; d < g.D_in; ++d) GPODE_XSG(sm.xs, d, r) = a.x[st.s[r] * g.D_in + d];
   P::eval_fwd(pipe, g, total, sm, [&](int k, const float (&fp)[R], const float (&fu)[R]) {
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -122,7 +123,7 @@ __global__ void GPODE_SWEEP_BOUNDS k_rollout_fwd(const RolloutFwdArgsT<typename 
             v = y0 + dt * (ksave[kb] - ksave[kb + ks] + ksave[kb + 2 * ks]);
           }
           a.xsave[((slab + i) * DS + d) * NL + st.s[r]] = v;
-          GPODE_XS(sm.xs, d, r) = v;
+          GPODE_XSG(sm.xs, d, r) = v;
           // order 2: the first q components of the derivative are the velocity part of the state
           if (g.order == 2 && d >= DP / 2) ksave[((slab + i) * DS + d - DP / 2) * NL + st.s[r]] = v;
         }
@@ -168,7 +169,7 @@ __global__ void GPODE_SWEEP_BOUNDS_BWD k_rollout_bwd(const RolloutBwdArgsT<typen
   GPODE_POLICY_CONSTS;
   extern __shared__ __align__(128) float smem[];
   const typename P::Geom& g = a.g;
-  const States<R> st = map_states<R>(g);
+  const States<R> st = map_states<R>(g, P::kStateThreads);
   const Tableau tb = make_tableau(a.method);
   const int stages = tb.stages;
   const long NL = g.NL;
@@ -203,7 +204,7 @@ __global__ void GPODE_SWEEP_BOUNDS_BWD k_rollout_bwd(const RolloutBwdArgsT<typen
           kb *= dt;
           kbar[d * NL + st.s[r]] = kb;
           if (d >= g.off) a.gsave[((slab + i) * g.D_out + (d - g.off)) * NL + st.s[r]] = kb;
-          GPODE_XS(sm.xs, d, r) = a.xsave[((slab + i) * DS + d) * NL + st.s[r]];
+          GPODE_XSG(sm.xs, d, r) = a.xsave[((slab + i) * DS + d) * NL + st.s[r]];
         }
       }
       P::vjp(pipe, g, total, sm, st, kbar + g.off * NL, a.ksave + ((slab + i) * DS + g.off) * NL, a.fpsave + (slab + i) * g.D_out * NL, NL,
@@ -214,7 +215,7 @@ __global__ void GPODE_SWEEP_BOUNDS_BWD k_rollout_bwd(const RolloutBwdArgsT<typen
         if (!st.ok[r]) continue;
 #pragma unroll 1
         for (int d = 0; d < DS; ++d) {
-          float v = GPODE_XS(sm.dx, d, r);
+          float v = GPODE_XSG(sm.dx, d, r);
           if (g.order == 2 && d >= DP / 2) v += kbar[(d - DP / 2) * NL + st.s[r]];
           ystage[(i * DS + d) * NL + st.s[r]] = v;
         }
@@ -246,18 +247,19 @@ __global__ void GPODE_SWEEP_BOUNDS_BWD k_field_bwd(const FieldBwdArgsT<typename 
   GPODE_POLICY_CONSTS;
   extern __shared__ __align__(128) float smem[];
   const typename P::Geom& g = a.g;
-  const States<R> st = map_states<R>(g);
+  const States<R> st = map_states<R>(g, P::kStateThreads);
   const long NL = g.NL;
   typename P::Smem sm = P::carve(smem, g);
   ChunkPipe pipe;
   const long total = P::setup(sm, pipe, g, a.packed, 1, true);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    for (int d = 0; d < g.D_in; ++d) {
-      const float v = a.x[st.s[r] * g.D_in + d];
-      GPODE_XS(sm.xs, d, r) = v;
-      if (st.ok[r]) a.xsave[d * NL + st.s[r]] = v;
-    }
+    if (P::kStateThreads == 0 || static_cast<int>(threadIdx.x) < P::kStateThreads)   // (helper warps of a policy own no staging slot)
+      for (int d = 0; d < g.D_in; ++d) {
+        const float v = a.x[st.s[r] * g.D_in + d];
+        GPODE_XSG(sm.xs, d, r) = v;
+        if (st.ok[r]) a.xsave[d * NL + st.s[r]] = v;
+      }
     if (st.ok[r])
       for (int k = 0; k < g.D_out; ++k) a.gsave[k * NL + st.s[r]] = a.gout[st.s[r] * g.D_out + k];
   }
@@ -265,7 +267,7 @@ __global__ void GPODE_SWEEP_BOUNDS_BWD k_field_bwd(const FieldBwdArgsT<typename 
 #pragma unroll
   for (int r = 0; r < R; ++r)
     if (st.ok[r])
-      for (int d = 0; d < g.D_in; ++d) a.dx[st.s[r] * g.D_in + d] = GPODE_XS(sm.dx, d, r);
+      for (int d = 0; d < g.D_in; ++d) a.dx[st.s[r] * g.D_in + d] = GPODE_XSG(sm.dx, d, r);
   __syncthreads();
   P::flush(sm, g, a.acc);
 }
