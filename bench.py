@@ -9,10 +9,12 @@
 One "step" = one pass of the hot path over one batch: fixed-grid RK4 (3/8 rule) rollout of every
 (trajectory, MC-sample) latent state over the T-point grid and its reverse sweep with all parameter
 gradients.  Default workload = BASELINE.json configs[4] ("scaled data-parallel rollout": 65,536
-trajectories x 8 MC samples, latent_dim 16, M=512 inducing, S=256 features, T=64, RK4) on EVERY GPU
-(weak scaling: ranks hold independent trajectory shards, parameters replicated, one NCCL all-reduce of
-the kernel-level gradients per step).  Unit of work: trajectory-step = one state advanced over one grid
-interval, all 4 stages, forward and backward.
+trajectories x 8 MC samples, latent_dim 16, M=512 inducing, S=256 features, T=64, RK4).  At N GPUs the
+SAME total problem is sharded by trajectory (65,536 / N trajectories x 8 samples
+per GPU; `--scaling weak` keeps the full problem on every GPU instead): ranks hold independent trajectory
+shards of one seeded z0, parameters and function samples are replicated, one NCCL all-reduce of the
+kernel-level gradients per step (timed separately).  Unit of work: trajectory-step = one state advanced
+over one grid interval, all 4 stages, forward and backward.
 
 Prints ONE JSON line (rank 0).  `value` = kernel path with inputs resident in HBM; `e2e` = the same
 metric through the public drop-in API (Flow.forward_samples -> build_cache -> rollout -> backward) with
@@ -61,8 +63,6 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "cfg5_rbf_d16_m512_t64_rk4"
 STAGES = {"euler": 1, "midpoint": 2, "rk4": 4}
-# cpu sample of the default workload: same per-trajectory-step work (D, M, S, RK4), fewer trajectories / grid points
-CPU_SAMPLE = dict(N=256, L=1, T=32)
 
 
 def algorithmic_work(w):
@@ -79,6 +79,37 @@ def algorithmic_work(w):
         f1 = 2 * w["D_out"] * (w["S"] + w["M"]) * (w["D_in"] + 1)
         s1 = w["D_out"] * (w["S"] + w["M"])
     return dict(flops=3 * st * f1, sfu=2 * st * s1, hbm_bytes=3 * w["D_in"] * 4)
+
+
+def pipe_model(w, tc_rates):
+    """Per trajectory-step: the time each pipe needs at its peak / measured issue rate, in SM-cycles summed over the chip's SMs
+    (divide by 148 x clock for seconds).  D <= 8 and DF: everything on the FP32 / MUFU pipes.  RBF at D > 8 on a chip-filling batch:
+    the D_in-long dot products run on the tensor pipes WITH their precision splits (that is executed work, stated as such):
+      forward  : tcgen05 kind::tf32, 3xTF32 along K = 56: 7 MMAs (128 x 128 x 8) per 128 x 128 block, measured cycles per MMA;
+      reverse  : mma.sync, 7 HMMA per (16 x 8) tile (3 fp16 k16 for theta, 2 x (TF32 k8 + bf16 k16) for the second product);
+      gradients: mma.sync, 7 HMMA per (16 x 8) tile of the INDUCING units (recomputation: no algorithmic work of its own);
+      an HMMA issues every 8.55 cycles per scheduler on B200 whatever its type (profiles/mma_peak_r01.txt).
+    SFU: algorithmic = 2 transcendentals per (state, k, unit) and stage; executed = 3 (the gradient pass re-evaluates)."""
+    st = STAGES[w["method"]]
+    work = algorithmic_work(w)
+    out = {"sfu_alg_cycles": work["sfu"] / 16.0, "fp32_alg_cycles": work["flops"] / 256.0, "tensor_cycles": 0.0, "fp32_residual_cycles": work["flops"] / 256.0}
+    tensor_path = w["variant"] != "df" and w["D_in"] > 8 and w["N"] * w["L"] >= 32768
+    if tensor_path:
+        units, ind = w["D_out"] * (w["S"] + w["M"]), w["D_out"] * w["M"]
+        fwd = st * units / 16384.0 * 7 * tc_rates["tcgen05_tf32_n128_cycles_per_mma"]
+        hmma = st * (units / 128.0 * 7 + ind / 128.0 * 7) * tc_rates["hmma_issue_cycles"] / 4.0
+        out["tensor_cycles"] = fwd + hmma
+        out["tensor_split"] = {"forward": "3xTF32 (K = 56 for D_in = 16)", "reverse_sweep": "fp16 head+remainder theta (3 MMAs) + TF32 head / bf16 cross second product (4 MMAs)",
+                               "parameter_gradients": "same 7 MMAs per tile, inducing units only"}
+        # what stays on the FP32 pipe algorithmically: everything except the D_in-long dot products (forward 1x, backward 2x)
+        moved = 3 * st * 2 * units * w["D_in"]
+        out["fp32_residual_cycles"] = max(work["flops"] - moved, 0) / 256.0
+        out["sfu_exec_cycles"] = (work["sfu"] + st * ind) / 16.0
+    else:
+        rbf = w["variant"] != "df"
+        ind = w["D_out"] * w["M"] if rbf else w["M"] * w["D_in"] ** 2
+        out["sfu_exec_cycles"] = (work["sfu"] + (st * ind if rbf else 0)) / 16.0
+    return out
 
 
 def measured_peaks():
@@ -166,12 +197,19 @@ def build_model(w, device, seed):
 
 def tc_forward(w):
     """mirrors rbf_fwd_use_tc (csrc/rbf.h): the tensor-memory forward adds one launch (its operand-tile pack) per step"""
-    if w["variant"] == "df" or w["D_in"] <= 8 or w["N"] * w["L"] < 32768 or os.environ.get("GPODE_FWD", "")[:1] == "m":
+    if w["variant"] == "df" or w["D_in"] <= 8 or w["N"] * w["L"] < 32768:
         return False
-    if os.environ.get("GPODE_FWD", "")[:1] == "t":
-        return True
     units = (-(-w["S"] // 256) + -(-w["M"] // 256)) * 256
     return units * 100 <= (w["S"] + w["M"]) * 115
+
+
+def kernel_launches(w):
+    """kernels of libgpode.so launched by one forward + backward rollout call (csrc/api.cu):
+    RBF forward: k_rbf_pack [+ k_rbf_pack_tc] + k_rollout_fwd; backward: k_rbf_pack + k_rollout_bwd + k_rbf_pgrad* + 2 finalize kernels;
+    DF forward: k_df_pack + k_rollout_fwd; backward: k_df_pack + k_rollout_bwd + k_df_pgrad + finalize."""
+    if w["variant"] == "df":
+        return 6
+    return 8 if tc_forward(w) else 7
 
 
 def run_ours(args):
@@ -190,8 +228,16 @@ def run_ours(args):
     w = dict(WORKLOADS[args.workload])
     if args.scale != 1.0:
         w["N"] = max(1, int(w["N"] * args.scale))
+    from gpode_b200.parallel import shard_bounds
+    N_total = w["N"]
+    if args.scaling == "strong" and world > 1:
+        lo, hi = shard_bounds(N_total, rank, world)     # contiguous trajectory shard of ONE global problem
+    else:
+        lo, hi = 0, N_total
+    w["N"] = hi - lo
     N, L, T, D = w["N"], w["L"], w["T"], w["D_in"]
-    steps_per_pass = N * L * (T - 1)
+    steps_per_pass = N * L * (T - 1)                      # this rank's share
+    steps_job = (N_total * L * (T - 1)) if (args.scaling == "strong" or world == 1) else world * N_total * L * (T - 1)
     work = algorithmic_work(w)
 
     # ---- resident inputs: L function samples (seeds 10..), z0, dL/dtraj ----------------------------------
@@ -205,9 +251,11 @@ def run_ours(args):
     fs = FieldSample.stack(samples)
     leaf = lambda v: v.detach().clone().requires_grad_(True)
     Z, nu, ell, var = leaf(fs.Z), leaf(fs.nu), leaf(fs.ell), leaf(fs.var)
-    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    z0 = torch.randn(N, D, device=dev, generator=gen).requires_grad_(True)
-    dtraj = torch.randn(L, N, T, D, device=dev, generator=gen)
+    # ONE seeded global z0 / upstream gradient (the same on every rank); strong scaling slices this rank's trajectories out of it,
+    # weak scaling gives every rank its own draw
+    gen = torch.Generator(device=dev).manual_seed(1000 if args.scaling == "strong" else 1000 + rank)
+    z0 = torch.randn(N_total, D, device=dev, generator=gen)[lo:hi].contiguous().requires_grad_(True)
+    dtraj = torch.randn(L, N_total, T, D, device=dev, generator=gen)[:, lo:hi].contiguous()
     ts = 0.1 * torch.arange(T, dtype=torch.float, device=dev)
     from gpode_b200 import gp_rollout
 
@@ -221,21 +269,20 @@ def run_ours(args):
         return None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    t_fwd = t_bwd = 0.0
 
     def kernel_step(record):
-        nonlocal t_fwd, t_bwd
         for v in (z0, Z, nu, ell, var):
             v.grad = None
-        e0, e1, e2 = ev(), ev(), ev()
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         e0.record()
         traj = gp_rollout(z0, ts, Z, nu, fs.eps, fs.phase, fs.w, ell, var, w["variant"], w["order"], w["method"], fs.B)
         e1.record()
         traj.backward(dtraj)
-        allreduce_grads([Z.grad, nu.grad, ell.grad, var.grad])
         e2.record()
+        allreduce_grads([Z.grad, nu.grad, ell.grad, var.grad] + ([fs.B.grad] if (fs.B is not None and fs.B.grad is not None) else []))
+        e3.record()
         if record is not None:
-            record.append((e0, e1, e2))
+            record.append((e0, e1, e2, e3))
 
     def barrier():
         if world > 1:
@@ -265,12 +312,17 @@ def run_ours(args):
 
     ms_total, rec, clocks = timed(kernel_step, args.steps, args.warmup)
     ms_step = ms_total / args.steps
-    fwd_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in rec]))
-    bwd_ms = float(np.mean([b.elapsed_time(c) for _, b, c in rec]))
-    value = world * steps_per_pass / (ms_step * 1e-3)
+    fwd_ms = float(np.mean([a.elapsed_time(b) for a, b, _, _ in rec]))
+    bwd_ms = float(np.mean([b.elapsed_time(c) for _, b, c, _ in rec]))
+    allreduce_ms = float(np.mean([c.elapsed_time(d) for _, _, c, d in rec]))
+    if world > 1:   # the slowest rank's phases (the step time already is the max over ranks)
+        ph = torch.tensor([fwd_ms, bwd_ms, allreduce_ms], device=dev)
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+        fwd_ms, bwd_ms, allreduce_ms = [float(v) for v in ph.tolist()]
+    value = steps_job / (ms_step * 1e-3)
 
     # ---- end to end through the drop-in API, host buffers in the timed region --------------------------
-    z0_host = torch.randn(N, D).pin_memory()
+    z0_host = z0.detach().cpu().pin_memory()
     h2d = [0]
     d2h = [0]
     params = [gp.kern.unconstrained_lengthscales, gp.kern.unconstrained_variance, gp.inducing_loc.optvar, gp.Um.optvar,
@@ -293,7 +345,7 @@ def run_ours(args):
 
     e2e_warm = min(args.warmup, 3)
     ms_e2e, _, _ = timed(e2e_step, args.steps, e2e_warm)
-    e2e_value = world * steps_per_pass / (ms_e2e / args.steps * 1e-3)
+    e2e_value = steps_job / (ms_e2e / args.steps * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -305,84 +357,132 @@ def run_ours(args):
     fp32_peak = 148 * 128 * 2 * sm_max          # FFMA lanes x 2 flop x max SM clock
     sfu_peak = 148 * 16 * sm_max
     per_gpu_rate = steps_per_pass / (ms_step * 1e-3)
-    t_fma = work["flops"] / fp32_peak
-    t_sfu = work["sfu"] / sfu_peak
-    bound_s = max(t_fma, t_sfu) * per_gpu_rate   # fraction of the binding pipe's peak
     achieved_tflops = work["flops"] * per_gpu_rate / 1e12
-    roof = {"bound": "fp32_fma" if t_fma >= t_sfu else "sfu", "achieved": round(achieved_tflops, 3), "peak": round(fp32_peak / 1e12, 2),
-            "unit": "TFLOP/s", "frac": round(bound_s, 4), "traffic": TRAFFIC.get(args.workload, (None, None))[0],
-            "traffic_source": TRAFFIC.get(args.workload, (None, None))[1],
-            "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json (%s); not an HBM-bound path" % peak_src,
-            "note": ("D > 8: the D-length dot products run on the warp-level tensor path (mma.sync: two-way fp16 split for theta, TF32 head + "
-                     "bf16 cross terms for the second products, fp32 accumulate; forward sweep: tcgen05.mma 3xTF32 into tensor memory); frac is still the ALGORITHMIC fp32 work over the FP32-pipe "
-                     "peak, so a call can exceed 1" if w["D_in"] > 8 and w["variant"] != "df"
-                     else "FP32 / MUFU pipes only"),
+    # measured issue rates of the tensor pipes (tools/tc_probe2, tools/mma_peak; fallbacks = the round-2 measurements under profiles/)
+    tc_rates = {"tcgen05_tf32_n128_cycles_per_mma": 452.0 / 7.0, "hmma_issue_cycles": 8.55, "source": "profiles/tc_probe2_r02.json, profiles/mma_peak_r01.txt"}
+    probe = os.path.join(ROOT, "tools", "tc_probe2")
+    if world == 1 and os.path.exists(probe) and not args.no_cpu_baseline:
+        try:
+            pj = json.loads(subprocess.check_output([probe], timeout=120).decode().strip().splitlines()[-1])
+            tc_rates["tcgen05_tf32_n128_cycles_per_mma"] = pj["cycles_per_rep"]["theta_7xSS_tf32_N128"][0] / 7.0
+            tc_rates["source"] = "tools/tc_probe2 run inside this bench; profiles/mma_peak_r01.txt"
+        except Exception:
+            pass
+    pm = pipe_model(w, tc_rates)
+    chip_cycles_per_s = 148 * sm_max
+    pipes = {"sfu": round(pm["sfu_alg_cycles"] * per_gpu_rate / chip_cycles_per_s, 4),
+             "sfu_executed": round(pm["sfu_exec_cycles"] * per_gpu_rate / chip_cycles_per_s, 4),
+             "tensor": round(pm["tensor_cycles"] * per_gpu_rate / chip_cycles_per_s, 4),
+             "fp32_residual": round(pm["fp32_residual_cycles"] * per_gpu_rate / chip_cycles_per_s, 4)}
+    binding = max(("sfu", "tensor", "fp32_residual"), key=lambda k: pipes[k])
+    frac_fp32_alg = round(work["flops"] * per_gpu_rate / fp32_peak, 4)
+    roof = {"bound": {"sfu": "sfu", "tensor": "tensor", "fp32_residual": "fp32_fma"}[binding], "frac": pipes[binding], "pipes": pipes,
+            "achieved": round(achieved_tflops, 3), "peak": round(fp32_peak / 1e12, 2), "unit": "TFLOP/s",
+            "frac_fp32_algorithmic": frac_fp32_alg,
+            "traffic": TRAFFIC.get(args.workload, (None, None))[0], "traffic_source": TRAFFIC.get(args.workload, (None, None))[1],
+            "peak_source": "FP32: 148 SM x 128 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json (%s); SFU: 148 x 16 / clk; tensor: measured issue rates (%s); "
+                           "not an HBM-bound path" % (peak_src, tc_rates["source"]),
+            "note": ("frac = the fraction of the measured time the BINDING pipe needs at its peak rate (pipes: sfu = algorithmic transcendentals, "
+                     "sfu_executed = incl. the re-evaluation in the parameter-gradient pass, tensor = the executed MMAs incl. their precision splits "
+                     "at the measured issue rates, fp32_residual = algorithmic FP32 work that stays on the FMA pipe).  achieved / peak / "
+                     "frac_fp32_algorithmic keep the SURVEY 8(d) definition: ALL algorithmic flops over the FP32-pipe peak (can exceed what the "
+                     "FP32 pipe really executes once the dot products run on tensor cores)."),
+            "tensor_split": pm.get("tensor_split"),
             "sfu_achieved_tops": round(work["sfu"] * per_gpu_rate / 1e12, 4), "sfu_peak_tops": round(sfu_peak / 1e12, 3),
-            "sfu_frac": round(work["sfu"] * per_gpu_rate / sfu_peak, 4),
             "hbm_achieved_gbs": round(work["hbm_bytes"] * per_gpu_rate / 1e9, 3), "hbm_peak_gbs": peaks.get("hbm_gbs"),
             "hbm_frac": round(work["hbm_bytes"] * per_gpu_rate / 1e9 / float(peaks.get("hbm_gbs", 6650.0)), 6),
             "flops_per_traj_step": work["flops"], "sfu_per_traj_step": work["sfu"], "bytes_per_traj_step": work["hbm_bytes"],
-            "fwd_call_ms": round(fwd_ms, 3), "bwd_call_ms": round(bwd_ms, 3),
-            "fwd_frac": round((work["flops"] / 3) * steps_per_pass / fp32_peak / (fwd_ms * 1e-3), 4),
-            "bwd_frac": round((2 * work["flops"] / 3) * steps_per_pass / fp32_peak / (bwd_ms * 1e-3), 4)}
+            "fwd_call_ms": round(fwd_ms, 3), "bwd_call_ms": round(bwd_ms, 3), "allreduce_ms": round(allreduce_ms, 3)}
     peaks_bin = os.path.join(ROOT, "tools", "peaks")
     if world == 1 and os.path.exists(peaks_bin) and not args.no_cpu_baseline:
         try:
             pk = json.loads(subprocess.check_output([peaks_bin], timeout=120).decode().strip().splitlines()[-1])
             roof["ffma_measured_tflops"] = pk["ffma_tflops"]
             roof["mufu_measured_tops"] = pk["ex2_tops"]
-            roof["frac_of_measured_ffma"] = round(achieved_tflops / pk["ffma_tflops"], 4)
         except Exception as exc:  # the microbenchmark is informative only
             roof["ffma_measured_tflops"] = "unavailable: %s" % exc
 
     line = {"metric": "GP-ODE RK4 latent traj-steps/s fwd+bwd", "value": round(value, 1), "unit": "traj-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "dtype_note": ("fp32 inputs, outputs, accumulation and transcendentals; where dot products run on tensor cores (RBF, D_in > 8) the operands are "
+                           "split so that >= 21 mantissa bits enter every product: forward 3xTF32, reverse sweep / parameter gradients fp16 head + 2^11-scaled "
+                           "remainder for theta, TF32 head + bf16 cross terms for the second product; the per-rollout setup (K(Z,Z), Cholesky, solves) runs in fp64"),
             "config": {"workload": args.workload, "per_gpu": {k: w[k] for k in ("N", "L", "T", "D_in", "D_out", "M", "S", "method", "order", "variant")},
-                       "traj_steps_per_gpu_per_step": steps_per_pass, "parallelism": "dp%d (trajectory shards, params replicated)" % world,
+                       "total_trajectories": N_total if args.scaling == "strong" or world == 1 else world * N_total,
+                       "traj_steps_per_gpu_per_step": steps_per_pass, "traj_steps_per_job_per_step": steps_job,
+                       "parallelism": "dp%d (%s: trajectory shards of one seeded problem, params and function samples replicated, one all-reduce of the kernel-level gradients)" % (world, args.scaling),
                        "cache": "inputs and saves (%.1f GB) far exceed the 126 MB L2; no flush needed" %
                                 ((T - 1) * STAGES[w["method"]] * (2 * D + w["D_out"]) * N * L * 4 / 1e9)},
             "roofline": roof,
             "e2e": {"value": round(e2e_value, 1), "unit": "traj-steps/s", "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "gpu_launches": (6 if w["variant"] == "df" else (8 if tc_forward(w) else 7)) * args.steps, "clocks": clocks}
+            "gpu_launches": kernel_launches(w) * args.steps, "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(w, reps=3, warmup=1)
         except Exception as exc:
-            line["cpu_baseline"] = {"value": None, "unit": "traj-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % exc}
+            line["cpu_baseline"] = {"value": None, "unit": "traj-steps/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % exc}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(w, reps, warmup):
-    """The reference's CPU path (oracle port with the reference's op sequence) on this box's host cores, on a bounded
-    sample of the workload.  Runs in a subprocess with CUDA hidden, like the reference would on a CPU-only host."""
-    cores = os.cpu_count() or 1
+def cpu_sample_shape(w):
+    """bounded sample of the workload for the CPU arm: BASELINE.md section 3 asks for 1,024 trajectories x 1 MC sample at the workload's
+    own T; the reference keeps the whole unrolled solve in its autograd graph (~1.1 GB per 64 trajectories x 60 evaluations at
+    D = 16, M = 512), so the trajectory count is halved until the estimate fits in a quarter of the host's free memory."""
     s = dict(w)
-    s.update(CPU_SAMPLE)
-    s["N"] = min(s["N"], w["N"])
-    s["T"] = min(s["T"], w["T"])
-    code = ("import sys, json; sys.path.insert(0, %r); import torch; from oracle import port_fp32 as P; "
-            "sec = P.time_rollout(%r, %d, %d, %d, %d, %d, %d, %d, %r, reps=%d, warmup=%d, threads=%d); print(json.dumps(sec))"
-            % (ROOT, s["variant"], s["N"], s["D_in"], s["D_out"], s["M"], s["S"], s["T"], s["order"], s["method"], reps, warmup, cores))
+    s["L"] = 1
+    s["N"] = min(1024, w["N"])
+    s["T"] = min(64, w["T"])
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    per_eval_state = 4.0 * w["D_out"] * (w["M"] * (36 if w["variant"] == "df" else 1) + w["S"]) * 6     # bytes: ~6 saved (D_out, M, N)-sized temporaries
+    evals = (s["T"] - 1) * STAGES[w["method"]]
+    while s["N"] > 32 and per_eval_state * evals * s["N"] > 0.25 * avail:
+        s["N"] //= 2
+    return s
+
+
+def cpu_baseline(w, reps, warmup):
+    """The reference's CPU path on this box's host cores, on a bounded sample of the workload, in a subprocess with CUDA hidden (the
+    reference puts its parameters on cuda:0 whenever a GPU is visible).  kind = "reference": the reference's OWN SVGP_Layer / Flow
+    modules (oracle/_ref, the verbatim copy oracle/fetch_ref.py makes; oracle/ref_timing.py) -- timed region build_cache + rollout +
+    backward; falls back to the bit-identical port (oracle/port_fp32.py, kind = "port") only where that copy is absent."""
+    cores = os.cpu_count() or 1
+    s = cpu_sample_shape(w)
+    sys.path.insert(0, ROOT)
+    from oracle import reference_harness as rh
+    kind = "reference" if rh.reference_available() else "port"
+    call = ("from oracle import ref_timing as R; sec = R.time_reference(" if kind == "reference" else "from oracle import port_fp32 as R; sec = R.time_rollout(")
+    code = ("import sys, json, warnings; warnings.filterwarnings('ignore'); sys.path.insert(0, %r); import torch; %s%r, %d, %d, %d, %d, %d, %d, %d, %r, "
+            "reps=%d, warmup=%d, threads=%d); print(json.dumps(sec))"
+            % (ROOT, call, s["variant"], s["N"], s["D_in"], s["D_out"], s["M"], s["S"], s["T"], s["order"], s["method"], reps, warmup, cores))
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
-    proc = subprocess.run([sys.executable, "-c", code], env=env, timeout=1200, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    proc = subprocess.run([sys.executable, "-c", code], env=env, timeout=1500, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     if proc.returncode != 0:
         raise RuntimeError("cpu baseline subprocess failed: %s" % proc.stderr.decode()[-2000:])
     sec = json.loads(proc.stdout.decode().strip().splitlines()[-1])
     n_steps = s["N"] * (s["T"] - 1)
-    return {"value": round(n_steps / sec, 1), "unit": "traj-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d trajectories x 1 MC sample, T=%d, same D=%d M=%d S=%d %s; best of %d after %d warm-up; oracle/port_fp32.py "
-                      "(reference op sequence, torch CPU fp32, %d threads)" % (s["N"], s["T"], s["D_in"], s["M"], s["S"], s["method"],
-                                                                            reps, warmup, cores),
+    try:
+        cpu_model = [ln.split(":", 1)[1].strip() for ln in open("/proc/cpuinfo") if ln.startswith("model name")][0]
+    except Exception:
+        cpu_model = "unknown"
+    what = ("the reference's own SVGP_Layer + Flow (oracle/_ref, unmodified; torchdiffeq replaced by the restated fixed-grid loop), build_cache + rollout + backward"
+            if kind == "reference" else "oracle/port_fp32.py (the reference's op sequence; oracle/_ref absent), rollout + backward")
+    return {"value": round(n_steps / sec, 1), "unit": "traj-steps/s", "cores": cores, "kind": kind,
+            "sample": "%d trajectories x 1 MC sample, T=%d, same D=%d M=%d S=%d %s %s; best of %d after %d warm-up; %s; torch CPU fp32, %d threads on %s" % (
+                s["N"], s["T"], s["D_in"], s["M"], s["S"], s["variant"], s["method"], reps, warmup, what, cores, cpu_model),
             "seconds_per_pass": round(sec, 3)}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference is Python and
-    /root/reference does not exist on the GPU box), all host threads, same metric / unit / config."""
+    """--impl reference: the reference's own CPU implementation of the path (the reference's modules from oracle/_ref; the port only if
+    that copy is absent), all host threads, same metric / unit / config; a bounded sample per step (cpu_sample_shape)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -391,7 +491,7 @@ def run_reference(args):
     value = base["value"]
     line = {"impl": "reference", "metric": "GP-ODE RK4 latent traj-steps/s fwd+bwd", "value": value, "unit": "traj-steps/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", str(args.gpus))), "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(base["seconds_per_pass"] * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(base["seconds_per_pass"] * 1e3, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "per_gpu": {k: w[k] for k in ("N", "L", "T", "D_in", "D_out", "M", "S", "method", "order", "variant")}},
             "cpu_baseline": base, "e2e": {"value": value, "unit": "traj-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -406,6 +506,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="scale the trajectory count (debugging only; not a valid bench line)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1 GPUs: strong = the workload's trajectories are sharded over the ranks (SURVEY 8d row 5); weak = every rank runs the full workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

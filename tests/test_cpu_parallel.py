@@ -58,3 +58,13 @@ def test_gloo_world2_allreduce_and_loss_normalisation():
         assert torch.allclose(out[r][2], z0.pow(2).sum().reshape(1))
         assert torch.allclose(out[r][3], torch.full((3, 2), 3.0))
         assert abs(out[r][4] - z0.mean().item()) < 1e-4
+
+
+def test_fewer_trajectories_than_ranks_fails_on_every_rank():
+    """an empty shard would raise inside the rollout on some ranks while the others block in the all-reduce: refuse up front, everywhere"""
+    import pytest
+    z0 = torch.zeros(3, 6)
+    for rank in range(4):
+        with pytest.raises(ValueError):
+            PL.shard_trajectories(z0, rank=rank, world=4)
+    assert PL.shard_trajectories(z0, rank=2, world=3).shape == (1, 6)

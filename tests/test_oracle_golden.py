@@ -84,3 +84,20 @@ def test_solver_restatement_properties():
     assert errs[0] / errs[1] > 12  # ~2^4
     with pytest.raises(ValueError):
         solvers.odeint(lambda s, y: -y, y0, ts, method="dopri5")
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_port_is_bit_identical_to_the_reference(name):
+    """oracle/port_fp32.py (bench.py's fallback CPU baseline and the fp32 comparison arm of tests/test_gpu_baseline_shapes.py) keeps the
+    reference's own op sequence: on the golden inputs its field and trajectories equal the reference's outputs BIT FOR BIT."""
+    from oracle import port_fp32 as PORT
+    g = load_golden(name)
+    m = g["meta"]
+    c = oracle_cache(g, torch.float32)
+    c = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in c.items()}
+    with torch.no_grad():
+        f = PORT.field(t(g["x"]), c)
+        assert np.array_equal(f.numpy(), g["field_f"]), float(np.abs(f.numpy() - g["field_f"]).max())
+        for method in ("euler", "rk4"):
+            traj = PORT.rollout(t(g["z0"]), t(g["ts"]), c, m["order"], method)
+            assert np.array_equal(traj.numpy(), g["traj_" + method]), (method, float(np.abs(traj.numpy() - g["traj_" + method]).max()))
