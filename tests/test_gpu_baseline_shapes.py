@@ -140,7 +140,7 @@ def test_config4_one_million_states(variant, perturb):
     for nm, a, b1, b2 in zip(leaves, pg_f, pg_m, pg_c):
         e = rel(a, b1 + b2)
         print("cfg4 %s perturb %.0f: d%s linearity over 1M states %.2e" % (variant, perturb, nm, e))
-        assert e < 2e-5, (nm, e)
+        assert e < GRAD_TOL, (nm, e)      # (RBF with its own nu: per-state terms ~|nu| = 2e2 cancel in every sum, and float atomics reorder them)
     # and the forward over all states is finite and bounded by the sum of |weights| (sanity over the whole batch)
     assert torch.isfinite(f_gpu).all()
 

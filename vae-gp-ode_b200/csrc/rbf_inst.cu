@@ -6,6 +6,7 @@
 #include "rbf_pgrad_mma.cuh"
 #include "rbf_fwd_tc.cuh"
 #include "rbf_bwd_tc.cuh"
+#include "rbf_small.cuh"
 
 #ifndef GPODE_DP
 #error "compile with -DGPODE_DP=<even 2..16>"
@@ -58,8 +59,20 @@ cudaError_t launch_fwd_tc(KernTc kern, const Args& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// small batches (rbf_small.cuh): 32 states per CTA, 16 warps splitting the rows of every output dimension, parameters resident in shared memory
+template <typename Args, typename KernSmall>
+cudaError_t launch_small(KernSmall kern, const Args& a, cudaStream_t st) {
+  const int smem = rbf_small_smem_bytes(a.g);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(static_cast<unsigned>((a.g.N + kSmStates - 1) / kSmStates), static_cast<unsigned>(a.g.L));
+  kern<<<grid, kSmThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 template <>
 cudaError_t rbf_field_fwd_dp<DP>(const RbfFieldFwdArgs& a, cudaStream_t st) {
+  if (rbf_use_small(a.g)) return launch_small(k_field_fwd<RbfSmallPolicy<DP>>, a, st);
   if constexpr (DP > 8) {   // (measured at D = 6: 1.17 vs 1.22 ms forward, 2.12 vs 2.10 ms reverse -- no gain below D = 9)
     if (rbf_fwd_use_tc(a.g)) return launch_fwd_tc(k_field_fwd<RbfTcFwdPolicy<DP>>, a, st);
     if (rbf_fwd_use_mma(a.g)) return launch_fwd_mma(k_field_fwd<RbfMmaFwdPolicy<DP>>, a, st);
@@ -86,6 +99,7 @@ cudaError_t launch_bwd_tc(KernTc kern, const Args& a, cudaStream_t st) {
 
 template <>
 cudaError_t rbf_field_bwd_dp<DP>(const RbfFieldBwdArgs& a, cudaStream_t st) {
+  if (rbf_use_small(a.g)) return launch_small(k_field_bwd<RbfSmallPolicy<DP>>, a, st);
   if constexpr (DP > 8) {   // (measured at D = 6: 1.17 vs 1.22 ms forward, 2.12 vs 2.10 ms reverse -- no gain below D = 9)
     if (rbf_bwd_use_tc(a.g)) return launch_bwd_tc(k_field_bwd<RbfTcBwdPolicy<DP>>, a, st);
     if (rbf_fwd_use_mma(a.g)) return launch_bwd_mma(k_field_bwd<RbfMmaBwdPolicy<DP>>, a, st);
@@ -94,6 +108,7 @@ cudaError_t rbf_field_bwd_dp<DP>(const RbfFieldBwdArgs& a, cudaStream_t st) {
 }
 template <>
 cudaError_t rbf_rollout_fwd_dp<DP>(const RbfRolloutFwdArgs& a, cudaStream_t st) {
+  if (rbf_use_small(a.g)) return launch_small(k_rollout_fwd<RbfSmallPolicy<DP>>, a, st);
   if constexpr (DP > 8) {   // (measured at D = 6: 1.17 vs 1.22 ms forward, 2.12 vs 2.10 ms reverse -- no gain below D = 9)
     if (rbf_fwd_use_tc(a.g)) return launch_fwd_tc(k_rollout_fwd<RbfTcFwdPolicy<DP>>, a, st);
     if (rbf_fwd_use_mma(a.g)) return launch_fwd_mma(k_rollout_fwd<RbfMmaFwdPolicy<DP>>, a, st);
@@ -102,6 +117,7 @@ cudaError_t rbf_rollout_fwd_dp<DP>(const RbfRolloutFwdArgs& a, cudaStream_t st) 
 }
 template <>
 cudaError_t rbf_rollout_bwd_dp<DP>(const RbfRolloutBwdArgs& a, cudaStream_t st) {
+  if (rbf_use_small(a.g)) return launch_small(k_rollout_bwd<RbfSmallPolicy<DP>>, a, st);
   if constexpr (DP > 8) {   // (measured at D = 6: 1.17 vs 1.22 ms forward, 2.12 vs 2.10 ms reverse -- no gain below D = 9)
     if (rbf_bwd_use_tc(a.g)) return launch_bwd_tc(k_rollout_bwd<RbfTcBwdPolicy<DP>>, a, st);
     if (rbf_fwd_use_mma(a.g)) return launch_bwd_mma(k_rollout_bwd<RbfMmaBwdPolicy<DP>>, a, st);
