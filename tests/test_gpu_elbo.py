@@ -156,7 +156,7 @@ def check(tag, g, scal, grads, strict=False):
             continue
         e_new, e_ref, e_nr = rel(new, t64), rel(r32, t64), rel(new, r32)
         worst = max(worst, e_new)
-        bar = max(1e-4, ref_noise(cfg, k))
+        bar = max(1e-4, NOISE_MARGIN * ref_noise(cfg, k))
         print("%s d %-52s new-vs-fp64 %.2e  ref-vs-fp64 %.2e  new-vs-ref %.2e  (bar %.1e)" % (tag, k, e_new, e_ref, e_nr, bar))
         assert e_new <= bar, (k, e_new, e_ref, bar)
     return worst
