@@ -42,12 +42,12 @@ __host__ __device__ inline uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn)
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_ss_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  asm volatile("{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void mma_ss_bf16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  asm volatile("{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void commit(uint64_t* bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void commit(uint64_t* bar) { asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory"); }
 
 constexpr int NQ = 48;
 constexpr int TILE_BYTES = 65536;            // tau tile
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(544) k_probe3(const uint4* tile_g, const uint4
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int done_flag;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role branches below may use the uniform datapath
   for (int i = tid; i < TILE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(sTile)[i] = tile_g[i];
   for (int i = tid; i < B1_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(sB1)[i] = b1_g[i];
   for (int i = tid; i < B2_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(sB2k)[i] = b2k_g[i];
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(544) k_probe3(const uint4* tile_g, const uint4
   uint32_t par0 = 0;
   if (variant < 0) {
     // ---- numerics ----
-    if (tid == 0) {
+    if (warp == 0) {
       issue_q(dQ, NQ, NQ);
       issue_pg(dPGk, 0, 128, 0);
       issue_pg(dPGm, 1, 128, 0);
@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(544) k_probe3(const uint4* tile_g, const uint4
       read_acc(dPGm, warp, tid, NQ, Dout + 2 * 128 * NQ);
       read_acc(dPG64, warp, tid, NQ, Dout + 3 * 128 * NQ);
     }
-  } else if (tid == 0) {
-    // ---- timing ----
+  } else if (warp == 0) {
+    // ---- timing (the whole warp runs the issue loop convergently; one elected lane issues) ----
     uint32_t par1 = 0;
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
@@ -175,21 +175,41 @@ __global__ void __launch_bounds__(544) k_probe3(const uint4* tile_g, const uint4
     const bool done = mbar_wait_bounded(&bar[1], par1);
     const long long t2 = clock64();
     done_flag = 1;
-    if (!done) status[0] = 2 + variant;
-    if (blockIdx.x == 0) {
+    if (!done && tid == 0) status[0] = 2 + variant;
+    if (blockIdx.x == 0 && tid == 0) {
       timing[0] = (t2 - t0) / reps;
       timing[1] = (t1 - t0) / reps;
     }
   } else if (writers && tid >= 32) {
-    // the epilogue's share of the shared-memory port: every warp streams conflict-free 512-byte st.shared.v4 rows into the theta region
+    // the epilogue's share of the shared-memory / tensor-memory ports: writers & 1: every warp streams conflict-free 512-byte st.shared.v4 rows
+    // into the theta region; writers & 2: every warp streams tcgen05.ld x16 of its lane quarter (64 B per thread per load)
     long long n = 0;
     const uint32_t base = th + ((tid - 32) & 511) * 16;
+    const uint32_t taddr = tmem + 256 + ((((tid - 32) >> 5) >> 2) * 32) + (static_cast<uint32_t>(((tid >> 5) & 3) * 32) << 16);
+    uint32_t sink = 0;
     while (!done_flag) {
+      if (writers & 1) {
 #pragma unroll
-      for (int j = 0; j < 6; ++j) asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(base + j * 8192), "r"(static_cast<uint32_t>(n)) : "memory");
+        for (int j = 0; j < 6; ++j) asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(base + j * 8192), "r"(static_cast<uint32_t>(n)) : "memory");
+      }
+      if (writers & 2) {
+        uint32_t r[16], q[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                       "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]),
+                       "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+                     : "r"(taddr + 16));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sink ^= r[j] ^ q[j];
+      }
       ++n;
     }
-    if (blockIdx.x == 0 && tid == 32) timing[2] = n * 6 * 16 * 512;   // bytes written by all 512 writer threads (all run the same loop)
+    if (sink == 0x12345u) status[1] = 1;
+    if (blockIdx.x == 0 && tid == 32) timing[2] = n * ((writers & 1) ? 6 * 16 : 0) * 512 + n * ((writers & 2) ? 128 : 0) * 512;   // bytes moved by all 512 threads (same loop)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -225,10 +245,10 @@ int main() {
     }
   uint4 *dT, *dB1, *dB2k, *dB2m; float* dD; long long* dTm; int* dS;
   cudaMalloc(&dT, TILE_BYTES); cudaMalloc(&dB1, B1_BYTES); cudaMalloc(&dB2k, B2_BYTES); cudaMalloc(&dB2m, B2_BYTES);
-  cudaMalloc(&dD, 4 * 128 * NQ * 4); cudaMalloc(&dTm, 4 * 8); cudaMalloc(&dS, 4);
+  cudaMalloc(&dD, 4 * 128 * NQ * 4); cudaMalloc(&dTm, 4 * 8); cudaMalloc(&dS, 8);
   cudaMemcpy(dT, tile.data(), TILE_BYTES, cudaMemcpyHostToDevice); cudaMemcpy(dB1, b1.data(), B1_BYTES, cudaMemcpyHostToDevice);
   cudaMemcpy(dB2k, b2k.data(), B2_BYTES, cudaMemcpyHostToDevice); cudaMemcpy(dB2m, b2m.data(), B2_BYTES, cudaMemcpyHostToDevice);
-  cudaMemset(dD, 0, 4 * 128 * NQ * 4); cudaMemset(dS, 0, 4);
+  cudaMemset(dD, 0, 4 * 128 * NQ * 4); cudaMemset(dS, 0, 8);
   const int smem = TILE_BYTES + B1_BYTES + 2 * B2_BYTES + TH_BYTES + 2048;
   cudaFuncSetAttribute(k_probe3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int reps = 64;
@@ -237,9 +257,9 @@ int main() {
   if (e != cudaSuccess) fprintf(stderr, "numerics: %s\n", cudaGetErrorString(e));
   std::vector<float> D(4 * 128 * NQ);
   cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
-  long long T[NV][2][3];
+  long long T[NV][4][3];
   memset(T, 0, sizeof(T));
-  for (int w = 0; w < 2 && e == cudaSuccess; ++w)
+  for (int w = 0; w < 4 && e == cudaSuccess; ++w)
     for (int v = 0; v < NV && e == cudaSuccess; ++v) {
       cudaMemset(dTm, 0, 4 * 8);
       k_probe3<<<148, 544, smem>>>(dT, dB1, dB2k, dB2m, dD, dTm, dS, reps, v, w);
@@ -272,8 +292,9 @@ int main() {
   const char* names[NV] = {"theta_7xSS_tf32_N128", "Q_16xSS_N48", "Q_8xN48_8xN16", "PG_16x_Amn_Bmn_N48", "PG_16x_Amn_Bk_N48", "PG_32x_M64", "theta_4xSS_f16_N128",
                            "item_tf32theta_Q_PG", "item_f16theta_Q_PG", "Q_8xN32_8xN16"};
   for (int v = 0; v < NV; ++v)
-    printf("\"%s\": {\"alone\": [%lld, %lld], \"with_writers\": [%lld, %lld], \"writer_bytes_per_cycle\": %.1f}%s", names[v], T[v][0][0], T[v][0][1], T[v][1][0], T[v][1][1],
-           T[v][1][0] > 0 ? double(T[v][1][2]) / (double(T[v][1][0]) * reps) : 0.0, v + 1 < NV ? ",\n  " : "");
-  printf("},\n \"note\": \"[total incl. completion, issue only] cycles per repetition; 148 CTAs x 544 threads; writers = 16 warps streaming st.shared.v4\"}\n");
+    printf("\"%s\": {\"alone\": %lld, \"with_sts\": [%lld, %.1f], \"with_ldtm\": [%lld, %.1f], \"with_both\": [%lld, %.1f]}%s", names[v], T[v][0][0], T[v][1][0],
+           T[v][1][0] > 0 ? double(T[v][1][2]) / (double(T[v][1][0]) * reps) : 0.0, T[v][2][0], T[v][2][0] > 0 ? double(T[v][2][2]) / (double(T[v][2][0]) * reps) : 0.0, T[v][3][0],
+           T[v][3][0] > 0 ? double(T[v][3][2]) / (double(T[v][3][0]) * reps) : 0.0, v + 1 < NV ? ",\n  " : "");
+  printf("},\n \"note\": \"cycles per repetition incl. completion [, bytes per cycle moved by the 16 side warps: st.shared.v4 streams / tcgen05.ld x16 streams / both]; 148 CTAs x 544 threads\"}\n");
   return 0;
 }

@@ -179,8 +179,9 @@ cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float
     pa.chunks = pgrad_chunks(n_te * g.N, g.D_out * g.L * pg_mblk, 6 * kPgThreads / pg_threads);
   }
   pa.acc = acc;
-  cudaError_t e = rbf_launch_pgrad(pa, st);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  // the fused tcgen05 reverse sweep has already filled dnu / pg (rbf_bwd_tc.cuh): no separate pass over the exponentials
+  if (!rbf_bwd_use_tc(g) && (e = rbf_launch_pgrad(pa, st)) != cudaSuccess) return e;
   RbfFinalizeArgs fa;
   fa.g = g;
   fa.variant = p->variant;

@@ -65,7 +65,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 #endif
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {   // non-blocking phase test
   uint32_t ok;
-  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  // (the last operand is the suspend-time hint in ns: the thread may sleep in hardware until the phase completes instead of re-polling)
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 2000;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
 // mbarrier.try_wait may suspend the thread for a hardware time slice when the phase is not complete; test_wait never does: use it

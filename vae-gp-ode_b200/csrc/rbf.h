@@ -34,18 +34,39 @@ constexpr int kTcfRows = 256;
 constexpr int kTcfChunks = 10;
 constexpr int kTcfBFloats = kTcfChunks * kTcfRows * 4;
 constexpr int kTcfTileFloats = kTcfBFloats + kTcfRows;
-// Reverse sweep / parameter gradients on tcgen05 (rbf_bwd_tc.cuh, rbf_pgrad_tc.cuh): behind the forward tiles, [L][D_out][items] tiles of kTcbUnits
-// units ("items": feature units first, inducing units after, each section padded to whole items):
-//   theta operand  : kTcfChunks x kTcbUnits x 16 B, the layout of the forward tiles (feature offsets carry + pi/2: cos(theta + pi/2) = -sin theta)
-//   second operand : B (N = kTcbQN columns x K = 2 kTcbUnits) of Q[state][n] = sum_r (tau_h[r] B[n][2r] + tau_l[r] B[n][2r+1]) in bf16, K-major core
-//                    matrices (8 columns x 8 k): 16-byte chunk c of column n at c * kTcbQN * 16 + (n / 8) * 128 + (n % 8) * 16 bytes.  Columns
-//                    n < 24: head part -- n = d < DP: P_h[r][d] on both k rows, n = 16: the weight's head (inducing units only: the A_k(x) term);
-//                    n >= 24: remainder part -- n = 24 + d: (P_l[r][d], 0), n = 40: (w_l, 0).  P[r][d] = weight_r x coefficient_rd.
+// Fused reverse sweep + parameter gradients on tcgen05 (rbf_bwd_tc.cuh): behind the forward tiles, [L][D_out][items] tiles of kTcbUnits units
+// ("items": feature units first, inducing units after, each section padded to whole items), 24 KB each, two 12 KB halves that stream
+// through separate rings.  All operand blocks are no-swizzle core matrices (8 rows x 16 bytes): 16-byte chunk c of unit r sits at
+// c * 2048 + (r / 8) * 128 + (r % 8) * 16 bytes of its block.
+//   theta half  (kTcbThBytes): G_h | G_l | off -- fp16 head and fp16 remainder of the 16 coefficients x s_k (2 chunks of 8 each: K = 16 of a
+//                kind::f16 step), then a kind::tf32 block of K = 8: (off_h, off_l, 0, 0 | 0 ..) x s_k.  s_k is the exact power-of-two
+//                block scale of output k (rbf_pow2_scale of the largest |coefficient|; 1 for every shape of the reference); feature
+//                offsets carry + pi/2 (cos(theta + pi/2) = -sin theta, the derivative of the forward's cosine).
+//   second half (kTcbPBytes) : B operand (N = kTcbQN columns x K = 128 units, bf16, K-major: chunk kc = unit / 8 of column n at
+//                kc * kTcbQN * 16 + (n / 8) * 128 + (n % 8) * 16) of Q[state][n] = sum_u tau[state][u] B[n][u]:
+//                n < 16: head of P[u][d = n] = weight_u x coefficient_ud, 16 <= n < 32: its remainder, n = 32 / 33: head / remainder of the
+//                weight (inducing units only: the sum the A_k(x) term needs), rest 0.
 constexpr int kTcbUnits = 128;
 constexpr int kTcbQN = 48;
-constexpr int kTcbThFloats = kTcfChunks * kTcbUnits * 4;            // 20,480 B
-constexpr int kTcbPFloats = kTcbQN * 2 * kTcbUnits * 2 / 4;         // 24,576 B
+constexpr int kTcbThBytes = 3 * 4096;
+constexpr int kTcbPBytes = kTcbQN * kTcbUnits * 2;
+constexpr int kTcbThFloats = kTcbThBytes / 4;
+constexpr int kTcbPFloats = kTcbPBytes / 4;
 constexpr int kTcbTileFloats = kTcbThFloats + kTcbPFloats;
+// exact power-of-two scale s (and 1 / s) of a block of fp16 operands with largest magnitude m: brings m into [2^13, 2^14), the top of
+// the fp16 range (products accumulate in fp32), so that the fp16 REMAINDER of every element down to 2^-15 of the maximum is still a
+// normal number -- head + remainder then carry 22 bits.  m = 0 (or subnormal): 1.
+__host__ __device__ inline void rbf_pow2_scale(float m, float& s, float& inv) {
+  union { float f; unsigned u; } c;
+  c.f = m;
+  const unsigned be = (c.u >> 23) & 255u;
+  unsigned bs = be == 0u ? 127u : 267u - be;
+  bs = bs > 253u ? 253u : bs;
+  c.u = bs << 23;
+  s = c.f;
+  c.u = (254u - bs) << 23;
+  inv = c.f;
+}
 __host__ __device__ inline int rbf_tc_blocks_s(const RbfGeom& g) { return (g.S + kTcfRows - 1) / kTcfRows; }
 __host__ __device__ inline int rbf_tc_blocks(const RbfGeom& g) { return rbf_tc_blocks_s(g) + (g.M + kTcfRows - 1) / kTcfRows; }
 inline size_t rbf_tc_floats(const RbfGeom& g) { return g.DP > 8 ? static_cast<size_t>(g.L) * g.D_out * rbf_tc_blocks(g) * kTcfTileFloats : 0; }
@@ -147,15 +168,12 @@ inline bool rbf_fwd_use_tc(const RbfGeom& g) {
   if (g.flags & GPODE_FLAG_FWD_TCGEN05) return true;    // (tests: force the tensor-memory kernel whatever the padding)
   return static_cast<long>(rbf_tc_blocks(g)) * kTcfRows * 100 <= static_cast<long>(g.S + g.M) * 115;
 }
-// Reverse sweep at D > 8 on a chip-filling batch: the mma.sync kernel (RbfMmaBwdPolicy) is the default; the tcgen05 / tensor-memory
-// kernel (rbf_bwd_tc.cuh) is selected with GPODE_FLAG_BWD_TCGEN05.  Measured at config-5 shapes: the tensor-memory
-// port serialises accumulator updates, the A-operand reads of the second product and the epilogue's tcgen05.ld / .st, which puts the
-// tensor-memory kernel at ~2,500 cycles per (128 states x 128 units) against ~3,100 for the mma.sync kernel on paper and behind it in
-// practice (41 vs 37.5 ms at T = 3) -- parity-tested, kept as the measured alternative, not the default.
+// Reverse sweep at D > 8 on a chip-filling batch: the fused tcgen05 kernel (rbf_bwd_tc.cuh: theta, the transcendental, the state
+// gradient AND the parameter-gradient statistics from one tile -- no separate parameter-gradient pass) is the default;
+// GPODE_FLAG_BWD_MMA selects the warp-level kernels (RbfMmaBwdPolicy + k_rbf_pgrad_mma).  Both are parity-tested against the oracle.
 inline bool rbf_bwd_use_tc(const RbfGeom& g) {
   if (g.DP <= 8 || static_cast<long>(g.N) * g.L < 32768) return false;
-  if (g.flags & GPODE_FLAG_BWD_MMA) return false;
-  return (g.flags & GPODE_FLAG_BWD_TCGEN05) != 0;
+  return (g.flags & GPODE_FLAG_BWD_MMA) == 0;
 }
 // inducing points per CTA of the tensor-path parameter-gradient kernel (8 warps x 16 MT rows)
 inline void rbf_pgrad_mma_shape(const RbfGeom& g, int& MT, int& n_mblk) {

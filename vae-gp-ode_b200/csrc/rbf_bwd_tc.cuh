@@ -1,55 +1,78 @@
-// RBF reverse sweep on the 5th-generation tensor cores (tcgen05.mma, accumulators AND the second product's A operand in tensor memory),
-// sm_100a, D > 8.  Structure of a fused attention backward (S = Q K^T -> P in place -> dQ = P V):
+// RBF reverse sweep FUSED with the parameter-gradient statistics on the 5th-generation tensor cores (tcgen05.mma, accumulators in tensor
+// memory), sm_100a, D > 8.  Structure of a fused attention backward (S = Q K^T -> P -> dQ = P K and dK = P^T Q from the SAME P):
 //
-// A CTA owns 128 states (row = TMEM lane = one state).  Per evaluation and output k the parameter rows arrive as operand tiles of
-// 128 units ("items", k_rbf_pack_tcb: layout in rbf.h), the theta operand and the second-product operand through separate bulk-copy
-// rings (their lifetimes differ by three items):
-//   1. theta (128 states x 128 units) = A B^T over K = 56, seven kind::tf32 k-steps (3xTF32 along K, exactly the forward's), into one of
-//      three 128-column accumulators;
-//   2. 16 epilogue warps (warp w: lanes 32 (w & 3).., columns 32 (w >> 2)..) read theta (tcgen05.ld), evaluate
+// A CTA owns 128 states.  Per evaluation and output k the parameter rows arrive as operand tiles of 128 units ("items", k_rbf_pack_tcb:
+// layout in rbf.h) in two halves through two bulk-copy rings.  Per item:
+//   1. theta (128 states x 128 units, fp32 in tensor memory) = s (x . G + off): three kind::f16 k-steps (fp16 head / remainder split of
+//      both operands, K = 16 = the input dimensions: X_h G_h + X_l G_h + X_h G_l, >= 21 bits) + one kind::tf32 k-step for the offsets
+//      (K = 8: (s_n, s_n, 0 ..) x (off_h, off_l, 0 ..)).  s = s_n s_k are exact power-of-two block scales (per state from max |x_d|, per
+//      output from max |coefficient|; both 1 for every shape of the reference) that keep the fp16 operands in range.
+//   2. 16 epilogue warps (warp w: states 32 (w & 3).., units 32 (w >> 2)..) read theta (tcgen05.ld), evaluate
 //          tau = -sin(theta)  (feature units; the + pi/2 is in the packed offset)      tau = 2^(theta + A_k(x))  (inducing units)
-//      split tau into a bf16 head and a bf16 remainder (16 mantissa bits, fp32 exponent range) and store the PAIR back over theta
-//      (tcgen05.st): one 32-bit column = two consecutive K elements of a kind::f16 A operand;
-//   3. Q_k (128 states x 48) += tau B2 with A read from TENSOR MEMORY (16 k-steps of kind::f16, K = 16 = 8 units x {head, remainder});
-//      B2 = [P_h | w_h || P_l | w_l] with P = weight x coefficient, so the head columns carry (tau_h + tau_l) P_h, the remainder columns
-//      tau_h P_l, and column 16 / 40 the weighted sum of tau that the A_k(x) term needs;
-//   4. once per k the warps read Q_k: dx_k = g_k (Q + 2 c_d x_d Es), dx += dx_k, lengthscale statistic sum_n x_d dx_kd (one warp reduction).
-// The legacy mma.sync kernel spends 7 HMMA + the operand splits per (16 x 8) tile in the instruction stream of the warps that also run
-// the transcendentals; here the epilogue stream is LDTM + MUFU + 3 ALU + STTM per element and the products run asynchronously:
-// per item the tensor pipe needs 452 + 800 cycles (tools/tc_probe2.cu: a TS kind::f16 MMA costs ~50 cycles whatever N -- it is bound by
-// reading the 4 KB A operand from tensor memory), the MUFU pipe 1,024.  A 17th warp issues every MMA and bulk copy; flow control is
-// mbarrier + tcgen05.commit, all waits time-bounded.  The tensor pipe executes in issue order, so theta(i + 3) overwriting the accumulator
-// of item i is safe once Q(i) has been issued.
+//      (un-scaling and A_k(x) are ONE FFMA), split tau into a bf16 head and a bf16 remainder (16 bits, fp32 exponent range) and store
+//      both planes into a SHARED-memory tile laid out so that it is at once the K-major A operand of product 3 (rows = states) and the
+//      MN-major A operand of product 4 (rows = units): 16-byte chunk (state s, plane p, units 8 c .. 8 c + 7) at (16 p + c) * 2048 + 16 s.
+//   3. Q_k (128 states x 48) += tau B: 16 k-steps of kind::f16 (bf16), B = [P_h | P_l | w_h w_l ..] with P = weight x coefficient --
+//      columns d and 16 + d sum to J^T contributions, 32 + 33 to the weighted sum of tau that the A_k(x) term needs.
+//   4. inducing items only: PG (128 units x 48) = tau^T X': 16 k-steps over the CTA's states, X' = [g x_d heads | remainders | g_h g_l ..]
+//      (one operand per output k, written by the epilogue warps, MN-major) -- columns d and 16 + d sum to sum_n g tau x_d, 32 + 33 to
+//      sum_n g tau: exactly the accumulators the separate parameter-gradient pass (k_rbf_pgrad_mma: theta and the exponentials a third
+//      time) used to fill.  The warps read PG two items later and add it to the global accumulators (red.global.add.f32).
+//   5. once per k the warps read Q_k: dx_k = g_k (Q + 2 c_d x_d Es), dx += dx_k, lengthscale statistic sum_n x_d dx_kd.
+// Every MMA is issued by one elected lane of a dedicated warp whose control flow is provably warp-uniform, so that descriptors live in
+// uniform registers (a divergent `if (lane == 0)` makes ptxas wrap each tcgen05.mma in a ~100-cycle uniformisation loop -- measured,
+// tools/tc_probe3.cu); a second helper warp issues the bulk copies.  Flow control is mbarrier + tcgen05.commit, all waits time-bounded.
+// Measured costs per item (tools/tc_probe3.cu): theta ~400 cycles, Q ~710, PG ~810 -- the second products are bound by reading the
+// 64 KB tau tile from shared memory (128 B / cycle), not by the tensor pipe; the transcendentals need 1,024 MUFU cycles per item.
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "rbf_kernels.cuh"
 #include "tc_common.cuh"
 
 namespace gpode {
 
+#ifndef GPODE_BT_EXP
+#define GPODE_BT_EXP 0   // timing experiments only (wrong results): 1 no PG MMAs, 2 no Q MMAs, 4 no transcendentals, 8 no tau stores, 16 no theta MMAs
+#endif
+
 constexpr int kBtStates = 128;                 // states per CTA
 constexpr int kBtEpiWarps = 16;
 constexpr int kBtEpi = kBtEpiWarps * 32;
-constexpr int kBtThreads = kBtEpi + 64;        // + MMA-issuer warp + bulk-copy producer warp (issuing a 20 KB copy stalls its thread ~800 cycles)
-constexpr int kBtThStages = 3;                 // theta-operand ring (freed when theta(i) has executed)
-constexpr int kBtPStages = 4;                  // second-operand ring (freed when Q(i) has executed)
-constexpr int kBtAFloats = kTcfChunks * kBtStates * 4;
-constexpr int kBtQCol = 3 * kTcbUnits;         // tensor-memory columns: 3 theta accumulators, then 2 Q buffers of 64
-constexpr int kBtNBars = 2 * kBtThStages + 2 * kBtPStages + 3 + 3 + 2 + 2;
+constexpr int kBtThreads = kBtEpi + 64;        // + MMA-issuer warp + bulk-copy producer warp
+constexpr int kBtTauBytes = 2 * 16 * 2048;     // one tau tile: 2 planes x 16 unit groups x (128 states x 16 B)
+constexpr int kBtABytes = 3 * 4096;            // state operand of theta: X_h | X_l | (s_n, s_n, 0 ..)
+constexpr int kBtXpBytes = 6 * 2048;           // X' (128 states x 48 columns bf16, MN-major: chunk (s, n / 8) at (n / 8) * 2048 + 16 s)
+constexpr int kBtQCol = 256, kBtPgCol = 352;   // tensor-memory columns: 2 theta accumulators of 128, 2 Q of 48, 2 PG of 48
+constexpr int kBtNBars = 26;
 
-__host__ __device__ constexpr uint32_t tc_idesc_bf16(int M, int N) {   // f32 accumulate, bf16 x bf16, both K-major
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t tc_idesc_f16(int M, int N) {   // f32 accumulate, fp16 x fp16, both K-major
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
-__device__ __forceinline__ void tc_mma_ts_bf16(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+__host__ __device__ constexpr uint32_t tc_idesc_bf16(int M, int N, int a_mn, int b_mn) {   // f32 accumulate, bf16 x bf16
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+// no-swizzle descriptor: lbo = byte step along K between core matrices, sbo = byte step along M / N between core matrices
+__device__ __forceinline__ uint64_t tc_desc2(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((saddr & 0x3FFFF) >> 4) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16) | (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (static_cast<uint64_t>(1) << 46);
+}
+// MMA / commit issued by ONE elected lane of a converged warp (operands warp-uniform)
+__device__ __forceinline__ void tcu_mma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b),
+               "r"(idesc), "r"(acc)
                : "memory");
 }
-__device__ __forceinline__ void tc_st16_async(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
-               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+__device__ __forceinline__ void tcu_mma_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b),
+               "r"(idesc), "r"(acc)
                : "memory");
+}
+__device__ __forceinline__ void tcu_commit(uint64_t* bar) {
+  asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_ld4(uint32_t taddr, float (&v)[4]) {
   uint32_t r0, r1, r2, r3;
@@ -60,42 +83,86 @@ __device__ __forceinline__ void tc_ld4(uint32_t taddr, float (&v)[4]) {
   v[2] = __uint_as_float(r2);
   v[3] = __uint_as_float(r3);
 }
-__device__ __forceinline__ float tc_ld1(uint32_t taddr) {
-  uint32_t r0;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0)::"memory");
-  return __uint_as_float(r0);
+__device__ __forceinline__ void tc_ld2(uint32_t taddr, float (&v)[2]) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0), "+r"(r1)::"memory");
+  v[0] = __uint_as_float(r0);
+  v[1] = __uint_as_float(r1);
 }
-// tau -> packed {bf16 head (bits 0..15: the even K element), bf16 remainder (bits 16..31)}: head by truncation (exact remainder), the
-// remainder rounded -- |tau - (h + l)| <= 2^-17 |tau|
-__device__ __forceinline__ uint32_t tc_split_bf16(float tau) {
-  const float h = __uint_as_float(__float_as_uint(tau) & 0xFFFF0000u);
-  uint32_t out;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(out) : "f"(tau - h), "f"(h));
-  return out;
+__device__ __forceinline__ void tc_ld4_async(uint32_t taddr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld2_async(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+}
+// orders later uses of asynchronously loaded registers behind the preceding tcgen05.wait::ld (volatile asm statements keep their order)
+__device__ __forceinline__ void tc_ld_fence(uint32_t (&r)[10]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9])::"memory");
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+#if GPODE_BT_EXP
+  if (GPODE_BT_EXP & 8) {
+    asm volatile("" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d));
+    return;
+  }
+#endif
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// (v0, v1) -> packed bf16 heads by truncation (element 0 in the low half) and packed bf16 remainders (rounded): |v - (h + l)| <= 2^-17 |v|
+__device__ __forceinline__ void bt_split2(float v0, float v1, uint32_t& hd, uint32_t& rm) {
+  hd = __byte_perm(__float_as_uint(v0), __float_as_uint(v1), 0x7632);
+  const float l0 = v0 - __uint_as_float(__float_as_uint(v0) & 0xFFFF0000u), l1 = v1 - __uint_as_float(__float_as_uint(v1) & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rm) : "f"(l1), "f"(l0));
 }
 
+#ifdef GPODE_BT_PROFILE
+#define BT_E0 long long et_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ec_ = clock64();
+#define BT_E(i) { const long long now_ = clock64(); et_[i] += now_ - ec_; ec_ = now_; }
+#define BT_EPRINT if (blockIdx.x == 5 && blockIdx.y == 0 && b0 == static_cast<long>(n) && (tid == 0 || tid == 480)) \
+  printf("bwd tc epilogue warp %d (cycles per item): first wait %lld, wait tau_empty %lld, ld issue + ld wait + arrives %lld, math+store %lld (+ wait next theta %lld), k setup + xprime %lld (+ wait xp_empty %lld), pg red %lld (+ waits pg_full / q_full %lld), q epilogue %lld (+ %lld)\n", warp, \
+         et_[0] / n, et_[1] / n, et_[2] / n, et_[3] / n, et_[7] / n, et_[4] / n, et_[8] / n, et_[5] / n, et_[9] / n, et_[6] / n, et_[10] / n);
+#define BT_I0 long long it_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ic_ = clock64();
+#define BT_I(i) { const long long now_ = clock64(); it_[i] += now_ - ic_; ic_ = now_; }
+#define BT_IPRINT if (blockIdx.x == 5 && blockIdx.y == 0 && b0 == static_cast<long>(n) && lane == 0) \
+  printf("bwd tc issuer (cycles per item): theta waits (tile, acc_empty) %lld, theta issue %lld, wait tau_full %lld, wait p tile %lld, wait q_empty/xp/pg_empty %lld, issue Q %lld, issue PG %lld\n", \
+         it_[0] / n, it_[1] / n, it_[2] / n, it_[3] / n, it_[4] / n, it_[5] / n, it_[6] / n);
+#else
+#define BT_E0
+#define BT_E(i)
+#define BT_EPRINT
+#define BT_I0
+#define BT_I(i)
+#define BT_IPRINT
+#endif
+
 struct BwdTcSmem {
-  float* xs;          // [DP][128] staged states (generic solver glue), stride kBtStates
-  float* dx;          // [DP][128] J^T g of this evaluation
-  float* hdr;         // [D_out][hdr_floats]
-  float* dell;        // [D_out][DP] lengthscale statistic, then dvar [D_out] (contiguous, like SweepSmem)
+  unsigned char* tau;   // 2 x kBtTauBytes
+  unsigned char* th;    // 2 x kTcbThBytes   theta-half ring
+  unsigned char* pp;    // 2 x kTcbPBytes    second-half ring
+  unsigned char* A;     // kBtABytes
+  unsigned char* xp;    // kBtXpBytes; after the last MMA of an evaluation its first 8 KB double as dx (J^T g, [DP][128] floats)
+  float* xs;            // [16][128] staged states (generic solver glue), stride kBtStates
+  float* dx;            // = xp
+  float* hdr;           // [D_out][hdr_floats]
+  float* dell;          // [D_out][DP] lengthscale statistic, then dvar [D_out] (contiguous, like SweepSmem)
   float* dvar;
-  float* A;           // state operand of theta (kBtAFloats)
-  float* Bth;         // kBtThStages x kTcbThFloats
-  float* Bp;          // kBtPStages x kTcbPFloats
+  float* sk;            // [D_out] 1 / s_k
+  float* g_pg;          // global accumulators of the launch (bind()): sum_n g tau x_d and sum_n g tau per inducing unit
+  float* g_dnu;
   uint64_t* bars;
   uint32_t* tmem_slot;
-  long* ring;         // issuer-only state: tiles fetched so far {theta, second operand}
-  const float* tiles; // operand tiles of this sample (global)
+  const float* tiles;   // operand tiles of this sample (global)
   uint32_t tmem;
-  long blk;           // running item counter of this CTA
-  long kk;            // running (evaluation, k) counter: Q buffer kk & 1
+  long blk;             // running item counter of this CTA
+  long kk;              // running (evaluation, k) counter: Q buffer kk & 1
+  long pgc;             // running inducing-item counter: PG buffer pgc & 1
   long total;
+  float stat[5];        // (epilogue threads, lane k) sum over the warp's states of x_d dx_kd for d = 4 q + t (t < 4) and, q = 0, of g (f - f_p / 2)
 };
 
 inline int rbf_bwd_tc_smem_bytes(const RbfGeom& g) {
-  return (kBtAFloats + kBtThStages * kTcbThFloats + kBtPStages * kTcbPFloats + 2 * 16 * kBtStates + g.D_out * g.hdr_floats + g.D_out * (g.DP + 1) + 8) * 4 +
+  return 2 * kBtTauBytes + 2 * kTcbThBytes + 2 * kTcbPBytes + kBtABytes + kBtXpBytes + 16 * kBtStates * 4 + (g.D_out * g.hdr_floats + g.D_out * (g.DP + 1) + g.D_out + 8) * 4 +
          kBtNBars * 8 + 64 + 1024;
 }
 
@@ -114,79 +181,96 @@ struct RbfTcBwdPolicy {
   using Smem = BwdTcSmem;
   static_assert(DP_ <= 16, "one 16-wide K block per operand part");
 
+  // ring / accumulator barriers (index = slot or buffer 0 / 1)
   __device__ static __forceinline__ uint64_t* th_full(const Smem& sm, int s) { return sm.bars + s; }
-  __device__ static __forceinline__ uint64_t* th_empty(const Smem& sm, int s) { return sm.bars + kBtThStages + s; }
-  __device__ static __forceinline__ uint64_t* p_full(const Smem& sm, int s) { return sm.bars + 2 * kBtThStages + s; }
-  __device__ static __forceinline__ uint64_t* p_empty(const Smem& sm, int s) { return sm.bars + 2 * kBtThStages + kBtPStages + s; }
-  __device__ static __forceinline__ uint64_t* acc_full(const Smem& sm, int a) { return sm.bars + 2 * kBtThStages + 2 * kBtPStages + a; }
-  __device__ static __forceinline__ uint64_t* tau_ready(const Smem& sm, int a) { return sm.bars + 2 * kBtThStages + 2 * kBtPStages + 3 + a; }
-  __device__ static __forceinline__ uint64_t* q_full(const Smem& sm, int q) { return sm.bars + 2 * kBtThStages + 2 * kBtPStages + 6 + q; }
-  __device__ static __forceinline__ uint64_t* q_empty(const Smem& sm, int q) { return sm.bars + 2 * kBtThStages + 2 * kBtPStages + 8 + q; }
+  __device__ static __forceinline__ uint64_t* th_empty(const Smem& sm, int s) { return sm.bars + 2 + s; }
+  __device__ static __forceinline__ uint64_t* p_full(const Smem& sm, int s) { return sm.bars + 4 + s; }
+  __device__ static __forceinline__ uint64_t* p_empty(const Smem& sm, int s) { return sm.bars + 6 + s; }
+  __device__ static __forceinline__ uint64_t* acc_full(const Smem& sm, int a) { return sm.bars + 8 + a; }     // theta(b) executed
+  __device__ static __forceinline__ uint64_t* acc_empty(const Smem& sm, int a) { return sm.bars + 10 + a; }   // every warp has read theta(b)
+  __device__ static __forceinline__ uint64_t* tau_full(const Smem& sm, int a) { return sm.bars + 12 + a; }    // every warp has stored tau(b)
+  __device__ static __forceinline__ uint64_t* tau_empty(const Smem& sm, int a) { return sm.bars + 14 + a; }   // Q(b) and PG(b) executed
+  __device__ static __forceinline__ uint64_t* q_full(const Smem& sm, int q) { return sm.bars + 16 + q; }
+  __device__ static __forceinline__ uint64_t* q_empty(const Smem& sm, int q) { return sm.bars + 18 + q; }
+  __device__ static __forceinline__ uint64_t* pg_full(const Smem& sm, int q) { return sm.bars + 20 + q; }
+  __device__ static __forceinline__ uint64_t* pg_empty(const Smem& sm, int q) { return sm.bars + 22 + q; }
+  __device__ static __forceinline__ uint64_t* xp_full(const Smem& sm) { return sm.bars + 24; }                // X' of this k written
+  __device__ static __forceinline__ uint64_t* xp_empty(const Smem& sm) { return sm.bars + 25; }               // last PG of this k executed
 
   __device__ static __forceinline__ Smem carve(float* smem, const Geom& g) {
     Smem s;
-    float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~static_cast<uintptr_t>(1023));
-    s.A = base;
-    s.Bth = s.A + kBtAFloats;
-    s.Bp = s.Bth + kBtThStages * kTcbThFloats;
-    s.xs = s.Bp + kBtPStages * kTcbPFloats;
-    s.dx = s.xs + 16 * kBtStates;
-    s.hdr = s.dx + 16 * kBtStates;
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~static_cast<uintptr_t>(1023));
+    s.tau = base;
+    s.th = s.tau + 2 * kBtTauBytes;
+    s.pp = s.th + 2 * kTcbThBytes;
+    s.A = s.pp + 2 * kTcbPBytes;
+    s.xp = s.A + kBtABytes;
+    s.xs = reinterpret_cast<float*>(s.xp + kBtXpBytes);
+    s.dx = reinterpret_cast<float*>(s.xp);
+    s.hdr = s.xs + 16 * kBtStates;
     s.dell = s.hdr + g.D_out * g.hdr_floats;
     s.dvar = s.dell + g.D_out * DP;
-    float* end = s.dvar + g.D_out;
+    s.sk = s.dvar + g.D_out;
+    float* end = s.sk + g.D_out;
     s.bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(end + 1) + 7) & ~static_cast<uintptr_t>(7));
-    s.ring = reinterpret_cast<long*>(s.bars + kBtNBars);
-    s.tmem_slot = reinterpret_cast<uint32_t*>(s.ring + 2);
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.bars + kBtNBars);
+    s.g_pg = nullptr;
+    s.g_dnu = nullptr;
     s.blk = 0;
     s.kk = 0;
+    s.pgc = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) s.stat[i] = 0.f;
     return s;
   }
 
   __device__ static __forceinline__ void fetch_th(const Smem& sm, const Geom& g, long b) {
     const int per_eval = g.D_out * rbf_tcb_items(g);
-    const int slot = static_cast<int>(b % kBtThStages);
+    const int slot = static_cast<int>(b & 1);
     const float* src = sm.tiles + static_cast<size_t>(b % per_eval) * kTcbTileFloats;
-    mbar_expect_tx(th_full(sm, slot), kTcbThFloats * 4u);
-    bulk_g2s(sm.Bth + slot * kTcbThFloats, src, kTcbThFloats * 4u, th_full(sm, slot));
+    mbar_expect_tx(th_full(sm, slot), kTcbThBytes);
+    bulk_g2s(sm.th + slot * kTcbThBytes, src, kTcbThBytes, th_full(sm, slot));
   }
   __device__ static __forceinline__ void fetch_p(const Smem& sm, const Geom& g, long b) {
     const int per_eval = g.D_out * rbf_tcb_items(g);
-    const int slot = static_cast<int>(b % kBtPStages);
+    const int slot = static_cast<int>(b & 1);
     const float* src = sm.tiles + static_cast<size_t>(b % per_eval) * kTcbTileFloats + kTcbThFloats;
-    mbar_expect_tx(p_full(sm, slot), kTcbPFloats * 4u);
-    bulk_g2s(sm.Bp + slot * kTcbPFloats, src, kTcbPFloats * 4u, p_full(sm, slot));
+    mbar_expect_tx(p_full(sm, slot), kTcbPBytes);
+    bulk_g2s(sm.pp + slot * kTcbPBytes, src, kTcbPBytes, p_full(sm, slot));
   }
 
   __device__ static __forceinline__ long setup(Smem& sm, ChunkPipe&, const Geom& g, const float* packed, long n_evals, bool) {
     const int l = blockIdx.y, tid = threadIdx.x;
     const float* hdr = rbf_hdr_ptr(packed, g, l);
     for (int i = tid; i < g.D_out * g.hdr_floats; i += blockDim.x) sm.hdr[i] = hdr[i];
-    for (int i = tid; i < 2 * 16 * kBtStates; i += blockDim.x) sm.xs[i] = 0.f;   // xs and dx
+    for (int i = tid; i < 16 * kBtStates; i += blockDim.x) sm.xs[i] = 0.f;
+    for (int i = tid; i < kBtXpBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm.xp)[i] = 0u;
+    for (int i = tid; i < kBtABytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm.A)[i] = 0u;
     for (int i = tid; i < g.D_out * (DP + 1); i += blockDim.x) sm.dell[i] = 0.f;  // dell and dvar
+    for (int i = tid; i < g.D_out; i += blockDim.x) {
+      float s, inv;
+      rbf_pow2_scale(rbf_maxabs_ptr(packed, g, l)[i], s, inv);
+      sm.sk[i] = inv;
+    }
     sm.tiles = rbf_tcb_tiles_ptr(packed, g, l);
     sm.total = n_evals * g.D_out * rbf_tcb_items(g);
-    if (tid < kBtStates) {   // constant chunks of the state operand: chunk 8 = (1, 1, 0, 0) meets (off_h, off_l, 0, 0); chunk 9 = 0
-      *reinterpret_cast<float4*>(sm.A + tc_chunk_off(128, tid, 8)) = make_float4(1.f, 1.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(sm.A + tc_chunk_off(128, tid, 9)) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     if (tid == 0) {
-      for (int i = 0; i < kBtThStages; ++i) {
+      for (int i = 0; i < 2; ++i) {
         mbar_init(th_full(sm, i), 1);
         mbar_init(th_empty(sm, i), 1);
-      }
-      for (int i = 0; i < kBtPStages; ++i) {
         mbar_init(p_full(sm, i), 1);
         mbar_init(p_empty(sm, i), 1);
-      }
-      for (int i = 0; i < 3; ++i) {
         mbar_init(acc_full(sm, i), 1);
-        mbar_init(tau_ready(sm, i), kBtEpiWarps);
-      }
-      for (int i = 0; i < 2; ++i) {
+        mbar_init(acc_empty(sm, i), kBtEpiWarps);
+        mbar_init(tau_full(sm, i), kBtEpiWarps);
+        mbar_init(tau_empty(sm, i), 1);
         mbar_init(q_full(sm, i), 1);
         mbar_init(q_empty(sm, i), kBtEpiWarps);
+        mbar_init(pg_full(sm, i), 1);
+        mbar_init(pg_empty(sm, i), kBtEpiWarps);
       }
+      mbar_init(xp_full(sm), kBtEpiWarps);
+      mbar_init(xp_empty(sm), 1);
       mbar_fence_init();
     }
     if (tid < 32) {
@@ -198,15 +282,11 @@ struct RbfTcBwdPolicy {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     sm.tmem = *sm.tmem_slot;
-#ifdef GPODE_DEBUG_WAIT
-    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) printf("bwd tc: bars at smem+%u (th_full 0.., th_empty %d.., p_full %d.., p_empty %d.., acc_full %d.., tau_ready %d.., q_full %d.., q_empty %d..) total %ld\n", smem_u32(sm.bars), kBtThStages, 2 * kBtThStages, 2 * kBtThStages + kBtPStages, 2 * kBtThStages + 2 * kBtPStages, 2 * kBtThStages + 2 * kBtPStages + 3, 2 * kBtThStages + 2 * kBtPStages + 6, 2 * kBtThStages + 2 * kBtPStages + 8, sm.total);
-#endif
     if (tid == kBtEpi + 32) {   // the producer thread owns the rings: first tiles of both
-      long f = 0;
-      for (; f < kBtThStages && f < sm.total; ++f) fetch_th(sm, g, f);
-      sm.ring[0] = f;
-      for (f = 0; f < kBtPStages && f < sm.total; ++f) fetch_p(sm, g, f);
-      sm.ring[1] = f;
+      for (long f = 0; f < 2 && f < sm.total; ++f) {
+        fetch_th(sm, g, f);
+        fetch_p(sm, g, f);
+      }
     }
     return sm.total;
   }
@@ -214,102 +294,76 @@ struct RbfTcBwdPolicy {
   __device__ static __forceinline__ void finish(Smem&) {}
 
   __device__ static __forceinline__ void flush(const Smem& sm, const Geom& g, const Accum& acc) {
-    for (int i = threadIdx.x; i < g.D_out * DP; i += blockDim.x) atomicAdd(&acc.dell_x[i], sm.dell[i]);
-    for (int i = threadIdx.x; i < g.D_out; i += blockDim.x) atomicAdd(&acc.dvar[i], sm.dvar[i]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp >> 2;
+    if (warp < kBtEpiWarps && lane < g.D_out) {   // lane k holds the statistics of output k (vjp)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (4 * q + t < DP) atomicAdd(&acc.dell_x[lane * DP + 4 * q + t], sm.stat[t]);
+      if (q == 0) atomicAdd(&acc.dvar[lane], sm.stat[4]);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem), "r"(512) : "memory");
   }
 
-  // the issuer is also the producer: before it waits for tile b it makes sure the copy of tile b has been issued (blocking on the slot's
-  // previous occupant if the non-blocking prefetch of refill() has not got there yet) -- otherwise it would wait for itself
-  __device__ static __forceinline__ void ensure_th(const Smem& sm, const Geom& g, long b) {
-    long f = sm.ring[0];
-    for (; f <= b; ++f) {
-      tc_wait(th_empty(sm, static_cast<int>(f % kBtThStages)), static_cast<uint32_t>(((f - kBtThStages) / kBtThStages) & 1));
-      fetch_th(sm, g, f);
-    }
-    sm.ring[0] = f;
-  }
-  __device__ static __forceinline__ void ensure_p(const Smem& sm, const Geom& g, long b) {
-    long f = sm.ring[1];
-    for (; f <= b; ++f) {
-      tc_wait(p_empty(sm, static_cast<int>(f % kBtPStages)), static_cast<uint32_t>(((f - kBtPStages) / kBtPStages) & 1));
-      fetch_p(sm, g, f);
-    }
-    sm.ring[1] = f;
-  }
-  // theta of item b (one thread): seven k-steps into accumulator b % 3; frees the ring slot when executed
-  __device__ static __forceinline__ void issue_theta(const Smem& sm, const Geom&, long b) {
-    const int slot = static_cast<int>(b % kBtThStages), acc = static_cast<int>(b % 3);
-    tc_wait(th_full(sm, slot), static_cast<uint32_t>((b / kBtThStages) & 1));
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t a0 = smem_u32(sm.A), b0 = smem_u32(sm.Bth + slot * kTcbThFloats);
-    constexpr uint32_t idesc = tc_idesc(128, kTcbUnits);
-    constexpr int ach[7] = {0, 2, 4, 6, 0, 2, 8}, bch[7] = {0, 2, 0, 2, 4, 6, 8};
-#pragma unroll
-    for (int s = 0; s < 7; ++s)
-      tc_mma_ss(sm.tmem + acc * kTcbUnits, tc_desc(a0 + ach[s] * 128 * 16, 128 * 16), tc_desc(b0 + bch[s] * kTcbUnits * 16, kTcbUnits * 16), idesc, s > 0);
-    tc_commit(acc_full(sm, acc));
-    tc_commit(th_empty(sm, slot));
-  }
-  // refill whatever ring slots have drained (non-blocking: the issuer never waits for a copy it does not need yet)
-  __device__ static __forceinline__ void refill(const Smem& sm, const Geom& g) {
-    long f = sm.ring[0];
-    while (f < sm.total && mbar_test(th_empty(sm, static_cast<int>(f % kBtThStages)), static_cast<uint32_t>(((f - kBtThStages) / kBtThStages) & 1))) {
-      fetch_th(sm, g, f);
-      ++f;
-    }
-    sm.ring[0] = f;
-    f = sm.ring[1];
-    while (f < sm.total && mbar_test(p_empty(sm, static_cast<int>(f % kBtPStages)), static_cast<uint32_t>(((f - kBtPStages) / kBtPStages) & 1))) {
-      fetch_p(sm, g, f);
-      ++f;
-    }
-    sm.ring[1] = f;
+  // the sweep kernels hand the launch's accumulators to policies that fill them during the sweep (sweep.cuh: bind_accum)
+  __device__ static __forceinline__ void bind(Smem& sm, const Accum& acc) {
+    sm.g_pg = acc.pg;
+    sm.g_dnu = acc.dnu;
   }
 
   __device__ static __forceinline__ void vjp(ChunkPipe&, const Geom& g, long, Smem& sm, const States<R>& st, const float* gvec, const float* fvec,
                                              const float* fpvec, long kstride, long sstride) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nbs = rbf_tcb_items_s(g), nbi = rbf_tcb_items(g);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role branches may use the uniform datapath
+    const int nbs = rbf_tcb_items_s(g), nbi = rbf_tcb_items(g), nbm = nbi - nbs;
     const int n = g.D_out * nbi;   // items of one evaluation
-    const long b0 = sm.blk, kk0 = sm.kk;
-    if (tid < kBtStates) {   // ---- this state's operand row: TF32 heads and remainders ----
+    const long b0 = sm.blk, kk0 = sm.kk, pg0 = sm.pgc;
+    (void)st;
+    if (tid < kBtStates) {   // ---- this state's operand row: block scale, fp16 heads and remainders, (s_n, s_n) for the offsets ----
+      float xv[16], mx = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float xv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xv[i] = 4 * c + i < DP ? sm.xs[(4 * c + i) * kBtStates + tid] : 0.f;
-        float4 hd, lo_;
-        hd.x = __uint_as_float(__float_as_uint(xv[0]) & 0xFFFFE000u);
-        hd.y = __uint_as_float(__float_as_uint(xv[1]) & 0xFFFFE000u);
-        hd.z = __uint_as_float(__float_as_uint(xv[2]) & 0xFFFFE000u);
-        hd.w = __uint_as_float(__float_as_uint(xv[3]) & 0xFFFFE000u);
-        lo_ = make_float4(xv[0] - hd.x, xv[1] - hd.y, xv[2] - hd.z, xv[3] - hd.w);
-        *reinterpret_cast<float4*>(sm.A + tc_chunk_off(128, tid, c)) = hd;
-        *reinterpret_cast<float4*>(sm.A + tc_chunk_off(128, tid, 4 + c)) = lo_;
+      for (int d = 0; d < 16; ++d) {
+        xv[d] = d < DP ? sm.xs[d * kBtStates + tid] : 0.f;
+        mx = fmaxf(mx, fabsf(xv[d]));
       }
+      float sn, inv;
+      rbf_pow2_scale(mx, sn, inv);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t hh[4], ll[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float v0 = xv[8 * c + 2 * i] * sn, v1 = xv[8 * c + 2 * i + 1] * sn;
+          const __half2 h = __floats2half2_rn(v0, v1);
+          const __half2 lo_ = __floats2half2_rn(v0 - __low2float(h), v1 - __high2float(h));
+          hh[i] = *reinterpret_cast<const uint32_t*>(&h);
+          ll[i] = *reinterpret_cast<const uint32_t*>(&lo_);
+        }
+        sts128(smem_u32(sm.A) + c * 2048 + tid * 16, hh[0], hh[1], hh[2], hh[3]);
+        sts128(smem_u32(sm.A) + 4096 + c * 2048 + tid * 16, ll[0], ll[1], ll[2], ll[3]);
+      }
+      sts128(smem_u32(sm.A) + 8192 + tid * 16, __float_as_uint(sn), __float_as_uint(sn), 0u, 0u);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     float dxa[4] = {0.f, 0.f, 0.f, 0.f};
-    const int q = warp >> 2;                                   // column quarter of every accumulator / dims 4 q .. 4 q + 3 of Q
-    const int sidx = 32 * (warp & 3) + lane;                   // state slot of this epilogue thread
-    if (tid >= kBtEpi + 32) {
-      // =============== bulk-copy producer (one thread): keeps both rings full, through this evaluation and into the next ===============
+    const int q = warp >> 2;                                   // unit quarter of every item / dims 4 q .. 4 q + 3 of Q and PG
+    const int sidx = 32 * (warp & 3) + lane;                   // state slot (Q) / unit slot (PG) of this epilogue thread
+    if (warp == kBtEpiWarps + 1) {
+      // =============== bulk-copy producer: keeps both rings full, through this evaluation and into the next ===============
       if (lane == 0) {
-        const long end_th = min(sm.total, b0 + n + kBtThStages), end_p = min(sm.total, b0 + n + kBtPStages);
-        long fth = sm.ring[0], fp = sm.ring[1];
+        const long end = min(sm.total, b0 + n + 2);
+        long fth = b0 + 2, fp = b0 + 2;   // tiles < b0 + 2 were fetched by setup() or by the tail of the previous evaluation
         unsigned long long idle_t0 = 0;
         int spins = 0;
-        while (fth < end_th || fp < end_p) {
+        while (fth < end || fp < end) {
           bool any = false;
-          if (fth < end_th && mbar_test(th_empty(sm, static_cast<int>(fth % kBtThStages)), static_cast<uint32_t>(((fth - kBtThStages) / kBtThStages) & 1))) {
+          if (fth < end && mbar_test(th_empty(sm, static_cast<int>(fth & 1)), static_cast<uint32_t>(((fth - 2) >> 1) & 1))) {
             fetch_th(sm, g, fth++);
             any = true;
           }
-          if (fp < end_p && mbar_test(p_empty(sm, static_cast<int>(fp % kBtPStages)), static_cast<uint32_t>(((fp - kBtPStages) / kBtPStages) & 1))) {
+          if (fp < end && mbar_test(p_empty(sm, static_cast<int>(fp & 1)), static_cast<uint32_t>(((fp - 2) >> 1) & 1))) {
             fetch_p(sm, g, fp++);
             any = true;
           }
@@ -320,161 +374,297 @@ struct RbfTcBwdPolicy {
             if (GPODE_WAIT_TIMEOUT_NS != 0ull && global_ns() - idle_t0 > GPODE_WAIT_TIMEOUT_NS) __trap();
           }
         }
-        sm.ring[0] = fth;
-        sm.ring[1] = fp;
       }
-    } else if (tid >= kBtEpi) {
-      // =============== MMA issuer (one thread) ===============
-      if (lane == 0) {
-#ifdef GPODE_BT_PROFILE
-        long long pt[6] = {0, 0, 0, 0, 0, 0}, pc;
-#define BT_T0 pc = clock64();
-#define BT_T(i) { const long long now_ = clock64(); pt[i] += now_ - pc; pc = now_; }
-#else
-#define BT_T0
-#define BT_T(i)
-#endif
-        BT_T0
-        for (int i = 0; i < 3 && i < n; ++i) issue_theta(sm, g, b0 + i);
-        BT_T(4)
-        constexpr uint32_t idq = tc_idesc_bf16(128, kTcbQN);
-        for (int i = 0; i < n; ++i) {
-          const long b = b0 + i;
-          const int acc = static_cast<int>(b % 3), ps = static_cast<int>(b % kBtPStages);
-          const int j = i % nbi;
-          const long kk = kk0 + i / nbi;
-          tc_wait(tau_ready(sm, acc), static_cast<uint32_t>((b / 3) & 1));
-          BT_T(0)
-          if (j == 0 && kk >= 2) tc_wait(q_empty(sm, static_cast<int>(kk & 1)), static_cast<uint32_t>(((kk - 2) >> 1) & 1));
-          BT_T(1)
-          tc_wait(p_full(sm, ps), static_cast<uint32_t>((b / kBtPStages) & 1));
-          BT_T(2)
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t dq = sm.tmem + kBtQCol + static_cast<uint32_t>(kk & 1) * 64, at = sm.tmem + acc * kTcbUnits;
-          const uint32_t bp = smem_u32(sm.Bp + ps * kTcbPFloats);
-#pragma unroll
-          for (int ks = 0; ks < 2 * kTcbUnits / 16; ++ks)
-            tc_mma_ts_bf16(dq, at + ks * 8, tc_desc(bp + ks * 2 * kTcbQN * 16, kTcbQN * 16), idq, (j > 0 || ks > 0) ? 1u : 0u);
-          tc_commit(p_empty(sm, ps));
-          if (j == nbi - 1) tc_commit(q_full(sm, static_cast<int>(kk & 1)));
-          BT_T(3)
-          if (i + 3 < n) issue_theta(sm, g, b + 3);
-          BT_T(4)
+    } else if (warp == kBtEpiWarps) {
+      // =============== MMA issuer: the whole warp walks the schedule, one elected lane issues ===============
+      const uint32_t aA = smem_u32(sm.A), aTau = smem_u32(sm.tau), aTh = smem_u32(sm.th), aP = smem_u32(sm.pp), aXp = smem_u32(sm.xp);
+      constexpr uint32_t id_th = tc_idesc_f16(128, kTcbUnits), id_off = tc_idesc(128, kTcbUnits), id_q = tc_idesc_bf16(128, kTcbQN, 0, 0),
+                         id_pg = tc_idesc_bf16(128, kTcbQN, 1, 1);
+      BT_I0
+      auto issue_theta = [&](long b) {
+        const int slot = static_cast<int>(b & 1);
+        tc_wait(th_full(sm, slot), static_cast<uint32_t>((b >> 1) & 1));
+        if (b >= 2) tc_wait(acc_empty(sm, slot), static_cast<uint32_t>(((b - 2) >> 1) & 1));
+        BT_I(0)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = sm.tmem + slot * kTcbUnits, bt = aTh + slot * kTcbThBytes;
+        if (!(GPODE_BT_EXP & 16)) {
+        tcu_mma_f16(d, tc_desc2(aA, 2048, 128), tc_desc2(bt, 2048, 128), id_th, 0u);                    // X_h G_h
+        tcu_mma_f16(d, tc_desc2(aA + 4096, 2048, 128), tc_desc2(bt, 2048, 128), id_th, 1u);            // X_l G_h
+        tcu_mma_f16(d, tc_desc2(aA, 2048, 128), tc_desc2(bt + 4096, 2048, 128), id_th, 1u);            // X_h G_l
+        tcu_mma_tf32(d, tc_desc2(aA + 8192, 2048, 128), tc_desc2(bt + 8192, 2048, 128), id_off, 1u);   // (s_n, s_n) x (off_h, off_l)
         }
-#ifdef GPODE_BT_PROFILE
-        if (blockIdx.x == 5 && blockIdx.y == 0 && b0 == static_cast<long>(n))
-          printf("bwd tc issuer (cycles per item over %d items): wait tau %lld, wait q_empty %lld, wait p tile %lld, issue Q %lld, issue theta (+ wait tile) %lld, refill %lld\n", n,
-                 pt[0] / n, pt[1] / n, pt[2] / n, pt[3] / n, pt[4] / n, pt[5] / n);
-#endif
+        tcu_commit(acc_full(sm, slot));
+        tcu_commit(th_empty(sm, slot));
+        BT_I(1)
+      };
+      // theta runs two items ahead of the second products and is issued IN FRONT of them (the tensor pipe executes in issue order):
+      // theta(b + 2) starts as soon as the epilogue of item b has released its accumulator, so the epilogue of b + 1 never waits for it
+      issue_theta(b0);
+      if (n > 1) issue_theta(b0 + 1);
+      int k = 0, j = 0;
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) {
+        const long b = b0 + i;
+        const int slot = static_cast<int>(b & 1);
+        const long kk = kk0 + k;
+        tc_wait(tau_full(sm, slot), static_cast<uint32_t>((b >> 1) & 1));
+        BT_I(2)
+        if (i + 2 < n) issue_theta(b + 2);
+        tc_wait(p_full(sm, slot), static_cast<uint32_t>((b >> 1) & 1));
+        BT_I(3)
+        if (j == 0 && kk >= 2) tc_wait(q_empty(sm, static_cast<int>(kk & 1)), static_cast<uint32_t>(((kk - 2) >> 1) & 1));
+        BT_I(4)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ta = aTau + slot * kBtTauBytes, bp = aP + slot * kTcbPBytes;
+        const uint32_t dq = sm.tmem + kBtQCol + static_cast<uint32_t>(kk & 1) * kTcbQN;
+#pragma unroll
+        for (int s = 0; s < ((GPODE_BT_EXP & 2) ? 0 : 16); ++s)   // k-step s: plane s / 8, units 16 (s % 8) ..
+          tcu_mma_f16(dq, tc_desc2(ta + s * 2 * 2048, 2048, 128), tc_desc2(bp + (s & 7) * 2 * kTcbQN * 16, kTcbQN * 16, 128), id_q, (j > 0 || s > 0) ? 1u : 0u);
+        tcu_commit(p_empty(sm, slot));
+        if (j == nbi - 1) tcu_commit(q_full(sm, static_cast<int>(kk & 1)));
+        BT_I(5)
+        if (j >= nbs) {
+          const long pc = pg0 + static_cast<long>(k) * nbm + (j - nbs);
+          if (j == nbs) tc_wait(xp_full(sm), static_cast<uint32_t>(kk & 1));
+          if (pc >= 2) tc_wait(pg_empty(sm, static_cast<int>(pc & 1)), static_cast<uint32_t>(((pc - 2) >> 1) & 1));
+          BT_I(4)
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t dpg = sm.tmem + kBtPgCol + static_cast<uint32_t>(pc & 1) * kTcbQN;
+#pragma unroll
+          for (int p = 0; p < ((GPODE_BT_EXP & 1) ? 0 : 2); ++p)
+#pragma unroll
+            for (int s = 0; s < 8; ++s)   // k-step: states 16 s .. 16 s + 15; A = tau^T (MN-major: next 8 states + 128 B, next 8 units + 2048 B)
+              tcu_mma_f16(dpg, tc_desc2(ta + p * 16 * 2048 + s * 2 * 128, 128, 2048), tc_desc2(aXp + s * 2 * 128, 128, 2048), id_pg, (p > 0 || s > 0) ? 1u : 0u);
+          tcu_commit(pg_full(sm, static_cast<int>(pc & 1)));
+          if (j == nbi - 1) tcu_commit(xp_empty(sm));
+        }
+        tcu_commit(tau_empty(sm, slot));
+        BT_I(6)
+        if (++j == nbi) {
+          j = 0;
+          ++k;
+        }
       }
+      BT_IPRINT
     } else {
       // =============== epilogue warps ===============
       const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      (void)st;                                                // (st belongs to the state threads; every epilogue warp derives its own)
       const long n_state = static_cast<long>(blockIdx.x) * kBtStates + sidx;
       const bool live = n_state < g.N;
       const long s_glob = static_cast<long>(blockIdx.y) * g.N + (live ? n_state : g.N - 1);
-      float Ak = 0.f, gk_cur = 0.f, gk_prev = 0.f, fv_cur = 0.f, fv_prev = 0.f;
-      auto q_epilogue = [&](int k, float gk, float fv) {
-        const long kk = kk0 + k;
-        const int qb = static_cast<int>(kk & 1);
-        tc_wait(q_full(sm, qb), static_cast<uint32_t>((kk >> 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tq = sm.tmem + kBtQCol + qb * 64 + lane_base;
-        float qh[4], ql[4];
-        tc_ld4(tq + 4 * q, qh);
-        tc_ld4(tq + 24 + 4 * q, ql);
-        const float es = tc_ld1(tq + 16) + tc_ld1(tq + 40);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) tc_arrive(q_empty(sm, qb));
-        const float* hdr_k = sm.hdr + k * g.hdr_floats;
+      // this state's block scale (as the state threads computed it) and its x
+      float xq[4], mx = 0.f;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int d = 4 * q + t;
-          float stat = 0.f;
-          if (d < DP) {
-            const float xv = sm.xs[d * kBtStates + sidx];
-            const float dxk = gk * fmaf(2.f * hdr_k[d] * xv, es, qh[t] + ql[t]);
-            dxa[t] += dxk;
-            stat = xv * dxk;
-          }
-          stat = warp_sum(stat);
-          if (lane == 0 && d < DP) atomicAdd(&sm.dell[k * DP + d], stat);
-        }
-        if (q == 0) {
-          const float v = warp_sum(fv);
-          if (lane == 0) atomicAdd(&sm.dvar[k], v);
-        }
-      };
-#ifdef GPODE_BT_PROFILE
-      long long et[4] = {0, 0, 0, 0}, ec = clock64();
-#define BE_T(i) { const long long now_ = clock64(); et[i] += now_ - ec; ec = now_; }
-#else
-#define BE_T(i)
-#endif
-      for (int i = 0; i < n; ++i) {
+      for (int d = 0; d < DP; ++d) mx = fmaxf(mx, fabsf(sm.xs[d * kBtStates + sidx]));
+#pragma unroll
+      for (int t = 0; t < 4; ++t) xq[t] = 4 * q + t < DP ? sm.xs[(4 * q + t) * kBtStates + sidx] : 0.f;
+      float sn_, inv_n;
+      rbf_pow2_scale(mx, sn_, inv_n);
+      float Ak = 0.f, inv_s = 1.f, g_cur = 0.f, f_cur = 0.f, fp_cur = 0.f, g_prev = 0.f, f_prev = 0.f, fp_prev = 0.f;
+      const uint32_t aTau = smem_u32(sm.tau), aXp = smem_u32(sm.xp);
+      const uint32_t tq0 = sm.tmem + kBtQCol + lane_base, tp0 = sm.tmem + kBtPgCol + lane_base, ta0 = sm.tmem + q * 32 + lane_base;
+      int k = 0, j = 0;              // coordinates of item i
+      int fk = 0, fj = 0;            // coordinates (output, inducing item) of the oldest PG tile not yet added to the global accumulators
+      int outstanding = 0;           // PG tiles produced and not yet flushed
+      long pcf = pg0;                // running index of that oldest tile
+      uint32_t rA[16], rB[16];
+      BT_E0
+      tc_wait(acc_full(sm, static_cast<int>(b0 & 1)), static_cast<uint32_t>((b0 >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tc_ld16_async(ta0 + static_cast<uint32_t>(b0 & 1) * kTcbUnits, rA);   // first half of the first item; later ones are prefetched below
+      BT_E(0)
+#pragma unroll 1
+      for (int i = 0; i <= n + 1; ++i) {   // i >= n: drain only (last Q epilogue, the two PG tiles still in flight)
+        const bool real = i < n;
         const long b = b0 + i;
-        const int acc = static_cast<int>(b % 3);
-        const int k = i / nbi, j = i - k * nbi;
-        const bool is_k = j >= nbs;
-        BE_T(3)
+        const int slot = static_cast<int>(b & 1);
+        const bool is_k = real && j >= nbs;
         if (j == 0) {
-          const float* hdr_k = sm.hdr + k * g.hdr_floats;
-          Ak = 0.f;
+          g_prev = g_cur;
+          f_prev = f_cur;
+          fp_prev = fp_cur;
+          if (real) {
+            const float* hdr_k = sm.hdr + k * g.hdr_floats;
+            Ak = 0.f;
 #pragma unroll
-          for (int d = 0; d < DP; ++d) {
-            const float xv = sm.xs[d * kBtStates + sidx];
-            Ak = fmaf(hdr_k[d] * xv, xv, Ak);
+            for (int d = 0; d < DP; ++d) {
+              const float xv = sm.xs[d * kBtStates + sidx];
+              Ak = fmaf(hdr_k[d] * xv, xv, Ak);
+            }
+            inv_s = inv_n * sm.sk[k];
+            const long at = k * kstride + s_glob * sstride;   // (used at the first inducing item / the Q epilogue: the loads complete under the items in between)
+            g_cur = live ? gvec[at] : 0.f;
+            f_cur = fvec[at];
+            fp_cur = fpvec[at];
           }
-          gk_prev = gk_cur;
-          fv_prev = fv_cur;
-          const long at = k * kstride + s_glob * sstride;
-          gk_cur = live ? gvec[at] : 0.f;
-          fv_cur = (q == 0 && live) ? gk_cur * (fvec[at] - 0.5f * fpvec[at]) : 0.f;
         }
-        tc_wait(acc_full(sm, acc), static_cast<uint32_t>((b / 3) & 1));
-        BE_T(0)
+        if (real && j == nbs) {
+          // X' of this k (MN-major B operand of PG): columns d (heads of g x_d), 16 + d (remainders), 32 / 33 (g).  The previous k's last
+          // PG was issued at least nbs items ago.
+          BT_E(4)
+          if (kk0 + k >= 1) tc_wait(xp_empty(sm), static_cast<uint32_t>((kk0 + k - 1) & 1));
+          BT_E(8)
+          uint32_t h01, l01, h23, l23;
+          bt_split2(g_cur * xq[0], g_cur * xq[1], h01, l01);
+          bt_split2(g_cur * xq[2], g_cur * xq[3], h23, l23);
+          const uint32_t row = aXp + sidx * 16 + (q & 1) * 8;
+          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(row + (q >> 1) * 2048), "r"(h01), "r"(h23) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(row + (2 + (q >> 1)) * 2048), "r"(l01), "r"(l23) : "memory");
+          if (q == 0) {
+            uint32_t hg, lg;
+            bt_split2(g_cur, 0.f, hg, lg);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(aXp + 4 * 2048 + sidx * 16), "r"((hg & 0xFFFFu) | (lg << 16)) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_arrive(xp_full(sm));
+        }
+        BT_E(4)
+        // ---- tensor-memory reads: the first theta half was prefetched under the previous item; the second half, the PG tile two inducing
+        //      items back (executed by now; its buffer is needed at the end of this item) and Q of the previous output (deferred to the
+        //      second item of this one) are loaded under the first half's transcendentals ----
+        const bool do_flush = outstanding > 0 && (!real || (is_k && outstanding >= 2));
+        const bool do_q = j == 1 && k > 0;
+        const long kq = kk0 + k - 1;
+        uint32_t pgr[10], qr[10];
+#pragma unroll
+        for (int v = 0; v < 10; ++v) pgr[v] = qr[v] = 0u;
+        if (do_flush) tc_wait(pg_full(sm, static_cast<int>(pcf & 1)), static_cast<uint32_t>((pcf >> 1) & 1));
+        if (do_q) tc_wait(q_full(sm, static_cast<int>(kq & 1)), static_cast<uint32_t>((kq >> 1) & 1));
+        BT_E(9)
+        if (real && b >= 2) tc_wait(tau_empty(sm, slot), static_cast<uint32_t>(((b - 2) >> 1) & 1));
+        BT_E(1)
+        tc_ld_wait(rA);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t ta = sm.tmem + acc * kTcbUnits + q * 32 + lane_base;
-        uint32_t r0[16], r1[16];
-        tc_ld16_async(ta, r0);
-        tc_ld16_async(ta + 16, r1);
-        tc_ld_wait(r0);
-        if (is_k) {
-#pragma unroll
-          for (int v = 0; v < 16; ++v) r0[v] = tc_split_bf16(ex2_approx(__uint_as_float(r0[v]) + Ak));
-        } else {
-#pragma unroll
-          for (int v = 0; v < 16; ++v) r0[v] = tc_split_bf16(__cosf(__uint_as_float(r0[v])));
+        if (real) tc_ld16_async(ta0 + slot * kTcbUnits + 16, rB);
+        if (do_flush) {
+          const uint32_t tp = tp0 + static_cast<uint32_t>(pcf & 1) * kTcbQN;
+          tc_ld4_async(tp + 4 * q, pgr[0], pgr[1], pgr[2], pgr[3]);
+          tc_ld4_async(tp + 16 + 4 * q, pgr[4], pgr[5], pgr[6], pgr[7]);
+          if (q == 0) tc_ld2_async(tp + 32, pgr[8], pgr[9]);
         }
-        tc_st16_async(ta, r0);
-        tc_ld_wait(r1);
-        if (is_k) {
-#pragma unroll
-          for (int v = 0; v < 16; ++v) r1[v] = tc_split_bf16(ex2_approx(__uint_as_float(r1[v]) + Ak));
-        } else {
-#pragma unroll
-          for (int v = 0; v < 16; ++v) r1[v] = tc_split_bf16(__cosf(__uint_as_float(r1[v])));
+        if (do_q) {
+          const uint32_t tq = tq0 + static_cast<uint32_t>(kq & 1) * kTcbQN;
+          tc_ld4_async(tq + 4 * q, qr[0], qr[1], qr[2], qr[3]);
+          tc_ld4_async(tq + 16 + 4 * q, qr[4], qr[5], qr[6], qr[7]);
+          tc_ld2_async(tq + 32, qr[8], qr[9]);
         }
-        tc_st16_async(ta + 16, r1);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        BT_E(2)
+        const float addk = is_k ? Ak : 0.f;
+        const uint32_t trow = aTau + slot * kBtTauBytes + sidx * 16 + (4 * q) * 2048;
+        if (real) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t hd[4], rm[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const float t0 = fmaf(__uint_as_float(rA[8 * c + 2 * v]), inv_s, addk), t1 = fmaf(__uint_as_float(rA[8 * c + 2 * v + 1]), inv_s, addk);
+              bt_split2((GPODE_BT_EXP & 4) ? t0 : (is_k ? ex2_approx(t0) : __cosf(t0)), (GPODE_BT_EXP & 4) ? t1 : (is_k ? ex2_approx(t1) : __cosf(t1)), hd[v], rm[v]);
+            }
+            sts128(trow + c * 2048, hd[0], hd[1], hd[2], hd[3]);
+            sts128(trow + (16 + c) * 2048, rm[0], rm[1], rm[2], rm[3]);
+          }
+        }
+        BT_E(3)
+        tc_ld_wait(rB);   // (tcgen05.wait::ld covers every outstanding load of the thread)
+        tc_ld_fence(pgr);
+        tc_ld_fence(qr);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) tc_arrive(tau_ready(sm, acc));
-        BE_T(1)
-        if (j == 0 && k > 0) q_epilogue(k - 1, gk_prev, fv_prev);   // deferred by one item: Q(k - 1) executes under this item's transcendentals
-        BE_T(2)
+        if (lane == 0) {
+          if (real) tc_arrive(acc_empty(sm, slot));
+          if (do_flush) tc_arrive(pg_empty(sm, static_cast<int>(pcf & 1)));
+          if (do_q) tc_arrive(q_empty(sm, static_cast<int>(kq & 1)));
+        }
+        BT_E(2)
+        if (do_flush) {
+          const int unit = fj * kTcbUnits + sidx;   // thread <-> unit of the tile, dims 4 q .. 4 q + 3 (+ the sum column for q = 0)
+          if (unit < g.M) {
+            const size_t base = (static_cast<size_t>(blockIdx.y) * g.D_out + fk) * (2 * g.MP2) + unit;
+            float* dst = sm.g_pg + base * DP + 4 * q;
+            float pv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) pv[t] = __uint_as_float(pgr[t]) + __uint_as_float(pgr[4 + t]);
+            if constexpr (DP == 16) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(pv[0]), "f"(pv[1]), "f"(pv[2]), "f"(pv[3]) : "memory");
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                if (4 * q + t < DP) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + t), "f"(pv[t]) : "memory");
+            }
+            if (q == 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(sm.g_dnu + base), "f"(__uint_as_float(pgr[8]) + __uint_as_float(pgr[9])) : "memory");
+          }
+          ++pcf;
+          --outstanding;
+          if (++fj == nbm) {
+            fj = 0;
+            ++fk;
+          }
+        }
+        BT_E(5)
+        // ---- state gradient and statistics of the previous output ----
+        if (do_q) {
+          const float es = __uint_as_float(qr[8]) + __uint_as_float(qr[9]);
+          const float* hdr_k = sm.hdr + (k - 1) * g.hdr_floats;
+          float red[5];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int d = 4 * q + t;
+            red[t] = 0.f;
+            if (d < DP) {
+              const float dxk = g_prev * fmaf(2.f * hdr_k[d] * xq[t], es, __uint_as_float(qr[t]) + __uint_as_float(qr[4 + t]));
+              dxa[t] += dxk;
+              red[t] = xq[t] * dxk;
+            }
+          }
+          red[4] = (q == 0 && live) ? g_prev * (f_prev - 0.5f * fp_prev) : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)   // five independent butterflies, interleaved
+#pragma unroll
+            for (int t = 0; t < 5; ++t) red[t] += __shfl_xor_sync(0xffffffffu, red[t], o);
+          if (lane == k - 1) {   // lane k' of the warp keeps sum_n x_d dx_k'd (and, q = 0, sum_n g (f - f_p / 2)) of the warp's states
+#pragma unroll
+            for (int t = 0; t < 5; ++t) sm.stat[t] += red[t];
+          }
+        }
+        BT_E(6)
+        if (real) {
+          if (i + 1 < n) {   // first half of the next item (its theta was issued in front of this item's second products): lands under the second half's transcendentals
+            tc_wait(acc_full(sm, slot ^ 1), static_cast<uint32_t>(((b + 1) >> 1) & 1));
+            BT_E(7)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc_ld16_async(ta0 + (slot ^ 1) * kTcbUnits, rA);
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t hd[4], rm[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const float t0 = fmaf(__uint_as_float(rB[8 * c + 2 * v]), inv_s, addk), t1 = fmaf(__uint_as_float(rB[8 * c + 2 * v + 1]), inv_s, addk);
+              bt_split2((GPODE_BT_EXP & 4) ? t0 : (is_k ? ex2_approx(t0) : __cosf(t0)), (GPODE_BT_EXP & 4) ? t1 : (is_k ? ex2_approx(t1) : __cosf(t1)), hd[v], rm[v]);
+            }
+            sts128(trow + (2 + c) * 2048, hd[0], hd[1], hd[2], hd[3]);
+            sts128(trow + (18 + c) * 2048, rm[0], rm[1], rm[2], rm[3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_arrive(tau_full(sm, slot));
+          if (is_k) ++outstanding;
+        }
+        BT_E(3)
+        BT_E(6)
+        if (++j == nbi) {
+          j = 0;
+          ++k;
+        }
       }
-      q_epilogue(g.D_out - 1, gk_cur, fv_cur);
-#ifdef GPODE_BT_PROFILE
-      if (blockIdx.x == 5 && blockIdx.y == 0 && b0 == static_cast<long>(n) && (tid == 0 || tid == 480))
-        printf("bwd tc epilogue warp %d (cycles per item): wait theta %lld, tau %lld, Q epilogue %lld, other %lld\n", warp, et[0] / n, et[1] / n, et[2] / n, et[3] / n);
-#endif
+      BT_EPRINT
     }
     sm.blk = b0 + n;
     sm.kk = kk0 + g.D_out;
-    __syncthreads();   // every epilogue of this evaluation is done: xs may change, dx is complete in registers
+    sm.pgc = pg0 + static_cast<long>(g.D_out) * nbm;
+    __syncthreads();   // every MMA of this evaluation has executed (the last Q commit covers them) and every epilogue is done: xs / X' may change
     if (tid < kBtEpi) {
 #pragma unroll
       for (int t = 0; t < 4; ++t)

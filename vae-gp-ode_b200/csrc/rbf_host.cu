@@ -1,5 +1,6 @@
 // RBF: parameter packing, gradient finalisation and the DP dispatch of the sweep kernels.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "rbf.h"
@@ -118,7 +119,7 @@ __global__ void k_rbf_pack_tc(const RbfPackArgs a) {
   tile[kTcfBFloats + r] = real ? row[2 * g.DP + 2] : 0.f;
 }
 
-// operand tiles of the tcgen05 reverse sweep / parameter gradients from the packed rows (layout: rbf.h); thread <-> unit of the item
+// operand tiles of the fused tcgen05 reverse sweep from the packed rows (layout: rbf.h); thread <-> unit of the item
 __global__ void k_rbf_pack_tcb(const RbfPackArgs a) {
   const RbfGeom& g = a.g;
   const int item = blockIdx.x, k = blockIdx.y, l = blockIdx.z, r = threadIdx.x;
@@ -127,34 +128,44 @@ __global__ void k_rbf_pack_tcb(const RbfPackArgs a) {
   const int unit = (is_m ? item - nbs : item) * kTcbUnits + r;
   const bool real = unit < (is_m ? g.M : g.S);
   const float* row = rbf_rows_ptr(a.packed, g, l) + (static_cast<size_t>(k) * (g.SP2 + g.MP2) + (is_m ? g.SP2 : 0) + (unit >> 1)) * g.row_floats + (unit & 1);
-  float* tile = const_cast<float*>(rbf_tcb_tiles_ptr(a.packed, g, l)) + (static_cast<size_t>(k) * nbi + item) * kTcbTileFloats;
-  auto at = [&](int c) { return tile + c * kTcbUnits * 4 + (r >> 3) * 32 + (r & 7) * 4; };
-  auto head = [](float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+  unsigned char* tile = reinterpret_cast<unsigned char*>(const_cast<float*>(rbf_tcb_tiles_ptr(a.packed, g, l)) + (static_cast<size_t>(k) * nbi + item) * kTcbTileFloats);
+  float sk, inv_sk;
+  rbf_pow2_scale(rbf_maxabs_ptr(a.packed, g, l)[k], sk, inv_sk);
+  const int core = (r >> 3) * 128 + (r & 7) * 16;   // this unit's 16-byte slot inside a chunk
   float coef[16];
   for (int d = 0; d < 16; ++d) coef[d] = (real && d < g.DP) ? row[2 * d] : 0.f;
-  for (int c = 0; c < 4; ++c) {
-    float h[4];
-    for (int i = 0; i < 4; ++i) h[i] = head(coef[4 * c + i]);
-    *reinterpret_cast<float4*>(at(c)) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(at(4 + c)) = make_float4(coef[4 * c] - h[0], coef[4 * c + 1] - h[1], coef[4 * c + 2] - h[2], coef[4 * c + 3] - h[3]);
+  // theta half: fp16 heads / remainders of the scaled coefficients (two chunks of 8 dims each), then the tf32 offset block
+  for (int c = 0; c < 2; ++c) {
+    __half hh[8], ll[8];
+    for (int i = 0; i < 8; ++i) {
+      const float v = coef[8 * c + i] * sk;
+      hh[i] = __float2half_rn(v);
+      ll[i] = __float2half_rn(v - __half2float(hh[i]));
+    }
+    *reinterpret_cast<uint4*>(tile + c * 2048 + core) = *reinterpret_cast<const uint4*>(hh);
+    *reinterpret_cast<uint4*>(tile + 4096 + c * 2048 + core) = *reinterpret_cast<const uint4*>(ll);
   }
   // feature units: cos(theta + pi/2) = -sin(theta), the derivative of the forward's cosine; inducing units: the exponent offset H
-  const float off = real ? row[2 * g.DP] + (is_m ? 0.f : 1.57079632679489662f) : 0.f, oh = head(off);
-  *reinterpret_cast<float4*>(at(8)) = make_float4(oh, off - oh, 0.f, 0.f);
-  *reinterpret_cast<float4*>(at(9)) = make_float4(0.f, 0.f, 0.f, 0.f);
-  // second operand: k rows 2 r (meets tau_h) and 2 r + 1 (meets tau_l) of every column n, one 32-bit word per column
+  const float off = (real ? row[2 * g.DP] + (is_m ? 0.f : 1.57079632679489662f) : 0.f) * sk;
+  const float oh = __uint_as_float(__float_as_uint(off) & 0xFFFFE000u);
+  *reinterpret_cast<float4*>(tile + 8192 + core) = make_float4(oh, off - oh, 0.f, 0.f);
+  *reinterpret_cast<float4*>(tile + 8192 + 2048 + core) = make_float4(0.f, 0.f, 0.f, 0.f);
+  // second half: column n of unit r (k index of the MMA = unit)
   const float wgt = real ? row[2 * g.DP + 2] : 0.f;
-  uint32_t* P = reinterpret_cast<uint32_t*>(tile + kTcbThFloats);
-  auto word = [&](int n) -> uint32_t& { return P[((r >> 2) * kTcbQN * 16 + (n >> 3) * 128 + (n & 7) * 16) / 4 + (r & 3)]; };
-  auto bits = [](float v) { return static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(v))); };
-  for (int n = 0; n < kTcbQN; ++n) word(n) = 0u;
+  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(tile + kTcbThBytes);
+  auto at = [&](int n) -> __nv_bfloat16& { return P[((r >> 3) * kTcbQN * 16 + (n >> 3) * 128 + (n & 7) * 16) / 2 + (r & 7)]; };
+  for (int n = 0; n < kTcbQN; ++n) at(n) = __float2bfloat16_rn(0.f);
   for (int d = 0; d <= 16; ++d) {
     const float pv = d < 16 ? wgt * coef[d] : (is_m ? wgt : 0.f);
-    const uint32_t ph = bits(pv);
-    const float phf = __uint_as_float(ph << 16);
-    const uint32_t pl = bits(pv - phf);
-    word(d) = ph | (ph << 16);          // (tau_h + tau_l) P_h
-    word(24 + d) = pl;                  // tau_h P_l
+    const __nv_bfloat16 ph = __float2bfloat16_rn(pv);
+    const __nv_bfloat16 pl = __float2bfloat16_rn(pv - __bfloat162float(ph));
+    if (d < 16) {
+      at(d) = ph;
+      at(16 + d) = pl;
+    } else {
+      at(32) = ph;
+      at(33) = pl;
+    }
   }
 }
 

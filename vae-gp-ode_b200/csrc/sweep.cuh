@@ -33,6 +33,12 @@ __device__ __forceinline__ States<R> map_states(const G& g, int state_threads = 
   return st;
 }
 
+// policies that fill global accumulators DURING the reverse sweep (the fused tcgen05 kernel) declare bind(Smem&, const Accum&)
+template <class P, class S, class A>
+__device__ __forceinline__ auto bind_accum(S& sm, const A& acc, int) -> decltype(P::bind(sm, acc), void()) { P::bind(sm, acc); }
+template <class P, class S, class A>
+__device__ __forceinline__ void bind_accum(S&, const A&, long) {}
+
 #define GPODE_SWEEP_BOUNDS __launch_bounds__(P::kThreads, P::kMinBlocks)
 #define GPODE_SWEEP_BOUNDS_BWD __launch_bounds__(P::kThreadsBwd, P::kMinBlocksBwd)
 
@@ -179,6 +185,7 @@ __global__ void GPODE_SWEEP_BOUNDS_BWD k_rollout_bwd(const RolloutBwdArgsT<typen
   typename P::Smem sm = P::carve(smem, g);
   ChunkPipe pipe;
   const long total = P::setup(sm, pipe, g, a.packed, static_cast<long>(a.T - 1) * stages, true);
+  bind_accum<P>(sm, a.acc, 0);
   float* ybar = a.ybar;
   float* ystage = a.ystage;
   float* kbar = a.kbar;
@@ -254,6 +261,7 @@ __global__ void GPODE_SWEEP_BOUNDS_BWD k_field_bwd(const FieldBwdArgsT<typename 
   typename P::Smem sm = P::carve(smem, g);
   ChunkPipe pipe;
   const long total = P::setup(sm, pipe, g, a.packed, 1, true);
+  bind_accum<P>(sm, a.acc, 0);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if (P::kXsStride == 0 || static_cast<int>(threadIdx.x) < P::kStateThreads)   // (helper warps of a tightly strided policy own no staging slot)
