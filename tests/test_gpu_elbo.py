@@ -16,18 +16,19 @@ new-vs-fp64, ref-vs-fp64, new-vs-ref.  Two tests per case:
     run in float64 on the GPU, the GP flow runs on the fp32 CUDA kernels (fp32 in, fp32 out): whatever separates the result from the
     fp64 truth is the new path's own error.
 
-Bars.  ELBO terms: 1e-4 (measured: <= 3e-7 deployed, <= 4e-8 isolated).  Parameter gradients:
-    new-vs-fp64 <= max(1e-4, NOISE_MARGIN x the reference's own fp32 error on that parameter),
-the reference's error being the larger of its errors over the solver variants of the same config, and NOISE_MARGIN = 2: one run is
-one sample of rounding noise, not a bound -- on config 3 the reference's Um gradient is 3.0e-4 from the truth with euler and 1.0e-5
-with rk4; on config 1 its lengthscale gradient is 1.07e-3 (euler) and 3.3e-4 (rk4); and the new path's own samples move the same way
-when only the summation ORDER changes (config 1 / rk4 / Um: 6.5e-4 with one warp per 32 states, 1.15e-3 with the rows split over 16
-warps, kernel-level gradients of both builds equally 2e-6 .. 1e-5 from the fp64 oracle in tests/test_gpu_rbf.py).
-Why 1e-4 flat is out of reach of ANY fp32 implementation of this model at the reference's settings: the gradients reach the leaf
-parameters through the whitening solves, d(loss)/du = Lc^-1 d(loss)/dnu with cond(K(Z,Z)) ~ 3e4 (config 1/3) .. 1e6, which
-amplifies the ~1e-6 relative rounding of the fp32 per-state sums by sqrt(cond) ~ 2e2; the reference's fp32 run is 2e-4 .. 4e-3 from
-the truth on configs 1 and 2.  Measured here (B200): new path 1e-5 .. 5e-4 deployed and isolated alike (so the fp32 VAE is not what
-limits it), below the reference's error on every parameter of configs 1 and 2, and inside its envelope on config 3.
+Bars.  ELBO terms: 1e-4 (measured: <= 3e-7 deployed, <= 4e-8 isolated).  Everything that is the NEW PATH's is held to 1e-4 FLAT by
+``test_flow_forward_and_backward_at_the_model_boundary`` (the truth's z0 in, the truth's dL/dztL as upstream gradient: latent
+trajectories <= 4e-6, dL/dz0 and all five GP leaf gradients <= 4e-5 on every config, where the reference's own fp32 run is 1e-5 .. 4e-3).
+The gradients of the WHOLE model cannot carry a flat bar, for a reason that has nothing to do with arithmetic precision: the conv
+decoder is piecewise linear, so the model's gradient is a DISCONTINUOUS function of the latent trajectories.  Config 1 / rk4: the new
+trajectories are 7.9e-7 from the truth's, one ReLU unit of 2,163,200 flips, and every gradient of the model moves by ~1e-3 (encoder
+1.3e-3, GP 1.15e-3, decoder 7e-4; reproduced exactly by feeding the new trajectories to the fp64 reference on the CPU; config 1 /
+euler, where no unit flips, is 5e-6 .. 2e-5 from the truth).  The reference's own fp32 run has the same property plus the fp32
+whitening solves (cond(K(Z,Z)) ~ 3e4 .. 1e6): over 32 fresh draws of the encoder noise its gradients are 4e-5 .. 2e-3 from the truth
+on config 1 (median 4e-4), 1e-5 .. 3e-3 on config 3, 3e-4 .. 6e-3 on config 2 (tests/golden/elbo_noise_*.npz, oracle/make_golden_elbo.py
+--noise).  The as-deployed and isolated tests therefore hold every parameter gradient to
+    new-vs-fp64 <= max(1e-4, NOISE_MARGIN x the largest error of the reference's fp32 run on that parameter over those samples),
+NOISE_MARGIN = 2, and print the three numbers (new-vs-fp64, ref-vs-fp64, new-vs-ref) of the golden sample beside it.
 """
 import ast
 import os
@@ -120,12 +121,17 @@ def build(g, cfg, solver, monkeypatch, batched_samples=False, vae_fp64=False):
     return ref, model, X, draws, enc, (n_gp, n_noise)
 
 
-NOISE_MARGIN = 2.0   # see the module docstring: the envelope is the max of TWO noise samples of the reference, not a bound
+NOISE_MARGIN = 2.0   # see the module docstring: the envelope is the max of a few dozen samples of the reference's error, not a bound
+_noise = {}
 
 
 def ref_noise(cfg, name):
-    """the reference's own fp32 error on one parameter gradient: the larger of its errors over the solver variants of the config"""
-    out = 0.0
+    """the reference's own fp32 error on one parameter gradient: the largest over the samples of tests/golden/elbo_noise_<cfg>.npz
+    (fresh encoder-noise draws x solver variants) and the golden runs themselves"""
+    if cfg not in _noise:
+        z = np.load(os.path.join(GOLDEN_DIR, "elbo_noise_%s.npz" % cfg))
+        _noise[cfg] = {k: float(z[k].max()) for k in z.files}
+    out = _noise[cfg].get(name, 0.0)
     for c, sv in CASES:
         if c == cfg:
             gg = load(c, sv)
@@ -197,6 +203,44 @@ def test_elbo_hot_path_isolated(cfg, solver, monkeypatch):
     assert draws.i == n_gp and enc.i == n_noise
     worst = check("%s/%s/isolated" % (cfg, solver), g, scal, grads, strict=True)
     print("%s/%s/isolated: worst parameter-gradient error vs fp64 truth %.2e" % (cfg, solver, worst))
+
+
+@pytest.mark.parametrize("cfg,solver", CASES)
+def test_flow_forward_and_backward_at_the_model_boundary(cfg, solver, monkeypatch):
+    """north_star bars 2 and 3 on everything that is the new path's, at the full model's own operating point and FLAT (1e-4, no
+    envelope): the reference's ``sample_trajectories`` (odegpvae.py:37-45) with the drop-in flow is fed the truth's encoder sample z0;
+    the latent trajectories must match the truth's, and with the truth's dL/dztL as upstream gradient (tests/golden/elbo_flow_*.npz,
+    oracle/make_golden_elbo.py --flow) the gradient of ``sum(ztL * dL/dztL) + kl_gp`` -- which IS the loss gradient for every GP leaf
+    parameter (lengthscales, variance, inducing locations, Um, Us_sqrt) and the rollouts' share of dL/dz0 -- must match the truth's.
+    Why the upstream gradient is pinned: the conv decoder is piecewise linear, and a 1e-6 change of ztL that flips ONE ReLU unit moves
+    every gradient of the model by ~1e-3 (config 1 / rk4: one unit of 2,163,200 flips between the truth's trajectories and the new
+    path's, which are 7.9e-7 apart; feeding the new trajectories to the fp64 reference reproduces the observed 1.3e-3 / 1.15e-3 / 7.3e-4
+    shifts of the encoder / GP / decoder gradients exactly) -- so the as-deployed tests above can only carry the envelope bars."""
+    g = load(cfg, solver)
+    fb = np.load(os.path.join(GOLDEN_DIR, "elbo_flow_%s_%s.npz" % (cfg, solver)))
+    ref, model, X, draws, enc, (n_gp, n_noise) = build(g, cfg, solver, monkeypatch)
+    L, _, T, _ = fb["ztL"].shape
+    z0 = torch.tensor(fb["z0"], dtype=torch.float32, device="cuda").requires_grad_(True)
+    for p in model.parameters():
+        p.grad = None
+    ztL = model.sample_trajectories(z0, T, L)                      # the reference's serial MC loop over the drop-in Flow
+    assert draws.i == n_gp
+    kl_gp = model.flow.kl()
+    ((ztL.double() * torch.tensor(fb["G"], device="cuda")).sum() + kl_gp.double()).backward()
+    tag = "%s/%s/boundary" % (cfg, solver)
+    e_traj, e_kl = rel(ztL.detach().cpu().numpy(), fb["ztL"]), abs(kl_gp.item() - float(fb["kl_gp"])) / abs(float(fb["kl_gp"]))
+    print("%s ztL new-vs-fp64 %.2e   kl_gp %.2e" % (tag, e_traj, e_kl))
+    assert e_traj <= 1e-5 and e_kl <= 1e-5                         # (north_star: trajectories 1e-4)
+    e = rel(z0.grad.cpu().numpy(), fb["dz0"])
+    print("%s d %-52s new-vs-fp64 %.2e" % (tag, "z0 (through the rollouts)", e))
+    assert e <= 1e-4
+    names = [n for n, _ in model.named_parameters() if n.startswith("flow.")]
+    assert len(names) == 5
+    for n, p in model.named_parameters():
+        if n in names:
+            e, e_ref = rel(p.grad.cpu().numpy(), g["ref64/grad/" + n]), rel(g["ref32/grad/" + n], g["ref64/grad/" + n])
+            print("%s d %-52s new-vs-fp64 %.2e   (the reference's fp32 run: %.2e)" % (tag, n, e, e_ref))
+            assert e <= 1e-4, (n, e)
 
 
 def test_elbo_batched_mc_samples_config2(monkeypatch):
