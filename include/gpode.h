@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GPODE_VERSION 200 /* major*100 + minor */
+#define GPODE_VERSION 210 /* major*100 + minor */
 
 /* kernel variants (core/kernels.py: RBF dimwise=False / dimwise=True :29-195, DivergenceFreeKernel :201-393) */
 enum { GPODE_RBF_SHARED = 0, GPODE_RBF_DIMWISE = 1, GPODE_DF = 2 };
@@ -140,19 +140,22 @@ int gpode_rollout_bwd(const GpodeProblem* p, const float* ts, int T, int method,
 
 /* ---------------------------------------------------------------------------------------------
  * Per-rollout setup at the M inducing points (what sits in the autograd graph of SVGP_Layer.build_cache),
- * batched over output dimensions and MC samples.  RBF variants only: the DF kernel's single (M D x M D)
- * system is not a small batched problem and stays on cuSOLVER (GPODE_E_UNSUPPORTED here).
+ * batched over output dimensions and MC samples.  RBF variants: one (M x M) system per output dimension (or one shared);
+ * divergence-free kernel: ONE (M D x M D) system shared by the L samples (D <= 8, M D <= 4096), factored by a blocked
+ * Cholesky spread over the chip.  All of it in double precision inside, fp32 at the ABI.
  * ------------------------------------------------------------------------------------------- */
 
 /* scratch bytes / forward->backward save floats of gpode_compute_nu_* (p: variant, L, M, D_in, D_out, Z, ell, var are read) */
 size_t gpode_nu_workspace_bytes(const GpodeProblem* p);
 size_t gpode_nu_save_floats(const GpodeProblem* p);
 
-/* RBF.compute_nu (core/kernels.py:155-172) fused with K(Z,Z) (core/kernels.py:98-110, called at svpy.py:118):
- *   Lc = chol(K(Z,Z) + 1e-5 I) (lower), nu = Lc^-T (u - Lc^-1 u_prior), one system per output dim (dimwise) or one shared.
+/* RBF.compute_nu (core/kernels.py:155-172) fused with K(Z,Z) (core/kernels.py:98-110, called at svpy.py:118), and
+ * DivergenceFreeKernel.compute_nu (core/kernels.py:376-387) fused with its block Gram matrix (core/kernels.py:289-303):
+ *   Lc = chol(K(Z,Z) + 1e-5 I) (lower triangle read, like torch.linalg.cholesky), nu = Lc^-T (u - Lc^-1 u_prior);
+ *   one system per output dim (dimwise), one shared (shared), or one of order M D (DF: rows m D + component).
  *   u_prior = rff_forward(Z) and u = sample_inducing() are (L,M,D_out); nu comes out in the GpodeProblem layout.
  *   save: gpode_nu_save_floats() floats (Cholesky factors + Lc^-1 u_prior) for the backward.
- *   info (optional, Kc int32): 0, or 1 + index of the first non-positive pivot (torch.linalg.cholesky raises there). */
+ *   info (optional, Kc int32; DF: 1): 0, or 1 + index of the first non-positive pivot (torch.linalg.cholesky raises there). */
 int gpode_compute_nu_fwd(const GpodeProblem* p, const float* u_prior, const float* u, float* nu, float* save, int32_t* info,
                          void* workspace, size_t workspace_bytes, void* stream);
 /* autograd backward of the above: d_nu (nu layout) -> d_u_prior, d_u (L,M,D_out) and the direct dependence of K(Z,Z) on
@@ -170,6 +173,28 @@ int gpode_inducing_sample_bwd(int L, int M, int D_out, const float* eps_u, const
  *   = 1/2 sum_d ( -sum_i log Lq_d[i,i]^2 + |Um[:,d]|^2 + |Lq_d|_F^2 - M );  d_kl is a device scalar. */
 int gpode_kl_fwd(int M, int D_out, const float* Lq_packed, const float* Um, float* kl, void* stream);
 int gpode_kl_bwd(int M, int D_out, const float* Lq_packed, const float* Um, const float* d_kl, float* d_Lq_packed, float* d_Um, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Either side of the flow.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Function-sample draws on the device instead of host numpy + H2D (core/kernels.py:13-26 sample_normal / sample_uniform as used by
+ * build_cache :126-137 / :305-316, and svpy.py:12-18,94): counter-based Philox4x32-10, up to four output segments in one launch
+ * (w, eps, phase01, eps_u).  Element i of segment s = lane i % 4 of philox(counter = (i / 4 + offset [64 bit], s, 0), key = seed);
+ * GPODE_DRAW_UNIFORM: (r >> 8) 2^-24 in [0, 1); GPODE_DRAW_NORMAL: Box-Muller on the lane pairs (0, 1) and (2, 3):
+ * sqrt(-2 ln u1) (cos, sin)(2 pi u2), u1 = ((r >> 8) + 1) 2^-24.  Same distribution as the reference's draws, not the same numbers
+ * (the reference's own are unseeded, kernels.py:17).  Advance `offset` by ceil(max count / 4) between calls. */
+enum { GPODE_DRAW_NORMAL = 0, GPODE_DRAW_UNIFORM = 1 };
+int gpode_philox_fill(int nseg, float* const* outs, const uint64_t* counts, const int32_t* kinds, uint64_t seed, uint64_t offset, void* stream);
+/* the bare generator, for known-answer tests: out[4 i .. 4 i + 3] = philox4x32_10(counters[4 i ..], keys[2 i ..]) (device pointers) */
+int gpode_philox_raw(const uint32_t* counters, const uint32_t* keys, uint32_t* out, int n, void* stream);
+
+/* Decoder.log_prob (core/vae.py:136-153, bernoulli) fused with the reduction of elbo() (create_model.py:51-53:
+ * lhood.sum([2,3,4,5]).mean(0)):  z (L,N,P) reconstructions, x (N,P) targets (P = T * pixels; x is NOT repeated L times),
+ *   lhood[n] = 1/L sum_{l,p} log(z) x + log(1 - z)(1 - x);      d_z = d_lhood[n] / L (x / z - (1 - x) / (1 - z)). */
+size_t gpode_bernoulli_workspace_bytes(int N);
+int gpode_bernoulli_lhood_fwd(int L, int N, int64_t P, const float* z, const float* x, float* lhood, void* workspace, size_t workspace_bytes, void* stream);
+int gpode_bernoulli_lhood_bwd(int L, int N, int64_t P, const float* z, const float* x, const float* d_lhood, float* d_z, void* stream);
 
 #ifdef __cplusplus
 }

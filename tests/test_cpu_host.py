@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert sorted(_lib.EXPORTS) == declared
     L = _lib.load()
-    assert L.gpode_version() == 200
+    assert L.gpode_version() == 210
     assert b"NULL" in L.gpode_error_string(-1)
     # argument checking happens before any CUDA call: NULL problem -> 0 bytes / error code
     assert L.gpode_workspace_bytes(None, 16, 2) == 0

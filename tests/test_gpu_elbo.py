@@ -243,6 +243,19 @@ def test_flow_forward_and_backward_at_the_model_boundary(cfg, solver, monkeypatc
             assert e <= 1e-4, (n, e)
 
 
+def test_elbo_fused_likelihood_config2(monkeypatch):
+    """config 2 with the reference's elbo() (create_model.py:37-58) replaced by gpode_b200.core.odegpvae.elbo -- the Bernoulli
+    log-likelihood and its (T, pixels, L) reduction in one fused kernel, no X.repeat(L) -- and all MC samples in one rollout launch:
+    same ELBO terms (1e-4), gradients inside the same envelope as the as-deployed run."""
+    from gpode_b200.core import odegpvae as GO
+    g = load("cfg2", "rk4")
+    ref, model, X, draws, enc, (n_gp, n_noise) = build(g, "cfg2", "rk4", monkeypatch, batched_samples=True)
+    monkeypatch.setattr(ref["create_model"], "elbo", GO.elbo)
+    scal, grads = EH.run_loss(ref["create_model"], model, X, g["meta"]["L"])
+    assert draws.i == n_gp and enc.i == n_noise
+    check("cfg2/rk4/fused-elbo", g, scal, grads)
+
+
 def test_elbo_batched_mc_samples_config2(monkeypatch):
     """config 2 (DF, N = 256, L = 4) with all four MC samples in ONE rollout launch (Flow.forward_samples) instead of the
     reference's serial loop: same draws in the same order, same ELBO and gradients."""

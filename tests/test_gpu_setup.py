@@ -62,6 +62,63 @@ def test_compute_nu_forward_backward(variant, M, D_in, D_out, L):
         assert e < max(5 * e32, 1e-4), (nm, e, e32)
 
 
+@pytest.mark.parametrize("M,D,L,ell0,asym", [(100, 6, 4, 0.7, 0.3), (100, 6, 1, 2.0, 0.0), (33, 3, 2, 0.7, 0.3), (256, 6, 2, 1.0, 0.05),
+                                                 (70, 8, 3, 0.7, 0.3), (10, 2, 1, 0.7, 0.3), (400, 8, 1, 0.5, 0.1), (100, 6, 12, 0.7, 0.3)])
+def test_df_compute_nu_forward_backward(M, D, L, ell0, asym):
+    """DivergenceFreeKernel.compute_nu fused with its (M D x M D) Gram matrix (kernels.py:289-303,376-387): K build, the
+    multi-CTA blocked Cholesky, both whitened solves and the closed-form backward, against the fp64 oracle and its autograd.
+    asym > 0: element-wise different lengthscales / per-column variances -> the Gram matrix is NOT symmetric and the reference
+    semantics (torch.linalg.cholesky reads the lower triangle; its backward feeds the symmetrised gradient to both triangles)
+    must be reproduced (asym is kept small enough for the lower-triangle matrix to stay positive definite).  Sizes: config 2 (600), config 4 (1,536), a ragged order (99), tiny (20) and a large one (3,200: 4-column solves)."""
+    rs = np.random.RandomState(M + D)
+    f64 = lambda a: torch.tensor(a, dtype=torch.float64)
+    Z = f64(rs.normal(size=(M, D)))
+    ell = f64(ell0 + asym * rs.uniform(size=(D, D)))
+    var = f64(1.0 + asym * rs.uniform(size=(D,)))
+    up, u = f64(rs.normal(size=(L, M, D))), f64(rs.normal(size=(L, M, D)))
+
+    def oracle(Z, ell, var, up, u):
+        Ku = OF.df_K(Z, None, ell, var)
+        return torch.stack([OF.compute_nu(Ku, up[l], u[l], "df") for l in range(L)])
+    big = M * D > 2000                                     # the fp64 CPU oracle of the largest case: forward and du only (autograd of a 4096^3 Cholesky is slow)
+    leaves = [v.clone().requires_grad_(True) for v in (Z, ell, var, up, u)]
+    nu64 = oracle(*leaves)
+    G = torch.tensor(np.random.RandomState(1).normal(size=tuple(nu64.shape)), dtype=torch.float64)
+    want = torch.autograd.grad((nu64 * G).sum(), leaves)
+    floor32 = None
+    e32 = 0.0
+    if not big:
+        try:                                               # (at ell = 2 the fp32 Gram matrix is not even positive definite any more)
+            leaves32 = [v.clone().float().requires_grad_(True) for v in (Z, ell, var, up, u)]
+            nu32 = oracle(*leaves32)
+            floor32 = torch.autograd.grad((nu32 * G.float()).sum(), leaves32)
+            e32 = rel(nu32, nu64)
+        except torch.linalg.LinAlgError:
+            floor32 = None
+    dev = [v.detach().float().cuda().requires_grad_(True) for v in (Z, ell, var, up, u)]
+    nu, info = _gp().compute_nu(*dev, "df", return_info=True)
+    assert nu.shape == (L, M * D, 1) and int(info.abs().max()) == 0
+    e = rel(nu, nu64)
+    print("df M=%d D=%d (order %d) nu: %.2e (torch fp32: %.2e)" % (M, D, M * D, e, e32))
+    assert e < max(5 * e32, 2e-5), (e, e32)
+    (nu * G.float().cuda()).sum().backward()
+    for i, nm in enumerate(("dZ", "dell", "dvar", "du_prior", "du")):
+        e = rel(dev[i].grad, want[i])
+        e32 = rel(floor32[i], want[i]) if floor32 is not None else 0.0
+        print("df M=%d D=%d %s: %.2e (torch fp32: %.2e)" % (M, D, nm, e, e32))
+        assert e < max(5 * e32, 1e-4), (nm, e, e32)
+
+
+def test_df_cholesky_failure_is_reported():
+    rs = np.random.RandomState(0)
+    M, D = 40, 3
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
+    Z, ell, var = f32(rs.normal(size=(M, D))), f32(0.7 + np.zeros((D, D))), f32(-np.ones(D))     # negative variance: not positive definite
+    up, u = f32(rs.normal(size=(1, M, D))), f32(rs.normal(size=(1, M, D)))
+    nu, info = _gp().compute_nu(Z, ell, var, up, u, "df", return_info=True)
+    assert int(info[0]) >= 1
+
+
 @pytest.mark.parametrize("name", ["rbf_dimwise_o1", "rbf_shared_o1", "rbf_dimwise_d16"])
 def test_compute_nu_matches_reference_golden(name):
     """reference nu (fp32 LAPACK, ell = 2 -> cond ~1e4..1e6): same inputs through the CUDA kernels; the bar is the

@@ -7,6 +7,7 @@
 #include "df.h"
 #include "rbf.h"
 #include "setup.h"
+#include "elbo.h"
 
 using namespace gpode;
 
@@ -511,14 +512,18 @@ int gpode_rollout_bwd(const GpodeProblem* p, const float* ts, int T, int method,
 /* ---- per-rollout setup: compute_nu, inducing sample, KL (setup_kernels.cu) ---- */
 static int nu_geom(const GpodeProblem* p, NuGeom* g) {
   if (!p) return GPODE_E_NULL;
-  if (p->variant != GPODE_RBF_SHARED && p->variant != GPODE_RBF_DIMWISE) return GPODE_E_UNSUPPORTED;  /* DF: (M D x M D) system, stays on cuSOLVER */
+  if (p->variant != GPODE_RBF_SHARED && p->variant != GPODE_RBF_DIMWISE && p->variant != GPODE_DF) return GPODE_E_ENUM;
   if (p->L < 1 || p->D_in < 1 || p->D_out < 1 || p->M < 1) return GPODE_E_SHAPE;
-  if (p->D_in > kMaxD || p->D_out > kMaxD || p->M > 512) return GPODE_E_UNSUPPORTED;
+  const bool df = p->variant == GPODE_DF;
+  if (df && p->D_in != p->D_out) return GPODE_E_SHAPE;
+  if (p->D_in > kMaxD || p->D_out > kMaxD || p->M > 512 || (df && (p->D_in > 8 || p->M * p->D_in > 4096))) return GPODE_E_UNSUPPORTED;
   if (!p->Z || !p->ell || !p->var) return GPODE_E_NULL;
   g->L = p->L; g->M = p->M; g->D_in = p->D_in; g->D_out = p->D_out;
   g->dimwise = p->variant == GPODE_RBF_DIMWISE ? 1 : 0;
+  g->df = df ? 1 : 0;
+  g->n = df ? p->M * p->D_in : p->M;
   g->Kc = g->dimwise ? p->D_out : 1;
-  g->NR = g->dimwise ? p->L : p->L * p->D_out;
+  g->NR = (g->dimwise || df) ? p->L : p->L * p->D_out;
   g->jitter = 1e-5f;
   return GPODE_OK;
 }
@@ -579,6 +584,40 @@ int gpode_kl_bwd(int M, int D_out, const float* Lq_packed, const float* Um, cons
   if (rc) return rc;
   if (!d_Um) return GPODE_E_NULL;
   return static_cast<int>(kl_backward(M, D_out, Lq_packed, Um, d_kl, d_Lq_packed, d_Um, static_cast<cudaStream_t>(stream)));
+}
+
+
+/* ---- either side of the flow: device draws, fused Bernoulli log-likelihood (elbo_kernels.cu) ---- */
+int gpode_philox_fill(int nseg, float* const* outs, const uint64_t* counts, const int32_t* kinds, uint64_t seed, uint64_t offset, void* stream) {
+  if (nseg < 1 || nseg > 4) return GPODE_E_SHAPE;
+  if (!outs || !counts || !kinds) return GPODE_E_NULL;
+  unsigned long long ns[4];
+  int ks[4];
+  for (int i = 0; i < nseg; ++i) {
+    if (!outs[i] && counts[i]) return GPODE_E_NULL;
+    if (kinds[i] != GPODE_DRAW_NORMAL && kinds[i] != GPODE_DRAW_UNIFORM) return GPODE_E_ENUM;
+    ns[i] = counts[i];
+    ks[i] = kinds[i];
+  }
+  return static_cast<int>(philox_fill(nseg, outs, ns, ks, seed, offset, static_cast<cudaStream_t>(stream)));
+}
+int gpode_philox_raw(const uint32_t* counters, const uint32_t* keys, uint32_t* out, int n, void* stream) {
+  if (n < 1) return GPODE_E_SHAPE;
+  if (!counters || !keys || !out) return GPODE_E_NULL;
+  return static_cast<int>(philox_raw(counters, keys, out, n, static_cast<cudaStream_t>(stream)));
+}
+size_t gpode_bernoulli_workspace_bytes(int N) { return N > 0 ? align_up(static_cast<size_t>(N) * 8, 256) : 0; }
+int gpode_bernoulli_lhood_fwd(int L, int N, int64_t P, const float* z, const float* x, float* lhood, void* workspace, size_t workspace_bytes, void* stream) {
+  if (L < 1 || N < 1 || P < 1) return GPODE_E_SHAPE;
+  if (!z || !x || !lhood) return GPODE_E_NULL;
+  int rc = check_ws(workspace, workspace_bytes, gpode_bernoulli_workspace_bytes(N));
+  if (rc) return rc;
+  return static_cast<int>(bernoulli_forward(L, N, static_cast<long>(P), z, x, lhood, static_cast<double*>(workspace), static_cast<cudaStream_t>(stream)));
+}
+int gpode_bernoulli_lhood_bwd(int L, int N, int64_t P, const float* z, const float* x, const float* d_lhood, float* d_z, void* stream) {
+  if (L < 1 || N < 1 || P < 1) return GPODE_E_SHAPE;
+  if (!z || !x || !d_lhood || !d_z) return GPODE_E_NULL;
+  return static_cast<int>(bernoulli_backward(L, N, static_cast<long>(P), z, x, d_lhood, d_z, static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

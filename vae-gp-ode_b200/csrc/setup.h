@@ -1,4 +1,4 @@
-// Host-side descriptors of the per-rollout setup kernels (setup_kernels.cu): K(Z,Z) + Cholesky + whitened solves
+// Host-side descriptors of the per-rollout setup kernels (setup_kernels.cu): K(Z,Z) (RBF or divergence-free) + Cholesky + whitened solves
 // (compute_nu), inducing sample and KL on the packed lower-triangular parameter.
 #pragma once
 #include <cuda_runtime.h>
@@ -9,8 +9,10 @@ namespace gpode {
 struct NuGeom {
   int L, M, D_in, D_out;
   int dimwise;     // 1: one (M x M) system per output dim (RBF dimwise); 0: one system shared by all output dims (RBF shared)
-  int Kc;          // number of matrices: D_out or 1
-  int NR;          // right-hand-side columns per matrix: L or L * D_out
+  int df;          // 1: divergence-free kernel -- ONE (M D x M D) system shared by the L samples (core/kernels.py:289-303,376-387)
+  int n;           // order of each matrix: M (RBF) or M * D (DF)
+  int Kc;          // number of matrices: D_out (RBF dimwise) or 1
+  int NR;          // right-hand-side columns per matrix: L (RBF dimwise, DF) or L * D_out (RBF shared)
   float jitter;    // 1e-5 (core/kernels.py:11)
 };
 

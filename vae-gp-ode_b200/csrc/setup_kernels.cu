@@ -2,11 +2,15 @@
 // (sm_100a): the pieces of SVGP_Layer.build_cache / compute_nu / kl that sit in the autograd graph
 // (reference experiments/model/core/svpy.py:88-121,144-175; core/kernels.py:98-110,155-172).
 //
-//   nu = Lc^-T (u - Lc^-1 u_prior),  Lc = chol(K(Z,Z) + 1e-5 I)        one (M x M) system per output dim (dimwise)
-//                                                                       or one shared by all output dims (shared)
-// Layout used inside: right-hand sides are (Kc, M, NR) row-major, Kc = number of matrices, NR = columns per
-// matrix (dimwise: the L samples; shared: L * D_out).  Matrices are (Kc, M, M) row-major; after the Cholesky the
-// lower triangle holds Lc and the strict upper triangle is garbage (never read).
+//   nu = Lc^-T (u - Lc^-1 u_prior),  Lc = chol(K(Z,Z) + 1e-5 I)        one (M x M) system per output dim (RBF dimwise),
+//                                                                       one shared by all output dims (RBF shared), or ONE
+//                                                                       (M D x M D) system for the divergence-free kernel
+//                                                                       (core/kernels.py:289-303,376-387), shared by the L samples
+// Layout used inside: right-hand sides are (Kc, n, NR) row-major, Kc = number of matrices, n = their order (M or M D), NR =
+// columns per matrix (dimwise / DF: the L samples; shared: L * D_out).  Matrices are (Kc, n, n) row-major; after the Cholesky the
+// lower triangle holds Lc and the strict upper triangle is garbage (never read).  Like torch.linalg.cholesky the factorisation
+// reads the LOWER triangle only (the DF Gram matrix is not symmetric once the (D,D) lengthscales / per-column variances differ,
+// SURVEY.md Appendix B.5) and its backward hands the symmetrised gradient to BOTH triangles of K.
 //
 // Backward (closed form, derivation checked against autograd in tests/test_setup_algebra.py): with
 //   bb = Lc^-1 nu_bar, r = Lc^-T bb, a = Lc^-1 u_prior (saved), q = Lc^-T a,
@@ -30,12 +34,14 @@ using real = double;
 
 // element (k, i, r) of a reference-layout (L, M, D_out) tensor seen as the (Kc, M, NR) right-hand-side array
 __device__ __forceinline__ size_t lmd_index(const NuGeom& g, int k, int i, int r) {
+  if (g.df) return static_cast<size_t>(r) * g.n + i;            // (L, M, D) flattened per sample: row i = m * D + component (kernels.py:384-386)
   const int l = g.dimwise ? r : r / g.D_out;
   const int kk = g.dimwise ? k : r - l * g.D_out;
   return (static_cast<size_t>(l) * g.M + i) * g.D_out + kk;
 }
 // element (k, i, r) of nu in its reference layout: dimwise (L, D_out, M, 1); shared (L, M, D_out)
 __device__ __forceinline__ size_t nu_index(const NuGeom& g, int k, int i, int r) {
+  if (g.df) return static_cast<size_t>(r) * g.n + i;            // (L, M D, 1)
   if (g.dimwise) return (static_cast<size_t>(r) * g.D_out + k) * g.M + i;
   return lmd_index(g, k, i, r);
 }
@@ -169,34 +175,38 @@ __global__ void __launch_bounds__(kSetupThreads) k_chol(const int M, real* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// blocked triangular solve with up to 32 right-hand-side columns per CTA, RHS block resident in shared memory:
+// blocked triangular solve with NC right-hand-side columns per CTA, RHS block resident in shared memory:
 //   TRANS = false:  Lc X = B  (top to bottom)        TRANS = true:  Lc^T X = B  (bottom to top)
 // src / dst are (Kc, M, NR) arrays (dst may alias src); src_t: read the source transposed ((Kc, NR, M), NR == M).
+// NC = 32 for the small RBF systems; 16 / 8 / 4 keep the resident block within shared memory for the (M D)-order DF system
+// (lane = (row in a group of 32 / NC, column)); `strip` rows of the off-diagonal panel are staged per pass (64, or 32 when tight).
 // ---------------------------------------------------------------------------------------------
-template <bool TRANS>
+template <bool TRANS, int NC>
 __global__ void __launch_bounds__(kSetupThreads) k_trsm(const int M, const int NR, const real* __restrict__ Lall, const real* src,
-                                                        real* dst, const int src_t) {
+                                                        real* dst, const int src_t, const int strip) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   real* sm = reinterpret_cast<real*>(sm_raw);
   const int Mp = (M + NB - 1) / NB * NB;
-  real* Xs = sm;                          // [Mp][NB+1]
-  real* Lb = Xs + Mp * (NB + 1);          // [NB][NB+1] diagonal block
-  real* Ls = Lb + NB * (NB + 1);          // [64][NB+1] rows of the off-diagonal strip
-  const int k = blockIdx.y, c0 = blockIdx.x * NB;
-  const int ncol = min(NB, NR - c0);
+  constexpr int XS = NC + 1, RPW = 32 / NC;
+  real* Xs = sm;                          // [Mp][NC+1]
+  real* Lb = Xs + Mp * XS;                // [NB][NB+1] diagonal block
+  real* Ls = Lb + NB * (NB + 1);          // [strip][NB+1] rows of the off-diagonal strip
+  const int k = blockIdx.y, c0 = blockIdx.x * NC;
+  const int ncol = min(NC, NR - c0);
   const real* Lc = Lall + static_cast<size_t>(k) * M * M;
   const real* S = src + static_cast<size_t>(k) * M * NR;
   real* Dd = dst + static_cast<size_t>(k) * M * NR;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int col = lane % NC, rsub = lane / NC;
   if (src_t) {
-    for (int e = tid; e < Mp * NB; e += blockDim.x) {
+    for (int e = tid; e < Mp * NC; e += blockDim.x) {
       const int c = e / Mp, i = e - c * Mp;                        // consecutive threads walk i: coalesced rows of the source
-      Xs[i * (NB + 1) + c] = (i < M && c < ncol) ? S[static_cast<size_t>(c0 + c) * M + i] : real(0);
+      Xs[i * XS + c] = (i < M && c < ncol) ? S[static_cast<size_t>(c0 + c) * M + i] : real(0);
     }
   } else {
-    for (int e = tid; e < Mp * NB; e += blockDim.x) {
-      const int i = e / NB, c = e - i * NB;
-      Xs[i * (NB + 1) + c] = (i < M && c < ncol) ? S[static_cast<size_t>(i) * NR + c0 + c] : real(0);
+    for (int e = tid; e < Mp * NC; e += blockDim.x) {
+      const int i = e / NC, c = e - i * NC;
+      Xs[i * XS + c] = (i < M && c < ncol) ? S[static_cast<size_t>(i) * NR + c0 + c] : real(0);
     }
   }
   const int nblk = Mp / NB;
@@ -210,10 +220,10 @@ __global__ void __launch_bounds__(kSetupThreads) k_trsm(const int M, const int N
       Lb[r * (NB + 1) + c] = (gr < M && gc < M && gc <= gr) ? Lc[static_cast<size_t>(gr) * M + gc] : (r == c ? real(1) : real(0));
     }
     __syncthreads();
-    if (warp == 0) {                       // lane = column: 32-step substitution on the diagonal block
+    if (warp == 0 && lane < NC) {          // lane = column: 32-step substitution on the diagonal block
       real x[NB];
 #pragma unroll
-      for (int r = 0; r < NB; ++r) x[r] = Xs[(j0 + r) * (NB + 1) + lane];
+      for (int r = 0; r < NB; ++r) x[r] = Xs[(j0 + r) * XS + lane];
       if (!TRANS) {
 #pragma unroll
         for (int r = 0; r < NB; ++r) {
@@ -232,13 +242,13 @@ __global__ void __launch_bounds__(kSetupThreads) k_trsm(const int M, const int N
         }
       }
 #pragma unroll
-      for (int r = 0; r < NB; ++r) Xs[(j0 + r) * (NB + 1) + lane] = x[r];
+      for (int r = 0; r < NB; ++r) Xs[(j0 + r) * XS + lane] = x[r];
     }
     __syncthreads();
     // update the remaining rows: non-trans rows i >= j0 + NB use Lc[i][j0 + c]; trans rows j < j0 use Lc[j0 + c][j]
     const int lo_row = TRANS ? 0 : j0 + NB, hi_row = TRANS ? j0 : Mp;
-    for (int s0 = lo_row; s0 < hi_row; s0 += 64) {
-      const int ns = min(64, hi_row - s0);
+    for (int s0 = lo_row; s0 < hi_row; s0 += strip) {
+      const int ns = min(strip, hi_row - s0);
       if (!TRANS) {
         for (int e = tid; e < ns * NB; e += blockDim.x) {
           const int rr = e / NB, c = e - rr * NB;
@@ -253,20 +263,407 @@ __global__ void __launch_bounds__(kSetupThreads) k_trsm(const int M, const int N
         }
       }
       __syncthreads();
-      for (int rr = warp; rr < ns; rr += nwarp) {
+      for (int rr = warp * RPW + rsub; rr < ns; rr += nwarp * RPW) {
         real acc = 0;
 #pragma unroll
-        for (int c = 0; c < NB; ++c) acc = fma(Ls[rr * (NB + 1) + c], Xs[(j0 + c) * (NB + 1) + lane], acc);
-        Xs[(s0 + rr) * (NB + 1) + lane] -= acc;
+        for (int c = 0; c < NB; ++c) acc = fma(Ls[rr * (NB + 1) + c], Xs[(j0 + c) * XS + col], acc);
+        Xs[(s0 + rr) * XS + col] -= acc;
       }
       __syncthreads();
     }
   }
   __syncthreads();
-  for (int e = tid; e < M * NB; e += blockDim.x) {
-    const int i = e / NB, c = e - i * NB;
-    if (c < ncol) Dd[static_cast<size_t>(i) * NR + c0 + c] = Xs[i * (NB + 1) + c];
+  for (int e = tid; e < M * NC; e += blockDim.x) {
+    const int i = e / NC, c = e - i * NC;
+    if (c < ncol) Dd[static_cast<size_t>(i) * NR + c0 + c] = Xs[i * XS + c];
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One step of a right-looking blocked Cholesky of ONE large matrix (the (M D)-order DF system) spread over the chip:
+// launch j0 = 0, NB, 2 NB ... (stream order is the only synchronisation).  Every CTA factors the current NB x NB diagonal
+// block itself (redundantly: 32 dependent column steps, cheaper than a grid-wide barrier), turns the panel rows of ITS two
+// 64-row tiles into columns of Lc (P = A[rows, j0..] D^-T) and subtracts P_I P_K^T from its tile of the trailing lower
+// triangle.  A is the working matrix (only its trailing part is ever written), Lc a separate output -- so no CTA reads
+// what another one writes within a launch.  CTAs of the first tile column store their panel rows, CTA 0 the diagonal block.
+// ---------------------------------------------------------------------------------------------
+constexpr int CT = 64;
+__global__ void __launch_bounds__(kSetupThreads) k_chol_step(const int n, const int j0, real* __restrict__ A, real* __restrict__ Lc, int* __restrict__ info) {
+  __shared__ real Dg[NB * (NB + 1)];
+  __shared__ real Rd[NB];
+  __shared__ real Pt[2][NB][CT + 2];     // panel rows of the I tile / K tile, transposed
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbk = min(NB, n - j0);
+  int ti = static_cast<int>((sqrtf(8.f * static_cast<float>(blockIdx.x) + 1.f) - 1.f) * 0.5f);
+  while (ti * (ti + 1) / 2 > static_cast<int>(blockIdx.x)) --ti;
+  while ((ti + 1) * (ti + 2) / 2 <= static_cast<int>(blockIdx.x)) ++ti;
+  const int tk = static_cast<int>(blockIdx.x) - ti * (ti + 1) / 2;
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int r = e / NB, c = e - r * NB;
+    Dg[r * (NB + 1) + c] = (r < nbk && c < nbk && c <= r) ? A[static_cast<size_t>(j0 + r) * n + j0 + c] : (r == c ? real(1) : real(0));
+  }
+  __syncthreads();
+  {   // every warp factors the block (lane = row, held in registers; column c is broadcast by shuffles): no divergent branch around
+      // the shuffles, no shared-memory round trips; warp 0 stores the result
+    int bad = 0;
+    real x[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) x[c] = Dg[lane * (NB + 1) + c];
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      const real piv = __shfl_sync(0xffffffffu, x[c], c);
+      if (!(piv > real(0)) && c < nbk && bad == 0) bad = j0 + c + 1;
+      const real rs = rsqrt(piv);
+      x[c] = lane == c ? piv * rs : x[c] * rs;
+      if (lane == c && warp == 0) Rd[c] = rs;                        // 1 / Lc[c][c] for the panel rows
+#pragma unroll
+      for (int cc = c + 1; cc < NB; ++cc) {
+        const real lcc = __shfl_sync(0xffffffffu, x[c], cc);
+        x[cc] = lane >= cc ? fma(-x[c], lcc, x[cc]) : x[cc];
+      }
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int c = 0; c < NB; ++c) Dg[lane * (NB + 1) + c] = c <= lane ? x[c] : real(0);
+      if (blockIdx.x == 0 && lane == 0 && info && bad != 0 && *info == 0) *info = bad;
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0)
+    for (int e = tid; e < nbk * nbk; e += blockDim.x) {
+      const int r = e / nbk, c = e - r * nbk;
+      if (c <= r) Lc[static_cast<size_t>(j0 + r) * n + j0 + c] = Dg[r * (NB + 1) + c];
+    }
+  const int r0 = j0 + NB;
+  if (r0 >= n) return;
+  const int rowI = r0 + ti * CT, rowK = r0 + tk * CT;
+  if (tid < 2 * CT) {      // one thread per panel row: forward substitution over the NB columns
+    const int which = tid / CT, rr = tid - which * CT;
+    const int grow = (which ? rowK : rowI) + rr;
+    real x[NB];
+    if (grow < n) {
+      const real* arow = A + static_cast<size_t>(grow) * n + j0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) x[c] = c < nbk ? arow[c] : real(0);
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        real v = x[c];
+#pragma unroll
+        for (int cc = 0; cc < c; ++cc) v = fma(-x[cc], Dg[c * (NB + 1) + cc], v);
+        x[c] = v * Rd[c];
+      }
+      if (which == 0 && tk == 0) {
+        real* lrow = Lc + static_cast<size_t>(grow) * n + j0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+          if (c < nbk) lrow[c] = x[c];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NB; ++c) x[c] = real(0);
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) Pt[which][c][rr] = x[c];
+  }
+  __syncthreads();
+  // trailing update of this tile: 16 x 16 threads, 4 x 4 entries each
+  const int ty = tid >> 4, tx = tid & 15;
+  real acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = real(0);
+#pragma unroll 4
+  for (int c = 0; c < NB; ++c) {
+    real vi[4], vj[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      vi[a] = Pt[0][c][4 * ty + a];
+      vj[a] = Pt[1][c][4 * tx + a];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fma(vi[a], vj[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = rowI + 4 * ty + a;
+    if (i >= n) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = rowK + 4 * tx + b;
+      if (j <= i) A[static_cast<size_t>(i) * n + j] -= acc[a][b];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Explicit inverse of the (large, single) Cholesky factor: Linv = Lc^-1, lower triangular.  Every later solve of the DF setup
+// -- two skinny ones in the forward, three skinny and two (n x n) ones in the backward -- then is a plain matrix product with
+// no sequential dependency (substitution on ONE matrix is a chain of n / 32 dependent steps whatever the number of SMs).
+//   level 0: the NB x NB diagonal blocks are inverted (one warp each: lane = column of the inverse);
+//   level l: pairs of finished diagonal blocks [A 0; B C] of size b = NB 2^l are joined: Linv[B part] = - C^-1 (B A^-1),
+//            two batched products per level (k_dgemm), log2(n / NB) levels.
+// fp64 throughout: cond(Lc) = sqrt(cond(K)) <= ~1e3 at the reference's settings, the products stay at 1e-12.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_diag_inv(const int n, const real* __restrict__ Lc, real* __restrict__ Linv) {
+  __shared__ real Dg[NB * (NB + 1)];
+  const int j0 = blockIdx.x * NB, lane = threadIdx.x;
+  const int nbk = min(NB, n - j0);
+  for (int e = lane; e < NB * NB; e += 32) {
+    const int r = e / NB, c = e - r * NB;
+    Dg[r * (NB + 1) + c] = (r < nbk && c < nbk && c <= r) ? Lc[static_cast<size_t>(j0 + r) * n + j0 + c] : (r == c ? real(1) : real(0));
+  }
+  __syncwarp();
+  real x[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    real v0 = r == lane ? real(1) : real(0), v1 = 0;
+#pragma unroll
+    for (int c = 0; c < r; ++c) {
+      if (c & 1) v1 = fma(-Dg[r * (NB + 1) + c], x[c], v1);
+      else v0 = fma(-Dg[r * (NB + 1) + c], x[c], v0);
+    }
+    x[r] = (v0 + v1) / Dg[r * (NB + 1) + r];
+  }
+  if (lane < nbk) {
+#pragma unroll
+    for (int r = 0; r < NB; ++r)
+      if (r < nbk) Linv[static_cast<size_t>(j0 + r) * n + j0 + lane] = r >= lane ? x[r] : real(0);
+  }
+}
+
+// out (n, NR) = Linv x (TRANS = 0) or Linv^T x (TRANS = 1) for a lower-triangular Linv (n, n) and NR <= 8 columns: the skinny solves of
+// the DF setup as matrix-vector products.  TRANS = 0: one warp per output row (lanes stride the row, k <= i); TRANS = 1: a CTA owns
+// 32 output columns j, its 8 warps stride the rows i >= j of Linv (coalesced along j), partial sums meet in shared memory.
+template <int TRANS>
+__global__ void __launch_bounds__(256) k_tri_matvec(const int n, const int NR, const real* __restrict__ Linv, const real* __restrict__ x, real* __restrict__ out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  real acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0;
+  if (!TRANS) {
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= n) return;
+    const real* row = Linv + static_cast<size_t>(i) * n;
+    for (int k = lane; k <= i; k += 32) {
+      const real a = row[k];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < NR) acc[r] = fma(a, x[static_cast<size_t>(k) * NR + r], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < NR) {
+        const real v = warp_sum_real(acc[r]);
+        if (lane == 0) out[static_cast<size_t>(i) * NR + r] = v;
+      }
+  } else {
+    __shared__ real part[8][8][33];
+    const int j = blockIdx.x * 32 + lane;
+    if (j < n)
+      for (int i = blockIdx.x * 32 + warp; i < n; i += 8) {
+        if (i < j) continue;
+        const real a = Linv[static_cast<size_t>(i) * n + j];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (r < NR) acc[r] = fma(a, x[static_cast<size_t>(i) * NR + r], acc[r]);
+      }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) part[warp][r][lane] = acc[r];
+    __syncthreads();
+    if (warp < NR && j < n) {
+      real v = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += part[w][warp][lane];
+      out[static_cast<size_t>(j) * NR + warp] = v;
+    }
+  }
+}
+
+// C = alpha op(A) B (+ beta C), row-major fp64, batched over blockIdx.z with element strides; op(A) = A^T when ta (A stored K x M).
+// Batch p uses M_eff = min(M, m_lim - p * m_lim_step) rows (ragged last block of the level-wise inverse; K_eff = M_eff when k_is_m).
+// 64 x 64 tile, 256 threads, 4 x 4 per thread, K in chunks of 16.
+constexpr int GT = 64, GK = 16;
+__global__ void __launch_bounds__(256) k_dgemm(int M, const int N, int K, const real alpha, const real* __restrict__ A, const int lda, const long sa, const int ta,
+                                               const real* __restrict__ B, const int ldb, const long sb, const real beta, real* __restrict__ C, const int ldc,
+                                               const long sc, const int m_lim, const int m_lim_step, const int k_is_m, const int tri) {
+  // tri (operand structure, skips all-zero K chunks): 1 = B lower triangular (k >= j), 2 = op(A) = A^T with A lower triangular (k >= i),
+  //                                                   4 = A lower triangular, not transposed (k <= i)
+  __shared__ real As[GK][GT + 4], Bs[GK][GT + 4];
+  const int p = blockIdx.z;
+  if (m_lim_step > 0 || m_lim > 0) {
+    const int lim = m_lim - p * m_lim_step;
+    if (lim < M) M = lim;
+    if (M <= 0) return;
+    if (k_is_m) K = M;
+  }
+  A += p * sa;
+  B += p * sb;
+  C += p * sc;
+  const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
+  if (i0 >= M || j0 >= N) return;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  real acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+  int k_begin = 0, k_end = K;
+  if (tri & 1) k_begin = max(k_begin, j0 / GK * GK);
+  if (tri & 2) k_begin = max(k_begin, i0 / GK * GK);
+  if (tri & 4) k_end = min(k_end, i0 + GT);
+  for (int k0 = k_begin; k0 < k_end; k0 += GK) {
+    for (int e = tid; e < GK * GT; e += 256) {
+      int kk, ii;
+      if (ta) { kk = e / GT; ii = e - kk * GT; } else { ii = e / GK; kk = e - ii * GK; }     // consecutive threads walk the contiguous direction
+      const int gi = i0 + ii, gk = k0 + kk;
+      As[kk][ii] = (gi < M && gk < K) ? (ta ? A[static_cast<size_t>(gk) * lda + gi] : A[static_cast<size_t>(gi) * lda + gk]) : real(0);
+    }
+    for (int e = tid; e < GK * GT; e += 256) {
+      const int kk = e / GT, jj = e - kk * GT;
+      const int gk = k0 + kk, gj = j0 + jj;
+      Bs[kk][jj] = (gk < K && gj < N) ? B[static_cast<size_t>(gk) * ldb + gj] : real(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      real va[4], vb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        va[a] = As[kk][4 * ty + a];
+        vb[a] = Bs[kk][4 * tx + a];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(va[a], vb[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int gi = i0 + 4 * ty + a;
+    if (gi >= M) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int gj = j0 + 4 * tx + b;
+      if (gj >= N) continue;
+      real* c = C + static_cast<size_t>(gi) * ldc + gj;
+      *c = beta == real(0) ? alpha * acc[a][b] : fma(alpha, acc[a][b], beta * *c);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// divergence-free Gram matrix K(Z,Z) + jitter I (core/kernels.py:289-303): row m D + i, column m' D + j,
+//   d = Z_m' - Z_m, c_ij = 1 / ell_ij^2:   var_j c_ij exp(-r2 c_ij / 2) (d_i d_j c_ij + delta_ij ((D - 1) - r2 c_ij))
+// one thread per (m, m') block.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_df_kzz_build(const NuGeom g, const float* __restrict__ Z, const float* __restrict__ ell, const float* __restrict__ var,
+                               real* __restrict__ A) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long>(g.M) * g.M) return;
+  const int D = g.D_in;
+  const int m = static_cast<int>(idx / g.M), mp = static_cast<int>(idx - static_cast<long>(m) * g.M);
+  real d[8], r2 = 0;
+  for (int k = 0; k < D; ++k) {
+    d[k] = static_cast<real>(Z[mp * D + k]) - static_cast<real>(Z[m * D + k]);
+    r2 = fma(d[k], d[k], r2);
+  }
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      const real e = ell[i * D + j], c = 1.0 / (e * e);
+      real v = static_cast<real>(var[j]) * c * exp(-0.5 * r2 * c) * (d[i] * d[j] * c + (i == j ? (D - 1.0) - r2 * c : 0.0));
+      if (m == mp && i == j) v += static_cast<real>(g.jitter);
+      A[(static_cast<size_t>(m) * D + i) * g.n + static_cast<size_t>(mp) * D + j] = v;
+    }
+}
+// A_bar = X + 1/2 sum_r (r_i q_j + q_i r_j) (symmetric; torch hands it to both triangles of K) contracted with dK/d(var, ell, Z)
+// of the divergence-free Gram matrix.  One CTA per inducing point m, threads over m': each thread contracts the (m, m') block
+// for the lengthscale / variance sums and the Z_m share of it (d = Z_m' - Z_m: -g), plus the (m', m) block for Z_m's share as
+// the COLUMN point (+g) -- so dZ needs no atomics.  acc (doubles): [D*D] lengthscales, then [D] variances.
+__global__ void __launch_bounds__(128) k_df_kzz_bwd(const NuGeom g, const float* __restrict__ Z, const float* __restrict__ ell, const float* __restrict__ var,
+                                                     const real* __restrict__ X, const real* __restrict__ rr_, const real* __restrict__ qq_,
+                                                     float* __restrict__ d_Z, real* __restrict__ acc) {
+  const int D = g.D_in, m = blockIdx.x, tid = threadIdx.x;
+  __shared__ real red[128];
+  real c_[64], dl[64], dv[8], dz[8];
+  for (int e = 0; e < D * D; ++e) {
+    const real l = ell[e];
+    c_[e] = 1.0 / (l * l);
+    dl[e] = 0;
+  }
+  for (int k = 0; k < D; ++k) dv[k] = dz[k] = 0;
+  for (int mp = tid; mp < g.M; mp += blockDim.x) {
+    real d[8], r2 = 0;
+    for (int k = 0; k < D; ++k) {
+      d[k] = static_cast<real>(Z[mp * D + k]) - static_cast<real>(Z[m * D + k]);
+      r2 = fma(d[k], d[k], r2);
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      // pass 0: block (m, m') with d;   pass 1: block (m', m) with -d (only its Z_m share is taken)
+      const int ra = pass == 0 ? m : mp, ca = pass == 0 ? mp : m;
+      const real sgn = pass == 0 ? 1.0 : -1.0;
+      for (int i = 0; i < D; ++i) {
+        const size_t row = static_cast<size_t>(ra) * D + i;
+        for (int j = 0; j < D; ++j) {
+          const size_t colx = static_cast<size_t>(ca) * D + j;
+          real ab = X[row * g.n + colx];
+          real rk = 0;
+          for (int r = 0; r < g.NR; ++r) rk += rr_[row * g.NR + r] * qq_[colx * g.NR + r] + qq_[row * g.NR + r] * rr_[colx * g.NR + r];
+          ab = fma(0.5, rk, ab);
+          const real c = c_[i * D + j], E = exp(-0.5 * r2 * c), vj = var[j];
+          const real di = sgn * d[i], dj = sgn * d[j];
+          const real H = di * dj * c + (i == j ? (D - 1.0) - r2 * c : 0.0);
+          if (pass == 0) {
+            dv[j] = fma(ab, c * E * H, dv[j]);
+            // d/dc: var E [H + c (-r2/2 H + d_i d_j - delta_ij r2)]
+            dl[i * D + j] = fma(ab, vj * E * (H + c * (-0.5 * r2 * H + di * dj - (i == j ? r2 : 0.0))), dl[i * D + j]);
+          }
+          // d/dd_k of var c E H (d = column point - row point): var c E [ -c d_k H + c (delta_ik d_j + delta_jk d_i) - 2 delta_ij c d_k ]
+          const real base = ab * vj * c * E * c;
+          for (int k = 0; k < D; ++k) {
+            const real dk = sgn * d[k];
+            real t = -dk * H - (i == j ? 2.0 * dk : 0.0);
+            if (k == i) t += dj;
+            if (k == j) t += di;
+            // Z_m is the row point in pass 0 (d/dZ_m = -d/dd) and the column point in pass 1 (+d/dd)
+            dz[k] = fma(pass == 0 ? -base : base, t, dz[k]);
+          }
+        }
+      }
+    }
+  }
+  auto block_sum = [&](real v) -> real {
+    v = warp_sum_real(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    real s = 0;
+    if (tid == 0)
+      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) s += red[w];
+    return s;
+  };
+  for (int k = 0; k < D; ++k) {
+    const real s = block_sum(dz[k]);
+    if (tid == 0 && d_Z) d_Z[m * D + k] = static_cast<float>(s);
+  }
+  for (int e = 0; e < D * D; ++e) {
+    const real s = block_sum(dl[e]);
+    if (tid == 0) atomicAdd(&acc[e], s * (-2.0 * c_[e] / static_cast<real>(ell[e])));     // dc/dell = -2 c / ell
+  }
+  for (int k = 0; k < D; ++k) {
+    const real s = block_sum(dv[k]);
+    if (tid == 0) atomicAdd(&acc[D * D + k], s);
+  }
+}
+__global__ void k_df_acc_out(const int D, const real* __restrict__ acc, float* __restrict__ d_ell, float* __restrict__ d_var) {
+  const int e = threadIdx.x;
+  if (e < D * D && d_ell) d_ell[e] = static_cast<float>(acc[e]);
+  if (e < D && d_var) d_var[e] = static_cast<float>(acc[D * D + e]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -274,33 +671,33 @@ __global__ void __launch_bounds__(kSetupThreads) k_trsm(const int M, const int N
 // ---------------------------------------------------------------------------------------------
 // rhs[k][i][r] = reference-layout (L, M, D_out) tensor
 __global__ void k_gather_lmd(const NuGeom g, const float* __restrict__ src, real* __restrict__ rhs) {
-  const long n = static_cast<long>(g.Kc) * g.M * g.NR;
+  const long n = static_cast<long>(g.Kc) * g.n * g.NR;
   for (long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.M), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.M));
+    const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.n), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.n));
     rhs[e] = src[lmd_index(g, k, i, r)];
   }
 }
 // b = u - a  (u in reference layout), in place on the a array
 __global__ void k_u_minus_a(const NuGeom g, const float* __restrict__ u, real* __restrict__ a_then_b) {
-  const long n = static_cast<long>(g.Kc) * g.M * g.NR;
+  const long n = static_cast<long>(g.Kc) * g.n * g.NR;
   for (long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.M), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.M));
+    const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.n), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.n));
     a_then_b[e] = static_cast<real>(u[lmd_index(g, k, i, r)]) - a_then_b[e];
   }
 }
 // scatter (Kc, M, NR) -> nu layout (mode 0) or (L, M, D_out) layout with a sign (mode 1)
 __global__ void k_scatter(const NuGeom g, const real* __restrict__ rhs, float* __restrict__ out, const int mode, const float scale) {
-  const long n = static_cast<long>(g.Kc) * g.M * g.NR;
+  const long n = static_cast<long>(g.Kc) * g.n * g.NR;
   for (long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.M), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.M));
+    const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.n), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.n));
     out[mode == 0 ? nu_index(g, k, i, r) : lmd_index(g, k, i, r)] = static_cast<float>(scale * rhs[e]);
   }
 }
 // gather nu-layout tensor into (Kc, M, NR)
 __global__ void k_gather_nu(const NuGeom g, const float* __restrict__ src, real* __restrict__ rhs) {
-  const long n = static_cast<long>(g.Kc) * g.M * g.NR;
+  const long n = static_cast<long>(g.Kc) * g.n * g.NR;
   for (long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.M), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.M));
+    const int r = static_cast<int>(e % g.NR), i = static_cast<int>((e / g.NR) % g.n), k = static_cast<int>(e / (static_cast<long>(g.NR) * g.n));
     rhs[e] = src[nu_index(g, k, i, r)];
   }
 }
@@ -308,12 +705,12 @@ __global__ void k_gather_nu(const NuGeom g, const float* __restrict__ src, real*
 __global__ void k_build_S(const NuGeom g, const float* __restrict__ u, const real* __restrict__ bb, real* __restrict__ S) {
   const int k = blockIdx.y;
   const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long>(g.M) * g.M) return;
-  const int i = static_cast<int>(idx / g.M), j = static_cast<int>(idx - static_cast<long>(i) * g.M);
+  if (idx >= static_cast<long>(g.n) * g.n) return;
+  const int i = static_cast<int>(idx / g.n), j = static_cast<int>(idx - static_cast<long>(i) * g.n);
   const int hi_ = i > j ? i : j, lo_ = i > j ? j : i;
   real acc = 0;
-  for (int r = 0; r < g.NR; ++r) acc = fma(static_cast<real>(u[lmd_index(g, k, hi_, r)]), bb[(static_cast<size_t>(k) * g.M + lo_) * g.NR + r], acc);
-  S[(static_cast<size_t>(k) * g.M + i) * g.M + j] = -0.5 * acc;
+  for (int r = 0; r < g.NR; ++r) acc = fma(static_cast<real>(u[lmd_index(g, k, hi_, r)]), bb[(static_cast<size_t>(k) * g.n + lo_) * g.NR + r], acc);
+  S[(static_cast<size_t>(k) * g.n + i) * g.n + j] = -0.5 * acc;
 }
 // A_bar = X + 1/2 sum_r (r_i q_j + q_i r_j) contracted with dK/d(var, ell, Z); one warp per (k, i) row
 __global__ void k_kzz_bwd(const NuGeom g, const float* __restrict__ Z, const float* __restrict__ ell, const float* __restrict__ var,
@@ -446,22 +843,94 @@ inline int blocks_for(long n, int threads, int cap = 148 * 8) {
   if (b < 1) b = 1;
   return static_cast<int>(b);
 }
-inline size_t trsm_smem(int M) {
+inline size_t trsm_smem(int M, int nc, int strip) {
   const int Mp = (M + NB - 1) / NB * NB;
-  return (static_cast<size_t>(Mp) * (NB + 1) + NB * (NB + 1) + 64 * (NB + 1)) * sizeof(real);
+  return (static_cast<size_t>(Mp) * (nc + 1) + NB * (NB + 1) + static_cast<size_t>(strip) * (NB + 1)) * sizeof(real);
 }
 inline size_t chol_smem(int M) {
   const int Mp = (M + NB - 1) / NB * NB;
   return (static_cast<size_t>(NB) * (NB + 1) + static_cast<size_t>(NB) * Mp) * sizeof(real);
 }
+constexpr size_t kSmemCap = 227 * 1024;
 
+template <bool TRANS, int NC>
+cudaError_t trsm_nc(int n, int Kc, int NR, int strip, const real* Lc, const real* src, real* dst, int src_t, cudaStream_t st) {
+  const size_t smem = trsm_smem(n, NC, strip);
+  cudaError_t e = cudaFuncSetAttribute(k_trsm<TRANS, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  dim3 grid((NR + NC - 1) / NC, Kc);
+  k_trsm<TRANS, NC><<<grid, kSetupThreads, smem, st>>>(n, NR, Lc, src, dst, src_t, strip);
+  return cudaGetLastError();
+}
+// widest column block whose resident right-hand sides fit in shared memory (and no wider than the columns there are)
 template <bool TRANS>
 cudaError_t trsm(const NuGeom& g, int NR, const real* Lc, const real* src, real* dst, int src_t, cudaStream_t st) {
-  const size_t smem = trsm_smem(g.M);
-  cudaError_t e = cudaFuncSetAttribute(k_trsm<TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  for (int nc = NR > 16 ? 32 : (NR > 8 ? 16 : 8); nc >= 4; nc >>= 1) {   // (few columns: a narrower block wastes no lanes)
+    for (int strip = 64; strip >= 32; strip >>= 1) {
+      if (trsm_smem(g.n, nc, strip) > kSmemCap) continue;
+      switch (nc) {
+        case 32: return trsm_nc<TRANS, 32>(g.n, g.Kc, NR, strip, Lc, src, dst, src_t, st);
+        case 16: return trsm_nc<TRANS, 16>(g.n, g.Kc, NR, strip, Lc, src, dst, src_t, st);
+        case 8: return trsm_nc<TRANS, 8>(g.n, g.Kc, NR, strip, Lc, src, dst, src_t, st);
+        default: return trsm_nc<TRANS, 4>(g.n, g.Kc, NR, strip, Lc, src, dst, src_t, st);
+      }
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+inline cudaError_t dgemm(int M, int N, int K, real alpha, const real* A, int lda, int ta, const real* B, int ldb, real beta, real* C, int ldc, cudaStream_t st,
+                         int tri = 0, int batch = 1, long sa = 0, long sb = 0, long sc = 0, int m_lim = 0, int m_lim_step = 0, int k_is_m = 0) {
+  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT, batch);
+  k_dgemm<<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sa, ta, B, ldb, sb, beta, C, ldc, sc, m_lim, m_lim_step, k_is_m, tri);
+  return cudaGetLastError();
+}
+inline cudaError_t tri_matvec(int n, int NR, const real* Linv, int trans, const real* x, real* out, cudaStream_t st) {
+  if (NR > 8) return dgemm(n, NR, n, 1.0, Linv, n, trans, x, NR, 0.0, out, NR, st, trans ? 2 : 4);
+  if (trans) k_tri_matvec<1><<<(n + 31) / 32, 256, 0, st>>>(n, NR, Linv, x, out);
+  else k_tri_matvec<0><<<(n + 7) / 8, 256, 0, st>>>(n, NR, Linv, x, out);
+  return cudaGetLastError();
+}
+// Linv = Lc^-1 (see k_diag_inv); T: (n, n) scratch
+cudaError_t invert_factor(int n, const real* Lc, real* Linv, real* T, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(Linv, 0, static_cast<size_t>(n) * n * sizeof(real), st);
   if (e != cudaSuccess) return e;
-  dim3 grid((NR + NB - 1) / NB, g.Kc);
-  k_trsm<TRANS><<<grid, kSetupThreads, smem, st>>>(g.M, NR, Lc, src, dst, src_t);
+  k_diag_inv<<<(n + NB - 1) / NB, 32, 0, st>>>(n, Lc, Linv);
+  for (int b = NB; b < n; b <<= 1) {
+    const int pairs = (n + 2 * b - 1) / (2 * b);                       // the last pair may have a short (or no) second block
+    const long st_diag = 2L * b * (n + 1);
+    // T[B part] = B A^-1      (rows r0 + b .. of Lc, columns r0 .. r0 + b)
+    if ((e = dgemm(b, b, b, 1.0, Lc + static_cast<size_t>(b) * n, n, 0, Linv, n, 0.0, T + static_cast<size_t>(b) * n, n, st, 1, pairs, st_diag, st_diag, st_diag, n - b,
+                   2 * b, 0)) != cudaSuccess)
+      return e;
+    // Linv[B part] = - C^-1 T
+    if ((e = dgemm(b, b, b, -1.0, Linv + static_cast<size_t>(b) * (n + 1), n, 0, T + static_cast<size_t>(b) * n, n, 0.0, Linv + static_cast<size_t>(b) * n, n, st, 4, pairs,
+                   st_diag, st_diag, st_diag, n - b, 2 * b, 1)) != cudaSuccess)
+      return e;
+  }
+  return cudaGetLastError();
+}
+
+// Cholesky of the Kc matrices in `Lc` (in place for the batched small systems; through the working copy `work` for one large system)
+cudaError_t cholesky(const NuGeom& g, real* Lc, real* work, int* info, cudaStream_t st) {
+  const size_t cs = chol_smem(g.n);
+  if (!g.df) {
+    if (cs > kSmemCap) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cs));
+    if (e != cudaSuccess) return e;
+    k_chol<<<g.Kc, kSetupThreads, cs, st>>>(g.n, Lc, info);
+    return cudaGetLastError();
+  }
+  // one large system: `work` holds K + jitter I, the factor goes to Lc
+  if (info) {
+    cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+  }
+  for (int j0 = 0; j0 < g.n; j0 += NB) {
+    const int rem = g.n - (j0 + NB);
+    const int nt = rem > 0 ? (rem + CT - 1) / CT : 0;
+    const int grid = nt > 0 ? nt * (nt + 1) / 2 : 1;
+    k_chol_step<<<grid, kSetupThreads, 0, st>>>(g.n, j0, work, Lc, info);
+  }
   return cudaGetLastError();
 }
 
@@ -474,24 +943,86 @@ cudaError_t trsm(const NuGeom& g, int NR, const real* Lc, const real* src, real*
   } while (0)
 
 // (sizes in FLOATS of the caller's buffers: the factors and right-hand sides are stored in `real` = double)
-size_t nu_save_floats(const NuGeom& g) { return (sizeof(real) / 4) * (static_cast<size_t>(g.Kc) * g.M * g.M + static_cast<size_t>(g.Kc) * g.M * g.NR); }
+size_t nu_save_floats(const NuGeom& g) { return (sizeof(real) / 4) * (static_cast<size_t>(g.Kc) * g.n * g.n + static_cast<size_t>(g.Kc) * g.n * g.NR); }
 size_t nu_ws_floats(const NuGeom& g) {
-  return (sizeof(real) / 4) * (2 * static_cast<size_t>(g.Kc) * g.M * g.M + 4 * static_cast<size_t>(g.Kc) * g.M * g.NR) + 64;
+  return (sizeof(real) / 4) * ((g.df ? 3 : 2) * static_cast<size_t>(g.Kc) * g.n * g.n + 4 * static_cast<size_t>(g.Kc) * g.n * g.NR + 128) + 64;
+}
+
+// DF: one large system.  save = [ Linv (n, n) | a = Lc^-1 u_prior (n, NR) ]
+static cudaError_t df_nu_forward(const NuGeom& g, const float* Z, const float* ell, const float* var, const float* u_prior, const float* u, float* nu,
+                                 real* save, int* info, real* ws, cudaStream_t st) {
+  const size_t nn = static_cast<size_t>(g.n) * g.n, rhs = static_cast<size_t>(g.n) * g.NR;
+  real* Linv = save;
+  real* a = save + nn;
+  real* b = ws;              // (n, NR)
+  real* pin = b + rhs;       // (n, NR) gathered u_prior
+  real* work = pin + rhs;    // (n, n)  K + jitter I, consumed by the factorisation; then scratch of the inversion
+  real* Lc = work + nn;      // (n, n)
+  const long mm = static_cast<long>(g.M) * g.M;
+  k_df_kzz_build<<<static_cast<unsigned>((mm + 127) / 128), 128, 0, st>>>(g, Z, ell, var, work);
+  GPODE_CK(cudaGetLastError());
+  GPODE_CK(cholesky(g, Lc, work, info, st));
+  GPODE_CK(invert_factor(g.n, Lc, Linv, work, st));
+  k_gather_lmd<<<blocks_for(static_cast<long>(rhs), 256), 256, 0, st>>>(g, u_prior, pin);
+  GPODE_CK(cudaGetLastError());
+  GPODE_CK(tri_matvec(g.n, g.NR, Linv, 0, pin, a, st));                                     // a = Lc^-1 u_prior
+  GPODE_CK(cudaMemcpyAsync(b, a, rhs * sizeof(real), cudaMemcpyDeviceToDevice, st));
+  k_u_minus_a<<<blocks_for(static_cast<long>(rhs), 256), 256, 0, st>>>(g, u, b);
+  GPODE_CK(cudaGetLastError());
+  GPODE_CK(tri_matvec(g.n, g.NR, Linv, 1, b, pin, st));                                     // nu = Lc^-T (u - a)
+  k_scatter<<<blocks_for(static_cast<long>(rhs), 256), 256, 0, st>>>(g, pin, nu, 0, 1.f);
+  return cudaGetLastError();
+}
+
+static cudaError_t df_nu_backward(const NuGeom& g, const float* Z, const float* ell, const float* var, const float* u, const real* save, const float* dnu,
+                                  float* d_uprior, float* d_u, float* d_Z, float* d_ell, float* d_var, real* ws, cudaStream_t st) {
+  const size_t nn = static_cast<size_t>(g.n) * g.n, rhs = static_cast<size_t>(g.n) * g.NR;
+  const real* Linv = save;
+  const real* a = save + nn;
+  real* S = ws;
+  real* Y = S + nn;
+  real* bb = Y + nn;
+  real* rr = bb + rhs;
+  real* qq = rr + rhs;
+  real* gin = qq + rhs;
+  real* dacc = gin + rhs;
+  k_gather_nu<<<blocks_for(static_cast<long>(rhs), 256), 256, 0, st>>>(g, dnu, gin);
+  GPODE_CK(cudaGetLastError());
+  GPODE_CK(tri_matvec(g.n, g.NR, Linv, 0, gin, bb, st));                                    // bb = Lc^-1 nu_bar   (= u_bar)
+  GPODE_CK(tri_matvec(g.n, g.NR, Linv, 1, bb, rr, st));                                     // r  = Lc^-T bb       (= -u_prior_bar)
+  GPODE_CK(tri_matvec(g.n, g.NR, Linv, 1, a, qq, st));                                      // q  = Lc^-T a
+  if (d_u) {
+    k_scatter<<<blocks_for(static_cast<long>(rhs), 256), 256, 0, st>>>(g, bb, d_u, 1, 1.f);
+    GPODE_CK(cudaGetLastError());
+  }
+  if (d_uprior) {
+    k_scatter<<<blocks_for(static_cast<long>(rhs), 256), 256, 0, st>>>(g, rr, d_uprior, 1, -1.f);
+    GPODE_CK(cudaGetLastError());
+  }
+  if (!d_Z && !d_ell && !d_var) return cudaSuccess;
+  const long m2 = static_cast<long>(g.n) * g.n;
+  k_build_S<<<dim3(static_cast<unsigned>((m2 + 255) / 256), 1), 256, 0, st>>>(g, u, bb, S);
+  GPODE_CK(cudaGetLastError());
+  GPODE_CK(dgemm(g.n, g.n, g.n, 1.0, S, g.n, 0, Linv, g.n, 0.0, Y, g.n, st, 1));            // Y = S Lc^-1
+  GPODE_CK(dgemm(g.n, g.n, g.n, 1.0, Linv, g.n, 1, Y, g.n, 0.0, S, g.n, st, 2));            // X = Lc^-T S Lc^-1 -> S
+  GPODE_CK(cudaMemsetAsync(dacc, 0, 128 * sizeof(real), st));
+  k_df_kzz_bwd<<<g.M, 128, 0, st>>>(g, Z, ell, var, S, rr, qq, d_Z, dacc);
+  GPODE_CK(cudaGetLastError());
+  k_df_acc_out<<<1, 64, 0, st>>>(g.D_in, dacc, d_ell, d_var);
+  return cudaGetLastError();
 }
 
 cudaError_t nu_forward(const NuGeom& g, const float* Z, const float* ell, const float* var, const float* u_prior, const float* u, float* nu,
                        float* save_f, int* info, float* ws_f, cudaStream_t st) {
   real* save = reinterpret_cast<real*>(save_f);
+  if (g.df) return df_nu_forward(g, Z, ell, var, u_prior, u, nu, save, info, reinterpret_cast<real*>(ws_f), st);
   real* Lc = save;                                                   // (Kc, M, M)
-  real* a = save + static_cast<size_t>(g.Kc) * g.M * g.M;            // (Kc, M, NR): Lc^-1 u_prior
+  real* a = save + static_cast<size_t>(g.Kc) * g.n * g.n;            // (Kc, M, NR): Lc^-1 u_prior
   real* b = reinterpret_cast<real*>(ws_f);                           // (Kc, M, NR)
-  const long mm = static_cast<long>(g.M) * g.M, rhs = static_cast<long>(g.Kc) * g.M * g.NR;
+  const long mm = static_cast<long>(g.M) * g.M, rhs = static_cast<long>(g.Kc) * g.n * g.NR;
   k_kzz_build<<<dim3(static_cast<unsigned>((mm + 255) / 256), g.Kc), 256, 0, st>>>(g, Z, ell, var, Lc);
   GPODE_CK(cudaGetLastError());
-  const size_t cs = chol_smem(g.M);
-  GPODE_CK(cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cs)));
-  k_chol<<<g.Kc, kSetupThreads, cs, st>>>(g.M, Lc, info);
-  GPODE_CK(cudaGetLastError());
+  GPODE_CK(cholesky(g, Lc, nullptr, info, st));
   k_gather_lmd<<<blocks_for(rhs, 256), 256, 0, st>>>(g, u_prior, a);
   GPODE_CK(cudaGetLastError());
   GPODE_CK(trsm<false>(g, g.NR, Lc, a, a, 0, st));
@@ -506,9 +1037,10 @@ cudaError_t nu_forward(const NuGeom& g, const float* Z, const float* ell, const 
 cudaError_t nu_backward(const NuGeom& g, const float* Z, const float* ell, const float* var, const float* u, const float* save_f, const float* dnu,
                         float* d_uprior, float* d_u, float* d_Z, float* d_ell, float* d_var, float* ws_f, cudaStream_t st) {
   const real* save = reinterpret_cast<const real*>(save_f);
+  if (g.df) return df_nu_backward(g, Z, ell, var, u, save, dnu, d_uprior, d_u, d_Z, d_ell, d_var, reinterpret_cast<real*>(ws_f), st);
   const real* Lc = save;
-  const real* a = save + static_cast<size_t>(g.Kc) * g.M * g.M;
-  const size_t mm = static_cast<size_t>(g.Kc) * g.M * g.M, rhs = static_cast<size_t>(g.Kc) * g.M * g.NR;
+  const real* a = save + static_cast<size_t>(g.Kc) * g.n * g.n;
+  const size_t mm = static_cast<size_t>(g.Kc) * g.n * g.n, rhs = static_cast<size_t>(g.Kc) * g.n * g.NR;
   real* S = reinterpret_cast<real*>(ws_f);   // (Kc, M, M)
   real* Y = S + mm;              // (Kc, M, M)
   real* bb = Y + mm;             // (Kc, M, NR)
@@ -528,11 +1060,11 @@ cudaError_t nu_backward(const NuGeom& g, const float* Z, const float* ell, const
     GPODE_CK(cudaGetLastError());
   }
   if (!d_Z && !d_ell && !d_var) return cudaSuccess;
-  const long m2 = static_cast<long>(g.M) * g.M;
+  const long m2 = static_cast<long>(g.n) * g.n;
   k_build_S<<<dim3(static_cast<unsigned>((m2 + 255) / 256), g.Kc), 256, 0, st>>>(g, u, bb, S);
   GPODE_CK(cudaGetLastError());
-  GPODE_CK(trsm<true>(g, g.M, Lc, S, Y, 0, st));                     // Y = Lc^-T S
-  GPODE_CK(trsm<true>(g, g.M, Lc, Y, S, 1, st));                     // X^T = Lc^-T Y^T  (X symmetric) -> S
+  GPODE_CK(trsm<true>(g, g.n, Lc, S, Y, 0, st));                     // Y = Lc^-T S
+  GPODE_CK(trsm<true>(g, g.n, Lc, Y, S, 1, st));                     // X^T = Lc^-T Y^T  (X symmetric) -> S
   if (d_Z) GPODE_CK(cudaMemsetAsync(d_Z, 0, static_cast<size_t>(g.M) * g.D_in * 4, st));
   if (d_ell) GPODE_CK(cudaMemsetAsync(d_ell, 0, static_cast<size_t>(g.dimwise ? g.D_out * g.D_in : g.D_in) * 4, st));
   if (d_var) GPODE_CK(cudaMemsetAsync(d_var, 0, static_cast<size_t>(g.dimwise ? g.D_out : 1) * 4, st));

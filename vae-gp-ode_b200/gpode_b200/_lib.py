@@ -30,7 +30,8 @@ class GpodeParamGrads(ctypes.Structure):
 EXPORTS = ["gpode_version", "gpode_error_string", "gpode_forward_kernel", "gpode_workspace_bytes", "gpode_rollout_save_floats",
            "gpode_field_fwd", "gpode_field_bwd", "gpode_rollout_fwd", "gpode_rollout_bwd",
            "gpode_nu_workspace_bytes", "gpode_nu_save_floats", "gpode_compute_nu_fwd", "gpode_compute_nu_bwd",
-           "gpode_inducing_sample_fwd", "gpode_inducing_sample_bwd", "gpode_kl_fwd", "gpode_kl_bwd"]
+           "gpode_inducing_sample_fwd", "gpode_inducing_sample_bwd", "gpode_kl_fwd", "gpode_kl_bwd",
+           "gpode_philox_fill", "gpode_philox_raw", "gpode_bernoulli_workspace_bytes", "gpode_bernoulli_lhood_fwd", "gpode_bernoulli_lhood_bwd"]
 
 _lib = None
 
@@ -80,6 +81,17 @@ def load():
     lib.gpode_kl_fwd.argtypes = [i32, i32, _fp, _fp, _fp, _fp]
     lib.gpode_kl_bwd.restype = i32
     lib.gpode_kl_bwd.argtypes = [i32, i32, _fp, _fp, _fp, _fp, _fp, _fp]
+    u64 = ctypes.c_uint64
+    lib.gpode_philox_fill.restype = i32
+    lib.gpode_philox_fill.argtypes = [i32, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), u64, u64, _fp]
+    lib.gpode_philox_raw.restype = i32
+    lib.gpode_philox_raw.argtypes = [_fp, _fp, _fp, i32, _fp]
+    lib.gpode_bernoulli_workspace_bytes.restype = sz
+    lib.gpode_bernoulli_workspace_bytes.argtypes = [i32]
+    lib.gpode_bernoulli_lhood_fwd.restype = i32
+    lib.gpode_bernoulli_lhood_fwd.argtypes = [i32, i32, ctypes.c_int64, _fp, _fp, _fp, _fp, sz, _fp]
+    lib.gpode_bernoulli_lhood_bwd.restype = i32
+    lib.gpode_bernoulli_lhood_bwd.argtypes = [i32, i32, ctypes.c_int64, _fp, _fp, _fp, _fp, _fp]
     _lib = lib
     return lib
 

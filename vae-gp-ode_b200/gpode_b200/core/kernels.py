@@ -157,6 +157,14 @@ class DivergenceFreeKernel(RBF):
         ww = torch.einsum("asb,csb->sac", omega, omega)
         return norm[:, None, :] * torch.eye(D, device=omega.device, dtype=omega.dtype) - ww / norm[:, None, :]
 
+    @staticmethod
+    def operator_B_batched(omega):
+        """operator_B for a stack of samples: omega (L,D,S,D) -> (L,S,D,D), one einsum"""
+        D = omega.shape[1]
+        norm = omega.square().sum(1).sqrt()                                   # (L,S,D)
+        ww = torch.einsum("lasb,lcsb->lsac", omega, omega)
+        return norm[:, :, None, :] * torch.eye(D, device=omega.device, dtype=omega.dtype) - ww / norm[:, :, None, :]
+
     def build_cache(self, S, device):
         self.rff_weights = sample_normal((2 * S, self.D_out)).to(device)
         self.rff_omega = self.sample_freq(S, device=device)

@@ -21,6 +21,22 @@ def sample_normal(shape, seed=None):
     return torch.tensor(rng.normal(size=shape).astype(np.float32))
 
 
+_rng = {"mode": "host", "stream": None}
+
+
+def set_rng(mode, seed=0):
+    """Where the function-sample draws (w, eps, phase, eps_u) come from.
+    "host" (default): the numpy helpers above and in core/kernels.py, like the reference -- and like the reference they are what the
+    parity tests patch to replay recorded draws; every draw is a host array copied to the device.
+    "device": a Philox4x32-10 stream on the GPU (functional.PhiloxStream, csrc/elbo_kernels.cu): all four tensors of all L samples in
+    one launch, no host RNG time and no H2D copy; same distributions, different numbers (the reference's own draws are unseeded,
+    kernels.py:17, so no run of it is reproducible either).  Only the fused CUDA setup paths use it."""
+    if mode not in ("host", "device"):
+        raise ValueError("rng mode must be 'host' or 'device'")
+    _rng["mode"] = mode
+    _rng["stream"] = GF.PhiloxStream(seed) if mode == "device" else None
+
+
 class FieldSample:
     """The tensors that pin one function sample (what build_cache leaves on the kernel), with a leading
     sample axis so that several samples can share one launch."""
@@ -82,41 +98,47 @@ class SVGP_Layer(torch.nn.Module):
         csrc/setup_kernels.cu; q_diag and CPU tensors (host-logic unit tests) use torch ops; DF see _df_batched_setup."""
         return self.kernel_n == "RBF" and not self.q_diag and self.inducing_loc.optvar.is_cuda and self.M <= 512
 
+    def _df_fused_setup(self):
+        return (self.kernel_n == "DF" and not self.q_diag and self.inducing_loc.optvar.is_cuda and self.D_in <= 8
+                and self.M <= 512 and self.M * self.D_in <= 4096)
+
     def _df_batched_setup(self, L):
         """DF kernel on a CUDA device: the L function samples of a rollout share Z, lengthscales and variance, hence ONE
         (M D x M D) Gram matrix and ONE Cholesky factor (the reference rebuilds and refactors it for every sample,
         kernels.py:376-387 called from svpy.py:118-121 inside the serial MC loop); the L right-hand sides are solved together.
-        The factorisation and the two triangular solves run in float64 (cuSOLVER / cuBLAS through torch.linalg): K(Z,Z) has
-        cond 1e4..1e6 and the fp32 factorisation is the largest single error of the reference's own
-        gradients -- here nu is exact to fp32 rounding.  Inducing sample, prior at Z (CUDA field kernel with nu = 0) and
-        B(omega) are batched over L as well."""
+        Gram matrix, factorisation (blocked, spread over the chip), both triangular solves and their closed-form backward run on
+        the setup kernels of libgpode.so in float64 (csrc/setup_kernels.cu): K(Z,Z) has cond 1e4..1e6 and an
+        fp32 factorisation is the largest single error of the reference's own gradients -- here nu is exact to fp32 rounding.
+        Inducing sample, prior at Z (CUDA field kernel with nu = 0) and B(omega) are batched over L as well."""
         k = self.kern
-        draws = [self._draw() for _ in range(L)]
-        eps, phase, w, eps_u = (torch.stack([d[i] for d in draws]) for i in range(4))
+        eps, phase, w, eps_u = self._draws(L)
         Z, ell, var = self.inducing_loc(), k.lengthscales, k.variance
         u = GF.inducing_sample(self.Us_sqrt.optvar, self.Um(), eps_u)                      # (L,M,D)
         omega = eps / ell.t()[None, :, None, :]                                            # (L,D,S,D)  sample_freq, kernels.py:120-124
-        B = torch.stack([k.operator_B(omega[l]) for l in range(L)])                        # (L,S,D,D)
+        B = k.operator_B_batched(omega)                                                    # (L,S,D,D)
         n = self.M * self.D_out
         nu0 = torch.zeros((L, n, 1), device=Z.device)
         u_prior, _ = GF.gp_field(Z[None].expand(L, -1, -1), Z, nu0, eps, phase, w, ell, var, k.variant, B)   # rff_forward(Z), (L,M,D)
-        f64 = torch.float64
-        X = Z.to(f64)
-        d = X[None, :, :] - X[:, None, :]
-        r2 = d.square().sum(-1)[:, :, None, None]
-        c = ell.to(f64).pow(-2)
-        H = d[:, :, :, None] * d[:, :, None, :] * c + torch.eye(self.D_in, device=Z.device, dtype=f64) * ((self.D_in - 1.0) - r2 * c)
-        Ku = (var.to(f64) * torch.exp(-0.5 * r2 * c) * H * c).permute(0, 2, 1, 3).reshape(n, n)    # kernels.py:289-303
-        Lc, info = torch.linalg.cholesky_ex(Ku + jitter * torch.eye(n, device=Z.device, dtype=f64))   # lower triangle only, like the reference
-        self.chol_info = info.reshape(1)
+        nu, self.chol_info = GF.compute_nu(Z, ell, var, u_prior, u, k.variant, return_info=True)             # (L, M D, 1)
         if self.check_cholesky:
             self.cholesky_ok(raise_error=True)
-        rhs_p = u_prior.reshape(L, n).t().to(f64)                                           # vec layout m*D+i (kernels.py:384-386)
-        rhs_u = u.reshape(L, n).t().to(f64)
-        a = torch.linalg.solve_triangular(Lc, rhs_p, upper=False)
-        nu = torch.linalg.solve_triangular(Lc.t(), rhs_u - a, upper=True).t().to(torch.float32).reshape(L, n, 1)
         k.rff_omega, k.rff_B, k.nu = omega[-1], B[-1], nu[-1]                               # the last sample stays on the kernel
         return FieldSample(k.variant, Z, ell, var, eps, phase, w, nu, B)
+
+    def _draws(self, L):
+        """(eps, phase, w, eps_u) of L function samples, each with a leading axis L"""
+        if _rng["mode"] == "device":
+            dev, k = self.inducing_loc.optvar.device, self.kern
+            shared = self.kernel_n == "RBF" and not k.dimwise
+            S2 = 2 * self.S if self.kernel_n == "DF" else self.S
+            w = torch.empty((L, S2, self.D_out), device=dev)
+            eps = torch.empty((L, self.D_in, self.S) if shared else (L, self.D_in, self.S, self.D_out), device=dev)
+            phase = torch.empty((L, 1, self.S) if shared else (L, 1, self.S, self.D_out), device=dev)
+            eps_u = torch.empty((L, self.M, self.D_out), device=dev)
+            _rng["stream"].fill([w, eps, phase, eps_u], [GF.NORMAL, GF.NORMAL, GF.UNIFORM, GF.NORMAL])
+            return eps, phase * (2 * np.pi), w, eps_u
+        draws = [self._draw() for _ in range(L)]
+        return tuple(torch.stack([d[i] for d in draws]) for i in range(4))
 
     def _draw(self):
         """host draws of one function sample in the reference's order (kernels.py:126-137, svpy.py:94): w, eps, phase, eps_u."""
@@ -129,7 +151,7 @@ class SVGP_Layer(torch.nn.Module):
         reference's order, the GPU work -- inducing sample, prior at Z, K(Z,Z) + Cholesky + whitened solves -- is one
         batched pass.  Returns a FieldSample with leading axis L."""
         self._cache = None      # a cache left by an earlier build_cache() is stale from here on
-        if self.kernel_n == "DF" and not self.q_diag and self.inducing_loc.optvar.is_cuda:
+        if self._df_fused_setup():
             return self._df_batched_setup(L)
         if not self._fused_setup():
             samples = []
@@ -137,8 +159,7 @@ class SVGP_Layer(torch.nn.Module):
                 self.build_cache()
                 samples.append(self.field_sample())
             return FieldSample.stack(samples)
-        draws = [self._draw() for _ in range(L)]
-        eps, phase, w, eps_u = (torch.stack([d[i] for d in draws]) for i in range(4))
+        eps, phase, w, eps_u = self._draws(L)
         k = self.kern
         Z, ell, var = self.inducing_loc(), k.lengthscales, k.variance
         u = GF.inducing_sample(self.Us_sqrt.optvar, self.Um(), eps_u)                      # (L,M,D_out)
@@ -168,7 +189,7 @@ class SVGP_Layer(torch.nn.Module):
 
     def build_cache(self):
         """Fix one function sample: feature draws, inducing sample, nu (svpy.py:103-121; same draw order)."""
-        if self._fused_setup() or (self.kernel_n == "DF" and not self.q_diag and self.inducing_loc.optvar.is_cuda):
+        if self._fused_setup() or self._df_fused_setup():
             self._cache = self.build_cache_batched(1)
             return
         self._cache = None

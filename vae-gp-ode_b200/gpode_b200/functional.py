@@ -153,8 +153,10 @@ def gp_rollout(z0, ts, Z, nu, eps, phase, w, ell, var, variant, order=1, method=
 # ------------------------------------------------------------------------------------------------
 class ComputeNu(torch.autograd.Function):
     """nu = Lc^-T (u - Lc^-1 u_prior), Lc = chol(K(Z,Z) + 1e-5 I) for L samples at once -- RBF.compute_nu fused with K(Z)
-    (reference experiments/model/core/kernels.py:98-110,155-172; svpy.py:118-121).  RBF variants only.
-    u_prior, u: (L,M,D_out); returns (nu, info): nu (L,D_out,M,1) [dimwise] or (L,M,D_out) [shared]; info (Kc,) int32 on the device,
+    (reference experiments/model/core/kernels.py:98-110,155-172; svpy.py:118-121), and DivergenceFreeKernel.compute_nu fused with
+    the (M D x M D) Gram matrix (kernels.py:289-303,376-387): the L samples share Z, lengthscales and variance, hence ONE matrix and
+    ONE factorisation (spread over the chip, csrc/setup_kernels.cu k_chol_step) where the reference refactors it per sample.
+    u_prior, u: (L,M,D_out); returns (nu, info): nu (L,D_out,M,1) [dimwise], (L,M,D_out) [shared] or (L,M*D,1) [DF]; info (Kc,) int32 on the device,
     0 or 1 + the index of the first non-positive pivot of K(Z,Z) + jitter -- where torch.linalg.cholesky raises in the reference.
     No host synchronisation happens here; SVGP_Layer reads info (one 4-byte D2H) when its check_cholesky attribute is set."""
 
@@ -173,11 +175,12 @@ class ComputeNu(torch.autograd.Function):
             nbytes = lib.gpode_nu_workspace_bytes(ctypes.byref(p))
             nsave = lib.gpode_nu_save_floats(ctypes.byref(p))
             if nbytes == 0 or nsave == 0:
-                raise RuntimeError("gpode_compute_nu: unsupported problem (RBF variants, M <= 512, D <= 16 only)")
+                raise RuntimeError("gpode_compute_nu: unsupported problem (M <= 512, D <= 16; DF: D <= 8 and M * D <= 4096)")
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             save = torch.empty(nsave, dtype=torch.float32, device=dev)
             info = torch.zeros(D_out if variant == _lib.RBF_DIMWISE else 1, dtype=torch.int32, device=dev)
-            nu = torch.empty((L, D_out, M, 1) if variant == _lib.RBF_DIMWISE else (L, M, D_out), dtype=torch.float32, device=dev)
+            shape = {_lib.RBF_DIMWISE: (L, D_out, M, 1), _lib.DF: (L, M * D_out, 1)}.get(variant, (L, M, D_out))
+            nu = torch.empty(shape, dtype=torch.float32, device=dev)
             rc = lib.gpode_compute_nu_fwd(ctypes.byref(p), _lib.ptr(u_prior), _lib.ptr(u), _lib.ptr(nu), _lib.ptr(save), _lib.ptr(info),
                                           _lib.ptr(ws), nbytes, _lib.stream_handle(dev))
         _lib.check(rc, "gpode_compute_nu_fwd")
@@ -285,3 +288,78 @@ def inducing_sample(Lq_packed, Um, eps_u):
 
 def whitened_kl(Lq_packed, Um):
     return WhitenedKL.apply(Lq_packed, Um)
+
+
+# ------------------------------------------------------------------------------------------------
+# either side of the flow (csrc/elbo_kernels.cu): device-side draws, fused Bernoulli log-likelihood
+# ------------------------------------------------------------------------------------------------
+NORMAL, UNIFORM = 0, 1
+
+
+class PhiloxStream:
+    """Counter-based draw stream on one CUDA device (Philox4x32-10, include/gpode.h gpode_philox_fill): a pure function of
+    (seed, offset) -- `offset` advances with every call, so a stream replays exactly from its seed.  Replaces the host numpy
+    helpers of the reference (kernels.py:13-26, svpy.py:12-18) and the H2D copies of their results when selected with
+    ``gpode_b200.set_rng("device", seed)``: same distributions, different numbers (the reference's own draws are unseeded)."""
+
+    def __init__(self, seed=0):
+        self.seed, self.offset = int(seed) & (2 ** 64 - 1), 0
+
+    def fill(self, outs, kinds):
+        """outs: up to four contiguous fp32 CUDA tensors filled in ONE launch; kinds: NORMAL / UNIFORM per tensor"""
+        lib = _lib.load()
+        n = len(outs)
+        assert 1 <= n <= 4 and len(kinds) == n
+        _lib.require_cuda(*outs)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in outs])
+        counts = (ctypes.c_uint64 * n)(*[t.numel() for t in outs])
+        ks = (ctypes.c_int32 * n)(*[int(k) for k in kinds])
+        dev = outs[0].device
+        with torch.cuda.device(dev):
+            rc = lib.gpode_philox_fill(n, ptrs, counts, ks, self.seed, self.offset, _lib.stream_handle(dev))
+        _lib.check(rc, "gpode_philox_fill")
+        self.offset += (max(t.numel() for t in outs) + 3) // 4
+        return outs
+
+
+class BernoulliLhood(torch.autograd.Function):
+    """lhood[n] = mean_l sum_{t,pixels} log(z) x + log(1 - z)(1 - x): Decoder.log_prob (reference core/vae.py:136-153) fused with
+    the reduction elbo() applies to it (create_model.py:51-53), without X.repeat(L) and without a (L,N,T,1,28,28) intermediate.
+    x (N,T,...) targets, z (L,N,T,...) reconstructions; gradient for z only (the data carries none)."""
+
+    @staticmethod
+    def forward(ctx, x, z):
+        lib = _lib.load()
+        x, z = x.contiguous(), z.contiguous()
+        _lib.require_cuda(x, z)
+        L, N = z.shape[0], z.shape[1]
+        P = z[0, 0].numel()
+        if x.shape[0] != N or x[0].numel() != P:
+            raise RuntimeError("x must be (N, ...) and z (L, N, ...) over the same trailing shape, got %s / %s" % (tuple(x.shape), tuple(z.shape)))
+        dev = z.device
+        lhood = torch.empty(N, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nbytes = lib.gpode_bernoulli_workspace_bytes(N)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            rc = lib.gpode_bernoulli_lhood_fwd(L, N, P, _lib.ptr(z), _lib.ptr(x), _lib.ptr(lhood), _lib.ptr(ws), nbytes, _lib.stream_handle(dev))
+        _lib.check(rc, "gpode_bernoulli_lhood_fwd")
+        ctx.save_for_backward(x, z)
+        return lhood
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, z = ctx.saved_tensors
+        L, N = z.shape[0], z.shape[1]
+        P = z[0, 0].numel()
+        g = g.contiguous().to(torch.float32)
+        dz = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            rc = lib.gpode_bernoulli_lhood_bwd(L, N, P, _lib.ptr(z), _lib.ptr(x), _lib.ptr(g), _lib.ptr(dz), _lib.stream_handle(z.device))
+        _lib.check(rc, "gpode_bernoulli_lhood_bwd")
+        return None, dz
+
+
+def bernoulli_lhood(x, z):
+    """(N,) per-trajectory Bernoulli log-likelihood of reconstructions z (L,N,T,...) for targets x (N,T,...), averaged over L"""
+    return BernoulliLhood.apply(x, z)
