@@ -84,27 +84,32 @@ def algorithmic_work(w):
 def pipe_model(w, tc_rates):
     """Per trajectory-step: the time each pipe needs at its peak / measured issue rate, in SM-cycles summed over the chip's SMs
     (divide by 148 x clock for seconds).  D <= 8 and DF: everything on the FP32 / MUFU pipes.  RBF at D > 8 on a chip-filling batch:
-    the D_in-long dot products run on the tensor pipes WITH their precision splits (that is executed work, stated as such):
-      forward  : tcgen05 kind::tf32, 3xTF32 along K = 56: 7 MMAs (128 x 128 x 8) per 128 x 128 block, measured cycles per MMA;
-      reverse  : mma.sync, 7 HMMA per (16 x 8) tile (3 fp16 k16 for theta, 2 x (TF32 k8 + bf16 k16) for the second product);
-      gradients: mma.sync, 7 HMMA per (16 x 8) tile of the INDUCING units (recomputation: no algorithmic work of its own);
-      an HMMA issues every 8.55 cycles per scheduler on B200 whatever its type (profiles/mma_peak_r01.txt).
-    SFU: algorithmic = 2 transcendentals per (state, k, unit) and stage; executed = 3 (the gradient pass re-evaluates)."""
+    the contractions run on tcgen05 WITH their precision splits (that is executed work, stated as such), per (128 states x 128 units)
+    item, cycles as measured in isolation (tools/tc_probe2, tools/tc_probe3 -> profiles/tc_probe*_r02.json):
+      forward  : kind::tf32, 3xTF32 along K = 56: 7 MMAs (128 x 128 x 8), ~452 cycles;
+      reverse  : theta = 3 kind::f16 MMAs (fp16 head / remainder) + 1 kind::tf32 for the offsets, ~400 cycles;
+                 Q = tau P: 16 kind::f16 (bf16 head + remainder planes) k-steps of N = 48, ~710 cycles (bound by reading the 64 KB tau tile);
+                 PG = tau^T X' (inducing items only): 16 k-steps, ~810 cycles -- the parameter-gradient statistics come from the SAME tau,
+                 so nothing is evaluated a third time (round 1: a separate recomputation pass).
+    SFU: 2 transcendentals per (state, k, unit) and stage, executed = algorithmic."""
     st = STAGES[w["method"]]
     work = algorithmic_work(w)
     out = {"sfu_alg_cycles": work["sfu"] / 16.0, "fp32_alg_cycles": work["flops"] / 256.0, "tensor_cycles": 0.0, "fp32_residual_cycles": work["flops"] / 256.0}
     tensor_path = w["variant"] != "df" and w["D_in"] > 8 and w["N"] * w["L"] >= 32768
     if tensor_path:
-        units, ind = w["D_out"] * (w["S"] + w["M"]), w["D_out"] * w["M"]
+        units = w["D_out"] * (w["S"] + w["M"])
+        items_s, items_m = w["D_out"] * -(-w["S"] // 128), w["D_out"] * -(-w["M"] // 128)        # items per evaluation of a 128-state tile
         fwd = st * units / 16384.0 * 7 * tc_rates["tcgen05_tf32_n128_cycles_per_mma"]
-        hmma = st * (units / 128.0 * 7 + ind / 128.0 * 7) * tc_rates["hmma_issue_cycles"] / 4.0
-        out["tensor_cycles"] = fwd + hmma
-        out["tensor_split"] = {"forward": "3xTF32 (K = 56 for D_in = 16)", "reverse_sweep": "fp16 head+remainder theta (3 MMAs) + TF32 head / bf16 cross second product (4 MMAs)",
-                               "parameter_gradients": "same 7 MMAs per tile, inducing units only"}
+        bwd = st * (items_s * (tc_rates["bwd_theta_cycles"] + tc_rates["bwd_q_cycles"]) +
+                    items_m * (tc_rates["bwd_theta_cycles"] + tc_rates["bwd_q_cycles"] + tc_rates["bwd_pg_cycles"])) / 128.0
+        out["tensor_cycles"] = fwd + bwd
+        out["tensor_split"] = {"forward": "3xTF32 (K = 56 for D_in = 16), tcgen05 kind::tf32",
+                               "reverse_sweep": "theta: fp16 head + remainder, 3 kind::f16 + 1 kind::tf32 MMA; Q = tau P and PG = tau^T X': bf16 head + remainder "
+                                                "planes of tau from shared memory, 16 kind::f16 k-steps each (fused: one tau per stage)"}
         # what stays on the FP32 pipe algorithmically: everything except the D_in-long dot products (forward 1x, backward 2x)
         moved = 3 * st * 2 * units * w["D_in"]
         out["fp32_residual_cycles"] = max(work["flops"] - moved, 0) / 256.0
-        out["sfu_exec_cycles"] = (work["sfu"] + st * ind) / 16.0
+        out["sfu_exec_cycles"] = work["sfu"] / 16.0
     else:
         rbf = w["variant"] != "df"
         ind = w["D_out"] * w["M"] if rbf else w["M"] * w["D_in"] ** 2
@@ -205,7 +210,8 @@ def tc_forward(w):
 
 def kernel_launches(w):
     """kernels of libgpode.so launched by one forward + backward rollout call (csrc/api.cu):
-    RBF forward: k_rbf_pack [+ k_rbf_pack_tc] + k_rollout_fwd; backward: k_rbf_pack + k_rollout_bwd + k_rbf_pgrad* + 2 finalize kernels;
+    RBF forward: k_rbf_pack [+ k_rbf_pack_tc] + k_rollout_fwd; backward: k_rbf_pack + k_rollout_bwd + (D <= 8: k_rbf_pgrad; D > 8 on a chip-filling
+    batch: k_rbf_pack_tcb, the parameter gradients come out of the fused reverse sweep) + 2 finalize kernels;
     DF forward: k_df_pack + k_rollout_fwd; backward: k_df_pack + k_rollout_bwd + k_df_pgrad + finalize."""
     if w["variant"] == "df":
         return 6
@@ -327,20 +333,22 @@ def run_ours(args):
     d2h = [0]
     params = [gp.kern.unconstrained_lengthscales, gp.kern.unconstrained_variance, gp.inducing_loc.optvar, gp.Um.optvar,
               gp.Us_sqrt.optvar]
-    seeded_draw_patch(77 + rank)
+    # function-sample draws on the device (gpode_b200.set_rng: one Philox launch per rollout instead of host numpy + H2D copies; the
+    # reference's own host draws are unseeded, so no number of them is pinned anywhere): the step's host input is z0
+    import gpode_b200
+    gpode_b200.set_rng("device", seed=77 if args.scaling == "strong" else 77 + rank)   # strong: every rank draws the SAME function samples
 
     def e2e_step(record):
         for p_ in params:
             p_.grad = None
         z = z0_host.to(dev, non_blocking=True).requires_grad_(True)
-        traj = flow.forward_samples(z, ts, L)                 # build_cache (host draws -> H2D) x L, one rollout launch
+        traj = flow.forward_samples(z, ts, L)                 # L function samples (device draws, batched setup), one rollout launch
         loss = (traj * dtraj).sum() + flow.kl()
         loss.backward()
         flat = allreduce_grads([p_.grad for p_ in params])
         host = [loss.detach().cpu()] + [p_.grad.cpu() for p_ in params] + [z.grad.cpu()]
         if record is not None and not h2d[0]:
-            draws = L * (w["S"] * w["D_out"] + w["D_in"] * w["S"] * w["D_out"] + w["S"] * w["D_out"] + w["M"] * w["D_out"]) * 4
-            h2d[0] = z0_host.numel() * 4 + draws
+            h2d[0] = z0_host.numel() * 4
             d2h[0] = sum(h.numel() * 4 for h in host)
 
     e2e_warm = min(args.warmup, 3)
@@ -359,13 +367,14 @@ def run_ours(args):
     per_gpu_rate = steps_per_pass / (ms_step * 1e-3)
     achieved_tflops = work["flops"] * per_gpu_rate / 1e12
     # measured issue rates of the tensor pipes (tools/tc_probe2, tools/mma_peak; fallbacks = the round-2 measurements under profiles/)
-    tc_rates = {"tcgen05_tf32_n128_cycles_per_mma": 452.0 / 7.0, "hmma_issue_cycles": 8.55, "source": "profiles/tc_probe2_r02.json, profiles/mma_peak_r01.txt"}
+    tc_rates = {"tcgen05_tf32_n128_cycles_per_mma": 452.0 / 7.0, "bwd_theta_cycles": 400.0, "bwd_q_cycles": 710.0, "bwd_pg_cycles": 810.0,
+                "source": "profiles/tc_probe2_r02.json, tools/tc_probe3 (csrc/rbf_bwd_tc.cuh header)"}
     probe = os.path.join(ROOT, "tools", "tc_probe2")
     if world == 1 and os.path.exists(probe) and not args.no_cpu_baseline:
         try:
             pj = json.loads(subprocess.check_output([probe], timeout=120).decode().strip().splitlines()[-1])
             tc_rates["tcgen05_tf32_n128_cycles_per_mma"] = pj["cycles_per_rep"]["theta_7xSS_tf32_N128"][0] / 7.0
-            tc_rates["source"] = "tools/tc_probe2 run inside this bench; profiles/mma_peak_r01.txt"
+            tc_rates["source"] = "tools/tc_probe2 run inside this bench; tools/tc_probe3 (csrc/rbf_bwd_tc.cuh header)"
         except Exception:
             pass
     pm = pipe_model(w, tc_rates)
@@ -383,7 +392,8 @@ def run_ours(args):
             "peak_source": "FP32: 148 SM x 128 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json (%s); SFU: 148 x 16 / clk; tensor: measured issue rates (%s); "
                            "not an HBM-bound path" % (peak_src, tc_rates["source"]),
             "note": ("frac = the fraction of the measured time the BINDING pipe needs at its peak rate (pipes: sfu = algorithmic transcendentals, "
-                     "sfu_executed = incl. the re-evaluation in the parameter-gradient pass, tensor = the executed MMAs incl. their precision splits "
+                     "sfu_executed = what the kernels evaluate (D <= 8: incl. the re-evaluation in the separate parameter-gradient pass; D > 8: fused, "
+                     "equal to algorithmic), tensor = the executed MMAs incl. their precision splits "
                      "at the measured issue rates, fp32_residual = algorithmic FP32 work that stays on the FMA pipe).  achieved / peak / "
                      "frac_fp32_algorithmic keep the SURVEY 8(d) definition: ALL algorithmic flops over the FP32-pipe peak (can exceed what the "
                      "FP32 pipe really executes once the dot products run on tensor cores)."),
@@ -406,8 +416,9 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "dtype_note": ("fp32 inputs, outputs, accumulation and transcendentals; where dot products run on tensor cores (RBF, D_in > 8) the operands are "
-                           "split so that >= 21 mantissa bits enter every product: forward 3xTF32, reverse sweep / parameter gradients fp16 head + 2^11-scaled "
-                           "remainder for theta, TF32 head + bf16 cross terms for the second product; the per-rollout setup (K(Z,Z), Cholesky, solves) runs in fp64"),
+                           "split so that >= 16-21 mantissa bits enter every product: forward 3xTF32; fused reverse sweep: fp16 head + 2^11-scaled remainder "
+                           "for theta, bf16 head + remainder planes of tau (fp32 exponent range) for the state- and parameter-gradient products, fp32 "
+                           "accumulation in tensor memory; the per-rollout setup (K(Z,Z), Cholesky, solves) runs in fp64"),
             "config": {"workload": args.workload, "per_gpu": {k: w[k] for k in ("N", "L", "T", "D_in", "D_out", "M", "S", "method", "order", "variant")},
                        "total_trajectories": N_total if args.scaling == "strong" or world == 1 else world * N_total,
                        "traj_steps_per_gpu_per_step": steps_per_pass, "traj_steps_per_job_per_step": steps_job,
@@ -416,7 +427,7 @@ def run_ours(args):
                                 ((T - 1) * STAGES[w["method"]] * (2 * D + w["D_out"]) * N * L * 4 / 1e9)},
             "roofline": roof,
             "e2e": {"value": round(e2e_value, 1), "unit": "traj-steps/s", "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),
-                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+                    "ms_per_step": round(ms_e2e / args.steps, 3), "draws": "device (Philox4x32-10, gpode_b200.set_rng('device'))"},
             "gpu_launches": kernel_launches(w) * args.steps, "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
         try:

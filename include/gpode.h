@@ -93,10 +93,11 @@ const char* gpode_error_string(int code);
  *   RBF variants at D_in > 8 and >= 32,768 states: */
 #define GPODE_FLAG_FWD_MMA 1      /* forward sweep on the warp-level tensor path (mma.sync) instead of tcgen05 */
 #define GPODE_FLAG_FWD_TCGEN05 2  /* forward sweep on tcgen05 even when its 256-unit operand tiles are > 15 % padding */
-#define GPODE_FLAG_BWD_MMA 4      /* reverse sweep on the warp-level tensor path (mma.sync): the default, the flag pins it */
-#define GPODE_FLAG_BWD_TCGEN05 16  /* reverse sweep on tcgen05 / tensor memory (rbf_bwd_tc.cuh): measured alternative, not the default */
-#define GPODE_FLAG_DETERMINISTIC 8 /* parameter-gradient partial sums are reduced in a fixed order (no float atomics on the
-                                      shared accumulators): bit-identical gradients run to run, slightly slower */
+#define GPODE_FLAG_BWD_MMA 4      /* reverse sweep + separate parameter-gradient pass on the warp-level tensor path (mma.sync) */
+#define GPODE_FLAG_BWD_TCGEN05 16 /* fused reverse sweep + parameter gradients on tcgen05 / tensor memory (rbf_bwd_tc.cuh): the default, the flag pins it */
+/* (bit 8 is reserved.)  Parameter gradients are sums over all state evaluations accumulated with floating-point atomics, so their
+ * last bits differ from run to run; tests/test_gpu_rbf.py::test_run_to_run_spread bounds the spread (<= 2e-6 of the gradient norm,
+ * below the parity error against the fp64 oracle).  Trajectories, f and dL/dz0 involve no atomics and are bit-reproducible. */
 /* Which forward-sweep kernel family gpode_field_fwd / gpode_rollout_fwd will launch for this problem (shapes and the flags
  * above decide; no CUDA call is made): */
 #define GPODE_FWD_FFMA 0   /* FP32 / MUFU pipes (every D_in <= 8, small batches, the divergence-free kernel) */

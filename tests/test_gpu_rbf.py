@@ -388,3 +388,32 @@ def test_tensor_path_extreme_magnitudes(fwd_kernel, bwd_kernel, scale_x, scale_e
         e = rel(a, b)
         print("extreme (%g, %g) %s: %.2e (tol %.1e)" % (scale_x, scale_ell, nm, e, gtol))
         assert e < gtol, (nm, e, gtol)
+
+
+@pytest.mark.parametrize("shape", ["small", "tensor"])
+def test_run_to_run_spread(shape):
+    """The parameter gradients are accumulated with floating-point atomics (include/gpode.h): two runs of the same backward differ
+    in their last bits.  This bounds the spread -- and pins what IS bit-reproducible (trajectories, dL/dz0: no atomics)."""
+    rs = np.random.RandomState(5)
+    if shape == "small":
+        D, M, S, N, T = 6, 100, 256, 2000, 6
+    else:
+        D, M, S, N, T = 16, 512, 256, 33000, 3          # the fused tcgen05 reverse sweep (red.global of the PG tiles)
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
+    Z, ell, var = f32(rs.normal(size=(M, D))), f32(1.5 + rs.uniform(size=(D, D))), f32(0.5 + rs.uniform(size=D))
+    nu, eps = f32(0.3 * rs.normal(size=(1, D, M, 1))), f32(rs.normal(size=(1, D, S, D)))
+    phase, w = f32(rs.uniform(size=(1, 1, S, D)) * 2 * np.pi), f32(rs.normal(size=(1, S, D)))
+    z0v, G = f32(rs.normal(size=(N, D))), f32(rs.normal(size=(1, N, T, D)))
+    ts = 0.1 * torch.arange(T, dtype=torch.float32, device="cuda")
+    runs = []
+    for _ in range(3):
+        leaves = [t_.clone().requires_grad_(True) for t_ in (z0v, Z, nu, ell, var)]
+        traj = _gp().gp_rollout(leaves[0], ts, leaves[1], leaves[2], eps, phase, w, leaves[3], leaves[4], "rbf_dimwise", 1, "rk4")
+        (traj * G).sum().backward()
+        runs.append([traj.detach()] + [t_.grad for t_ in leaves])
+    for r in runs[1:]:
+        assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1])           # trajectories and dz0: bit-identical
+        for nm, a, b in zip(("dZ", "dnu", "dell", "dvar"), r[2:], runs[0][2:]):
+            e = rel(a, b)
+            print("%s run-to-run %s: %.2e" % (shape, nm, e))
+            assert e < 2e-6, (nm, e)

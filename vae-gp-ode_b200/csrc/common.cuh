@@ -97,10 +97,29 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#pragma unroll 1
-  for (int i = 0; i < 4096; ++i)
-    if (mbar_try(bar, parity)) return;
-  mbar_wait_slow(bar, parity);
+  // fast path: a PTX-level poll loop (3 instructions per wake-up; the address and the parity stay in registers -- the C++ loop this
+  // replaces re-derived both on every iteration, ~15 instructions per poll and a third of all instructions the fused reverse sweep
+  // issued).  try_wait suspends the thread in hardware until the barrier is touched or the hint expires.
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 n;\n"
+      "mov.u32 n, 0;\n"
+      "GPODE_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 2000;\n"
+      "@p bra GPODE_DONE;\n"
+      "add.u32 n, n, 1;\n"
+      "setp.lt.u32 p, n, 65536;\n"
+      "@p bra GPODE_WAIT;\n"
+      "setp.ne.u32 p, n, n;\n"
+      "GPODE_DONE:\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  if (!done) mbar_wait_slow(bar, parity);
 }
 // global -> shared bulk copy, completion counted in bytes on `bar`; bytes % 16 == 0, both 16-B aligned
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

@@ -35,7 +35,7 @@
 namespace gpode {
 
 #ifndef GPODE_BT_EXP
-#define GPODE_BT_EXP 0   // timing experiments only (wrong results): 1 no PG MMAs, 2 no Q MMAs, 4 no transcendentals, 8 no tau stores, 16 no theta MMAs
+#define GPODE_BT_EXP 0   // timing experiments only (wrong results): 1 no PG MMAs, 2 no Q MMAs, 4 no transcendentals, 8 no tau stores, 16 no theta MMAs, 32 no proxy fence after the tau stores
 #endif
 
 constexpr int kBtStates = 128;                 // states per CTA
@@ -647,7 +647,7 @@ struct RbfTcBwdPolicy {
             sts128(trow + (2 + c) * 2048, hd[0], hd[1], hd[2], hd[3]);
             sts128(trow + (18 + c) * 2048, rm[0], rm[1], rm[2], rm[3]);
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (!(GPODE_BT_EXP & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) tc_arrive(tau_full(sm, slot));
           if (is_k) ++outstanding;

@@ -515,19 +515,33 @@ __global__ void __launch_bounds__(256) k_dgemm(int M, const int N, int K, const 
   if (tri & 1) k_begin = max(k_begin, j0 / GK * GK);
   if (tri & 2) k_begin = max(k_begin, i0 / GK * GK);
   if (tri & 4) k_end = min(k_end, i0 + GT);
-  for (int k0 = k_begin; k0 < k_end; k0 += GK) {
-    for (int e = tid; e < GK * GT; e += 256) {
+  // software pipeline: the global loads of chunk k0 + GK are in flight (registers) while chunk k0 is multiplied out of shared memory
+  real ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = tid + 256 * t;
       int kk, ii;
       if (ta) { kk = e / GT; ii = e - kk * GT; } else { ii = e / GK; kk = e - ii * GK; }     // consecutive threads walk the contiguous direction
       const int gi = i0 + ii, gk = k0 + kk;
-      As[kk][ii] = (gi < M && gk < K) ? (ta ? A[static_cast<size_t>(gk) * lda + gi] : A[static_cast<size_t>(gi) * lda + gk]) : real(0);
+      ra[t] = (gi < M && gk < K) ? (ta ? A[static_cast<size_t>(gk) * lda + gi] : A[static_cast<size_t>(gi) * lda + gk]) : real(0);
+      const int kb = e / GT, jj = e - kb * GT;
+      const int gkb = k0 + kb, gj = j0 + jj;
+      rb[t] = (gkb < K && gj < N) ? B[static_cast<size_t>(gkb) * ldb + gj] : real(0);
     }
-    for (int e = tid; e < GK * GT; e += 256) {
-      const int kk = e / GT, jj = e - kk * GT;
-      const int gk = k0 + kk, gj = j0 + jj;
-      Bs[kk][jj] = (gk < K && gj < N) ? B[static_cast<size_t>(gk) * ldb + gj] : real(0);
+  };
+  if (k_begin < k_end) fetch(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += GK) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = tid + 256 * t;
+      int kk, ii;
+      if (ta) { kk = e / GT; ii = e - kk * GT; } else { ii = e / GK; kk = e - ii * GK; }
+      As[kk][ii] = ra[t];
+      Bs[e / GT][e % GT] = rb[t];
     }
     __syncthreads();
+    if (k0 + GK < k_end) fetch(k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
       real va[4], vb[4];

@@ -40,7 +40,11 @@ template <class P, class S, class A>
 __device__ __forceinline__ void bind_accum(S&, const A&, long) {}
 
 #define GPODE_SWEEP_BOUNDS __launch_bounds__(P::kThreads, P::kMinBlocks)
+#ifdef GPODE_BWD_MAXNREG   // timing experiments: register cap by __maxnreg__ instead of launch bounds
+#define GPODE_SWEEP_BOUNDS_BWD __maxnreg__(GPODE_BWD_MAXNREG)
+#else
 #define GPODE_SWEEP_BOUNDS_BWD __launch_bounds__(P::kThreadsBwd, P::kMinBlocksBwd)
+#endif
 
 // smem slot of component d of this thread's r-th state (policies whose helper warps own no state may use a tighter stride: kXsStride)
 #define GPODE_XS(buf, d, r) (buf)[((d) * R + (r)) * blockDim.x + threadIdx.x]

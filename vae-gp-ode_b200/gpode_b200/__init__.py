@@ -13,7 +13,7 @@ There is no CPU path and no fallback: every evaluation goes through libgpode.so 
 raises if the library or a GPU is missing.
 """
 from . import _lib  # noqa: F401
-from ._lib import kernel_flags, FLAG_FWD_MMA, FLAG_FWD_TCGEN05, FLAG_BWD_MMA, FLAG_DETERMINISTIC, FLAG_BWD_TCGEN05  # noqa: F401
+from ._lib import kernel_flags, FLAG_FWD_MMA, FLAG_FWD_TCGEN05, FLAG_BWD_MMA, FLAG_BWD_TCGEN05  # noqa: F401
 from .functional import (gp_field, gp_rollout, GPField, GPRollout, compute_nu, inducing_sample, whitened_kl,  # noqa: F401
                          ComputeNu, InducingSample, WhitenedKL, PhiloxStream, BernoulliLhood, bernoulli_lhood)
 from .core.svpy import set_rng  # noqa: F401

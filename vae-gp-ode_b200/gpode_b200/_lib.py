@@ -121,7 +121,7 @@ def require_cuda(*tensors):
 
 
 # GpodeProblem.flags (include/gpode.h): kernel selection for the parity tests / A-B measurements; 0 = shape-driven defaults
-FLAG_FWD_MMA, FLAG_FWD_TCGEN05, FLAG_BWD_MMA, FLAG_DETERMINISTIC, FLAG_BWD_TCGEN05 = 1, 2, 4, 8, 16
+FLAG_FWD_MMA, FLAG_FWD_TCGEN05, FLAG_BWD_MMA, FLAG_BWD_TCGEN05 = 1, 2, 4, 16
 _flags = 0
 
 
