@@ -65,7 +65,7 @@ def load_reference():
     if "torchdiffeq" not in sys.modules:
         m = types.ModuleType("torchdiffeq")
         m.odeint = solvers.odeint
-        m.odeint_adjoint = solvers.odeint
+        m.odeint_adjoint = solvers.odeint_adjoint
         sys.modules["torchdiffeq"] = m
     if "matplotlib" not in sys.modules:
         try:

@@ -47,3 +47,68 @@ def odeint(func, y0, t, rtol=None, atol=None, method="rk4", options=None, **unus
         y = step(func, t0, t1 - t0, y, method)
         ys.append(y)
     return torch.stack(ys, 0)
+
+
+def _axpy(y, h, ks, cs):
+    """y + h * sum_j cs[j] * ks[j] on tuples of tensors"""
+    return tuple(yi + h * sum(c * k[i] for c, k in zip(cs, ks)) for i, yi in enumerate(y))
+
+
+def _step_tuple(F, t0, dt, y0, method):
+    """one fixed-grid step on a tuple state (torchdiffeq flattens the tuple into one vector; componentwise is the same arithmetic)"""
+    if method == "euler":
+        return _axpy(y0, dt, [F(t0, y0)], [1.0])
+    if method == "midpoint":
+        k1 = F(t0, y0)
+        return _axpy(y0, dt, [F(t0 + 0.5 * dt, _axpy(y0, dt, [k1], [0.5]))], [1.0])
+    if method == "rk4":
+        third = 1.0 / 3.0
+        k1 = F(t0, y0)
+        k2 = F(t0 + dt * third, _axpy(y0, dt, [k1], [third]))
+        k3 = F(t0 + dt * 2.0 * third, _axpy(y0, dt, [k2, k1], [1.0, -third]))
+        k4 = F(t0 + dt, _axpy(y0, dt, [k1, k2, k3], [1.0, -1.0, 1.0]))
+        return _axpy(y0, dt, [k1, k2, k3, k4], [0.125, 0.375, 0.375, 0.125])
+    raise ValueError(method)
+
+
+class _OdeintAdjoint(torch.autograd.Function):
+    """torchdiffeq/_impl/adjoint.py OdeintAdjointMethod restated for fixed-grid methods without options (the reference's call,
+    core/flow.py:76-85): forward = odeint under no_grad, keeping only the solution at the grid points; backward = for i = T-1 .. 1
+    one step of the SAME method from t[i] to t[i-1] on the augmented state (y, adj_y, adj_params) with dynamics
+    (f, -vjp_y, -vjp_params), y reset to the stored y[i-1] and dL/dy[i-1] added to adj_y after every interval.  t carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, func, method, y0, t, *params):
+        with torch.no_grad():
+            ys = odeint(func, y0, t, method=method)
+        ctx.func, ctx.method = func, method
+        ctx.save_for_backward(t, ys, *params)
+        return ys
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        t, ys, *params = ctx.saved_tensors
+        func, method = ctx.func, ctx.method
+        params = tuple(params)
+
+        def aug(tt, state):
+            y, adj_y = state[0], state[1]
+            with torch.enable_grad():
+                y = y.detach().requires_grad_(True)
+                fe = func(tt, y)
+                vjps = torch.autograd.grad(fe, (y,) + params, -adj_y, allow_unused=True)
+            vjps = [torch.zeros_like(v) if g is None else g for g, v in zip(vjps, (y,) + params)]
+            return (fe.detach(), vjps[0]) + tuple(vjps[1:])
+
+        state = (ys[-1], grad_y[-1]) + tuple(torch.zeros_like(p) for p in params)
+        for i in range(t.shape[0] - 1, 0, -1):
+            state = _step_tuple(aug, t[i], t[i - 1] - t[i], state, method)
+            state = (ys[i - 1], state[1] + grad_y[i - 1]) + tuple(state[2:])
+        return (None, None, state[1], None) + tuple(state[2:])
+
+
+def odeint_adjoint(func, y0, t, rtol=None, atol=None, method="rk4", options=None, adjoint_params=None, **unused):
+    """torchdiffeq.odeint_adjoint for the fixed-grid methods; adjoint_params defaults to func.parameters() like torchdiffeq"""
+    if adjoint_params is None:
+        adjoint_params = tuple(p for p in func.parameters() if p.requires_grad)
+    return _OdeintAdjoint.apply(func, method, y0, t, *tuple(adjoint_params))

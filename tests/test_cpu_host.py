@@ -140,5 +140,50 @@ def test_no_cpu_path():
     from gpode_b200.core.flow import Flow
     with pytest.raises(NotImplementedError):
         Flow(gp, order=1, solver="dopri5")(torch.zeros(4, 6), torch.arange(3.0))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):                 # the adjoint mode runs on the same CUDA kernels: CPU tensors raise there too
         Flow(gp, order=1, solver="rk4", use_adjoint=True)(torch.zeros(4, 6), torch.arange(3.0))
+
+
+def test_time_grid_helpers():
+    """misc/torch_utils.py:49-61 mirrors: same values as the reference's helpers"""
+    from gpode_b200.misc.torch_utils import compute_ts_dense, insert_zero_t0
+    ts = 0.1 * torch.arange(5, dtype=torch.float)
+    d = compute_ts_dense(ts, 4)
+    want = torch.cat([torch.linspace(t1, t2, 4)[:-1] for (t1, t2) in zip(ts[:-1], ts[1:])] + [ts[-1:]])      # the reference's expression
+    assert torch.equal(d, want) and d.shape[0] == 3 * 4 + 1 and torch.equal(d[::3], ts)
+    assert compute_ts_dense(ts, 1) is ts
+    z = insert_zero_t0(ts)
+    assert torch.equal(z, torch.cat([torch.tensor([0.0]), ts + ts[1] - ts[0]]))
+
+
+def test_oracle_adjoint_converges_to_the_discrete_gradient():
+    """oracle/solvers.py odeint_adjoint (torchdiffeq's adjoint restated): on a small nonlinear ODE its gradients approach the
+    exact gradients of the discrete solve as the grid is refined, at the order of the method -- and for euler on a LINEAR field
+    with a symmetric matrix both coincide exactly."""
+    from oracle import solvers
+    torch.manual_seed(0)
+
+    class Lin(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            A = torch.randn(3, 3, dtype=torch.float64)
+            self.A = torch.nn.Parameter(0.3 * (A + A.t()))
+
+        def forward(self, t, y):
+            return torch.tanh(y @ self.A)
+    f = Lin()
+    y0 = torch.randn(5, 3, dtype=torch.float64)
+    G = torch.randn(1, dtype=torch.float64)
+    errs = []
+    for T in (9, 17, 33):
+        t = torch.linspace(0, 0.8, T, dtype=torch.float64)
+        w = torch.randn(T, 5, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(1))[: T] * 0 + 1.0
+        ya = y0.clone().requires_grad_(True)
+        f.zero_grad()
+        (solvers.odeint_adjoint(f, ya, t, method="rk4") * w).sum().backward()
+        ga, gA = ya.grad.clone(), f.A.grad.clone()
+        yb = y0.clone().requires_grad_(True)
+        f.zero_grad()
+        (solvers.odeint(f, yb, t, method="rk4") * w).sum().backward()
+        errs.append(max(float((ga - yb.grad).norm() / yb.grad.norm()), float((gA - f.A.grad).norm() / f.A.grad.norm())))
+    assert errs[0] < 1e-3 and errs[2] < errs[1] < errs[0] and errs[2] < errs[0] / 20, errs

@@ -4,13 +4,16 @@
 (N,T,D_s)) but the whole fixed-grid solve -- every stage of every step, plus its reverse sweep -- is
 one CUDA launch per direction instead of a torchdiffeq Python loop.  ``Flow.forward_samples`` is the
 batched form of the serial MC loop in experiments/model/core/odegpvae.py:37-45: L function samples,
-one launch.  Fixed-grid solvers only (euler, midpoint, rk4 = 3/8 rule); adaptive solvers and the
-adjoint method are outside this path and raise."""
+one launch.  Fixed-grid solvers only (euler, midpoint, rk4 = 3/8 rule); adaptive solvers raise.
+``use_adjoint=True`` (flow.py:76, odeint_adjoint) keeps the fused forward launch and computes the gradients
+by torchdiffeq's adjoint method on the field kernels (functional.GPRolloutAdjoint).  ``ts_dense_scale``
+(main.py:83, misc/torch_utils.py:54-61) integrates on the densified grid and returns the states at ``ts``."""
 import torch
 import torch.nn as nn
 
 from .. import functional as GF
 from .._lib import METHODS, STAGES
+from ..misc.torch_utils import compute_ts_dense
 from .svpy import FieldSample
 
 
@@ -59,16 +62,17 @@ class Flow(nn.Module):
         if self.solver not in METHODS:
             raise NotImplementedError("gpode_b200 implements the fixed-grid solvers %s; got %r (adaptive solvers are "
                                       "outside the CUDA hot path)" % (sorted(METHODS), self.solver))
-        if self.use_adjoint:
-            raise NotImplementedError("use_adjoint=True is not part of the CUDA path: the fused reverse sweep already "
-                                      "differentiates the discrete solver exactly with O(T) saved stages")
         return METHODS[self.solver]
 
     def _rollout(self, z0, ts, sample):
         method = self._method()
-        traj = GF.gp_rollout(z0, ts, sample.Z, sample.nu, sample.eps, sample.phase, sample.w, sample.ell, sample.var,
-                             sample.variant, self.odefunc.order, method, sample.B)
-        self.odefunc._num_evals.fill_((ts.shape[0] - 1) * STAGES[method])
+        scale = int(getattr(self, "ts_dense_scale", 1) or 1)
+        grid = compute_ts_dense(ts, scale) if scale > 2 else ts            # (scale = 2 adds no point: linspace(t1, t2, 2)[:-1] = [t1])
+        traj = GF.gp_rollout(z0, grid, sample.Z, sample.nu, sample.eps, sample.phase, sample.w, sample.ell, sample.var,
+                             sample.variant, self.odefunc.order, method, sample.B, adjoint=self.use_adjoint)
+        self.odefunc._num_evals.fill_((grid.shape[0] - 1) * STAGES[method])
+        if grid is not ts:
+            traj = traj[:, :, :: scale - 1]                                # the states at the requested time points
         return traj
 
     def forward(self, z0, ts):

@@ -135,17 +135,103 @@ class GPRollout(torch.autograd.Function):
         return dz0, None, dZ, dnu, None, None, None, dell, dvar, dB, None, None, None
 
 
+class GPRolloutAdjoint(torch.autograd.Function):
+    """Flow.forward with ``use_adjoint=True`` (reference core/flow.py:76: torchdiffeq.odeint_adjoint): the forward is the same fused
+    rollout launch and keeps NO stage saves; the backward integrates torchdiffeq's augmented system
+        d/dt (z, a, g_theta) = (f(z), -J(z)^T a, -(df/dtheta)(z)^T a)
+    backwards over every grid interval with ONE step of the same fixed-grid method, restarting z from the stored trajectory and
+    adding dL/dz_i to a at every grid point (torchdiffeq/_impl/adjoint.py OdeintAdjointMethod.backward, restated in
+    oracle/solvers.py odeint_adjoint).  Each stage is one field evaluation + one field VJP on the CUDA kernels (gpode_field_fwd /
+    gpode_field_bwd); the stage combinations are a handful of small tensor ops.  Memory O(T) states instead of O(T stages) saves;
+    gradients are those of the continuous adjoint discretised by the solver (they differ from the default mode's exact gradient
+    of the discrete solve at O(dt^p), exactly as in the reference)."""
+
+    @staticmethod
+    def forward(ctx, z0, ts, Z, nu, eps, phase, w, ell, var, B, variant, order, method):
+        with torch.no_grad():
+            traj = GPRollout.apply(z0.detach(), ts, Z.detach(), nu.detach(), eps, phase, w, ell.detach(), var.detach(),
+                                   None if B is None else B.detach(), variant, order, method)
+        ctx.save_for_backward(ts, Z, nu, eps, phase, w, ell, var, B if B is not None else ts.new_empty(0), traj)
+        ctx.cfg = (variant, order, method, z0.dim() == 3, B is not None)
+        return traj
+
+    @staticmethod
+    def backward(ctx, dtraj):
+        lib = _lib.load()
+        ts, Z, nu, eps, phase, w, ell, var, B, traj = ctx.saved_tensors
+        variant, order, method, per_sample, has_B = ctx.cfg
+        B = B if has_B else None
+        L, M, D_in, D_out, S = _dims(variant, Z, w, nu, eps)
+        N, T = traj.shape[1], traj.shape[2]
+        dev = traj.device
+        dtraj = dtraj.contiguous()
+        tsh = ts.detach().cpu().tolist()
+        q = D_out
+        with torch.cuda.device(dev):
+            p = _lib.make_problem(variant, L, N, D_in, D_out, M, S, Z, ell, var, eps, phase, w, nu, B)
+            ws, nbytes = _lib.workspace(p, 2, _lib.EULER, dev)
+            stream = _lib.stream_handle(dev)
+            f, fp = torch.empty((L, N, D_out), device=dev), torch.empty((L, N, D_out), device=dev)
+            names = ["Z", "ell", "var", "nu"] + (["B"] if has_B else [])
+            like = dict(Z=Z, ell=ell, var=var, nu=nu, B=B)
+            acc = {k: torch.zeros_like(like[k]) for k in names}
+            buf = {k: torch.empty_like(like[k]) for k in names}
+            grads = _lib.GpodeParamGrads(_lib.ptr(buf["Z"]), _lib.ptr(buf["ell"]), _lib.ptr(buf["var"]), _lib.ptr(buf["nu"]),
+                                         _lib.ptr(buf["B"]) if has_B else None)
+            dx = torch.empty((L, N, D_in), device=dev)
+
+            def F(z, a, weight):
+                """(dz/dt, da/dt) at (z, a); adds weight * d g_theta / dt to acc"""
+                z = z.contiguous()
+                _lib.check(lib.gpode_field_fwd(ctypes.byref(p), _lib.ptr(z), _lib.ptr(f), _lib.ptr(fp), _lib.ptr(ws), nbytes, stream), "gpode_field_fwd")
+                g = a if order == 1 else a[..., q:]
+                g = g.contiguous()
+                _lib.check(lib.gpode_field_bwd(ctypes.byref(p), _lib.ptr(z), _lib.ptr(g), _lib.ptr(f), _lib.ptr(fp), _lib.ptr(dx), ctypes.byref(grads),
+                                               _lib.ptr(ws), nbytes, stream), "gpode_field_bwd")
+                for k in names:
+                    acc[k].add_(buf[k], alpha=-weight)
+                if order == 1:
+                    return f.clone(), -dx
+                fz = torch.cat([z[..., q:], f], -1)
+                ka = -dx
+                ka[..., q:] -= a[..., :q]            # d/dv of the position rows dz_s/dt = v
+                return fz, ka
+
+            a = dtraj[:, :, T - 1].clone()
+            for i in range(T - 1, 0, -1):
+                h = tsh[i - 1] - tsh[i]
+                z = traj[:, :, i]
+                if method == _lib.EULER:
+                    k1z, k1a = F(z, a, h)
+                    a = a + h * k1a
+                elif method == _lib.MIDPOINT:
+                    k1z, k1a = F(z, a, 0.0)
+                    _, k2a = F(z + 0.5 * h * k1z, a + 0.5 * h * k1a, h)
+                    a = a + h * k2a
+                else:   # rk4 = 3/8 rule (torchdiffeq rk4_alt_step_func)
+                    k1z, k1a = F(z, a, h / 8)
+                    k2z, k2a = F(z + h * k1z / 3, a + h * k1a / 3, 3 * h / 8)
+                    k3z, k3a = F(z + h * (k2z - k1z / 3), a + h * (k2a - k1a / 3), 3 * h / 8)
+                    _, k4a = F(z + h * (k1z - k2z + k3z), a + h * (k1a - k2a + k3a), h / 8)
+                    a = a + h * (k1a + 3 * (k2a + k3a) + k4a) / 8
+                a = a + dtraj[:, :, i - 1]
+        dz0 = a if per_sample else a.sum(0)
+        return dz0, None, acc["Z"], acc["nu"], None, None, None, acc["ell"], acc["var"], acc.get("B"), None, None, None
+
+
 def gp_field(x, Z, nu, eps, phase, w, ell, var, variant, B=None):
     """x (L,N,D_in) -> (f, f_prior), both (L,N,D_out)."""
     v = _lib.VARIANTS[variant] if isinstance(variant, str) else variant
     return GPField.apply(x, Z, nu, eps, phase, w, ell, var, B, v)
 
 
-def gp_rollout(z0, ts, Z, nu, eps, phase, w, ell, var, variant, order=1, method="rk4", B=None):
-    """z0 (N,D_s) or (L,N,D_s), ts (T,) -> trajectories (L,N,T,D_s)."""
+def gp_rollout(z0, ts, Z, nu, eps, phase, w, ell, var, variant, order=1, method="rk4", B=None, adjoint=False):
+    """z0 (N,D_s) or (L,N,D_s), ts (T,) -> trajectories (L,N,T,D_s).  adjoint: gradients by torchdiffeq's adjoint method (GPRolloutAdjoint)
+    instead of the exact reverse sweep through the discrete solve."""
     v = _lib.VARIANTS[variant] if isinstance(variant, str) else variant
     m = _lib.METHODS[method] if isinstance(method, str) else method
-    return GPRollout.apply(z0, ts, Z, nu, eps, phase, w, ell, var, B, v, order, m)
+    fn = GPRolloutAdjoint if adjoint else GPRollout
+    return fn.apply(z0, ts, Z, nu, eps, phase, w, ell, var, B, v, order, m)
 
 
 # ------------------------------------------------------------------------------------------------
