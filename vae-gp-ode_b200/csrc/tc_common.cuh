@@ -1,4 +1,4 @@
-// tcgen05 / tensor-memory helpers shared by the tensor-memory kernels (rbf_fwd_tc.cuh, rbf_bwd_tc.cuh, rbf_pgrad_tc2.cuh), sm_100a:
+// tcgen05 / tensor-memory helpers shared by the tensor-memory kernels (rbf_fwd_tc.cuh, rbf_bwd_tc.cuh), sm_100a:
 // shared-memory matrix descriptors (no-swizzle K-major core matrices), instruction descriptors, MMA issue (operands from shared
 // memory or A from tensor memory), commit -> mbarrier, tensor-memory loads / stores, bounded mbarrier waits.
 #pragma once
