@@ -49,12 +49,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- mbarrier + bulk async copy (TMA 1-D) -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// (the mbarrier / bulk-copy helpers below take either a pointer or a ready 32-bit shared-window address: kernels under register pressure
+//  keep ONE opaque base address and add constants -- the compiler otherwise re-derives every address from the generic pointer, each
+//  time through S2R SR_CgaCtaId)
+__device__ __forceinline__ uint32_t smem_u32(uint32_t a) { return a; }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+template <class B>
+__device__ __forceinline__ void mbar_init(B bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+template <class B>
+__device__ __forceinline__ void mbar_expect_tx(B bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Every mbarrier wait in the library is bounded in TIME, not in polls: a lost arrival (a bug) traps after kWaitTimeoutNs of no
@@ -63,7 +69,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 #ifndef GPODE_WAIT_TIMEOUT_NS
 #define GPODE_WAIT_TIMEOUT_NS 20000000000ull   /* 20 s */
 #endif
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {   // non-blocking phase test
+template <class B>
+__device__ __forceinline__ bool mbar_try(B bar, uint32_t parity) {   // non-blocking phase test
   uint32_t ok;
   // (the last operand is the suspend-time hint in ns: the thread may sleep in hardware until the phase completes instead of re-polling)
   asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 2000;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
@@ -71,7 +78,8 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {   // 
 }
 // mbarrier.try_wait may suspend the thread for a hardware time slice when the phase is not complete; test_wait never does: use it
 // where the caller has other work to do (the MMA issuer polling for drained ring slots)
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+template <class B>
+__device__ __forceinline__ bool mbar_test(B bar, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
@@ -81,13 +89,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const unsigned long long t0 = global_ns();
   while (!mbar_try(bar, parity)) {
     __nanosleep(128);
 #ifdef GPODE_DEBUG_WAIT   // development aid: name the barrier that never completed and carry on (results are garbage) instead of trapping
     if (global_ns() - t0 > 300000000ull) {
-      printf("gpode wait timeout: barrier smem+%u parity %u thread %d block (%d,%d)\n", smem_u32(bar), parity, static_cast<int>(threadIdx.x),
+      printf("gpode wait timeout: barrier smem+%u parity %u thread %d block (%d,%d)\n", bar, parity, static_cast<int>(threadIdx.x),
              static_cast<int>(blockIdx.x), static_cast<int>(blockIdx.y));
       return;
     }
@@ -96,7 +104,8 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
 #endif
   }
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+template <class B>
+__device__ __forceinline__ void mbar_wait(B bar, uint32_t parity) {
   // fast path: a PTX-level poll loop (3 instructions per wake-up; the address and the parity stay in registers -- the C++ loop this
   // replaces re-derived both on every iteration, ~15 instructions per poll and a third of all instructions the fused reverse sweep
   // issued).  try_wait suspends the thread in hardware until the barrier is touched or the hint expires.
@@ -119,10 +128,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(done)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
-  if (!done) mbar_wait_slow(bar, parity);
+  if (!done) mbar_wait_slow(smem_u32(bar), parity);
 }
 // global -> shared bulk copy, completion counted in bytes on `bar`; bytes % 16 == 0, both 16-B aligned
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+template <class Dst, class B>
+__device__ __forceinline__ void bulk_g2s(Dst dst, const void* src, uint32_t bytes, B bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");

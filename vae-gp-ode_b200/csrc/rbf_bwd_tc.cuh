@@ -47,6 +47,9 @@ constexpr int kBtABytes = 3 * 4096;            // state operand of theta: X_h | 
 constexpr int kBtXpBytes = 6 * 2048;           // X' (128 states x 48 columns bf16, MN-major: chunk (s, n / 8) at (n / 8) * 2048 + 16 s)
 constexpr int kBtQCol = 256, kBtPgCol = 352;   // tensor-memory columns: 2 theta accumulators of 128, 2 Q of 48, 2 PG of 48
 constexpr int kBtNBars = 26;
+// byte offsets of the operand regions from the CTA's 1 KB-aligned shared-memory base (BwdTcSmem::sb)
+constexpr uint32_t kBtOffTau = 0, kBtOffTh = 2 * kBtTauBytes, kBtOffP = kBtOffTh + 2 * kTcbThBytes, kBtOffA = kBtOffP + 2 * kTcbPBytes, kBtOffXp = kBtOffA + kBtABytes,
+                   kBtOffXs = kBtOffXp + kBtXpBytes;
 
 __host__ __device__ constexpr uint32_t tc_idesc_f16(int M, int N) {   // f32 accumulate, fp16 x fp16, both K-major
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
@@ -71,8 +74,8 @@ __device__ __forceinline__ void tcu_mma_tf32(uint32_t d, uint64_t a, uint64_t b,
                "r"(idesc), "r"(acc)
                : "memory");
 }
-__device__ __forceinline__ void tcu_commit(uint64_t* bar) {
-  asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void tcu_commit(uint32_t bar) {
+  asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_ld4(uint32_t taddr, float (&v)[4]) {
   uint32_t r0, r1, r2, r3;
@@ -148,9 +151,12 @@ struct BwdTcSmem {
   float* dell;          // [D_out][DP] lengthscale statistic, then dvar [D_out] (contiguous, like SweepSmem)
   float* dvar;
   float* sk;            // [D_out] 1 / s_k
+  float* gs;            // [16][128] upstream gradient g_k of the CTA's states for the evaluation in flight (staged by the state threads)
   float* g_pg;          // global accumulators of the launch (bind()): sum_n g tau x_d and sum_n g tau per inducing unit
   float* g_dnu;
   uint64_t* bars;
+  uint32_t sb;          // shared-window address of the region base (opaque to the compiler: every operand address is sb + constant)
+  uint32_t sbars;       // ... of bars
   uint32_t* tmem_slot;
   const float* tiles;   // operand tiles of this sample (global)
   uint32_t tmem;
@@ -158,11 +164,11 @@ struct BwdTcSmem {
   long kk;              // running (evaluation, k) counter: Q buffer kk & 1
   long pgc;             // running inducing-item counter: PG buffer pgc & 1
   long total;
-  float stat[5];        // (epilogue threads, lane k) sum over the warp's states of x_d dx_kd for d = 4 q + t (t < 4) and, q = 0, of g (f - f_p / 2)
+  float stat[5];        // (epilogue threads, lane k) sum over the warp's states of x_d dx_kd for d = 4 q + t (t < 4); [4]: (state warps, lane k) sum of g (f - f_p / 2)
 };
 
 inline int rbf_bwd_tc_smem_bytes(const RbfGeom& g) {
-  return 2 * kBtTauBytes + 2 * kTcbThBytes + 2 * kTcbPBytes + kBtABytes + kBtXpBytes + 16 * kBtStates * 4 + (g.D_out * g.hdr_floats + g.D_out * (g.DP + 1) + g.D_out + 8) * 4 +
+  return 2 * kBtTauBytes + 2 * kTcbThBytes + 2 * kTcbPBytes + kBtABytes + kBtXpBytes + 2 * 16 * kBtStates * 4 + (g.D_out * g.hdr_floats + g.D_out * (g.DP + 1) + g.D_out + 8) * 4 +
          kBtNBars * 8 + 64 + 1024;
 }
 
@@ -182,24 +188,30 @@ struct RbfTcBwdPolicy {
   static_assert(DP_ <= 16, "one 16-wide K block per operand part");
 
   // ring / accumulator barriers (index = slot or buffer 0 / 1)
-  __device__ static __forceinline__ uint64_t* th_full(const Smem& sm, int s) { return sm.bars + s; }
-  __device__ static __forceinline__ uint64_t* th_empty(const Smem& sm, int s) { return sm.bars + 2 + s; }
-  __device__ static __forceinline__ uint64_t* p_full(const Smem& sm, int s) { return sm.bars + 4 + s; }
-  __device__ static __forceinline__ uint64_t* p_empty(const Smem& sm, int s) { return sm.bars + 6 + s; }
-  __device__ static __forceinline__ uint64_t* acc_full(const Smem& sm, int a) { return sm.bars + 8 + a; }     // theta(b) executed
-  __device__ static __forceinline__ uint64_t* acc_empty(const Smem& sm, int a) { return sm.bars + 10 + a; }   // every warp has read theta(b)
-  __device__ static __forceinline__ uint64_t* tau_full(const Smem& sm, int a) { return sm.bars + 12 + a; }    // every warp has stored tau(b)
-  __device__ static __forceinline__ uint64_t* tau_empty(const Smem& sm, int a) { return sm.bars + 14 + a; }   // Q(b) and PG(b) executed
-  __device__ static __forceinline__ uint64_t* q_full(const Smem& sm, int q) { return sm.bars + 16 + q; }
-  __device__ static __forceinline__ uint64_t* q_empty(const Smem& sm, int q) { return sm.bars + 18 + q; }
-  __device__ static __forceinline__ uint64_t* pg_full(const Smem& sm, int q) { return sm.bars + 20 + q; }
-  __device__ static __forceinline__ uint64_t* pg_empty(const Smem& sm, int q) { return sm.bars + 22 + q; }
-  __device__ static __forceinline__ uint64_t* xp_full(const Smem& sm) { return sm.bars + 24; }                // X' of this k written
-  __device__ static __forceinline__ uint64_t* xp_empty(const Smem& sm) { return sm.bars + 25; }               // last PG of this k executed
+  __device__ static __forceinline__ uint32_t th_full(const Smem& sm, int s) { return sm.sbars + 8u * static_cast<uint32_t>(s); }
+  __device__ static __forceinline__ uint32_t th_empty(const Smem& sm, int s) { return sm.sbars + 8u * static_cast<uint32_t>(2 + s); }
+  __device__ static __forceinline__ uint32_t p_full(const Smem& sm, int s) { return sm.sbars + 8u * static_cast<uint32_t>(4 + s); }
+  __device__ static __forceinline__ uint32_t p_empty(const Smem& sm, int s) { return sm.sbars + 8u * static_cast<uint32_t>(6 + s); }
+  __device__ static __forceinline__ uint32_t acc_full(const Smem& sm, int a) { return sm.sbars + 8u * static_cast<uint32_t>(8 + a); }     // theta(b) executed
+  __device__ static __forceinline__ uint32_t acc_empty(const Smem& sm, int a) { return sm.sbars + 8u * static_cast<uint32_t>(10 + a); }   // every warp has read theta(b)
+  __device__ static __forceinline__ uint32_t tau_full(const Smem& sm, int a) { return sm.sbars + 8u * static_cast<uint32_t>(12 + a); }    // every warp has stored tau(b)
+  __device__ static __forceinline__ uint32_t tau_empty(const Smem& sm, int a) { return sm.sbars + 8u * static_cast<uint32_t>(14 + a); }   // Q(b) and PG(b) executed
+  __device__ static __forceinline__ uint32_t q_full(const Smem& sm, int q) { return sm.sbars + 8u * static_cast<uint32_t>(16 + q); }
+  __device__ static __forceinline__ uint32_t q_empty(const Smem& sm, int q) { return sm.sbars + 8u * static_cast<uint32_t>(18 + q); }
+  __device__ static __forceinline__ uint32_t pg_full(const Smem& sm, int q) { return sm.sbars + 8u * static_cast<uint32_t>(20 + q); }
+  __device__ static __forceinline__ uint32_t pg_empty(const Smem& sm, int q) { return sm.sbars + 8u * static_cast<uint32_t>(22 + q); }
+  __device__ static __forceinline__ uint32_t xp_full(const Smem& sm) { return sm.sbars + 8u * 24u; }                // X' of this k written
+  __device__ static __forceinline__ uint32_t xp_empty(const Smem& sm) { return sm.sbars + 8u * 25u; }               // last PG of this k executed
 
   __device__ static __forceinline__ Smem carve(float* smem, const Geom& g) {
     Smem s;
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~static_cast<uintptr_t>(1023));
+    // (the 1 KB alignment is applied as an OFFSET to the shared-memory array: a pointer rebuilt from an integer loses its address space,
+    //  and every access through it becomes a generic LD / ST with a window check -- measured: the epilogue loop was full of them)
+    uint32_t pad = (1024u - (smem_u32(smem) & 1023u)) & 1023u;
+    asm volatile("" : "+r"(pad));   // opaque: never re-derived
+    unsigned char* base = reinterpret_cast<unsigned char*>(smem) + pad;
+    s.sb = smem_u32(base);
+    asm volatile("" : "+r"(s.sb));
     s.tau = base;
     s.th = s.tau + 2 * kBtTauBytes;
     s.pp = s.th + 2 * kTcbThBytes;
@@ -211,8 +223,11 @@ struct RbfTcBwdPolicy {
     s.dell = s.hdr + g.D_out * g.hdr_floats;
     s.dvar = s.dell + g.D_out * DP;
     s.sk = s.dvar + g.D_out;
-    float* end = s.sk + g.D_out;
-    s.bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(end + 1) + 7) & ~static_cast<uintptr_t>(7));
+    s.gs = s.sk + ((g.D_out + 3) & ~3);
+    float* end = s.gs + 16 * kBtStates;   // (base is 1 KB aligned and every block before this is a multiple of 8 bytes)
+    s.bars = reinterpret_cast<uint64_t*>(end + ((g.D_out * g.hdr_floats + g.D_out * (DP + 1)) & 1));
+    s.sbars = smem_u32(s.bars);
+    asm volatile("" : "+r"(s.sbars));
     s.tmem_slot = reinterpret_cast<uint32_t*>(s.bars + kBtNBars);
     s.g_pg = nullptr;
     s.g_dnu = nullptr;
@@ -229,14 +244,14 @@ struct RbfTcBwdPolicy {
     const int slot = static_cast<int>(b & 1);
     const float* src = sm.tiles + static_cast<size_t>(b % per_eval) * kTcbTileFloats;
     mbar_expect_tx(th_full(sm, slot), kTcbThBytes);
-    bulk_g2s(sm.th + slot * kTcbThBytes, src, kTcbThBytes, th_full(sm, slot));
+    bulk_g2s(sm.sb + kBtOffTh + slot * kTcbThBytes, src, kTcbThBytes, th_full(sm, slot));
   }
   __device__ static __forceinline__ void fetch_p(const Smem& sm, const Geom& g, long b) {
     const int per_eval = g.D_out * rbf_tcb_items(g);
     const int slot = static_cast<int>(b & 1);
     const float* src = sm.tiles + static_cast<size_t>(b % per_eval) * kTcbTileFloats + kTcbThFloats;
     mbar_expect_tx(p_full(sm, slot), kTcbPBytes);
-    bulk_g2s(sm.pp + slot * kTcbPBytes, src, kTcbPBytes, p_full(sm, slot));
+    bulk_g2s(sm.sb + kBtOffP + slot * kTcbPBytes, src, kTcbPBytes, p_full(sm, slot));
   }
 
   __device__ static __forceinline__ long setup(Smem& sm, ChunkPipe&, const Geom& g, const float* packed, long n_evals, bool) {
@@ -340,16 +355,31 @@ struct RbfTcBwdPolicy {
           hh[i] = *reinterpret_cast<const uint32_t*>(&h);
           ll[i] = *reinterpret_cast<const uint32_t*>(&lo_);
         }
-        sts128(smem_u32(sm.A) + c * 2048 + tid * 16, hh[0], hh[1], hh[2], hh[3]);
-        sts128(smem_u32(sm.A) + 4096 + c * 2048 + tid * 16, ll[0], ll[1], ll[2], ll[3]);
+        sts128(sm.sb + kBtOffA + c * 2048 + tid * 16, hh[0], hh[1], hh[2], hh[3]);
+        sts128(sm.sb + kBtOffA + 4096 + c * 2048 + tid * 16, ll[0], ll[1], ll[2], ll[3]);
       }
-      sts128(smem_u32(sm.A) + 8192 + tid * 16, __float_as_uint(sn), __float_as_uint(sn), 0u, 0u);
+      sts128(sm.sb + kBtOffA + 8192 + tid * 16, __float_as_uint(sn), __float_as_uint(sn), 0u, 0u);
+      // the upstream gradient of this evaluation goes to shared memory here (the item loop below must not hold global loads in flight:
+      // with 96 registers their results were spilled on arrival, i.e. the warp sat out the full DRAM latency once per output), and the
+      // variance statistic sum_n g_k (f_k - f_p,k / 2) is finished on the spot: lane k of the state warps keeps output k
+      const long n_st = static_cast<long>(blockIdx.x) * kBtStates + tid;
+      const bool live_st = n_st < g.N;
+      const long s_st = static_cast<long>(blockIdx.y) * g.N + (live_st ? n_st : g.N - 1);
+#pragma unroll 4
+      for (int k = 0; k < g.D_out; ++k) {
+        const long at = k * kstride + s_st * sstride;
+        const float gk = live_st ? gvec[at] : 0.f;
+        sm.gs[k * kBtStates + tid] = gk;
+        const float v = warp_sum(gk * (fvec[at] - 0.5f * fpvec[at]));
+        if (lane == k) sm.stat[4] += v;
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     float dxa[4] = {0.f, 0.f, 0.f, 0.f};
     const int q = warp >> 2;                                   // unit quarter of every item / dims 4 q .. 4 q + 3 of Q and PG
-    const int sidx = 32 * (warp & 3) + lane;                   // state slot (Q) / unit slot (PG) of this epilogue thread
+    int sidx = 32 * (warp & 3) + lane;                         // state slot (Q) / unit slot (PG) of this epilogue thread
+    asm volatile("" : "+r"(sidx));                             // (opaque: otherwise re-derived from S2R SR_TID.X inside the item loop)
     if (warp == kBtEpiWarps + 1) {
       // =============== bulk-copy producer: keeps both rings full, through this evaluation and into the next ===============
       if (lane == 0) {
@@ -377,7 +407,7 @@ struct RbfTcBwdPolicy {
       }
     } else if (warp == kBtEpiWarps) {
       // =============== MMA issuer: the whole warp walks the schedule, one elected lane issues ===============
-      const uint32_t aA = smem_u32(sm.A), aTau = smem_u32(sm.tau), aTh = smem_u32(sm.th), aP = smem_u32(sm.pp), aXp = smem_u32(sm.xp);
+      const uint32_t aA = sm.sb + kBtOffA, aTau = sm.sb + kBtOffTau, aTh = sm.sb + kBtOffTh, aP = sm.sb + kBtOffP, aXp = sm.sb + kBtOffXp;
       constexpr uint32_t id_th = tc_idesc_f16(128, kTcbUnits), id_off = tc_idesc(128, kTcbUnits), id_q = tc_idesc_bf16(128, kTcbQN, 0, 0),
                          id_pg = tc_idesc_bf16(128, kTcbQN, 1, 1);
       BT_I0
@@ -450,9 +480,6 @@ struct RbfTcBwdPolicy {
     } else {
       // =============== epilogue warps ===============
       const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      const long n_state = static_cast<long>(blockIdx.x) * kBtStates + sidx;
-      const bool live = n_state < g.N;
-      const long s_glob = static_cast<long>(blockIdx.y) * g.N + (live ? n_state : g.N - 1);
       // this state's block scale (as the state threads computed it) and its x
       float xq[4], mx = 0.f;
 #pragma unroll
@@ -461,8 +488,8 @@ struct RbfTcBwdPolicy {
       for (int t = 0; t < 4; ++t) xq[t] = 4 * q + t < DP ? sm.xs[(4 * q + t) * kBtStates + sidx] : 0.f;
       float sn_, inv_n;
       rbf_pow2_scale(mx, sn_, inv_n);
-      float Ak = 0.f, inv_s = 1.f, g_cur = 0.f, f_cur = 0.f, fp_cur = 0.f, g_prev = 0.f, f_prev = 0.f, fp_prev = 0.f;
-      const uint32_t aTau = smem_u32(sm.tau), aXp = smem_u32(sm.xp);
+      float Ak = 0.f, inv_s = 1.f;
+      const uint32_t aTau = sm.sb + kBtOffTau, aXp = sm.sb + kBtOffXp;
       const uint32_t tq0 = sm.tmem + kBtQCol + lane_base, tp0 = sm.tmem + kBtPgCol + lane_base, ta0 = sm.tmem + q * 32 + lane_base;
       int k = 0, j = 0;              // coordinates of item i
       int fk = 0, fj = 0;            // coordinates (output, inducing item) of the oldest PG tile not yet added to the global accumulators
@@ -481,9 +508,6 @@ struct RbfTcBwdPolicy {
         const int slot = static_cast<int>(b & 1);
         const bool is_k = real && j >= nbs;
         if (j == 0) {
-          g_prev = g_cur;
-          f_prev = f_cur;
-          fp_prev = fp_cur;
           if (real) {
             const float* hdr_k = sm.hdr + k * g.hdr_floats;
             Ak = 0.f;
@@ -493,10 +517,6 @@ struct RbfTcBwdPolicy {
               Ak = fmaf(hdr_k[d] * xv, xv, Ak);
             }
             inv_s = inv_n * sm.sk[k];
-            const long at = k * kstride + s_glob * sstride;   // (used at the first inducing item / the Q epilogue: the loads complete under the items in between)
-            g_cur = live ? gvec[at] : 0.f;
-            f_cur = fvec[at];
-            fp_cur = fpvec[at];
           }
         }
         if (real && j == nbs) {
@@ -506,6 +526,7 @@ struct RbfTcBwdPolicy {
           if (kk0 + k >= 1) tc_wait(xp_empty(sm), static_cast<uint32_t>((kk0 + k - 1) & 1));
           BT_E(8)
           uint32_t h01, l01, h23, l23;
+          const float g_cur = sm.gs[k * kBtStates + sidx];
           bt_split2(g_cur * xq[0], g_cur * xq[1], h01, l01);
           bt_split2(g_cur * xq[2], g_cur * xq[3], h23, l23);
           const uint32_t row = aXp + sidx * 16 + (q & 1) * 8;
@@ -607,7 +628,8 @@ struct RbfTcBwdPolicy {
         if (do_q) {
           const float es = __uint_as_float(qr[8]) + __uint_as_float(qr[9]);
           const float* hdr_k = sm.hdr + (k - 1) * g.hdr_floats;
-          float red[5];
+          const float g_prev = sm.gs[(k - 1) * kBtStates + sidx];
+          float red[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int d = 4 * q + t;
@@ -618,14 +640,13 @@ struct RbfTcBwdPolicy {
               red[t] = xq[t] * dxk;
             }
           }
-          red[4] = (q == 0 && live) ? g_prev * (f_prev - 0.5f * fp_prev) : 0.f;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1)   // five independent butterflies, interleaved
+          for (int o = 16; o > 0; o >>= 1)   // four independent butterflies, interleaved
 #pragma unroll
-            for (int t = 0; t < 5; ++t) red[t] += __shfl_xor_sync(0xffffffffu, red[t], o);
-          if (lane == k - 1) {   // lane k' of the warp keeps sum_n x_d dx_k'd (and, q = 0, sum_n g (f - f_p / 2)) of the warp's states
+            for (int t = 0; t < 4; ++t) red[t] += __shfl_xor_sync(0xffffffffu, red[t], o);
+          if (lane == k - 1) {   // lane k' of the warp keeps sum_n x_d dx_k'd of the warp's states
 #pragma unroll
-            for (int t = 0; t < 5; ++t) sm.stat[t] += red[t];
+            for (int t = 0; t < 4; ++t) sm.stat[t] += red[t];
           }
         }
         BT_E(6)

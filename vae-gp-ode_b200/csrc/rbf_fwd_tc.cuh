@@ -45,7 +45,8 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[16]) {
                  "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :: "memory");
 }
-__device__ __forceinline__ bool tc_try(uint64_t* bar, uint32_t parity) { return mbar_try(bar, parity); }
+template <class B>
+__device__ __forceinline__ bool tc_try(B bar, uint32_t parity) { return mbar_try(bar, parity); }
 __device__ __forceinline__ void lds128(uint32_t saddr, float& a, float& b, float& c, float& d) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(saddr));
 }

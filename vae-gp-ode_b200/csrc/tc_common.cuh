@@ -25,10 +25,12 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t 
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
                : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+template <class B>
+__device__ __forceinline__ void tc_commit(B bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }   // time-bounded (common.cuh)
+template <class B>
+__device__ __forceinline__ void tc_wait(B bar, uint32_t parity) { mbar_wait(bar, parity); }   // time-bounded (common.cuh)
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
@@ -47,6 +49,7 @@ __device__ __forceinline__ float tc_hi(float x) {
   return __uint_as_float(r);
 }
 
-__device__ __forceinline__ void tc_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+template <class B>
+__device__ __forceinline__ void tc_arrive(B bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
 }  // namespace gpode
