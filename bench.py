@@ -38,7 +38,8 @@ import torch  # noqa: E402
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (the reverse sweep), per launch, from the ncu capture named here
 # (one B200; the stage saves make it ~9x the algorithmic 192 B per trajectory-step, and still < 1 % of the HBM peak)
 TRAFFIC = {
-    "cfg5_rbf_d16_m512_t64_rk4": (54192663552, "k_rollout_bwd<RbfMmaBwdPolicy<16>>, profiles/traffic_r01_cfg5_default.txt"),
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (fused tcgen05 reverse sweep), one launch of the full workload
+    "cfg5_rbf_d16_m512_t64_rk4": (28000580864 + 9321114368, "k_rollout_bwd<RbfTcBwdPolicy<16>>, profiles/traffic_r02_cfg5_default.csv"),
 }
 
 WORKLOADS = {

@@ -176,3 +176,50 @@ def test_stale_cache_is_not_served_after_batched_samples(monkeypatch):
     assert rel(f_after, f_first) > 1e-2                      # not the stale sample
     gp.build_cache()
     assert rel(gp(x), f_after) < 1e-5                        # the same draws and parameters reproduce it
+
+
+@pytest.mark.parametrize("name", ["rbf_dimwise_o1", "df_o1"])
+def test_q_diag_layer_runs_the_fused_setup(name, monkeypatch):
+    """q_diag=True (reference svpy.py:79-82,96-97,152-167): diagonal q(u).  Only the inducing sample and the KL differ (both elementwise,
+    M x D_out); K(Z,Z), the factorisation and the whitened solves run on the same setup kernels as the full-covariance layer.  Trajectories,
+    KL and every leaf gradient against the fp64 oracle run with its own nu (no golden of the reference exists for q_diag)."""
+    from gpode_b200.core import kernels as K
+    from gpode_b200.core import svpy as SV
+    from gpode_b200.core.flow import Flow
+    g = load_golden(name)
+    m = g["meta"]
+    np.random.seed(1)
+    gp = SV.SVGP_Layer(D_in=m["D_in"], D_out=m["D_out"], M=m["M"], S=m["S"], q_diag=True, dimwise=m["dimwise"], device="cuda", kernel=m["kernel"])
+    assert gp._fused_setup() or gp._df_fused_setup()
+    flow = Flow(diffeq=gp, order=m["order"], solver="rk4", use_adjoint=False)
+    raw_s = np.random.RandomState(5).normal(size=(m["M"], m["D_out"])) * 0.3 - 1.0     # unconstrained diagonal scales
+    with torch.no_grad():
+        gp.kern.unconstrained_lengthscales.copy_(t(g["p_raw_ell"]))
+        gp.kern.unconstrained_variance.copy_(t(g["p_raw_var"]))
+        gp.inducing_loc.optvar.copy_(t(g["p_Z"]))
+        gp.Um.optvar.copy_(t(g["p_Um"]))
+        gp.Us_sqrt.optvar.copy_(t(raw_s))
+    d = Draws(g)
+    monkeypatch.setattr(K, "sample_normal", d)
+    monkeypatch.setattr(K, "sample_uniform", d)
+    monkeypatch.setattr(SV, "sample_normal", d)
+    z0 = t(g["z0"], device="cuda").requires_grad_(True)
+    traj = flow(z0, t(g["ts"], device="cuda"))
+    kl = flow.kl()
+    ((traj * t(g["G"], device="cuda")).sum() + kl).backward()
+    # fp64 truth
+    f64 = torch.float64
+    lv = {k: t(g["p_" + k], f64).requires_grad_(True) for k in ("raw_ell", "raw_var", "Z", "Um")}
+    rs = t(raw_s, f64).requires_grad_(True)
+    sq = torch.nn.functional.softplus(rs) + 1e-12
+    draws = dict(w=t(g["draw_w"], f64), eps=t(g["draw_eps"], f64), phase01=t(g["draw_phase01"], f64), eps_u=t(g["draw_eps_u"], f64))
+    c = OF.build_cache(m["variant"], lv["Z"], lv["raw_ell"], lv["raw_var"], lv["Um"], sq, draws, q_diag=True)
+    z64 = t(g["z0"], f64).requires_grad_(True)
+    want = OF.rollout(z64, t(g["ts"], f64), c, m["order"], "rk4")
+    kl64 = OF.kl_whitened(lv["Um"], sq, q_diag=True)
+    gr = torch.autograd.grad((want * t(g["G"], f64)).sum() + kl64, [z64, lv["raw_ell"], lv["raw_var"], lv["Z"], lv["Um"], rs])
+    got = [z0.grad, gp.kern.unconstrained_lengthscales.grad, gp.kern.unconstrained_variance.grad, gp.inducing_loc.optvar.grad, gp.Um.optvar.grad,
+           gp.Us_sqrt.optvar.grad]
+    errs = [rel(traj, want), abs(kl.item() - kl64.item()) / abs(kl64.item())] + [rel(a, b) for a, b in zip(got, gr)]
+    print(name, "q_diag: traj %.2e kl %.2e dz0 %.2e dell %.2e dvar %.2e dZ %.2e dUm %.2e dUs %.2e" % tuple(errs))
+    assert max(errs) < 1e-4

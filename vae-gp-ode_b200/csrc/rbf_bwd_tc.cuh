@@ -164,7 +164,6 @@ struct BwdTcSmem {
   long kk;              // running (evaluation, k) counter: Q buffer kk & 1
   long pgc;             // running inducing-item counter: PG buffer pgc & 1
   long total;
-  float stat[5];        // (epilogue threads, lane k) sum over the warp's states of x_d dx_kd for d = 4 q + t (t < 4); [4]: (state warps, lane k) sum of g (f - f_p / 2)
 };
 
 inline int rbf_bwd_tc_smem_bytes(const RbfGeom& g) {
@@ -180,6 +179,7 @@ struct RbfTcBwdPolicy {
   static constexpr int kMinBlocks = 1;
   static constexpr int kStateThreads = kBtStates;
   static constexpr int kXsStride = kBtStates;
+  static constexpr bool kCoopGlue = true;   // sweep.cuh: the solver glue between evaluations is spread over all 576 threads
   static constexpr int kThreadsBwd = kBtThreads;
   static constexpr int kMinBlocksBwd = 1;
   using Geom = RbfGeom;
@@ -234,8 +234,6 @@ struct RbfTcBwdPolicy {
     s.blk = 0;
     s.kk = 0;
     s.pgc = 0;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) s.stat[i] = 0.f;
     return s;
   }
 
@@ -309,13 +307,9 @@ struct RbfTcBwdPolicy {
   __device__ static __forceinline__ void finish(Smem&) {}
 
   __device__ static __forceinline__ void flush(const Smem& sm, const Geom& g, const Accum& acc) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp >> 2;
-    if (warp < kBtEpiWarps && lane < g.D_out) {   // lane k holds the statistics of output k (vjp)
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (4 * q + t < DP) atomicAdd(&acc.dell_x[lane * DP + 4 * q + t], sm.stat[t]);
-      if (q == 0) atomicAdd(&acc.dvar[lane], sm.stat[4]);
-    }
+    // (the sweep kernels synchronise the CTA before flush(): the shared-memory accumulators are complete)
+    for (int i = threadIdx.x; i < g.D_out * DP; i += blockDim.x) atomicAdd(&acc.dell_x[i], sm.dell[i]);
+    for (int i = threadIdx.x; i < g.D_out; i += blockDim.x) atomicAdd(&acc.dvar[i], sm.dvar[i]);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem), "r"(512) : "memory");
@@ -359,19 +353,22 @@ struct RbfTcBwdPolicy {
         sts128(sm.sb + kBtOffA + 4096 + c * 2048 + tid * 16, ll[0], ll[1], ll[2], ll[3]);
       }
       sts128(sm.sb + kBtOffA + 8192 + tid * 16, __float_as_uint(sn), __float_as_uint(sn), 0u, 0u);
+    }
+    if (tid < kBtEpi) {
       // the upstream gradient of this evaluation goes to shared memory here (the item loop below must not hold global loads in flight:
       // with 96 registers their results were spilled on arrival, i.e. the warp sat out the full DRAM latency once per output), and the
-      // variance statistic sum_n g_k (f_k - f_p,k / 2) is finished on the spot: lane k of the state warps keeps output k
-      const long n_st = static_cast<long>(blockIdx.x) * kBtStates + tid;
-      const bool live_st = n_st < g.N;
-      const long s_st = static_cast<long>(blockIdx.y) * g.N + (live_st ? n_st : g.N - 1);
+      // variance statistic sum_n g_k (f_k - f_p,k / 2) is finished on the spot.  Element (k, state slot) <-> thread: <= 4 independent
+      // loads per thread, one round trip; a warp's lanes share k.
 #pragma unroll 4
-      for (int k = 0; k < g.D_out; ++k) {
-        const long at = k * kstride + s_st * sstride;
+      for (int e = tid; e < g.D_out * kBtStates; e += kBtEpi) {
+        const int k = e / kBtStates, sl = e - k * kBtStates;
+        const long n_st = static_cast<long>(blockIdx.x) * kBtStates + sl;
+        const bool live_st = n_st < g.N;
+        const long at = k * kstride + (static_cast<long>(blockIdx.y) * g.N + (live_st ? n_st : g.N - 1)) * sstride;
         const float gk = live_st ? gvec[at] : 0.f;
-        sm.gs[k * kBtStates + tid] = gk;
+        sm.gs[e] = gk;
         const float v = warp_sum(gk * (fvec[at] - 0.5f * fpvec[at]));
-        if (lane == k) sm.stat[4] += v;
+        if (lane == 0) atomicAdd(&sm.dvar[k], v);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -541,40 +538,19 @@ struct RbfTcBwdPolicy {
           __syncwarp();
           if (lane == 0) tc_arrive(xp_full(sm));
         }
-        BT_E(4)
-        // ---- tensor-memory reads: the first theta half was prefetched under the previous item; the second half, the PG tile two inducing
-        //      items back (executed by now; its buffer is needed at the end of this item) and Q of the previous output (deferred to the
-        //      second item of this one) are loaded under the first half's transcendentals ----
+        // ---- the first theta half was prefetched under the previous item; the second half is loaded under the first half's
+        //      transcendentals ----
         const bool do_flush = outstanding > 0 && (!real || (is_k && outstanding >= 2));
         const bool do_q = j == 1 && k > 0;
         const long kq = kk0 + k - 1;
-        uint32_t pgr[10], qr[10];
-#pragma unroll
-        for (int v = 0; v < 10; ++v) pgr[v] = qr[v] = 0u;
-        if (do_flush) tc_wait(pg_full(sm, static_cast<int>(pcf & 1)), static_cast<uint32_t>((pcf >> 1) & 1));
-        if (do_q) tc_wait(q_full(sm, static_cast<int>(kq & 1)), static_cast<uint32_t>((kq >> 1) & 1));
-        BT_E(9)
         if (real && b >= 2) tc_wait(tau_empty(sm, slot), static_cast<uint32_t>(((b - 2) >> 1) & 1));
         BT_E(1)
         tc_ld_wait(rA);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (real) tc_ld16_async(ta0 + slot * kTcbUnits + 16, rB);
-        if (do_flush) {
-          const uint32_t tp = tp0 + static_cast<uint32_t>(pcf & 1) * kTcbQN;
-          tc_ld4_async(tp + 4 * q, pgr[0], pgr[1], pgr[2], pgr[3]);
-          tc_ld4_async(tp + 16 + 4 * q, pgr[4], pgr[5], pgr[6], pgr[7]);
-          if (q == 0) tc_ld2_async(tp + 32, pgr[8], pgr[9]);
-        }
-        if (do_q) {
-          const uint32_t tq = tq0 + static_cast<uint32_t>(kq & 1) * kTcbQN;
-          tc_ld4_async(tq + 4 * q, qr[0], qr[1], qr[2], qr[3]);
-          tc_ld4_async(tq + 16 + 4 * q, qr[4], qr[5], qr[6], qr[7]);
-          tc_ld2_async(tq + 32, qr[8], qr[9]);
-        }
-        BT_E(2)
-        const float addk = is_k ? Ak : 0.f;
-        const uint32_t trow = aTau + slot * kBtTauBytes + sidx * 16 + (4 * q) * 2048;
         if (real) {
+          tc_ld16_async(ta0 + slot * kTcbUnits + 16, rB);
+          const float addk = is_k ? Ak : 0.f;
+          const uint32_t trow = aTau + slot * kBtTauBytes + sidx * 16 + (4 * q) * 2048;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t hd[4], rm[4];
@@ -586,71 +562,11 @@ struct RbfTcBwdPolicy {
             sts128(trow + c * 2048, hd[0], hd[1], hd[2], hd[3]);
             sts128(trow + (16 + c) * 2048, rm[0], rm[1], rm[2], rm[3]);
           }
-        }
-        BT_E(3)
-        tc_ld_wait(rB);   // (tcgen05.wait::ld covers every outstanding load of the thread)
-        tc_ld_fence(pgr);
-        tc_ld_fence(qr);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (real) tc_arrive(acc_empty(sm, slot));
-          if (do_flush) tc_arrive(pg_empty(sm, static_cast<int>(pcf & 1)));
-          if (do_q) tc_arrive(q_empty(sm, static_cast<int>(kq & 1)));
-        }
-        BT_E(2)
-        if (do_flush) {
-          const int unit = fj * kTcbUnits + sidx;   // thread <-> unit of the tile, dims 4 q .. 4 q + 3 (+ the sum column for q = 0)
-          if (unit < g.M) {
-            const size_t base = (static_cast<size_t>(blockIdx.y) * g.D_out + fk) * (2 * g.MP2) + unit;
-            float* dst = sm.g_pg + base * DP + 4 * q;
-            float pv[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) pv[t] = __uint_as_float(pgr[t]) + __uint_as_float(pgr[4 + t]);
-            if constexpr (DP == 16) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(pv[0]), "f"(pv[1]), "f"(pv[2]), "f"(pv[3]) : "memory");
-            } else {
-#pragma unroll
-              for (int t = 0; t < 4; ++t)
-                if (4 * q + t < DP) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + t), "f"(pv[t]) : "memory");
-            }
-            if (q == 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(sm.g_dnu + base), "f"(__uint_as_float(pgr[8]) + __uint_as_float(pgr[9])) : "memory");
-          }
-          ++pcf;
-          --outstanding;
-          if (++fj == nbm) {
-            fj = 0;
-            ++fk;
-          }
-        }
-        BT_E(5)
-        // ---- state gradient and statistics of the previous output ----
-        if (do_q) {
-          const float es = __uint_as_float(qr[8]) + __uint_as_float(qr[9]);
-          const float* hdr_k = sm.hdr + (k - 1) * g.hdr_floats;
-          const float g_prev = sm.gs[(k - 1) * kBtStates + sidx];
-          float red[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int d = 4 * q + t;
-            red[t] = 0.f;
-            if (d < DP) {
-              const float dxk = g_prev * fmaf(2.f * hdr_k[d] * xq[t], es, __uint_as_float(qr[t]) + __uint_as_float(qr[4 + t]));
-              dxa[t] += dxk;
-              red[t] = xq[t] * dxk;
-            }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1)   // four independent butterflies, interleaved
-#pragma unroll
-            for (int t = 0; t < 4; ++t) red[t] += __shfl_xor_sync(0xffffffffu, red[t], o);
-          if (lane == k - 1) {   // lane k' of the warp keeps sum_n x_d dx_k'd of the warp's states
-#pragma unroll
-            for (int t = 0; t < 4; ++t) sm.stat[t] += red[t];
-          }
-        }
-        BT_E(6)
-        if (real) {
+          BT_E(3)
+          tc_ld_wait(rB);
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_arrive(acc_empty(sm, slot));
           if (i + 1 < n) {   // first half of the next item (its theta was issued in front of this item's second products): lands under the second half's transcendentals
             tc_wait(acc_full(sm, slot ^ 1), static_cast<uint32_t>(((b + 1) >> 1) & 1));
             BT_E(7)
@@ -670,9 +586,93 @@ struct RbfTcBwdPolicy {
           }
           if (!(GPODE_BT_EXP & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0) tc_arrive(tau_full(sm, slot));
-          if (is_k) ++outstanding;
+          if (lane == 0) tc_arrive(tau_full(sm, slot));   // the issuer may go: theta(b + 2), Q(b), PG(b)
         }
+        BT_E(3)
+        // ---- behind the hand-over, off the issuer's critical path: the PG tile two inducing items back goes to the global accumulators (its
+        //      buffer is the one PG(b) writes: the issuer waits for pg_empty only after theta(b + 2) and Q(b)), and, in the second item of
+        //      an output, the state gradient of the previous output ----
+        if (do_flush || do_q) {
+          uint32_t pgr[10], qr[10];
+#pragma unroll
+          for (int v = 0; v < 10; ++v) pgr[v] = qr[v] = 0u;
+          if (do_flush) {
+            tc_wait(pg_full(sm, static_cast<int>(pcf & 1)), static_cast<uint32_t>((pcf >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tp = tp0 + static_cast<uint32_t>(pcf & 1) * kTcbQN;
+            tc_ld4_async(tp + 4 * q, pgr[0], pgr[1], pgr[2], pgr[3]);
+            tc_ld4_async(tp + 16 + 4 * q, pgr[4], pgr[5], pgr[6], pgr[7]);
+            if (q == 0) tc_ld2_async(tp + 32, pgr[8], pgr[9]);
+          }
+          if (do_q) {
+            tc_wait(q_full(sm, static_cast<int>(kq & 1)), static_cast<uint32_t>((kq >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tq = tq0 + static_cast<uint32_t>(kq & 1) * kTcbQN;
+            tc_ld4_async(tq + 4 * q, qr[0], qr[1], qr[2], qr[3]);
+            tc_ld4_async(tq + 16 + 4 * q, qr[4], qr[5], qr[6], qr[7]);
+            tc_ld2_async(tq + 32, qr[8], qr[9]);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");   // (covers every outstanding load of the thread, the prefetched theta half included)
+          tc_ld_fence(pgr);
+          tc_ld_fence(qr);
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (do_flush) tc_arrive(pg_empty(sm, static_cast<int>(pcf & 1)));
+            if (do_q) tc_arrive(q_empty(sm, static_cast<int>(kq & 1)));
+          }
+          if (do_flush) {
+            const int unit = fj * kTcbUnits + sidx;   // thread <-> unit of the tile, dims 4 q .. 4 q + 3 (+ the sum column for q = 0)
+            if (unit < g.M) {
+              const size_t base = (static_cast<size_t>(blockIdx.y) * g.D_out + fk) * (2 * g.MP2) + unit;
+              float* dst = sm.g_pg + base * DP + 4 * q;
+              float pv[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) pv[t] = __uint_as_float(pgr[t]) + __uint_as_float(pgr[4 + t]);
+              if constexpr (DP == 16) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(pv[0]), "f"(pv[1]), "f"(pv[2]), "f"(pv[3]) : "memory");
+              } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  if (4 * q + t < DP) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + t), "f"(pv[t]) : "memory");
+              }
+              if (q == 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(sm.g_dnu + base), "f"(__uint_as_float(pgr[8]) + __uint_as_float(pgr[9])) : "memory");
+            }
+            ++pcf;
+            --outstanding;
+            if (++fj == nbm) {
+              fj = 0;
+              ++fk;
+            }
+          }
+          // ---- state gradient and statistics of the previous output ----
+          if (do_q) {
+            const float es = __uint_as_float(qr[8]) + __uint_as_float(qr[9]);
+            const float* hdr_k = sm.hdr + (k - 1) * g.hdr_floats;
+            const float g_prev = sm.gs[(k - 1) * kBtStates + sidx];
+            float red[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int d = 4 * q + t;
+              red[t] = 0.f;
+              if (d < DP) {
+                const float dxk = g_prev * fmaf(2.f * hdr_k[d] * xq[t], es, __uint_as_float(qr[t]) + __uint_as_float(qr[4 + t]));
+                dxa[t] += dxk;
+                red[t] = xq[t] * dxk;
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)   // four independent butterflies, interleaved
+#pragma unroll
+              for (int t = 0; t < 4; ++t) red[t] += __shfl_xor_sync(0xffffffffu, red[t], o);
+            // sum_n x_d dx_kd of the warp's states joins the CTA's shared-memory accumulator (per-thread accumulators carried through the
+            // item loop were spilled: with 227 KB of the SM's 256 KB carved out as shared memory the L1 holds next to nothing and every
+            // LDL of the loop went to L2)
+            const float rv = lane == 0 ? red[0] : lane == 1 ? red[1] : lane == 2 ? red[2] : red[3];
+            if (lane < 4 && 4 * q + lane < DP) atomicAdd(&sm.dell[(k - 1) * DP + 4 * q + lane], rv);
+          }
+        }
+        if (is_k) ++outstanding;
         BT_E(3)
         BT_E(6)
         if (++j == nbi) {

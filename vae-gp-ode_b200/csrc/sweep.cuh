@@ -39,6 +39,38 @@ __device__ __forceinline__ auto bind_accum(S& sm, const A& acc, int) -> decltype
 template <class P, class S, class A>
 __device__ __forceinline__ void bind_accum(S&, const A&, long) {}
 
+// policies with helper warps may declare kCoopGlue = true (needs R == 1 and kXsStride == kStateThreads): the solver glue between two
+// evaluations of the reverse sweep -- loads of saves and adjoints, a dependent round trip to L2 / HBM per component when one thread
+// walks the components of its state -- is then spread over ALL threads of the CTA, element (component d, state slot) <-> thread
+// e % blockDim.x, every load of a thread independent (measured on the fused tcgen05 reverse sweep: 10 % of all warp time sat at the
+// CTA barrier behind 128 state threads walking 16 components each)
+template <class P, class = void>
+struct coop_glue { static constexpr bool value = false; };
+template <class P>
+struct coop_glue<P, decltype((void)P::kCoopGlue, void())> { static constexpr bool value = P::kCoopGlue; };
+
+// f(d, s, slot): component d of the state with global index s whose staging slot in the xs / dx buffers is `slot` (+ d * stride)
+template <class P, class G, class F>
+__device__ __forceinline__ void glue_each(const G& g, const States<P::R>& st, int DS, F&& f) {
+  if constexpr (coop_glue<P>::value) {
+    static_assert(P::R == 1 && P::kXsStride == P::kStateThreads, "cooperative glue: one state per state thread, tight staging stride");
+    const int total = DS * P::kStateThreads;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int d = e / P::kStateThreads, slot = e - d * P::kStateThreads;
+      const long n = static_cast<long>(blockIdx.x) * P::kStateThreads + slot;
+      if (n < g.N) f(d, static_cast<long>(blockIdx.y) * g.N + n, d * P::kStateThreads + slot);
+    }
+  } else {
+    constexpr int R = P::R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!st.ok[r]) continue;
+#pragma unroll 1
+      for (int d = 0; d < DS; ++d) f(d, st.s[r], (d * R + r) * (P::kXsStride ? P::kXsStride : static_cast<int>(blockDim.x)) + static_cast<int>(threadIdx.x));
+    }
+  }
+}
+
 #define GPODE_SWEEP_BOUNDS __launch_bounds__(P::kThreads, P::kMinBlocks)
 #ifdef GPODE_BWD_MAXNREG   // timing experiments: register cap by __maxnreg__ instead of launch bounds
 #define GPODE_SWEEP_BOUNDS_BWD __maxnreg__(GPODE_BWD_MAXNREG)
@@ -195,10 +227,7 @@ __global__ void GPODE_SWEEP_BOUNDS_BWD k_rollout_bwd(const RolloutBwdArgsT<typen
   float* kbar = a.kbar;
 
   // adjoint of z_{T-1}
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (st.ok[r])
-      for (int d = 0; d < DS; ++d) ybar[d * NL + st.s[r]] = a.dtraj[(st.s[r] * a.T + (a.T - 1)) * DS + d];
+  glue_each<P>(g, st, DS, [&](int d, long s, int) { ybar[d * NL + s] = a.dtraj[(s * a.T + (a.T - 1)) * DS + d]; });
 
 #pragma unroll 1
   for (int t = a.T - 2; t >= 0; --t) {
@@ -207,47 +236,33 @@ __global__ void GPODE_SWEEP_BOUNDS_BWD k_rollout_bwd(const RolloutBwdArgsT<typen
 #pragma unroll 1
     for (int i = stages - 1; i >= 0; --i) {
       // kbar_i = dt (b_i ybar + sum_{j>i} a_ji ybar_j); stage input back from the forward saves
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (!st.ok[r]) continue;
-#pragma unroll 1
-        for (int d = 0; d < DS; ++d) {
-          float kb = tb.b[i] * ybar[d * NL + st.s[r]];
-          for (int j = i + 1; j < stages; ++j) kb = fmaf(tb.a[j][i], ystage[(j * DS + d) * NL + st.s[r]], kb);
-          kb *= dt;
-          kbar[d * NL + st.s[r]] = kb;
-          if (d >= g.off) a.gsave[((slab + i) * g.D_out + (d - g.off)) * NL + st.s[r]] = kb;
-          GPODE_XSG(sm.xs, d, r) = a.xsave[((slab + i) * DS + d) * NL + st.s[r]];
-        }
-      }
+      glue_each<P>(g, st, DS, [&](int d, long s, int slot) {
+        float kb = tb.b[i] * ybar[d * NL + s];
+        for (int j = i + 1; j < stages; ++j) kb = fmaf(tb.a[j][i], ystage[(j * DS + d) * NL + s], kb);
+        kb *= dt;
+        kbar[d * NL + s] = kb;
+        if (d >= g.off) a.gsave[((slab + i) * g.D_out + (d - g.off)) * NL + s] = kb;
+        sm.xs[slot] = a.xsave[((slab + i) * DS + d) * NL + s];
+      });
+      if constexpr (coop_glue<P>::value) __syncthreads();   // kbar (read by every warp of vjp) and xs were written by other threads
       P::vjp(pipe, g, total, sm, st, kbar + g.off * NL, a.ksave + ((slab + i) * DS + g.off) * NL, a.fpsave + (slab + i) * g.D_out * NL, NL,
              1);
       // ybar_i = J^T kbar_i (+ order 2: d(state derivative)[0:q] = state[q:2q], adjoint flows to the velocity part)
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (!st.ok[r]) continue;
-#pragma unroll 1
-        for (int d = 0; d < DS; ++d) {
-          float v = GPODE_XSG(sm.dx, d, r);
-          if (g.order == 2 && d >= DP / 2) v += kbar[(d - DP / 2) * NL + st.s[r]];
-          ystage[(i * DS + d) * NL + st.s[r]] = v;
-        }
-      }
+      glue_each<P>(g, st, DS, [&](int d, long s, int slot) {
+        float v = sm.dx[slot];
+        if (g.order == 2 && d >= DP / 2) v += kbar[(d - DP / 2) * NL + s];
+        ystage[(i * DS + d) * NL + s] = v;
+      });
+      if constexpr (coop_glue<P>::value) __syncthreads();   // dx (aliases an operand buffer of the next evaluation) is consumed
     }
     // ybar_t = ybar_{t+1} + sum_i ybar_i + dL/dz_t
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (st.ok[r])
-        for (int d = 0; d < DS; ++d) {
-          float v = ybar[d * NL + st.s[r]] + a.dtraj[(st.s[r] * a.T + t) * DS + d];
-          for (int j = 0; j < stages; ++j) v += ystage[(j * DS + d) * NL + st.s[r]];
-          ybar[d * NL + st.s[r]] = v;
-        }
+    glue_each<P>(g, st, DS, [&](int d, long s, int) {
+      float v = ybar[d * NL + s] + a.dtraj[(s * a.T + t) * DS + d];
+      for (int j = 0; j < stages; ++j) v += ystage[(j * DS + d) * NL + s];
+      ybar[d * NL + s] = v;
+    });
   }
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (st.ok[r])
-      for (int d = 0; d < DS; ++d) a.dz0[st.s[r] * DS + d] = ybar[d * NL + st.s[r]];
+  glue_each<P>(g, st, DS, [&](int d, long s, int) { a.dz0[s * DS + d] = ybar[d * NL + s]; });
   __syncthreads();
   P::flush(sm, g, a.acc);
 }

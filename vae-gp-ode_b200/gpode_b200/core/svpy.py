@@ -94,13 +94,20 @@ class SVGP_Layer(torch.nn.Module):
         return torch.einsum("dnm,md->nd", self.Us_sqrt(), eps) + self.Um()
 
     def _fused_setup(self):
-        """RBF kernels with a full (non-diagonal) q(u) on a CUDA device run the per-rollout setup on the kernels of
-        csrc/setup_kernels.cu; q_diag and CPU tensors (host-logic unit tests) use torch ops; DF see _df_batched_setup."""
-        return self.kernel_n == "RBF" and not self.q_diag and self.inducing_loc.optvar.is_cuda and self.M <= 512
+        """RBF kernels on a CUDA device run the per-rollout setup on the kernels of csrc/setup_kernels.cu (q_diag too: only the
+        inducing sample differs, see _inducing_batched); CPU tensors (host-logic unit tests) use torch ops; DF see _df_batched_setup."""
+        return self.kernel_n == "RBF" and self.inducing_loc.optvar.is_cuda and self.M <= 512
 
     def _df_fused_setup(self):
-        return (self.kernel_n == "DF" and not self.q_diag and self.inducing_loc.optvar.is_cuda and self.D_in <= 8
+        return (self.kernel_n == "DF" and self.inducing_loc.optvar.is_cuda and self.D_in <= 8
                 and self.M <= 512 and self.M * self.D_in <= 4096)
+
+    def _inducing_batched(self, eps_u):
+        """u = Lq eps + m for L samples (L,M,D_out).  Full q(u): the packed-parameter kernel (no (D_out,M,M) scatter); q_diag=True: the
+        reference's own elementwise form `Us_sqrt() * eps + Um()` (svpy.py:96-97) broadcast over L -- M x D_out elements, nothing to fuse."""
+        if self.q_diag:
+            return self.Us_sqrt()[None] * eps_u + self.Um()[None]
+        return GF.inducing_sample(self.Us_sqrt.optvar, self.Um(), eps_u)
 
     def _df_batched_setup(self, L):
         """DF kernel on a CUDA device: the L function samples of a rollout share Z, lengthscales and variance, hence ONE
@@ -113,7 +120,7 @@ class SVGP_Layer(torch.nn.Module):
         k = self.kern
         eps, phase, w, eps_u = self._draws(L)
         Z, ell, var = self.inducing_loc(), k.lengthscales, k.variance
-        u = GF.inducing_sample(self.Us_sqrt.optvar, self.Um(), eps_u)                      # (L,M,D)
+        u = self._inducing_batched(eps_u)                                                   # (L,M,D)
         omega = eps / ell.t()[None, :, None, :]                                            # (L,D,S,D)  sample_freq, kernels.py:120-124
         B = k.operator_B_batched(omega)                                                    # (L,S,D,D)
         n = self.M * self.D_out
@@ -162,7 +169,7 @@ class SVGP_Layer(torch.nn.Module):
         eps, phase, w, eps_u = self._draws(L)
         k = self.kern
         Z, ell, var = self.inducing_loc(), k.lengthscales, k.variance
-        u = GF.inducing_sample(self.Us_sqrt.optvar, self.Um(), eps_u)                      # (L,M,D_out)
+        u = self._inducing_batched(eps_u)                                                   # (L,M,D_out)
         nu0 = torch.zeros((L, self.D_out, self.M, 1) if k.dimwise else (L, self.M, self.D_out), device=Z.device)
         u_prior, _ = GF.gp_field(Z[None].expand(L, -1, -1), Z, nu0, eps, phase, w, ell, var, k.variant)   # rff_forward(Z)
         nu, self.chol_info = GF.compute_nu(Z, ell, var, u_prior, u, k.variant, return_info=True)
