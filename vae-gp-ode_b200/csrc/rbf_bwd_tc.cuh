@@ -34,6 +34,9 @@
 
 namespace gpode {
 
+#ifndef GPODE_BT_SLEEP_NS
+#define GPODE_BT_SLEEP_NS 64   // poll interval of the epilogue warps' "I am ahead" waits (tau_empty, pg_full, q_full, xp_empty)
+#endif
 #ifndef GPODE_BT_EXP
 #define GPODE_BT_EXP 0   // timing experiments only (wrong results): 1 no PG MMAs, 2 no Q MMAs, 4 no transcendentals, 8 no tau stores, 16 no theta MMAs, 32 no proxy fence after the tau stores
 #endif
@@ -395,10 +398,10 @@ struct RbfTcBwdPolicy {
             any = true;
           }
           if (any) spins = 0;
-          else if (++spins > 64) {   // time-bounded like every other wait (common.cuh)
-            if (spins == 65) idle_t0 = global_ns();
-            __nanosleep(64);
-            if (GPODE_WAIT_TIMEOUT_NS != 0ull && global_ns() - idle_t0 > GPODE_WAIT_TIMEOUT_NS) __trap();
+          else {   // a tile is needed a whole item after its slot drains: poll at leisure; time-bounded like every other wait (common.cuh)
+            __nanosleep(2 * GPODE_BT_SLEEP_NS);
+            if (++spins == 64) idle_t0 = global_ns();
+            if (spins > 64 && (spins & 63) == 0 && GPODE_WAIT_TIMEOUT_NS != 0ull && global_ns() - idle_t0 > GPODE_WAIT_TIMEOUT_NS) __trap();
           }
         }
       }
@@ -520,7 +523,7 @@ struct RbfTcBwdPolicy {
           // X' of this k (MN-major B operand of PG): columns d (heads of g x_d), 16 + d (remainders), 32 / 33 (g).  The previous k's last
           // PG was issued at least nbs items ago.
           BT_E(4)
-          if (kk0 + k >= 1) tc_wait(xp_empty(sm), static_cast<uint32_t>((kk0 + k - 1) & 1));
+          if (kk0 + k >= 1) mbar_wait_sleepy(xp_empty(sm), static_cast<uint32_t>((kk0 + k - 1) & 1), GPODE_BT_SLEEP_NS);
           BT_E(8)
           uint32_t h01, l01, h23, l23;
           const float g_cur = sm.gs[k * kBtStates + sidx];
@@ -543,7 +546,7 @@ struct RbfTcBwdPolicy {
         const bool do_flush = outstanding > 0 && (!real || (is_k && outstanding >= 2));
         const bool do_q = j == 1 && k > 0;
         const long kq = kk0 + k - 1;
-        if (real && b >= 2) tc_wait(tau_empty(sm, slot), static_cast<uint32_t>(((b - 2) >> 1) & 1));
+        if (real && b >= 2) mbar_wait_sleepy(tau_empty(sm, slot), static_cast<uint32_t>(((b - 2) >> 1) & 1), GPODE_BT_SLEEP_NS);
         BT_E(1)
         tc_ld_wait(rA);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -597,7 +600,7 @@ struct RbfTcBwdPolicy {
 #pragma unroll
           for (int v = 0; v < 10; ++v) pgr[v] = qr[v] = 0u;
           if (do_flush) {
-            tc_wait(pg_full(sm, static_cast<int>(pcf & 1)), static_cast<uint32_t>((pcf >> 1) & 1));
+            mbar_wait_sleepy(pg_full(sm, static_cast<int>(pcf & 1)), static_cast<uint32_t>((pcf >> 1) & 1), GPODE_BT_SLEEP_NS);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tp = tp0 + static_cast<uint32_t>(pcf & 1) * kTcbQN;
             tc_ld4_async(tp + 4 * q, pgr[0], pgr[1], pgr[2], pgr[3]);
@@ -605,7 +608,7 @@ struct RbfTcBwdPolicy {
             if (q == 0) tc_ld2_async(tp + 32, pgr[8], pgr[9]);
           }
           if (do_q) {
-            tc_wait(q_full(sm, static_cast<int>(kq & 1)), static_cast<uint32_t>((kq >> 1) & 1));
+            mbar_wait_sleepy(q_full(sm, static_cast<int>(kq & 1)), static_cast<uint32_t>((kq >> 1) & 1), GPODE_BT_SLEEP_NS);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tq = tq0 + static_cast<uint32_t>(kq & 1) * kTcbQN;
             tc_ld4_async(tq + 4 * q, qr[0], qr[1], qr[2], qr[3]);
