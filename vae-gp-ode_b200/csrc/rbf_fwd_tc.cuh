@@ -32,24 +32,6 @@ constexpr int kFtAFloats = kTcfChunks * 128 * 4;     // operand tile of 128 stat
 constexpr int kFtHalf = 128;                         // units per MMA (N): every state tile has two accumulators of 128 columns -- the MMAs of one
                                                      // run under the epilogue of the other
 
-#ifndef GPODE_FT_POLY
-#define GPODE_FT_POLY 0   // > 0: every GPODE_FT_POLY-th exponential of the inducing section is evaluated on the FMA pipe (ex2_poly) instead of MUFU.EX2
-#endif
-// 2^x on the FMA / ALU pipes: round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-5 minimax polynomial (max relative error 1.9e-7
-// in fp32 Horner form, the class of MUFU.EX2's 2^-22), exponent inserted by integer add.  The forward sweep is MUFU-bound with the FMA
-// pipe three quarters idle: moving a share of the exponentials over shortens the MUFU queue.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.f);
-  const float t = x + 12582912.f;   // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float f = x - (t - 12582912.f);
-  float p = 0.0013264842564240098f;
-  p = fmaf(p, f, 0.009671512991189957f);
-  p = fmaf(p, f, 0.05550733208656311f);
-  p = fmaf(p, f, 0.24022242426872253f);
-  p = fmaf(p, f, 0.6931470036506653f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
 // tensor-memory load without the wait (16 consecutive columns of this thread's lane) / the wait, which hands the registers over
 __device__ __forceinline__ void tc_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -96,6 +78,7 @@ struct RbfTcFwdPolicy {
   static constexpr int kMinBlocks = 1;
   static constexpr int kStateThreads = kFtStates;
   static constexpr int kXsStride = 0;       // staging buffers xs / dx are strided by the block size
+  static constexpr bool kCoopGlue = true;   // sweep.cuh: the solver glue between evaluations is spread over all 544 threads
   static constexpr int kThreadsBwd = kFtThreads;
   static constexpr int kMinBlocksBwd = 1;
   using Geom = RbfGeom;
@@ -311,9 +294,8 @@ struct RbfTcFwdPolicy {
             if (is_k) {
 #pragma unroll
               for (int v = 0; v < 16; v += 2) {
-                const float x0 = __uint_as_float(r[s & 1][v]) + Ak, x1 = __uint_as_float(r[s & 1][v + 1]) + Ak;
-                acc0 = fmaf((GPODE_FT_POLY > 0 && v % GPODE_FT_POLY == 0) ? ex2_poly(x0) : ex2_approx(x0), w[v], acc0);
-                acc1 = fmaf((GPODE_FT_POLY > 0 && (v + 1) % GPODE_FT_POLY == 0) ? ex2_poly(x1) : ex2_approx(x1), w[v + 1], acc1);
+                acc0 = fmaf(ex2_approx(__uint_as_float(r[s & 1][v]) + Ak), w[v], acc0);
+                acc1 = fmaf(ex2_approx(__uint_as_float(r[s & 1][v + 1]) + Ak), w[v + 1], acc1);
               }
             } else {
 #pragma unroll

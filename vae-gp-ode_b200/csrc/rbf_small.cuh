@@ -44,6 +44,7 @@ struct RbfSmallPolicy {
   static constexpr int kMinBlocks = 1;
   static constexpr int kStateThreads = kSmStates;
   static constexpr int kXsStride = kSmStates;
+  static constexpr bool kCoopGlue = true;   // sweep.cuh: the solver glue (dependent L2 round trips) is spread over the CTA's 512 threads
   static constexpr int kThreadsBwd = kSmThreads;
   static constexpr int kMinBlocksBwd = 1;
   using Geom = RbfGeom;
@@ -187,8 +188,8 @@ struct RbfSmallPolicy {
     if (warp == 0) {
 #pragma unroll
       for (int d = 0; d < DP; ++d) sm.dx[d * kSmStates + lane] = dxs[d];
-      __syncwarp();
     }
+    __syncthreads();   // dx is consumed by the cooperative glue (all threads)
   }
 };
 

@@ -39,8 +39,8 @@ __device__ __forceinline__ auto bind_accum(S& sm, const A& acc, int) -> decltype
 template <class P, class S, class A>
 __device__ __forceinline__ void bind_accum(S&, const A&, long) {}
 
-// policies with helper warps may declare kCoopGlue = true (needs R == 1 and kXsStride == kStateThreads): the solver glue between two
-// evaluations of the reverse sweep -- loads of saves and adjoints, a dependent round trip to L2 / HBM per component when one thread
+// policies with helper warps may declare kCoopGlue = true (needs R == 1): the solver glue between two
+// evaluations of a rollout -- loads of saves and adjoints, a dependent round trip to L2 / HBM per component when one thread
 // walks the components of its state -- is then spread over ALL threads of the CTA, element (component d, state slot) <-> thread
 // e % blockDim.x, every load of a thread independent (measured on the fused tcgen05 reverse sweep: 10 % of all warp time sat at the
 // CTA barrier behind 128 state threads walking 16 components each)
@@ -53,12 +53,13 @@ struct coop_glue<P, decltype((void)P::kCoopGlue, void())> { static constexpr boo
 template <class P, class G, class F>
 __device__ __forceinline__ void glue_each(const G& g, const States<P::R>& st, int DS, F&& f) {
   if constexpr (coop_glue<P>::value) {
-    static_assert(P::R == 1 && P::kXsStride == P::kStateThreads, "cooperative glue: one state per state thread, tight staging stride");
+    static_assert(P::R == 1 && P::kStateThreads > 0, "cooperative glue: one state per state thread");
     const int total = DS * P::kStateThreads;
+    const int stride = P::kXsStride ? P::kXsStride : static_cast<int>(blockDim.x);
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
-      const int d = e / P::kStateThreads, slot = e - d * P::kStateThreads;
-      const long n = static_cast<long>(blockIdx.x) * P::kStateThreads + slot;
-      if (n < g.N) f(d, static_cast<long>(blockIdx.y) * g.N + n, d * P::kStateThreads + slot);
+      const int d = e / P::kStateThreads, sl = e - d * P::kStateThreads;
+      const long n = static_cast<long>(blockIdx.x) * P::kStateThreads + sl;
+      if (n < g.N) f(d, static_cast<long>(blockIdx.y) * g.N + n, d * stride + sl);
     }
   } else {
     constexpr int R = P::R;
@@ -130,12 +131,10 @@ __global__ void GPODE_SWEEP_BOUNDS k_rollout_fwd(const RolloutFwdArgsT<typename 
   ChunkPipe pipe;
   const long total = P::setup(sm, pipe, g, a.packed, static_cast<long>(a.T - 1) * stages, false);
 
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const long zrow = a.z0_per_sample ? st.s[r] : (st.s[r] - static_cast<long>(blockIdx.y) * g.N);
-    if (st.ok[r])
-      for (int d = 0; d < DS; ++d) a.traj[(st.s[r] * a.T) * DS + d] = a.z0[zrow * DS + d];
-  }
+  glue_each<P>(g, st, DS, [&](int d, long s, int) {
+    const long zrow = a.z0_per_sample ? s : (s - static_cast<long>(blockIdx.y) * g.N);
+    a.traj[(s * a.T) * DS + d] = a.z0[zrow * DS + d];
+  });
   float* ksave = a.ksave;  // plain pointers: values written below are re-read by the same thread
   float* traj = a.traj;
   const long ks = static_cast<long>(DS) * NL;  // K_j[d] sits j*ks after K_0[d]
@@ -146,32 +145,28 @@ __global__ void GPODE_SWEEP_BOUNDS k_rollout_fwd(const RolloutFwdArgsT<typename 
     const long slab = a.keep ? static_cast<long>(t) * stages : 0;
 #pragma unroll 1
     for (int i = 0; i < stages; ++i) {
-      // stage input, in the operation order of torchdiffeq's fixed-grid step functions
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (!st.ok[r]) continue;  // padded lanes keep whatever finite values the staging buffer holds (zeros)
-#pragma unroll 1
-        for (int d = 0; d < DS; ++d) {
-          const float y0 = traj[(st.s[r] * a.T + t) * DS + d];
-          const long kb = (slab * DS + d) * NL + st.s[r];
-          float v;
-          if (i == 0) {
-            v = y0;
-          } else if (a.method == GPODE_MIDPOINT) {
-            v = y0 + ksave[kb] * (0.5f * dt);
-          } else if (i == 1) {
-            v = y0 + dt * ksave[kb] * (1.f / 3.f);
-          } else if (i == 2) {
-            v = y0 + dt * (ksave[kb + ks] - ksave[kb] * (1.f / 3.f));
-          } else {
-            v = y0 + dt * (ksave[kb] - ksave[kb + ks] + ksave[kb + 2 * ks]);
-          }
-          a.xsave[((slab + i) * DS + d) * NL + st.s[r]] = v;
-          GPODE_XSG(sm.xs, d, r) = v;
-          // order 2: the first q components of the derivative are the velocity part of the state
-          if (g.order == 2 && d >= DP / 2) ksave[((slab + i) * DS + d - DP / 2) * NL + st.s[r]] = v;
+      // stage input, in the operation order of torchdiffeq's fixed-grid step functions (padded lanes keep the zeros of the staging buffer)
+      glue_each<P>(g, st, DS, [&](int d, long s, int slot) {
+        const float y0 = traj[(s * a.T + t) * DS + d];
+        const long kb = (slab * DS + d) * NL + s;
+        float v;
+        if (i == 0) {
+          v = y0;
+        } else if (a.method == GPODE_MIDPOINT) {
+          v = y0 + ksave[kb] * (0.5f * dt);
+        } else if (i == 1) {
+          v = y0 + dt * ksave[kb] * (1.f / 3.f);
+        } else if (i == 2) {
+          v = y0 + dt * (ksave[kb + ks] - ksave[kb] * (1.f / 3.f));
+        } else {
+          v = y0 + dt * (ksave[kb] - ksave[kb + ks] + ksave[kb + 2 * ks]);
         }
-      }
+        a.xsave[((slab + i) * DS + d) * NL + s] = v;
+        sm.xs[slot] = v;
+        // order 2: the first q components of the derivative are the velocity part of the state
+        if (g.order == 2 && d >= DP / 2) ksave[((slab + i) * DS + d - DP / 2) * NL + s] = v;
+      });
+      if constexpr (coop_glue<P>::value) __syncthreads();   // xs was staged by other threads than the ones that read it
       P::eval_fwd(pipe, g, total, sm, [&](int k, const float (&fp)[R], const float (&fu)[R]) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
@@ -180,26 +175,22 @@ __global__ void GPODE_SWEEP_BOUNDS k_rollout_fwd(const RolloutFwdArgsT<typename 
             a.fpsave[((slab + i) * g.D_out + k) * NL + st.s[r]] = fp[r];
           }
       });
+      if constexpr (coop_glue<P>::value) __syncthreads();   // the stage derivatives (global) are read back by other threads
     }
     // step update
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (!st.ok[r]) continue;
-#pragma unroll 1
-      for (int d = 0; d < DS; ++d) {
-        const float y0 = traj[(st.s[r] * a.T + t) * DS + d];
-        const long kb = (slab * DS + d) * NL + st.s[r];
-        float v;
-        if (a.method == GPODE_EULER) {
-          v = y0 + dt * ksave[kb];
-        } else if (a.method == GPODE_MIDPOINT) {
-          v = y0 + dt * ksave[kb + ks];
-        } else {
-          v = y0 + (ksave[kb] + 3.f * (ksave[kb + ks] + ksave[kb + 2 * ks]) + ksave[kb + 3 * ks]) * dt * 0.125f;
-        }
-        traj[(st.s[r] * a.T + (t + 1)) * DS + d] = v;
+    glue_each<P>(g, st, DS, [&](int d, long s, int) {
+      const float y0 = traj[(s * a.T + t) * DS + d];
+      const long kb = (slab * DS + d) * NL + s;
+      float v;
+      if (a.method == GPODE_EULER) {
+        v = y0 + dt * ksave[kb];
+      } else if (a.method == GPODE_MIDPOINT) {
+        v = y0 + dt * ksave[kb + ks];
+      } else {
+        v = y0 + (ksave[kb] + 3.f * (ksave[kb + ks] + ksave[kb + 2 * ks]) + ksave[kb + 3 * ks]) * dt * 0.125f;
       }
-    }
+      traj[(s * a.T + (t + 1)) * DS + d] = v;
+    });
   }
   P::finish(sm);
 }
