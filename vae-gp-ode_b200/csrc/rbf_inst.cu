@@ -65,9 +65,21 @@ cudaError_t launch_small(KernSmall kern, const Args& a, cudaStream_t st) {
   const int smem = rbf_small_smem_bytes(a.g);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  dim3 grid(static_cast<unsigned>((a.g.N + kSmStates - 1) / kSmStates), static_cast<unsigned>(a.g.L));
-  kern<<<grid, kSmThreads, smem, st>>>(a);
-  return cudaGetLastError();
+  // the outputs of a state block are split over a thread-block cluster along z when the launch leaves SMs idle (rbf_small.cuh)
+  const int C = rbf_small_cluster(a.g);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>((a.g.N + kSmStates - 1) / kSmStates), static_cast<unsigned>(a.g.L), static_cast<unsigned>(C));
+  cfg.blockDim = dim3(kSmThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = static_cast<unsigned>(C);
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 template <>
