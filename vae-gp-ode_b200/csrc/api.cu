@@ -195,7 +195,7 @@ cudaError_t rbf_param_grads(const GpodeProblem* p, const RbfGeom& g, const float
   return rbf_launch_finalize(fa, st);
 }
 
-int df_check_smem(const DfGeom& g) { return df_smem_bytes(g, 128, 2, true) <= kSmemLimit ? GPODE_OK : GPODE_E_UNSUPPORTED; }
+int df_check_smem(const DfGeom& g) { return df_smem_bytes(g, 128, 2, true, false) + 48 * 1024 <= kSmemLimit ? GPODE_OK : GPODE_E_UNSUPPORTED; }
 
 cudaError_t df_pack(const GpodeProblem* p, const DfGeom& g, float* packed, cudaStream_t st) {
   DfPackArgs a;

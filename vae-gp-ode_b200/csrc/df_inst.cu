@@ -17,9 +17,20 @@ cudaError_t launch_sweep(Kern kern, const Args& a, int threads, int R, bool bwd,
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   const long per = static_cast<long>(threads) * R;
-  dim3 grid(static_cast<unsigned>((a.g.N + per - 1) / per), static_cast<unsigned>(a.g.L));
-  kern<<<grid, threads, smem, st>>>(a);
-  return cudaGetLastError();
+  const int C = df_cluster(a.g, threads, R);   // small batches: the rows of every chunk are split over a thread-block cluster along z
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>((a.g.N + per - 1) / per), static_cast<unsigned>(a.g.L), static_cast<unsigned>(C));
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = static_cast<unsigned>(C);
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 #define GPODE_DF_DISPATCH_R(KERNEL, a, bwd, st)                                            \

@@ -41,7 +41,30 @@ struct DfSmem {
   float* dvar;
   float* dcs;
   float* pacc;        // [MP2][4D]: per inducing pair {dnu even, dnu odd, dZ even, dZ odd}, summed over this CTA's states
+  float* xch;         // cluster launches: [2][C][2 D][threads] all-gathered partial sums of one evaluation (double-buffered over evaluations)
+  int ev;             // running evaluation counter (buffer parity)
 };
+
+// Small batches (the reference's own training shapes, e.g. 256 trajectories x 4 samples): a few dozen warps each walking every parameter
+// row serially leave the chip idle (config 2: 32 one-warp CTAs).  The ROWS of every streamed chunk are then split over a thread-block
+// cluster along grid z (df_cluster(), <= 8 CTAs): every CTA streams all chunks but evaluates only its slice of the rows, the partial
+// sums of the field (forward) / of J^T g (reverse sweep) are all-gathered through distributed shared memory with one cluster barrier per
+// evaluation, and every CTA runs the tiny solver glue redundantly on identical values -- the generic sweep kernels need no cross-CTA logic.
+// Statistics that are sums over rows stay per CTA (each adds its share to the global accumulators); the variance statistic (no row sum)
+// is taken by rank 0 only.
+__device__ __forceinline__ void df_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void df_st_cluster(uint32_t local_saddr, int rank, float v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+// rows [lo, lo + cnt) of a chunk of n rows that cluster rank `rank` of C evaluates
+__device__ __forceinline__ void df_slice(int n, int C, int rank, int& lo, int& cnt) {
+  lo = n * rank / C;
+  cnt = n * (rank + 1) / C - lo;
+}
 
 // ---------------------------------------------------------------------------------------------
 // prior part, one chunk of n feature rows of block a:  row = {Om'_d}_d<D, b', {B'_c}_c<D, pad  (float2 pairs)
@@ -284,7 +307,9 @@ struct DfPolicy {
     float* hdr = s.stages + kPipeStages * g.stage_floats;
     s.kc = reinterpret_cast<const float4*>(hdr);
     s.h = hdr + 4 * D * D;
-    s.xs = hdr + g.hdr_floats;
+    s.xch = hdr + g.hdr_floats;
+    s.ev = 0;
+    s.xs = s.xch + (gridDim.z > 1 ? 2 * static_cast<int>(gridDim.z) * 2 * D * R * static_cast<int>(blockDim.x) : 0);
     s.dx = s.xs + D * R * blockDim.x;
     s.dell = s.dx + D * R * blockDim.x;
     s.dvar = s.dell + D * D;
@@ -310,7 +335,8 @@ struct DfPolicy {
   }
 
   template <class Store>
-  __device__ static __forceinline__ void eval_fwd(ChunkPipe& pipe, const Geom& g, long total, const Smem& sm, Store&& store) {
+  __device__ static __forceinline__ void eval_fwd(ChunkPipe& pipe, const Geom& g, long total, Smem& sm, Store&& store) {
+    const int C = gridDim.z, rank = blockIdx.z;   // cluster = the z extent of the grid (1: no cluster)
     float x[R][D];
     load_x(sm, x);
     float2 acc[R][D];
@@ -322,7 +348,9 @@ struct DfPolicy {
     for (int a = 0; a < D; ++a)
       for (int c = 0; c < g.NCs; ++c) {
         const float* chunk = pipe.acquire(g.cg);
-        df_rows_prior_fwd<D, R>(chunk, min(g.RCs, g.SP2 - c * g.RCs), x, acc);
+        int lo, cnt;
+        df_slice(min(g.RCs, g.SP2 - c * g.RCs), C, rank, lo, cnt);
+        df_rows_prior_fwd<D, R>(chunk + lo * g.rowf_s, cnt, x, acc);
         pipe.release(g.cg, total);
       }
 #pragma unroll
@@ -334,22 +362,55 @@ struct DfPolicy {
       }
     for (int c = 0; c < g.NCm; ++c) {
       const float* chunk = pipe.acquire(g.cg);
-      df_rows_k_fwd<D, R>(chunk, min(g.RCm, g.MP2 - c * g.RCm), sm, x, acc);
+      int lo, cnt;
+      df_slice(min(g.RCm, g.MP2 - c * g.RCm), C, rank, lo, cnt);
+      df_rows_k_fwd<D, R>(chunk + lo * g.rowf_m, cnt, sm, x, acc);
       pipe.release(g.cg, total);
     }
+    if (C == 1) {
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-      float fu[R];
+      for (int k = 0; k < D; ++k) {
+        float fu[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) fu[r] = acc[r][k].x + acc[r][k].y;
-      store(k, fpv[k], fu);
+        for (int r = 0; r < R; ++r) fu[r] = acc[r][k].x + acc[r][k].y;
+        store(k, fpv[k], fu);
+      }
+    } else {   // all-gather the partial sums of the C row slices, then every CTA finishes all outputs
+      const int T = blockDim.x, tid = threadIdx.x;
+      float* xb = sm.xch + (sm.ev & 1) * C * 2 * D * R * T;
+#pragma unroll
+      for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint32_t a0 = smem_u32(xb + ((rank * 2 * D + 2 * k) * R + r) * T + tid);
+          for (int q = 0; q < C; ++q) {
+            df_st_cluster(a0, q, fpv[k][r]);
+            df_st_cluster(a0 + R * T * 4, q, acc[r][k].x + acc[r][k].y);
+          }
+        }
+      df_cluster_sync();
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        float fp[R], fu[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          fp[r] = fu[r] = 0.f;
+          for (int q = 0; q < C; ++q) {
+            fp[r] += xb[((q * 2 * D + 2 * k) * R + r) * T + tid];
+            fu[r] += xb[((q * 2 * D + 2 * k + 1) * R + r) * T + tid];
+          }
+        }
+        store(k, fp, fu);
+      }
     }
+    ++sm.ev;
   }
 
   // all-output VJP at one evaluation: leaves dL/dx in sm.dx, folds the lengthscale (theta path) and variance statistics
-  __device__ static __forceinline__ void vjp(ChunkPipe& pipe, const Geom& g, long total, const Smem& sm, const States<R>& st,
+  __device__ static __forceinline__ void vjp(ChunkPipe& pipe, const Geom& g, long total, Smem& sm, const States<R>& st,
                                              const float* gvec, const float* fvec, const float* fpvec, long kstride, long sstride) {
     const int lane = threadIdx.x & 31;
+    const int C = gridDim.z, rank = blockIdx.z;   // cluster = the z extent of the grid (1: no cluster)
     float x[R][D], gg[R][D], dxs[R][D];
     load_x(sm, x);
 #pragma unroll
@@ -363,7 +424,7 @@ struct DfPolicy {
         dxs[r][k] = 0.f;
       }
       v = warp_sum(v);
-      if (lane == 0) atomicAdd(&sm.dvar[k], v);
+      if (lane == 0 && rank == 0) atomicAdd(&sm.dvar[k], v);   // (no sum over rows in it: one CTA of the cluster takes it)
     }
     for (int a = 0; a < D; ++a) {
       float Q[R][D];
@@ -373,7 +434,9 @@ struct DfPolicy {
         for (int d = 0; d < D; ++d) Q[r][d] = 0.f;
       for (int c = 0; c < g.NCs; ++c) {
         const float* chunk = pipe.acquire(g.cg);
-        df_rows_prior_bwd<D, R>(chunk, min(g.RCs, g.SP2 - c * g.RCs), x, gg, Q);
+        int lo, cnt;
+        df_slice(min(g.RCs, g.SP2 - c * g.RCs), C, rank, lo, cnt);
+        df_rows_prior_bwd<D, R>(chunk + lo * g.rowf_s, cnt, x, gg, Q);
         pipe.release(g.cg, total);
       }
 #pragma unroll
@@ -398,7 +461,9 @@ struct DfPolicy {
     const int my_idx = xred_index(4 * D, lane);
     for (int c = 0; c < g.NCm; ++c) {
       const float* chunk = pipe.acquire(g.cg);
-      df_rows_k_bwd<D>(chunk, min(g.RCm, g.MP2 - c * g.RCm), c * g.RCm, sm, x[0], gg[0], DX, dc, lane, my_idx);
+      int lo, cnt;
+      df_slice(min(g.RCm, g.MP2 - c * g.RCm), C, rank, lo, cnt);
+      df_rows_k_bwd<D>(chunk + lo * g.rowf_m, cnt, c * g.RCm + lo, sm, x[0], gg[0], DX, dc, lane, my_idx);
       pipe.release(g.cg, total);
     }
 #pragma unroll
@@ -406,8 +471,27 @@ struct DfPolicy {
       const float v = warp_sum(dc[i]);
       if (lane == 0) atomicAdd(&sm.dcs[i], v);
     }
+    if (C == 1) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) GPODE_XS(sm.dx, d, 0) = dxs[0][d] + DX[d].x + DX[d].y;
+      for (int d = 0; d < D; ++d) GPODE_XS(sm.dx, d, 0) = dxs[0][d] + DX[d].x + DX[d].y;
+    } else {   // all-gather the partial J^T g of the C row slices
+      const int T = blockDim.x, tid = threadIdx.x;
+      float* xb = sm.xch + (sm.ev & 1) * C * 2 * D * T;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const uint32_t a0 = smem_u32(xb + (rank * 2 * D + d) * T + tid);
+        const float v = dxs[0][d] + DX[d].x + DX[d].y;
+        for (int q = 0; q < C; ++q) df_st_cluster(a0, q, v);
+      }
+      df_cluster_sync();
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float v = 0.f;
+        for (int q = 0; q < C; ++q) v += xb[(q * 2 * D + d) * T + tid];
+        GPODE_XS(sm.dx, d, 0) = v;
+      }
+    }
+    ++sm.ev;
   }
 
   __device__ static __forceinline__ void flush(const Smem& sm, const Geom& g, const Accum& acc) {
