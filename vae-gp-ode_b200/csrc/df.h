@@ -99,8 +99,8 @@ cudaError_t df_launch_rollout_bwd(const DfRolloutBwdArgs& a, cudaStream_t st);
 cudaError_t df_launch_pgrad(const DfPgradArgs& a, cudaStream_t st);
 cudaError_t df_launch_pack(const DfPackArgs& a, cudaStream_t st);
 cudaError_t df_launch_finalize(const DfFinalizeArgs& a, cudaStream_t st);
-int df_smem_bytes(const DfGeom& g, int threads, int R, bool bwd, bool cluster = true);
-int df_cluster(const DfGeom& g, int threads, int R);
+int df_smem_bytes(const DfGeom& g, int threads, int R, bool bwd, bool cluster = true, int W = 0);
+int df_cluster(const DfGeom& g, int states_per_cta);
 
 // per-D instantiations (df_inst.cu compiled once per GPODE_DF_D)
 template <int D> cudaError_t df_field_fwd_d(const DfFieldFwdArgs& a, cudaStream_t st);

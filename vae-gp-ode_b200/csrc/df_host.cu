@@ -68,19 +68,23 @@ DfAccum df_acc(float* base, const DfGeom& g) {
 
 // cluster size of a launch (rows of every chunk split over the CTAs of a cluster along grid z, df_kernels.cuh): small batches only --
 // while the whole launch, cluster included, fits the chip once
-int df_cluster(const DfGeom& g, int threads, int R) {
-  const long ctas = ((static_cast<long>(g.N) + static_cast<long>(threads) * R - 1) / (static_cast<long>(threads) * R)) * g.L;
+// (states_per_cta: threads x R of the thread <-> state instantiations, 32 of the warp-split small-batch one)
+int df_cluster(const DfGeom& g, int states_per_cta) {
+  const long ctas = ((static_cast<long>(g.N) + states_per_cta - 1) / states_per_cta) * g.L;
   long c = 148 / (ctas > 0 ? ctas : 1);
   if (c > 8) c = 8;
-  while (c > 1 && 2 * c * 2 * g.D * R * threads * 4 > 48 * 1024) --c;   // exchange buffers of at most 48 KB
+  while (c > 1 && 2 * c * 2 * g.D * states_per_cta * 4 > 48 * 1024) --c;   // exchange buffers of at most 48 KB
   return c < 2 ? 1 : static_cast<int>(c);
 }
-// (cluster = false: the worst-case footprint without the exchange buffers of a cluster launch -- the shape check of the ABI)
-int df_smem_bytes(const DfGeom& g, int threads, int R, bool bwd, bool cluster) {
-  int floats = 32 + kPipeStages * g.stage_floats + g.hdr_floats + g.D * R * threads;
-  const int C = cluster ? df_cluster(g, threads, R) : 1;
-  if (C > 1) floats += 2 * C * 2 * g.D * R * threads;
-  if (bwd) floats += g.D * R * threads + 2 * g.D * g.D + g.D + g.MP2 * 4 * g.D;
+// (cluster = false: the worst-case footprint without the exchange buffers of a cluster launch -- the shape check of the ABI;
+//  W > 0: the warp-split instantiation, staging buffers of 32 states + the warps' partial-sum buffer)
+int df_smem_bytes(const DfGeom& g, int threads, int R, bool bwd, bool cluster, int W) {
+  const int states = W > 0 ? 32 : threads * R;
+  int floats = 32 + kPipeStages * g.stage_floats + g.hdr_floats + g.D * states;
+  const int C = cluster ? df_cluster(g, states) : 1;
+  if (C > 1) floats += 2 * C * 2 * g.D * states;
+  if (W > 0) floats += W * 2 * g.D * 32;
+  if (bwd) floats += g.D * states + 2 * g.D * g.D + g.D + g.MP2 * 4 * g.D;
   return floats * 4;
 }
 

@@ -12,12 +12,12 @@ namespace {
 constexpr int D = GPODE_DF_D;
 
 template <typename Kern, typename Args>
-cudaError_t launch_sweep(Kern kern, const Args& a, int threads, int R, bool bwd, cudaStream_t st) {
-  const int smem = df_smem_bytes(a.g, threads, R, bwd);
+cudaError_t launch_sweep(Kern kern, const Args& a, int threads, int R, bool bwd, cudaStream_t st, int W = 0) {
+  const int smem = df_smem_bytes(a.g, threads, R, bwd, true, W);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  const long per = static_cast<long>(threads) * R;
-  const int C = df_cluster(a.g, threads, R);   // small batches: the rows of every chunk are split over a thread-block cluster along z
+  const long per = W > 0 ? 32 : static_cast<long>(threads) * R;
+  const int C = df_cluster(a.g, static_cast<int>(per));   // small batches: the rows of every chunk are split over a thread-block cluster along z
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>((a.g.N + per - 1) / per), static_cast<unsigned>(a.g.L), static_cast<unsigned>(C));
   cfg.blockDim = dim3(static_cast<unsigned>(threads));
@@ -34,6 +34,7 @@ cudaError_t launch_sweep(Kern kern, const Args& a, int threads, int R, bool bwd,
 }
 
 #define GPODE_DF_DISPATCH_R(KERNEL, a, bwd, st)                                            \
+  if (df_use_small((a).g)) return launch_sweep(KERNEL<DfPolicy<D, 1, kDfSmallW>>, a, 32 * kDfSmallW, 1, bwd, st, kDfSmallW); \
   int threads, R;                                                                          \
   df_pick_shape((a).g, bwd, threads, R);                                                   \
   if (R == 2) return launch_sweep(KERNEL<DfPolicy<D, 2>>, a, threads, 2, bwd, st);         \
@@ -45,9 +46,15 @@ cudaError_t df_field_fwd_d<D>(const DfFieldFwdArgs& a, cudaStream_t st) { GPODE_
 template <>
 cudaError_t df_rollout_fwd_d<D>(const DfRolloutFwdArgs& a, cudaStream_t st) { GPODE_DF_DISPATCH_R(k_rollout_fwd, a, false, st) }
 template <>
-cudaError_t df_field_bwd_d<D>(const DfFieldBwdArgs& a, cudaStream_t st) { return launch_sweep(k_field_bwd<DfPolicy<D, 1>>, a, [&] { int t, r; df_pick_shape(a.g, true, t, r); return t; }(), 1, true, st); }
+cudaError_t df_field_bwd_d<D>(const DfFieldBwdArgs& a, cudaStream_t st) {
+  if (df_use_small(a.g)) return launch_sweep(k_field_bwd<DfPolicy<D, 1, kDfSmallW>>, a, 32 * kDfSmallW, 1, true, st, kDfSmallW);
+  return launch_sweep(k_field_bwd<DfPolicy<D, 1>>, a, [&] { int t, r; df_pick_shape(a.g, true, t, r); return t; }(), 1, true, st);
+}
 template <>
-cudaError_t df_rollout_bwd_d<D>(const DfRolloutBwdArgs& a, cudaStream_t st) { return launch_sweep(k_rollout_bwd<DfPolicy<D, 1>>, a, [&] { int t, r; df_pick_shape(a.g, true, t, r); return t; }(), 1, true, st); }
+cudaError_t df_rollout_bwd_d<D>(const DfRolloutBwdArgs& a, cudaStream_t st) {
+  if (df_use_small(a.g)) return launch_sweep(k_rollout_bwd<DfPolicy<D, 1, kDfSmallW>>, a, 32 * kDfSmallW, 1, true, st, kDfSmallW);
+  return launch_sweep(k_rollout_bwd<DfPolicy<D, 1>>, a, [&] { int t, r; df_pick_shape(a.g, true, t, r); return t; }(), 1, true, st);
+}
 
 template <>
 cudaError_t df_pgrad_d<D>(const DfPgradArgs& a, cudaStream_t st) {

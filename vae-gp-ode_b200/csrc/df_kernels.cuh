@@ -42,6 +42,7 @@ struct DfSmem {
   float* dcs;
   float* pacc;        // [MP2][4D]: per inducing pair {dnu even, dnu odd, dZ even, dZ odd}, summed over this CTA's states
   float* xch;         // cluster launches: [2][C][2 D][threads] all-gathered partial sums of one evaluation (double-buffered over evaluations)
+  float* loc;         // W > 0: [W][2 D][32] partial sums of the CTA's warps
   int ev;             // running evaluation counter (buffer parity)
 };
 
@@ -51,7 +52,9 @@ struct DfSmem {
 // sums of the field (forward) / of J^T g (reverse sweep) are all-gathered through distributed shared memory with one cluster barrier per
 // evaluation, and every CTA runs the tiny solver glue redundantly on identical values -- the generic sweep kernels need no cross-CTA logic.
 // Statistics that are sums over rows stay per CTA (each adds its share to the global accumulators); the variance statistic (no row sum)
-// is taken by rank 0 only.
+// is taken by rank 0 only.  With W > 0 (DfPolicy<D, 1, W>, the small-batch instantiation) a CTA owns 32 states and brings W warps that
+// split the row slice once more (lane <-> state in every warp; the warps' partial sums meet in shared memory before the all-gather):
+// config 2 runs 128 CTAs x 8 warps instead of 32 CTAs x 1 warp.
 __device__ __forceinline__ void df_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -284,20 +287,25 @@ __device__ __forceinline__ void df_rows_k_bwd(const float* __restrict__ chunk, i
   }
 }
 
-template <int D_, int R_>
+template <int D_, int R_, int W_ = 0>
 struct DfPolicy {
   static constexpr int DP = D_;
   static constexpr int D = D_;
   static constexpr int R = R_;
-  static constexpr int kThreads = 128;
-  static constexpr int kMinBlocks = 3;
-  static constexpr int kStateThreads = 0;
-  static constexpr int kXsStride = 0;       // staging buffers xs / dx are strided by the block size
-  static constexpr int kThreadsBwd = 128;
-  static constexpr int kMinBlocksBwd = D_ <= 6 ? 3 : 2;   // the reverse sweep also carries the D x D lengthscale accumulators
+  static constexpr int W = W_;              // 0: thread <-> R states; > 0: 32 states per CTA, W warps splitting the rows (small batches)
+  static constexpr int kThreads = W_ ? 32 * W_ : 128;
+  static constexpr int kMinBlocks = W_ ? 1 : 3;
+  static constexpr int kStateThreads = W_ ? 32 : 0;
+  static constexpr int kXsStride = W_ ? 32 : 0;       // 0: staging buffers xs / dx are strided by the block size
+  static constexpr bool kCoopGlue = W_ > 0;           // sweep.cuh: solver glue spread over all threads
+  static constexpr int kThreadsBwd = W_ ? 32 * W_ : 128;
+  static constexpr int kMinBlocksBwd = W_ ? 1 : (D_ <= 6 ? 3 : 2);   // the reverse sweep also carries the D x D lengthscale accumulators
+  static_assert(W_ == 0 || R_ == 1, "the warp-split instantiation runs one state per lane");
   using Geom = DfGeom;
   using Accum = DfAccum;
   using Smem = DfSmem;
+  __device__ static __forceinline__ int xstride() { return W_ ? 32 : static_cast<int>(blockDim.x); }          // stride of the staging buffers
+  __device__ static __forceinline__ int sslot() { return W_ ? static_cast<int>(threadIdx.x & 31) : static_cast<int>(threadIdx.x); }
 
   __device__ static __forceinline__ void finish(Smem&) {}
   __device__ static __forceinline__ Smem carve(float* smem, const Geom& g) {
@@ -309,9 +317,10 @@ struct DfPolicy {
     s.h = hdr + 4 * D * D;
     s.xch = hdr + g.hdr_floats;
     s.ev = 0;
-    s.xs = s.xch + (gridDim.z > 1 ? 2 * static_cast<int>(gridDim.z) * 2 * D * R * static_cast<int>(blockDim.x) : 0);
-    s.dx = s.xs + D * R * blockDim.x;
-    s.dell = s.dx + D * R * blockDim.x;
+    s.loc = s.xch + (gridDim.z > 1 ? 2 * static_cast<int>(gridDim.z) * 2 * D * R * xstride() : 0);
+    s.xs = s.loc + (W_ ? W_ * 2 * D * 32 : 0);
+    s.dx = s.xs + D * R * xstride();
+    s.dell = s.dx + D * R * xstride();
     s.dvar = s.dell + D * D;
     s.dcs = s.dvar + D;
     s.pacc = s.dcs + D * D;
@@ -321,7 +330,7 @@ struct DfPolicy {
     const long total = n_evals * chunks_per_eval(g.cg);
     float* hdr = sm.stages + kPipeStages * g.stage_floats;
     for (int i = threadIdx.x; i < g.hdr_floats; i += blockDim.x) hdr[i] = packed[i];
-    for (int i = threadIdx.x; i < D * R * blockDim.x; i += blockDim.x) sm.xs[i] = 0.f;
+    for (int i = threadIdx.x; i < D * R * xstride(); i += blockDim.x) sm.xs[i] = 0.f;
     if (bwd)
       for (int i = threadIdx.x; i < 2 * D * D + D + g.MP2 * 4 * D; i += blockDim.x) sm.dell[i] = 0.f;
     pipe.init(sm.stages, sm.bars, df_rows_ptr(packed, g, blockIdx.y), g.cg, total);  // contains the publishing __syncthreads
@@ -331,12 +340,14 @@ struct DfPolicy {
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int d = 0; d < D; ++d) x[r][d] = GPODE_XS(sm.xs, d, r);
+      for (int d = 0; d < D; ++d) x[r][d] = sm.xs[(d * R + r) * xstride() + sslot()];
   }
 
   template <class Store>
   __device__ static __forceinline__ void eval_fwd(ChunkPipe& pipe, const Geom& g, long total, Smem& sm, Store&& store) {
     const int C = gridDim.z, rank = blockIdx.z;   // cluster = the z extent of the grid (1: no cluster)
+    const int NS = C * (W_ ? W_ : 1), si = rank * (W_ ? W_ : 1) + (W_ ? static_cast<int>(threadIdx.x >> 5) : 0);   // row slices, this warp's
+    if constexpr (W_ > 0) __syncthreads();   // the stage input staged by the state warp is visible to every warp
     float x[R][D];
     load_x(sm, x);
     float2 acc[R][D];
@@ -349,7 +360,7 @@ struct DfPolicy {
       for (int c = 0; c < g.NCs; ++c) {
         const float* chunk = pipe.acquire(g.cg);
         int lo, cnt;
-        df_slice(min(g.RCs, g.SP2 - c * g.RCs), C, rank, lo, cnt);
+        df_slice(min(g.RCs, g.SP2 - c * g.RCs), NS, si, lo, cnt);
         df_rows_prior_fwd<D, R>(chunk + lo * g.rowf_s, cnt, x, acc);
         pipe.release(g.cg, total);
       }
@@ -363,44 +374,72 @@ struct DfPolicy {
     for (int c = 0; c < g.NCm; ++c) {
       const float* chunk = pipe.acquire(g.cg);
       int lo, cnt;
-      df_slice(min(g.RCm, g.MP2 - c * g.RCm), C, rank, lo, cnt);
+      df_slice(min(g.RCm, g.MP2 - c * g.RCm), NS, si, lo, cnt);
       df_rows_k_fwd<D, R>(chunk + lo * g.rowf_m, cnt, sm, x, acc);
       pipe.release(g.cg, total);
     }
-    if (C == 1) {
+    if constexpr (W_ > 0) {   // the warps' partial sums meet in shared memory; warp 0 carries the CTA's sums on
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
       for (int k = 0; k < D; ++k) {
-        float fu[R];
+        sm.loc[(warp * 2 * D + 2 * k) * 32 + lane] = fpv[k][0];
+        sm.loc[(warp * 2 * D + 2 * k + 1) * 32 + lane] = acc[0][k].x + acc[0][k].y;
+      }
+      __syncthreads();
+      if (warp == 0) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) fu[r] = acc[r][k].x + acc[r][k].y;
-        store(k, fpv[k], fu);
+        for (int k = 0; k < D; ++k) {
+          float a = 0.f, b = 0.f;
+          for (int w = 0; w < W_; ++w) {
+            a += sm.loc[(w * 2 * D + 2 * k) * 32 + lane];
+            b += sm.loc[(w * 2 * D + 2 * k + 1) * 32 + lane];
+          }
+          fpv[k][0] = a;
+          acc[0][k] = make_float2(b, 0.f);
+        }
+      }
+    }
+    const bool owner = W_ == 0 || threadIdx.x < 32;   // threads that hold a state's sums
+    if (C == 1) {
+      if (owner) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          float fu[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) fu[r] = acc[r][k].x + acc[r][k].y;
+          store(k, fpv[k], fu);
+        }
       }
     } else {   // all-gather the partial sums of the C row slices, then every CTA finishes all outputs
-      const int T = blockDim.x, tid = threadIdx.x;
+      const int T = xstride(), tid = sslot();
       float* xb = sm.xch + (sm.ev & 1) * C * 2 * D * R * T;
+      if (owner) {
 #pragma unroll
-      for (int k = 0; k < D; ++k)
+        for (int k = 0; k < D; ++k)
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const uint32_t a0 = smem_u32(xb + ((rank * 2 * D + 2 * k) * R + r) * T + tid);
-          for (int q = 0; q < C; ++q) {
-            df_st_cluster(a0, q, fpv[k][r]);
-            df_st_cluster(a0 + R * T * 4, q, acc[r][k].x + acc[r][k].y);
+          for (int r = 0; r < R; ++r) {
+            const uint32_t a0 = smem_u32(xb + ((rank * 2 * D + 2 * k) * R + r) * T + tid);
+            for (int q = 0; q < C; ++q) {
+              df_st_cluster(a0, q, fpv[k][r]);
+              df_st_cluster(a0 + R * T * 4, q, acc[r][k].x + acc[r][k].y);
+            }
           }
-        }
+      }
       df_cluster_sync();
+      if (owner) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        float fp[R], fu[R];
+        for (int k = 0; k < D; ++k) {
+          float fp[R], fu[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          fp[r] = fu[r] = 0.f;
-          for (int q = 0; q < C; ++q) {
-            fp[r] += xb[((q * 2 * D + 2 * k) * R + r) * T + tid];
-            fu[r] += xb[((q * 2 * D + 2 * k + 1) * R + r) * T + tid];
+          for (int r = 0; r < R; ++r) {
+            fp[r] = fu[r] = 0.f;
+            for (int q = 0; q < C; ++q) {
+              fp[r] += xb[((q * 2 * D + 2 * k) * R + r) * T + tid];
+              fu[r] += xb[((q * 2 * D + 2 * k + 1) * R + r) * T + tid];
+            }
           }
+          store(k, fp, fu);
         }
-        store(k, fp, fu);
       }
     }
     ++sm.ev;
@@ -411,20 +450,35 @@ struct DfPolicy {
                                              const float* gvec, const float* fvec, const float* fpvec, long kstride, long sstride) {
     const int lane = threadIdx.x & 31;
     const int C = gridDim.z, rank = blockIdx.z;   // cluster = the z extent of the grid (1: no cluster)
+    const int NS = C * (W_ ? W_ : 1), si = rank * (W_ ? W_ : 1) + (W_ ? static_cast<int>(threadIdx.x >> 5) : 0);   // row slices, this warp's
+    if constexpr (W_ > 0) __syncthreads();   // the stage input staged by the state warp is visible to every warp
     float x[R][D], gg[R][D], dxs[R][D];
     load_x(sm, x);
+    long s_of[R];
+    bool ok_of[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if constexpr (W_ > 0) {   // every warp of the CTA works on the same 32 states: lane <-> state
+        const long n = static_cast<long>(blockIdx.x) * 32 + lane;
+        ok_of[r] = n < g.N;
+        s_of[r] = static_cast<long>(blockIdx.y) * g.N + (ok_of[r] ? n : g.N - 1);
+      } else {
+        ok_of[r] = st.ok[r];
+        s_of[r] = st.s[r];
+      }
+    }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       float v = 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const long at = k * kstride + st.s[r] * sstride;
-        gg[r][k] = st.ok[r] ? gvec[at] : 0.f;
+        const long at = k * kstride + s_of[r] * sstride;
+        gg[r][k] = ok_of[r] ? gvec[at] : 0.f;
         v += gg[r][k] * (fvec[at] - 0.5f * fpvec[at]);
         dxs[r][k] = 0.f;
       }
       v = warp_sum(v);
-      if (lane == 0 && rank == 0) atomicAdd(&sm.dvar[k], v);   // (no sum over rows in it: one CTA of the cluster takes it)
+      if (lane == 0 && si == 0) atomicAdd(&sm.dvar[k], v);   // (no sum over rows in it: one warp of the cluster takes it)
     }
     for (int a = 0; a < D; ++a) {
       float Q[R][D];
@@ -435,7 +489,7 @@ struct DfPolicy {
       for (int c = 0; c < g.NCs; ++c) {
         const float* chunk = pipe.acquire(g.cg);
         int lo, cnt;
-        df_slice(min(g.RCs, g.SP2 - c * g.RCs), C, rank, lo, cnt);
+        df_slice(min(g.RCs, g.SP2 - c * g.RCs), NS, si, lo, cnt);
         df_rows_prior_bwd<D, R>(chunk + lo * g.rowf_s, cnt, x, gg, Q);
         pipe.release(g.cg, total);
       }
@@ -462,7 +516,7 @@ struct DfPolicy {
     for (int c = 0; c < g.NCm; ++c) {
       const float* chunk = pipe.acquire(g.cg);
       int lo, cnt;
-      df_slice(min(g.RCm, g.MP2 - c * g.RCm), C, rank, lo, cnt);
+      df_slice(min(g.RCm, g.MP2 - c * g.RCm), NS, si, lo, cnt);
       df_rows_k_bwd<D>(chunk + lo * g.rowf_m, cnt, c * g.RCm + lo, sm, x[0], gg[0], DX, dc, lane, my_idx);
       pipe.release(g.cg, total);
     }
@@ -471,27 +525,51 @@ struct DfPolicy {
       const float v = warp_sum(dc[i]);
       if (lane == 0) atomicAdd(&sm.dcs[i], v);
     }
+    float part[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) part[d] = dxs[0][d] + DX[d].x + DX[d].y;
+    if constexpr (W_ > 0) {   // the warps' partial J^T g meet in shared memory; warp 0 carries the CTA's sum on
+      const int warp = threadIdx.x >> 5;
+#pragma unroll
+      for (int d = 0; d < D; ++d) sm.loc[(warp * 2 * D + d) * 32 + lane] = part[d];
+      __syncthreads();
+      if (warp == 0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          float v = 0.f;
+          for (int w = 0; w < W_; ++w) v += sm.loc[(w * 2 * D + d) * 32 + lane];
+          part[d] = v;
+        }
+      }
+    }
+    const bool owner = W_ == 0 || threadIdx.x < 32;
+    const int T = xstride(), tid = sslot();
     if (C == 1) {
+      if (owner) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) GPODE_XS(sm.dx, d, 0) = dxs[0][d] + DX[d].x + DX[d].y;
+        for (int d = 0; d < D; ++d) sm.dx[d * T + tid] = part[d];
+      }
     } else {   // all-gather the partial J^T g of the C row slices
-      const int T = blockDim.x, tid = threadIdx.x;
       float* xb = sm.xch + (sm.ev & 1) * C * 2 * D * T;
+      if (owner) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const uint32_t a0 = smem_u32(xb + (rank * 2 * D + d) * T + tid);
-        const float v = dxs[0][d] + DX[d].x + DX[d].y;
-        for (int q = 0; q < C; ++q) df_st_cluster(a0, q, v);
+        for (int d = 0; d < D; ++d) {
+          const uint32_t a0 = smem_u32(xb + (rank * 2 * D + d) * T + tid);
+          for (int q = 0; q < C; ++q) df_st_cluster(a0, q, part[d]);
+        }
       }
       df_cluster_sync();
+      if (owner) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        float v = 0.f;
-        for (int q = 0; q < C; ++q) v += xb[(q * 2 * D + d) * T + tid];
-        GPODE_XS(sm.dx, d, 0) = v;
+        for (int d = 0; d < D; ++d) {
+          float v = 0.f;
+          for (int q = 0; q < C; ++q) v += xb[(q * 2 * D + d) * T + tid];
+          sm.dx[d * T + tid] = v;
+        }
       }
     }
     ++sm.ev;
+    if constexpr (W_ > 0) __syncthreads();   // dx is consumed by the cooperative glue (all threads); loc may be rewritten
   }
 
   __device__ static __forceinline__ void flush(const Smem& sm, const Geom& g, const Accum& acc) {
@@ -589,6 +667,9 @@ __global__ void __launch_bounds__(kDfPgThreads, 4) k_df_pgrad(const DfPgradArgs 
   }
 }
 
+constexpr int kDfSmallW = 8;   // warps per 32 states of the small-batch instantiation DfPolicy<D, 1, kDfSmallW>
+// small batch: fewer states than one warp per SM can cover -- rows are split over the warps of a CTA and over a cluster instead
+inline bool df_use_small(const DfGeom& g) { return static_cast<long>(g.N) * g.L <= 148L * 32; }
 // launch-shape heuristic of the DF sweep kernels (states per CTA = 128 * R)
 inline void df_pick_shape(const DfGeom& g, bool bwd, int& threads, int& R) {
   const long want = 2L * 148;
