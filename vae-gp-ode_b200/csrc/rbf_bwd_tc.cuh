@@ -118,8 +118,9 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 // (v0, v1) -> packed bf16 heads by truncation (element 0 in the low half) and packed bf16 remainders (rounded): |v - (h + l)| <= 2^-17 |v|
 __device__ __forceinline__ void bt_split2(float v0, float v1, uint32_t& hd, uint32_t& rm) {
   hd = __byte_perm(__float_as_uint(v0), __float_as_uint(v1), 0x7632);
-  const float l0 = v0 - __uint_as_float(__float_as_uint(v0) & 0xFFFF0000u), l1 = v1 - __uint_as_float(__float_as_uint(v1) & 0xFFFF0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rm) : "f"(l1), "f"(l0));
+  // both remainders in ONE packed subtraction (FFMA2): the epilogue warps are issue-bound, every instruction saved per pair counts
+  const float2 l = fma2(make_float2(__uint_as_float(__float_as_uint(v0) & 0xFFFF0000u), __uint_as_float(__float_as_uint(v1) & 0xFFFF0000u)), bc(-1.f), make_float2(v0, v1));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rm) : "f"(l.y), "f"(l.x));
 }
 
 #ifdef GPODE_BT_PROFILE
@@ -559,7 +560,8 @@ struct RbfTcBwdPolicy {
             uint32_t hd[4], rm[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-              const float t0 = fmaf(__uint_as_float(rA[8 * c + 2 * v]), inv_s, addk), t1 = fmaf(__uint_as_float(rA[8 * c + 2 * v + 1]), inv_s, addk);
+              const float2 tt = fma2(make_float2(__uint_as_float(rA[8 * c + 2 * v]), __uint_as_float(rA[8 * c + 2 * v + 1])), bc(inv_s), bc(addk));   // un-scaling and A_k(x): one packed FFMA2 per pair
+              const float t0 = tt.x, t1 = tt.y;
               bt_split2((GPODE_BT_EXP & 4) ? t0 : (is_k ? ex2_approx(t0) : __cosf(t0)), (GPODE_BT_EXP & 4) ? t1 : (is_k ? ex2_approx(t1) : __cosf(t1)), hd[v], rm[v]);
             }
             sts128(trow + c * 2048, hd[0], hd[1], hd[2], hd[3]);
@@ -581,7 +583,8 @@ struct RbfTcBwdPolicy {
             uint32_t hd[4], rm[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-              const float t0 = fmaf(__uint_as_float(rB[8 * c + 2 * v]), inv_s, addk), t1 = fmaf(__uint_as_float(rB[8 * c + 2 * v + 1]), inv_s, addk);
+              const float2 tt = fma2(make_float2(__uint_as_float(rB[8 * c + 2 * v]), __uint_as_float(rB[8 * c + 2 * v + 1])), bc(inv_s), bc(addk));   // un-scaling and A_k(x): one packed FFMA2 per pair
+              const float t0 = tt.x, t1 = tt.y;
               bt_split2((GPODE_BT_EXP & 4) ? t0 : (is_k ? ex2_approx(t0) : __cosf(t0)), (GPODE_BT_EXP & 4) ? t1 : (is_k ? ex2_approx(t1) : __cosf(t1)), hd[v], rm[v]);
             }
             sts128(trow + (2 + c) * 2048, hd[0], hd[1], hd[2], hd[3]);
