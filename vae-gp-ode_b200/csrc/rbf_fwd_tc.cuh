@@ -94,7 +94,11 @@ struct RbfTcFwdPolicy {
 
   __device__ static __forceinline__ Smem carve(float* smem, const Geom& g) {
     Smem s;
-    float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~static_cast<uintptr_t>(1023));
+    // (1 KB alignment as an OFFSET to the shared-memory array: a pointer rebuilt from an integer loses its address space and every access
+    //  through it becomes a generic LD / ST -- see rbf_bwd_tc.cuh)
+    uint32_t pad = (1024u - (smem_u32(smem) & 1023u)) & 1023u;
+    asm volatile("" : "+r"(pad));
+    float* base = smem + pad / 4;
     s.A = base;
     s.B = s.A + 2 * kFtAFloats;
     s.xs = s.B + kFtStages * kTcfTileFloats;
