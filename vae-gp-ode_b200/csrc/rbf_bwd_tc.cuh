@@ -44,7 +44,8 @@ namespace gpode {
 constexpr int kBtStates = 128;                 // states per CTA
 constexpr int kBtEpiWarps = 16;
 constexpr int kBtEpi = kBtEpiWarps * 32;
-constexpr int kBtThreads = kBtEpi + 64;        // + MMA-issuer warp + bulk-copy producer warp
+constexpr int kBtFlushWarps = 4;               // drain warps: one per tensor-memory lane quarter (PG / Q accumulators -> global / shared memory)
+constexpr int kBtThreads = kBtEpi + 64 + 32 * kBtFlushWarps;   // + MMA-issuer warp + bulk-copy producer warp + drain warps
 constexpr int kBtTauBytes = 2 * 16 * 2048;     // one tau tile: 2 planes x 16 unit groups x (128 states x 16 B)
 constexpr int kBtABytes = 3 * 4096;            // state operand of theta: X_h | X_l | (s_n, s_n, 0 ..)
 constexpr int kBtXpBytes = 6 * 2048;           // X' (128 states x 48 columns bf16, MN-major: chunk (s, n / 8) at (n / 8) * 2048 + 16 s)
@@ -282,11 +283,11 @@ struct RbfTcBwdPolicy {
         mbar_init(tau_full(sm, i), kBtEpiWarps);
         mbar_init(tau_empty(sm, i), 1);
         mbar_init(q_full(sm, i), 1);
-        mbar_init(q_empty(sm, i), kBtEpiWarps);
+        mbar_init(q_empty(sm, i), kBtFlushWarps);
         mbar_init(pg_full(sm, i), 1);
-        mbar_init(pg_empty(sm, i), kBtEpiWarps);
+        mbar_init(pg_empty(sm, i), kBtFlushWarps);
       }
-      mbar_init(xp_full(sm), kBtEpiWarps);
+      mbar_init(xp_full(sm), kBtFlushWarps);
       mbar_init(xp_empty(sm), 1);
       mbar_fence_init();
     }
@@ -377,7 +378,6 @@ struct RbfTcBwdPolicy {
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    float dxa[4] = {0.f, 0.f, 0.f, 0.f};
     const int q = warp >> 2;                                   // unit quarter of every item / dims 4 q .. 4 q + 3 of Q and PG
     int sidx = 32 * (warp & 3) + lane;                         // state slot (Q) / unit slot (PG) of this epilogue thread
     asm volatile("" : "+r"(sidx));                             // (opaque: otherwise re-derived from S2R SR_TID.X inside the item loop)
@@ -478,226 +478,214 @@ struct RbfTcBwdPolicy {
         }
       }
       BT_IPRINT
-    } else {
-      // =============== epilogue warps ===============
+    } else if (warp >= kBtEpiWarps + 2) {
+      // =============== drain warps (one per tensor-memory lane quarter; thread <-> unit of a PG tile / state of a Q tile) ===============
+      // Everything that is not theta -> tau runs here, off the 16 epilogue warps that pace the kernel: X' of every output (the B operand of
+      // the parameter-gradient product), the PG tiles (tensor memory -> red.global into the launch's accumulators) and, once per output,
+      // the state gradient with its lengthscale statistic.  (Measured before the split: a fifth of the epilogue warps' time.)
       const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      // this state's block scale (as the state threads computed it) and its x
-      float xq[4], mx = 0.f;
+      const uint32_t aXp = sm.sb + kBtOffXp;
+      const uint32_t tq0 = sm.tmem + kBtQCol + lane_base, tp0 = sm.tmem + kBtPgCol + lane_base;
+      float xv[16], dxa[16];
 #pragma unroll
-      for (int d = 0; d < DP; ++d) mx = fmaxf(mx, fabsf(sm.xs[d * kBtStates + sidx]));
-#pragma unroll
-      for (int t = 0; t < 4; ++t) xq[t] = 4 * q + t < DP ? sm.xs[(4 * q + t) * kBtStates + sidx] : 0.f;
-      float sn_, inv_n;
-      rbf_pow2_scale(mx, sn_, inv_n);
-      float Ak = 0.f, inv_s = 1.f;
-      const uint32_t aTau = sm.sb + kBtOffTau, aXp = sm.sb + kBtOffXp;
-      const uint32_t tq0 = sm.tmem + kBtQCol + lane_base, tp0 = sm.tmem + kBtPgCol + lane_base, ta0 = sm.tmem + q * 32 + lane_base;
-      int k = 0, j = 0;              // coordinates of item i
-      int fk = 0, fj = 0;            // coordinates (output, inducing item) of the oldest PG tile not yet added to the global accumulators
-      int outstanding = 0;           // PG tiles produced and not yet flushed
-      long pcf = pg0;                // running index of that oldest tile
-      uint32_t rA[16], rB[16];
-      BT_E0
-      tc_wait(acc_full(sm, static_cast<int>(b0 & 1)), static_cast<uint32_t>((b0 >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tc_ld16_async(ta0 + static_cast<uint32_t>(b0 & 1) * kTcbUnits, rA);   // first half of the first item; later ones are prefetched below
-      BT_E(0)
+      for (int d = 0; d < 16; ++d) {
+        xv[d] = d < DP ? sm.xs[d * kBtStates + sidx] : 0.f;
+        dxa[d] = 0.f;
+      }
+      long pc = pg0;
 #pragma unroll 1
-      for (int i = 0; i <= n + 1; ++i) {   // i >= n: drain only (last Q epilogue, the two PG tiles still in flight)
-        const bool real = i < n;
-        const long b = b0 + i;
-        const int slot = static_cast<int>(b & 1);
-        const bool is_k = real && j >= nbs;
-        if (j == 0) {
-          if (real) {
-            const float* hdr_k = sm.hdr + k * g.hdr_floats;
-            Ak = 0.f;
+      for (int k = 0; k < g.D_out; ++k) {
+        const long kk = kk0 + k;
+        const float gk = sm.gs[k * kBtStates + sidx];
+        // ---- X' of this k (MN-major B operand of PG): columns d (heads of g x_d), 16 + d (remainders), 32 / 33 (g); the previous k's
+        //      last PG must have executed ----
+        if (kk >= 1) mbar_wait_sleepy(xp_empty(sm), static_cast<uint32_t>((kk - 1) & 1), GPODE_BT_SLEEP_NS);
+        {
+          uint32_t hd[8], rm[8];
 #pragma unroll
-            for (int d = 0; d < DP; ++d) {
-              const float xv = sm.xs[d * kBtStates + sidx];
-              Ak = fmaf(hdr_k[d] * xv, xv, Ak);
+          for (int v = 0; v < 8; ++v) bt_split2(gk * xv[2 * v], gk * xv[2 * v + 1], hd[v], rm[v]);
+          const uint32_t row = aXp + sidx * 16;
+          sts128(row, hd[0], hd[1], hd[2], hd[3]);
+          sts128(row + 2048, hd[4], hd[5], hd[6], hd[7]);
+          sts128(row + 2 * 2048, rm[0], rm[1], rm[2], rm[3]);
+          sts128(row + 3 * 2048, rm[4], rm[5], rm[6], rm[7]);
+          uint32_t hg, lg;
+          bt_split2(gk, 0.f, hg, lg);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(row + 4 * 2048), "r"((hg & 0xFFFFu) | (lg << 16)) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_arrive(xp_full(sm));
+        // ---- the PG tiles of this k: tensor memory -> global accumulators ----
+#pragma unroll 1
+        for (int jm = 0; jm < nbm; ++jm, ++pc) {
+          mbar_wait_sleepy(pg_full(sm, static_cast<int>(pc & 1)), static_cast<uint32_t>((pc >> 1) & 1), GPODE_BT_SLEEP_NS);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tp = tp0 + static_cast<uint32_t>(pc & 1) * kTcbQN;
+          uint32_t ph[16], pl[16], ps0, ps1;
+          tc_ld16_async(tp, ph);
+          tc_ld16_async(tp + 16, pl);
+          tc_ld2_async(tp + 32, ps0, ps1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("" : "+r"(ps0), "+r"(ps1)::"memory");
+          tc_ld_wait(ph);   // (orders the uses below behind the wait)
+          tc_ld_wait(pl);
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_arrive(pg_empty(sm, static_cast<int>(pc & 1)));
+          const int unit = jm * kTcbUnits + sidx;
+          if (unit < g.M) {
+            const size_t base = (static_cast<size_t>(blockIdx.y) * g.D_out + k) * (2 * g.MP2) + unit;
+            float* dst = sm.g_pg + base * DP;
+            if constexpr (DP == 16) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4 * c), "f"(__uint_as_float(ph[4 * c]) + __uint_as_float(pl[4 * c])),
+                             "f"(__uint_as_float(ph[4 * c + 1]) + __uint_as_float(pl[4 * c + 1])), "f"(__uint_as_float(ph[4 * c + 2]) + __uint_as_float(pl[4 * c + 2])),
+                             "f"(__uint_as_float(ph[4 * c + 3]) + __uint_as_float(pl[4 * c + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int d = 0; d < DP; ++d) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + d), "f"(__uint_as_float(ph[d]) + __uint_as_float(pl[d])) : "memory");
             }
-            inv_s = inv_n * sm.sk[k];
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(sm.g_dnu + base), "f"(__uint_as_float(ps0) + __uint_as_float(ps1)) : "memory");
           }
         }
-        if (real && j == nbs) {
-          // X' of this k (MN-major B operand of PG): columns d (heads of g x_d), 16 + d (remainders), 32 / 33 (g).  The previous k's last
-          // PG was issued at least nbs items ago.
-          BT_E(4)
-          if (kk0 + k >= 1) mbar_wait_sleepy(xp_empty(sm), static_cast<uint32_t>((kk0 + k - 1) & 1), GPODE_BT_SLEEP_NS);
-          BT_E(8)
-          uint32_t h01, l01, h23, l23;
-          const float g_cur = sm.gs[k * kBtStates + sidx];
-          bt_split2(g_cur * xq[0], g_cur * xq[1], h01, l01);
-          bt_split2(g_cur * xq[2], g_cur * xq[3], h23, l23);
-          const uint32_t row = aXp + sidx * 16 + (q & 1) * 8;
-          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(row + (q >> 1) * 2048), "r"(h01), "r"(h23) : "memory");
-          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(row + (2 + (q >> 1)) * 2048), "r"(l01), "r"(l23) : "memory");
-          if (q == 0) {
-            uint32_t hg, lg;
-            bt_split2(g_cur, 0.f, hg, lg);
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(aXp + 4 * 2048 + sidx * 16), "r"((hg & 0xFFFFu) | (lg << 16)) : "memory");
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // ---- Q of this k: state gradient dx_k = g_k (Q + 2 c_d x_d Es) and the lengthscale statistic sum_n x_d dx_kd ----
+        mbar_wait_sleepy(q_full(sm, static_cast<int>(kk & 1)), static_cast<uint32_t>((kk >> 1) & 1), GPODE_BT_SLEEP_NS);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+          const uint32_t tq = tq0 + static_cast<uint32_t>(kk & 1) * kTcbQN;
+          uint32_t qh[16], ql[16], qs0, qs1;
+          tc_ld16_async(tq, qh);
+          tc_ld16_async(tq + 16, ql);
+          tc_ld2_async(tq + 32, qs0, qs1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("" : "+r"(qs0), "+r"(qs1)::"memory");
+          tc_ld_wait(qh);
+          tc_ld_wait(ql);
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) tc_arrive(xp_full(sm));
+          if (lane == 0) tc_arrive(q_empty(sm, static_cast<int>(kk & 1)));
+          const float es = __uint_as_float(qs0) + __uint_as_float(qs1);
+          const float* hdr_k = sm.hdr + k * g.hdr_floats;
+          float red[16];
+#pragma unroll
+          for (int d = 0; d < 16; ++d) {
+            red[d] = 0.f;
+            if (d < DP) {
+              const float dxk = gk * fmaf(2.f * hdr_k[d] * xv[d], es, __uint_as_float(qh[d]) + __uint_as_float(ql[d]));
+              dxa[d] += dxk;
+              red[d] = xv[d] * dxk;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)   // DP independent butterflies, interleaved
+#pragma unroll
+            for (int d = 0; d < DP; ++d) red[d] += __shfl_xor_sync(0xffffffffu, red[d], o);
+          float rv = 0.f;
+#pragma unroll
+          for (int d = 0; d < DP; ++d) rv = lane == d ? red[d] : rv;
+          if (lane < DP) atomicAdd(&sm.dell[k * DP + lane], rv);   // shared-memory accumulator of the CTA (flush() adds it to the launch's)
+        }
+      }
+      sm.blk = b0 + n;
+      sm.kk = kk0 + g.D_out;
+      sm.pgc = pg0 + static_cast<long>(g.D_out) * nbm;
+      __syncthreads();   // every MMA of this evaluation has executed and every epilogue is done: xs / X' may change (dx aliases X')
+#pragma unroll
+      for (int d = 0; d < DP; ++d) sm.dx[d * kBtStates + sidx] = dxa[d];
+      __syncthreads();
+      return;
+    } else {
+      // =============== epilogue warps: theta -> tau, nothing else ===============
+      const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+      float mx = 0.f;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) mx = fmaxf(mx, fabsf(sm.xs[d * kBtStates + sidx]));
+      float sn_, inv_n;
+      rbf_pow2_scale(mx, sn_, inv_n);   // this state's block scale (as the state threads computed it)
+      float Ak = 0.f, inv_s = 1.f;
+      const uint32_t aTau = sm.sb + kBtOffTau;
+      const uint32_t ta0 = sm.tmem + q * 32 + lane_base;
+      int k = 0, j = 0;              // coordinates of item i
+      uint32_t rA[16], rB[16];
+      const uint32_t b0u = static_cast<uint32_t>(b0);   // (slots and phase bits need the low bits only; 64-bit counters were spilled in this loop)
+      int i_wait = b0 >= 2 ? 0 : static_cast<int>(2 - b0);   // first item of this evaluation whose tau buffer was used before
+      asm volatile("" : "+r"(i_wait));                              // (opaque: not re-derived from the spilled 64-bit counter in the loop)
+      tc_wait(acc_full(sm, static_cast<int>(b0u & 1)), (b0u >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tc_ld16_async(ta0 + (b0u & 1) * kTcbUnits, rA);   // first half of the first item; later ones are prefetched below
+      uint32_t b = b0u;              // running item index (low bits)
+#pragma unroll 1
+      for (int i = 0; i < n; ++i, ++b) {
+        const int slot = static_cast<int>(b & 1);
+        const bool is_k = j >= nbs;
+        if (j == 0) {
+          const float* hdr_k = sm.hdr + k * g.hdr_floats;
+          Ak = 0.f;
+#pragma unroll
+          for (int d = 0; d < DP; ++d) {
+            const float xv = sm.xs[d * kBtStates + sidx];
+            Ak = fmaf(hdr_k[d] * xv, xv, Ak);
+          }
+          inv_s = inv_n * sm.sk[k];
         }
         // ---- the first theta half was prefetched under the previous item; the second half is loaded under the first half's
         //      transcendentals ----
-        const bool do_flush = outstanding > 0 && (!real || (is_k && outstanding >= 2));
-        const bool do_q = j == 1 && k > 0;
-        const long kq = kk0 + k - 1;
-        if (real && b >= 2) mbar_wait_sleepy(tau_empty(sm, slot), static_cast<uint32_t>(((b - 2) >> 1) & 1), GPODE_BT_SLEEP_NS);
-        BT_E(1)
+        if (i >= i_wait) mbar_wait_sleepy(tau_empty(sm, slot), ((b - 2u) >> 1) & 1u, GPODE_BT_SLEEP_NS);
         tc_ld_wait(rA);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (real) {
-          tc_ld16_async(ta0 + slot * kTcbUnits + 16, rB);
-          const float addk = is_k ? Ak : 0.f;
-          const uint32_t trow = aTau + slot * kBtTauBytes + sidx * 16 + (4 * q) * 2048;
+        tc_ld16_async(ta0 + slot * kTcbUnits + 16, rB);
+        const float addk = is_k ? Ak : 0.f;
+        const uint32_t trow = aTau + slot * kBtTauBytes + sidx * 16 + (4 * q) * 2048;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t hd[4], rm[4];
+        for (int c = 0; c < 2; ++c) {
+          uint32_t hd[4], rm[4];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const float2 tt = fma2(make_float2(__uint_as_float(rA[8 * c + 2 * v]), __uint_as_float(rA[8 * c + 2 * v + 1])), bc(inv_s), bc(addk));   // un-scaling and A_k(x): one packed FFMA2 per pair
-              const float t0 = tt.x, t1 = tt.y;
-              bt_split2((GPODE_BT_EXP & 4) ? t0 : (is_k ? ex2_approx(t0) : __cosf(t0)), (GPODE_BT_EXP & 4) ? t1 : (is_k ? ex2_approx(t1) : __cosf(t1)), hd[v], rm[v]);
-            }
-            sts128(trow + c * 2048, hd[0], hd[1], hd[2], hd[3]);
-            sts128(trow + (16 + c) * 2048, rm[0], rm[1], rm[2], rm[3]);
+          for (int v = 0; v < 4; ++v) {
+            const float2 tt = fma2(make_float2(__uint_as_float(rA[8 * c + 2 * v]), __uint_as_float(rA[8 * c + 2 * v + 1])), bc(inv_s), bc(addk));   // un-scaling and A_k(x): one packed FFMA2 per pair
+            const float t0 = tt.x, t1 = tt.y;
+            bt_split2((GPODE_BT_EXP & 4) ? t0 : (is_k ? ex2_approx(t0) : __cosf(t0)), (GPODE_BT_EXP & 4) ? t1 : (is_k ? ex2_approx(t1) : __cosf(t1)), hd[v], rm[v]);
           }
-          BT_E(3)
-          tc_ld_wait(rB);
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) tc_arrive(acc_empty(sm, slot));
-          if (i + 1 < n) {   // first half of the next item (its theta was issued in front of this item's second products): lands under the second half's transcendentals
-            tc_wait(acc_full(sm, slot ^ 1), static_cast<uint32_t>(((b + 1) >> 1) & 1));
-            BT_E(7)
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            tc_ld16_async(ta0 + (slot ^ 1) * kTcbUnits, rA);
-          }
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t hd[4], rm[4];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const float2 tt = fma2(make_float2(__uint_as_float(rB[8 * c + 2 * v]), __uint_as_float(rB[8 * c + 2 * v + 1])), bc(inv_s), bc(addk));   // un-scaling and A_k(x): one packed FFMA2 per pair
-              const float t0 = tt.x, t1 = tt.y;
-              bt_split2((GPODE_BT_EXP & 4) ? t0 : (is_k ? ex2_approx(t0) : __cosf(t0)), (GPODE_BT_EXP & 4) ? t1 : (is_k ? ex2_approx(t1) : __cosf(t1)), hd[v], rm[v]);
-            }
-            sts128(trow + (2 + c) * 2048, hd[0], hd[1], hd[2], hd[3]);
-            sts128(trow + (18 + c) * 2048, rm[0], rm[1], rm[2], rm[3]);
-          }
-          if (!(GPODE_BT_EXP & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) tc_arrive(tau_full(sm, slot));   // the issuer may go: theta(b + 2), Q(b), PG(b)
+          sts128(trow + c * 2048, hd[0], hd[1], hd[2], hd[3]);
+          sts128(trow + (16 + c) * 2048, rm[0], rm[1], rm[2], rm[3]);
         }
-        BT_E(3)
-        // ---- behind the hand-over, off the issuer's critical path: the PG tile two inducing items back goes to the global accumulators (its
-        //      buffer is the one PG(b) writes: the issuer waits for pg_empty only after theta(b + 2) and Q(b)), and, in the second item of
-        //      an output, the state gradient of the previous output ----
-        if (do_flush || do_q) {
-          uint32_t pgr[10], qr[10];
-#pragma unroll
-          for (int v = 0; v < 10; ++v) pgr[v] = qr[v] = 0u;
-          if (do_flush) {
-            mbar_wait_sleepy(pg_full(sm, static_cast<int>(pcf & 1)), static_cast<uint32_t>((pcf >> 1) & 1), GPODE_BT_SLEEP_NS);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tp = tp0 + static_cast<uint32_t>(pcf & 1) * kTcbQN;
-            tc_ld4_async(tp + 4 * q, pgr[0], pgr[1], pgr[2], pgr[3]);
-            tc_ld4_async(tp + 16 + 4 * q, pgr[4], pgr[5], pgr[6], pgr[7]);
-            if (q == 0) tc_ld2_async(tp + 32, pgr[8], pgr[9]);
-          }
-          if (do_q) {
-            mbar_wait_sleepy(q_full(sm, static_cast<int>(kq & 1)), static_cast<uint32_t>((kq >> 1) & 1), GPODE_BT_SLEEP_NS);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tq = tq0 + static_cast<uint32_t>(kq & 1) * kTcbQN;
-            tc_ld4_async(tq + 4 * q, qr[0], qr[1], qr[2], qr[3]);
-            tc_ld4_async(tq + 16 + 4 * q, qr[4], qr[5], qr[6], qr[7]);
-            tc_ld2_async(tq + 32, qr[8], qr[9]);
-          }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");   // (covers every outstanding load of the thread, the prefetched theta half included)
-          tc_ld_fence(pgr);
-          tc_ld_fence(qr);
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            if (do_flush) tc_arrive(pg_empty(sm, static_cast<int>(pcf & 1)));
-            if (do_q) tc_arrive(q_empty(sm, static_cast<int>(kq & 1)));
-          }
-          if (do_flush) {
-            const int unit = fj * kTcbUnits + sidx;   // thread <-> unit of the tile, dims 4 q .. 4 q + 3 (+ the sum column for q = 0)
-            if (unit < g.M) {
-              const size_t base = (static_cast<size_t>(blockIdx.y) * g.D_out + fk) * (2 * g.MP2) + unit;
-              float* dst = sm.g_pg + base * DP + 4 * q;
-              float pv[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) pv[t] = __uint_as_float(pgr[t]) + __uint_as_float(pgr[4 + t]);
-              if constexpr (DP == 16) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(pv[0]), "f"(pv[1]), "f"(pv[2]), "f"(pv[3]) : "memory");
-              } else {
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                  if (4 * q + t < DP) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + t), "f"(pv[t]) : "memory");
-              }
-              if (q == 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(sm.g_dnu + base), "f"(__uint_as_float(pgr[8]) + __uint_as_float(pgr[9])) : "memory");
-            }
-            ++pcf;
-            --outstanding;
-            if (++fj == nbm) {
-              fj = 0;
-              ++fk;
-            }
-          }
-          // ---- state gradient and statistics of the previous output ----
-          if (do_q) {
-            const float es = __uint_as_float(qr[8]) + __uint_as_float(qr[9]);
-            const float* hdr_k = sm.hdr + (k - 1) * g.hdr_floats;
-            const float g_prev = sm.gs[(k - 1) * kBtStates + sidx];
-            float red[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int d = 4 * q + t;
-              red[t] = 0.f;
-              if (d < DP) {
-                const float dxk = g_prev * fmaf(2.f * hdr_k[d] * xq[t], es, __uint_as_float(qr[t]) + __uint_as_float(qr[4 + t]));
-                dxa[t] += dxk;
-                red[t] = xq[t] * dxk;
-              }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)   // four independent butterflies, interleaved
-#pragma unroll
-              for (int t = 0; t < 4; ++t) red[t] += __shfl_xor_sync(0xffffffffu, red[t], o);
-            // sum_n x_d dx_kd of the warp's states joins the CTA's shared-memory accumulator (per-thread accumulators carried through the
-            // item loop were spilled: with 227 KB of the SM's 256 KB carved out as shared memory the L1 holds next to nothing and every
-            // LDL of the loop went to L2)
-            const float rv = lane == 0 ? red[0] : lane == 1 ? red[1] : lane == 2 ? red[2] : red[3];
-            if (lane < 4 && 4 * q + lane < DP) atomicAdd(&sm.dell[(k - 1) * DP + 4 * q + lane], rv);
-          }
+        tc_ld_wait(rB);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_arrive(acc_empty(sm, slot));
+        if (i + 1 < n) {   // first half of the next item (its theta was issued in front of this item's second products): lands under the second half's transcendentals
+          tc_wait(acc_full(sm, slot ^ 1), ((b + 1u) >> 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          tc_ld16_async(ta0 + (slot ^ 1) * kTcbUnits, rA);
         }
-        if (is_k) ++outstanding;
-        BT_E(3)
-        BT_E(6)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t hd[4], rm[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float2 tt = fma2(make_float2(__uint_as_float(rB[8 * c + 2 * v]), __uint_as_float(rB[8 * c + 2 * v + 1])), bc(inv_s), bc(addk));
+            const float t0 = tt.x, t1 = tt.y;
+            bt_split2((GPODE_BT_EXP & 4) ? t0 : (is_k ? ex2_approx(t0) : __cosf(t0)), (GPODE_BT_EXP & 4) ? t1 : (is_k ? ex2_approx(t1) : __cosf(t1)), hd[v], rm[v]);
+          }
+          sts128(trow + (2 + c) * 2048, hd[0], hd[1], hd[2], hd[3]);
+          sts128(trow + (18 + c) * 2048, rm[0], rm[1], rm[2], rm[3]);
+        }
+        if (!(GPODE_BT_EXP & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_arrive(tau_full(sm, slot));   // the issuer may go: theta(b + 2), Q(b), PG(b)
         if (++j == nbi) {
           j = 0;
           ++k;
         }
       }
-      BT_EPRINT
     }
     sm.blk = b0 + n;
     sm.kk = kk0 + g.D_out;
     sm.pgc = pg0 + static_cast<long>(g.D_out) * nbm;
     __syncthreads();   // every MMA of this evaluation has executed (the last Q commit covers them) and every epilogue is done: xs / X' may change
-    if (tid < kBtEpi) {
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (4 * q + t < DP) sm.dx[(4 * q + t) * kBtStates + sidx] = dxa[t];
-    }
-    __syncthreads();
+    __syncthreads();   // (the drain warps write dx between the two barriers)
   }
 };
 
