@@ -384,25 +384,17 @@ struct RbfTcBwdPolicy {
     if (warp == kBtEpiWarps + 1) {
       // =============== bulk-copy producer: keeps both rings full, through this evaluation and into the next ===============
       if (lane == 0) {
+        // The slots drain in the issuer's own order -- theta(b + 2) then Q(b) per item -- so the producer blocks on them in that order
+        // (hardware wake-up, no polling): tile f + 2 of the theta ring follows theta(f), tile f of the second ring follows Q(f - 2).
         const long end = min(sm.total, b0 + n + 2);
-        long fth = b0 + 2, fp = b0 + 2;   // tiles < b0 + 2 were fetched by setup() or by the tail of the previous evaluation
-        unsigned long long idle_t0 = 0;
-        int spins = 0;
-        while (fth < end || fp < end) {
-          bool any = false;
-          if (fth < end && mbar_test(th_empty(sm, static_cast<int>(fth & 1)), static_cast<uint32_t>(((fth - 2) >> 1) & 1))) {
-            fetch_th(sm, g, fth++);
-            any = true;
+        for (long f = b0; f < end; ++f) {   // tiles < b0 + 2 were fetched by setup() or by the tail of the previous evaluation
+          if (f + 2 < end) {
+            tc_wait(th_empty(sm, static_cast<int>(f & 1)), static_cast<uint32_t>((f >> 1) & 1));
+            fetch_th(sm, g, f + 2);
           }
-          if (fp < end && mbar_test(p_empty(sm, static_cast<int>(fp & 1)), static_cast<uint32_t>(((fp - 2) >> 1) & 1))) {
-            fetch_p(sm, g, fp++);
-            any = true;
-          }
-          if (any) spins = 0;
-          else {   // a tile is needed a whole item after its slot drains: poll at leisure; time-bounded like every other wait (common.cuh)
-            __nanosleep(2 * GPODE_BT_SLEEP_NS);
-            if (++spins == 64) idle_t0 = global_ns();
-            if (spins > 64 && (spins & 63) == 0 && GPODE_WAIT_TIMEOUT_NS != 0ull && global_ns() - idle_t0 > GPODE_WAIT_TIMEOUT_NS) __trap();
+          if (f >= b0 + 2) {
+            tc_wait(p_empty(sm, static_cast<int>(f & 1)), static_cast<uint32_t>(((f - 2) >> 1) & 1));
+            fetch_p(sm, g, f);
           }
         }
       }
@@ -633,7 +625,7 @@ struct RbfTcBwdPolicy {
         }
         // ---- the first theta half was prefetched under the previous item; the second half is loaded under the first half's
         //      transcendentals ----
-        if (i >= i_wait) mbar_wait_sleepy(tau_empty(sm, slot), ((b - 2u) >> 1) & 1u, GPODE_BT_SLEEP_NS);
+        if (i >= i_wait) tc_wait(tau_empty(sm, slot), ((b - 2u) >> 1) & 1u);   // (on the critical path since the drain warps exist: hardware wake-up, no sleep)
         tc_ld_wait(rA);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tc_ld16_async(ta0 + slot * kTcbUnits + 16, rB);
