@@ -478,36 +478,38 @@ struct RbfTcBwdPolicy {
       const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
       const uint32_t aXp = sm.sb + kBtOffXp;
       const uint32_t tq0 = sm.tmem + kBtQCol + lane_base, tp0 = sm.tmem + kBtPgCol + lane_base;
-      float xv[16], dxa[16];
+      float dxa[16];
 #pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        xv[d] = d < DP ? sm.xs[d * kBtStates + sidx] : 0.f;
-        dxa[d] = 0.f;
-      }
+      for (int d = 0; d < 16; ++d) dxa[d] = 0.f;
+      // X' of output k (MN-major B operand of PG): columns d (heads of g x_d), 16 + d (remainders), 32 / 33 (g); the last PG of the
+      // previous output must have executed.  (x is re-read from shared memory where it is needed: registers are short in these warps.)
+      auto write_xprime = [&](int k, long kk) {
+        if (kk >= 1) mbar_wait_sleepy(xp_empty(sm), static_cast<uint32_t>((kk - 1) & 1), GPODE_BT_SLEEP_NS);
+        const float gk = sm.gs[k * kBtStates + sidx];
+        const uint32_t row = aXp + sidx * 16;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t hd[4], rm[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int d = 8 * c + 2 * v;
+            bt_split2(d < DP ? gk * sm.xs[d * kBtStates + sidx] : 0.f, d + 1 < DP ? gk * sm.xs[(d + 1) * kBtStates + sidx] : 0.f, hd[v], rm[v]);
+          }
+          sts128(row + c * 2048, hd[0], hd[1], hd[2], hd[3]);
+          sts128(row + (2 + c) * 2048, rm[0], rm[1], rm[2], rm[3]);
+        }
+        uint32_t hg, lg;
+        bt_split2(gk, 0.f, hg, lg);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(row + 4 * 2048), "r"((hg & 0xFFFFu) | (lg << 16)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_arrive(xp_full(sm));
+      };
+      write_xprime(0, kk0);
       long pc = pg0;
 #pragma unroll 1
       for (int k = 0; k < g.D_out; ++k) {
         const long kk = kk0 + k;
-        const float gk = sm.gs[k * kBtStates + sidx];
-        // ---- X' of this k (MN-major B operand of PG): columns d (heads of g x_d), 16 + d (remainders), 32 / 33 (g); the previous k's
-        //      last PG must have executed ----
-        if (kk >= 1) mbar_wait_sleepy(xp_empty(sm), static_cast<uint32_t>((kk - 1) & 1), GPODE_BT_SLEEP_NS);
-        {
-          uint32_t hd[8], rm[8];
-#pragma unroll
-          for (int v = 0; v < 8; ++v) bt_split2(gk * xv[2 * v], gk * xv[2 * v + 1], hd[v], rm[v]);
-          const uint32_t row = aXp + sidx * 16;
-          sts128(row, hd[0], hd[1], hd[2], hd[3]);
-          sts128(row + 2048, hd[4], hd[5], hd[6], hd[7]);
-          sts128(row + 2 * 2048, rm[0], rm[1], rm[2], rm[3]);
-          sts128(row + 3 * 2048, rm[4], rm[5], rm[6], rm[7]);
-          uint32_t hg, lg;
-          bt_split2(gk, 0.f, hg, lg);
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(row + 4 * 2048), "r"((hg & 0xFFFFu) | (lg << 16)) : "memory");
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) tc_arrive(xp_full(sm));
         // ---- the PG tiles of this k: tensor memory -> global accumulators ----
 #pragma unroll 1
         for (int jm = 0; jm < nbm; ++jm, ++pc) {
@@ -543,7 +545,10 @@ struct RbfTcBwdPolicy {
             asm volatile("red.global.add.f32 [%0], %1;" ::"l"(sm.g_dnu + base), "f"(__uint_as_float(ps0) + __uint_as_float(ps1)) : "memory");
           }
         }
-        // ---- Q of this k: state gradient dx_k = g_k (Q + 2 c_d x_d Es) and the lengthscale statistic sum_n x_d dx_kd ----
+        // ---- X' of the NEXT output first (the issuer needs it two items into that output), then Q of this k: state gradient
+        //      dx_k = g_k (Q + 2 c_d x_d Es) and the lengthscale statistic sum_n x_d dx_kd ----
+        if (k + 1 < g.D_out) write_xprime(k + 1, kk + 1);
+        const float gk = sm.gs[k * kBtStates + sidx];
         mbar_wait_sleepy(q_full(sm, static_cast<int>(kk & 1)), static_cast<uint32_t>((kk >> 1) & 1), GPODE_BT_SLEEP_NS);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
@@ -566,9 +571,10 @@ struct RbfTcBwdPolicy {
           for (int d = 0; d < 16; ++d) {
             red[d] = 0.f;
             if (d < DP) {
-              const float dxk = gk * fmaf(2.f * hdr_k[d] * xv[d], es, __uint_as_float(qh[d]) + __uint_as_float(ql[d]));
+              const float xd = sm.xs[d * kBtStates + sidx];
+              const float dxk = gk * fmaf(2.f * hdr_k[d] * xd, es, __uint_as_float(qh[d]) + __uint_as_float(ql[d]));
               dxa[d] += dxk;
-              red[d] = xv[d] * dxk;
+              red[d] = xd * dxk;
             }
           }
 #pragma unroll
