@@ -45,7 +45,8 @@ constexpr int kBtStates = 128;                 // states per CTA
 constexpr int kBtEpiWarps = 16;
 constexpr int kBtEpi = kBtEpiWarps * 32;
 constexpr int kBtFlushWarps = 4;               // drain warps: one per tensor-memory lane quarter (PG / Q accumulators -> global / shared memory)
-constexpr int kBtThreads = kBtEpi + 64 + 32 * kBtFlushWarps;   // + MMA-issuer warp + bulk-copy producer warp + drain warps
+constexpr int kBtThreads = kBtEpi + 64 + 32 * kBtFlushWarps + 32;   // + MMA-issuer warp (theta, Q) + bulk-copy producer warp + drain warps + second MMA-issuer warp (PG)
+constexpr int kBtPgIssuer = kBtEpiWarps + 2 + kBtFlushWarps;        // warp index of the second issuer
 constexpr int kBtTauBytes = 2 * 16 * 2048;     // one tau tile: 2 planes x 16 unit groups x (128 states x 16 B)
 constexpr int kBtABytes = 3 * 4096;            // state operand of theta: X_h | X_l | (s_n, s_n, 0 ..)
 constexpr int kBtXpBytes = 6 * 2048;           // X' (128 states x 48 columns bf16, MN-major: chunk (s, n / 8) at (n / 8) * 2048 + 16 s)
@@ -281,7 +282,7 @@ struct RbfTcBwdPolicy {
         mbar_init(acc_full(sm, i), 1);
         mbar_init(acc_empty(sm, i), kBtEpiWarps);
         mbar_init(tau_full(sm, i), kBtEpiWarps);
-        mbar_init(tau_empty(sm, i), 1);
+        mbar_init(tau_empty(sm, i), 2);   // both issuer warps: Q(b) executed, PG(b) executed (or nothing to do)
         mbar_init(q_full(sm, i), 1);
         mbar_init(q_empty(sm, i), kBtFlushWarps);
         mbar_init(pg_full(sm, i), 1);
@@ -400,9 +401,8 @@ struct RbfTcBwdPolicy {
       }
     } else if (warp == kBtEpiWarps) {
       // =============== MMA issuer: the whole warp walks the schedule, one elected lane issues ===============
-      const uint32_t aA = sm.sb + kBtOffA, aTau = sm.sb + kBtOffTau, aTh = sm.sb + kBtOffTh, aP = sm.sb + kBtOffP, aXp = sm.sb + kBtOffXp;
-      constexpr uint32_t id_th = tc_idesc_f16(128, kTcbUnits), id_off = tc_idesc(128, kTcbUnits), id_q = tc_idesc_bf16(128, kTcbQN, 0, 0),
-                         id_pg = tc_idesc_bf16(128, kTcbQN, 1, 1);
+      const uint32_t aA = sm.sb + kBtOffA, aTau = sm.sb + kBtOffTau, aTh = sm.sb + kBtOffTh, aP = sm.sb + kBtOffP;
+      constexpr uint32_t id_th = tc_idesc_f16(128, kTcbUnits), id_off = tc_idesc(128, kTcbUnits), id_q = tc_idesc_bf16(128, kTcbQN, 0, 0);
       BT_I0
       auto issue_theta = [&](long b) {
         const int slot = static_cast<int>(b & 1);
@@ -431,9 +431,11 @@ struct RbfTcBwdPolicy {
         const long b = b0 + i;
         const int slot = static_cast<int>(b & 1);
         const long kk = kk0 + k;
+        // theta(b + 2) goes out as soon as the epilogue warps have READ theta(b) (mid-item: its accumulator is free), not after they have
+        // handed tau(b) over: it executes under the second half of their item and is off the chain tau_full(b) -> Q(b), PG(b) -> tau_empty(b)
+        if (i + 2 < n) issue_theta(b + 2);
         tc_wait(tau_full(sm, slot), static_cast<uint32_t>((b >> 1) & 1));
         BT_I(2)
-        if (i + 2 < n) issue_theta(b + 2);
         tc_wait(p_full(sm, slot), static_cast<uint32_t>((b >> 1) & 1));
         BT_I(3)
         if (j == 0 && kk >= 2) tc_wait(q_empty(sm, static_cast<int>(kk & 1)), static_cast<uint32_t>(((kk - 2) >> 1) & 1));
@@ -447,12 +449,33 @@ struct RbfTcBwdPolicy {
         tcu_commit(p_empty(sm, slot));
         if (j == nbi - 1) tcu_commit(q_full(sm, static_cast<int>(kk & 1)));
         BT_I(5)
+        tcu_commit(tau_empty(sm, slot));
+        BT_I(6)
+        if (++j == nbi) {
+          j = 0;
+          ++k;
+        }
+      }
+      BT_IPRINT
+    } else if (warp == kBtPgIssuer) {
+      // =============== second MMA issuer: the parameter-gradient product PG(b) = tau(b)^T X' of the inducing items ===============
+      // Its dependencies (X' of the output, the PG accumulator two tiles back) are handed over by the drain warps; blocking on them in
+      // the first issuer stalled theta and Q behind them (measured: a third of that warp's time was such waits).
+      const uint32_t aTau = sm.sb + kBtOffTau, aXp = sm.sb + kBtOffXp;
+      constexpr uint32_t id_pg = tc_idesc_bf16(128, kTcbQN, 1, 1);
+      int k = 0, j = 0;
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) {
+        const long b = b0 + i;
+        const int slot = static_cast<int>(b & 1);
+        const long kk = kk0 + k;
+        tc_wait(tau_full(sm, slot), static_cast<uint32_t>((b >> 1) & 1));
         if (j >= nbs) {
           const long pc = pg0 + static_cast<long>(k) * nbm + (j - nbs);
           if (j == nbs) tc_wait(xp_full(sm), static_cast<uint32_t>(kk & 1));
           if (pc >= 2) tc_wait(pg_empty(sm, static_cast<int>(pc & 1)), static_cast<uint32_t>(((pc - 2) >> 1) & 1));
-          BT_I(4)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ta = aTau + slot * kBtTauBytes;
           const uint32_t dpg = sm.tmem + kBtPgCol + static_cast<uint32_t>(pc & 1) * kTcbQN;
 #pragma unroll
           for (int p = 0; p < ((GPODE_BT_EXP & 1) ? 0 : 2); ++p)
@@ -462,14 +485,12 @@ struct RbfTcBwdPolicy {
           tcu_commit(pg_full(sm, static_cast<int>(pc & 1)));
           if (j == nbi - 1) tcu_commit(xp_empty(sm));
         }
-        tcu_commit(tau_empty(sm, slot));
-        BT_I(6)
+        tcu_commit(tau_empty(sm, slot));   // (feature items: no MMA of this warp is pending, the arrival is immediate)
         if (++j == nbi) {
           j = 0;
           ++k;
         }
       }
-      BT_IPRINT
     } else if (warp >= kBtEpiWarps + 2) {
       // =============== drain warps (one per tensor-memory lane quarter; thread <-> unit of a PG tile / state of a Q tile) ===============
       // Everything that is not theta -> tau runs here, off the 16 epilogue warps that pace the kernel: X' of every output (the B operand of
