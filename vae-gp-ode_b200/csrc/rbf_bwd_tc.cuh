@@ -45,8 +45,9 @@ constexpr int kBtStates = 128;                 // states per CTA
 constexpr int kBtEpiWarps = 16;
 constexpr int kBtEpi = kBtEpiWarps * 32;
 constexpr int kBtFlushWarps = 4;               // drain warps: one per tensor-memory lane quarter (PG / Q accumulators -> global / shared memory)
-constexpr int kBtThreads = kBtEpi + 64 + 32 * kBtFlushWarps + 32;   // + MMA-issuer warp (theta, Q) + bulk-copy producer warp + drain warps + second MMA-issuer warp (PG)
-constexpr int kBtPgIssuer = kBtEpiWarps + 2 + kBtFlushWarps;        // warp index of the second issuer
+constexpr int kBtThreads = kBtEpi + 64 + 32 * kBtFlushWarps + 64;   // + MMA-issuer warp (Q) + bulk-copy producer warp + drain warps + two more MMA-issuer warps (PG, theta)
+constexpr int kBtPgIssuer = kBtEpiWarps + 2 + kBtFlushWarps;        // warp index of the PG issuer
+constexpr int kBtThIssuer = kBtPgIssuer + 1;                        // ... of the theta issuer
 constexpr int kBtTauBytes = 2 * 16 * 2048;     // one tau tile: 2 planes x 16 unit groups x (128 states x 16 B)
 constexpr int kBtABytes = 3 * 4096;            // state operand of theta: X_h | X_l | (s_n, s_n, 0 ..)
 constexpr int kBtXpBytes = 6 * 2048;           // X' (128 states x 48 columns bf16, MN-major: chunk (s, n / 8) at (n / 8) * 2048 + 16 s)
@@ -401,39 +402,15 @@ struct RbfTcBwdPolicy {
       }
     } else if (warp == kBtEpiWarps) {
       // =============== MMA issuer: the whole warp walks the schedule, one elected lane issues ===============
-      const uint32_t aA = sm.sb + kBtOffA, aTau = sm.sb + kBtOffTau, aTh = sm.sb + kBtOffTh, aP = sm.sb + kBtOffP;
-      constexpr uint32_t id_th = tc_idesc_f16(128, kTcbUnits), id_off = tc_idesc(128, kTcbUnits), id_q = tc_idesc_bf16(128, kTcbQN, 0, 0);
+      const uint32_t aTau = sm.sb + kBtOffTau, aP = sm.sb + kBtOffP;
+      constexpr uint32_t id_q = tc_idesc_bf16(128, kTcbQN, 0, 0);
       BT_I0
-      auto issue_theta = [&](long b) {
-        const int slot = static_cast<int>(b & 1);
-        tc_wait(th_full(sm, slot), static_cast<uint32_t>((b >> 1) & 1));
-        if (b >= 2) tc_wait(acc_empty(sm, slot), static_cast<uint32_t>(((b - 2) >> 1) & 1));
-        BT_I(0)
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = sm.tmem + slot * kTcbUnits, bt = aTh + slot * kTcbThBytes;
-        if (!(GPODE_BT_EXP & 16)) {
-        tcu_mma_f16(d, tc_desc2(aA, 2048, 128), tc_desc2(bt, 2048, 128), id_th, 0u);                    // X_h G_h
-        tcu_mma_f16(d, tc_desc2(aA + 4096, 2048, 128), tc_desc2(bt, 2048, 128), id_th, 1u);            // X_l G_h
-        tcu_mma_f16(d, tc_desc2(aA, 2048, 128), tc_desc2(bt + 4096, 2048, 128), id_th, 1u);            // X_h G_l
-        tcu_mma_tf32(d, tc_desc2(aA + 8192, 2048, 128), tc_desc2(bt + 8192, 2048, 128), id_off, 1u);   // (s_n, s_n) x (off_h, off_l)
-        }
-        tcu_commit(acc_full(sm, slot));
-        tcu_commit(th_empty(sm, slot));
-        BT_I(1)
-      };
-      // theta runs two items ahead of the second products and is issued IN FRONT of them (the tensor pipe executes in issue order):
-      // theta(b + 2) starts as soon as the epilogue of item b has released its accumulator, so the epilogue of b + 1 never waits for it
-      issue_theta(b0);
-      if (n > 1) issue_theta(b0 + 1);
       int k = 0, j = 0;
 #pragma unroll 1
       for (int i = 0; i < n; ++i) {
         const long b = b0 + i;
         const int slot = static_cast<int>(b & 1);
         const long kk = kk0 + k;
-        // theta(b + 2) goes out as soon as the epilogue warps have READ theta(b) (mid-item: its accumulator is free), not after they have
-        // handed tau(b) over: it executes under the second half of their item and is off the chain tau_full(b) -> Q(b), PG(b) -> tau_empty(b)
-        if (i + 2 < n) issue_theta(b + 2);
         tc_wait(tau_full(sm, slot), static_cast<uint32_t>((b >> 1) & 1));
         BT_I(2)
         tc_wait(p_full(sm, slot), static_cast<uint32_t>((b >> 1) & 1));
@@ -457,6 +434,32 @@ struct RbfTcBwdPolicy {
         }
       }
       BT_IPRINT
+    } else if (warp == kBtThIssuer) {
+      // =============== third MMA issuer: theta(b) = s (x . G + off), two items ahead of the epilogue warps ===============
+      // theta(b + 2) goes out as soon as the epilogue warps have READ theta(b) (mid-item: its accumulator is free) and its operand tile has
+      // landed; on a warp of its own these waits stall nothing else.
+      const uint32_t aA = sm.sb + kBtOffA, aTh = sm.sb + kBtOffTh;
+      constexpr uint32_t id_th = tc_idesc_f16(128, kTcbUnits), id_off = tc_idesc(128, kTcbUnits);
+      BT_I0
+      auto issue_theta = [&](long b) {
+        const int slot = static_cast<int>(b & 1);
+        tc_wait(th_full(sm, slot), static_cast<uint32_t>((b >> 1) & 1));
+        if (b >= 2) tc_wait(acc_empty(sm, slot), static_cast<uint32_t>(((b - 2) >> 1) & 1));
+        BT_I(0)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = sm.tmem + slot * kTcbUnits, bt = aTh + slot * kTcbThBytes;
+        if (!(GPODE_BT_EXP & 16)) {
+        tcu_mma_f16(d, tc_desc2(aA, 2048, 128), tc_desc2(bt, 2048, 128), id_th, 0u);                    // X_h G_h
+        tcu_mma_f16(d, tc_desc2(aA + 4096, 2048, 128), tc_desc2(bt, 2048, 128), id_th, 1u);            // X_l G_h
+        tcu_mma_f16(d, tc_desc2(aA, 2048, 128), tc_desc2(bt + 4096, 2048, 128), id_th, 1u);            // X_h G_l
+        tcu_mma_tf32(d, tc_desc2(aA + 8192, 2048, 128), tc_desc2(bt + 8192, 2048, 128), id_off, 1u);   // (s_n, s_n) x (off_h, off_l)
+        }
+        tcu_commit(acc_full(sm, slot));
+        tcu_commit(th_empty(sm, slot));
+        BT_I(1)
+      };
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) issue_theta(b0 + i);
     } else if (warp == kBtPgIssuer) {
       // =============== second MMA issuer: the parameter-gradient product PG(b) = tau(b)^T X' of the inducing items ===============
       // Its dependencies (X' of the output, the PG accumulator two tiles back) are handed over by the drain warps; blocking on them in
@@ -491,7 +494,7 @@ struct RbfTcBwdPolicy {
           ++k;
         }
       }
-    } else if (warp >= kBtEpiWarps + 2) {
+    } else if (warp >= kBtEpiWarps + 2 && warp < kBtPgIssuer) {
       // =============== drain warps (one per tensor-memory lane quarter; thread <-> unit of a PG tile / state of a Q tile) ===============
       // Everything that is not theta -> tau runs here, off the 16 epilogue warps that pace the kernel: X' of every output (the B operand of
       // the parameter-gradient product), the PG tiles (tensor memory -> red.global into the launch's accumulators) and, once per output,
