@@ -15,13 +15,16 @@
 //   3. Q_k (128 states x 48) += tau B: 16 k-steps of kind::f16 (bf16), B = [P_h | P_l | w_h w_l ..] with P = weight x coefficient --
 //      columns d and 16 + d sum to J^T contributions, 32 + 33 to the weighted sum of tau that the A_k(x) term needs.
 //   4. inducing items only: PG (128 units x 48) = tau^T X': 16 k-steps over the CTA's states, X' = [g x_d heads | remainders | g_h g_l ..]
-//      (one operand per output k, written by the epilogue warps, MN-major) -- columns d and 16 + d sum to sum_n g tau x_d, 32 + 33 to
+//      (one operand per output k, written by the drain warps, MN-major) -- columns d and 16 + d sum to sum_n g tau x_d, 32 + 33 to
 //      sum_n g tau: exactly the accumulators the separate parameter-gradient pass (k_rbf_pgrad_mma: theta and the exponentials a third
-//      time) used to fill.  The warps read PG two items later and add it to the global accumulators (red.global.add.f32).
-//   5. once per k the warps read Q_k: dx_k = g_k (Q + 2 c_d x_d Es), dx += dx_k, lengthscale statistic sum_n x_d dx_kd.
-// Every MMA is issued by one elected lane of a dedicated warp whose control flow is provably warp-uniform, so that descriptors live in
-// uniform registers (a divergent `if (lane == 0)` makes ptxas wrap each tcgen05.mma in a ~100-cycle uniformisation loop -- measured,
-// tools/tc_probe3.cu); a second helper warp issues the bulk copies.  Flow control is mbarrier + tcgen05.commit, all waits time-bounded.
+//      time) used to fill.  The drain warps read PG as soon as it has executed and add it to the global accumulators (red.global.add.f32).
+//   5. once per k the drain warps read Q_k: dx_k = g_k (Q + 2 c_d x_d Es), dx += dx_k, lengthscale statistic sum_n x_d dx_kd.
+// Warp roles (24 warps): 16 epilogue warps do step 2 and nothing else (they pace the kernel); three MMA-issuer warps -- Q, PG, theta --
+// each issue their products through one elected lane with provably warp-uniform control flow, so that descriptors live in uniform
+// registers (a divergent `if (lane == 0)` makes ptxas wrap each tcgen05.mma in a ~100-cycle uniformisation loop -- measured,
+// tools/tc_probe3.cu) and each block on their OWN hand-overs only (one issuer for all three spent a third of its time in such waits); one
+// warp issues the bulk copies; four drain warps (one per tensor-memory lane quarter) write X' and do steps 4 (flush) and 5.  Flow
+// control is mbarrier + tcgen05.commit, all waits time-bounded.
 // Measured costs per item (tools/tc_probe3.cu): theta ~400 cycles, Q ~710, PG ~810 -- the second products are bound by reading the
 // 64 KB tau tile from shared memory (128 B / cycle), not by the tensor pipe; the transcendentals need 1,024 MUFU cycles per item.
 #pragma once
