@@ -39,7 +39,7 @@ import torch  # noqa: E402
 # (one B200; the stage saves make it ~9x the algorithmic 192 B per trajectory-step, and still < 1 % of the HBM peak)
 TRAFFIC = {
     # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (fused tcgen05 reverse sweep), one launch of the full workload
-    "cfg5_rbf_d16_m512_t64_rk4": (27790457088 + 8895649792, "k_rollout_bwd<RbfTcBwdPolicy<16>>, profiles/traffic_r02_cfg5_default.csv"),
+    "cfg5_rbf_d16_m512_t64_rk4": (27873726464 + 9134574592, "k_rollout_bwd<RbfTcBwdPolicy<16>>, profiles/traffic_r02_cfg5_default.csv"),
 }
 
 WORKLOADS = {
