@@ -30,7 +30,14 @@ cudaError_t launch_sweep(Kern kern, const Args& a, int threads, int R, bool bwd,
   attr[0].val.clusterDim.z = static_cast<unsigned>(C);
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, a);
+  cudaError_t e2 = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e2 != cudaSuccess && C > 1) {   // a cluster of this size cannot be placed (partitioned device, ...): the same kernel without the split
+    (void)cudaGetLastError();         // (the exchange buffers sized for C stay allocated; gridDim.z = 1 makes the kernels skip them)
+    cfg.gridDim.z = 1;
+    attr[0].val.clusterDim.z = 1;
+    e2 = cudaLaunchKernelEx(&cfg, kern, a);
+  }
+  return e2;
 }
 
 #define GPODE_DF_DISPATCH_R(KERNEL, a, bwd, st)                                            \

@@ -79,7 +79,14 @@ cudaError_t launch_small(KernSmall kern, const Args& a, cudaStream_t st) {
   attr[0].val.clusterDim.z = static_cast<unsigned>(C);
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, a);
+  cudaError_t e2 = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e2 != cudaSuccess && C > 1) {   // a cluster of this size cannot be placed (partitioned device, ...): the same kernel without the split
+    (void)cudaGetLastError();
+    cfg.gridDim.z = 1;
+    attr[0].val.clusterDim.z = 1;
+    e2 = cudaLaunchKernelEx(&cfg, kern, a);
+  }
+  return e2;
 }
 
 template <>
