@@ -95,7 +95,8 @@ def pipe_model(w, tc_rates):
     SFU: 2 transcendentals per (state, k, unit) and stage, executed = algorithmic."""
     st = STAGES[w["method"]]
     work = algorithmic_work(w)
-    out = {"sfu_alg_cycles": work["sfu"] / 16.0, "fp32_alg_cycles": work["flops"] / 256.0, "tensor_cycles": 0.0, "fp32_residual_cycles": work["flops"] / 256.0}
+    out = {"sfu_alg_cycles": work["sfu"] / 16.0, "fp32_alg_cycles": work["flops"] / 256.0, "tensor_cycles": 0.0, "smem_cycles": 0.0,
+           "fp32_residual_cycles": work["flops"] / 256.0}
     tensor_path = w["variant"] != "df" and w["D_in"] > 8 and w["N"] * w["L"] >= 32768
     if tensor_path:
         units = w["D_out"] * (w["S"] + w["M"])
@@ -104,6 +105,18 @@ def pipe_model(w, tc_rates):
         bwd = st * (items_s * (tc_rates["bwd_theta_cycles"] + tc_rates["bwd_q_cycles"]) +
                     items_m * (tc_rates["bwd_theta_cycles"] + tc_rates["bwd_q_cycles"] + tc_rates["bwd_pg_cycles"])) / 128.0
         out["tensor_cycles"] = fwd + bwd
+        # L1 / shared-memory data pipe (128 B per cycle per SM), bytes the DESIGN moves per (128 states x 128 units) item:
+        #   reverse: tau tile stored once by the epilogue warps (64 KB: bf16 head + remainder planes) and read by Q (64 KB) and, inducing
+        #            items, PG (64 KB); theta operands 4 MMAs x (4 + 4 KB); P tile 16 k-steps x 1.5 KB; X' 16 x 1.5 KB (inducing);
+        #            bulk-copy writes of the operand tiles 24 KB
+        #   forward: per block of 256 units x 2 state tiles: 4 accumulators x 7 k-steps x (4 + 4 KB), bulk-copy write 42 KB, weights read by
+        #            16 warps x 2 halves x 16 broadcast LDS.128 (one 128-B wavefront each)  -> per item-equivalent a quarter of it
+        KB = 1024.0
+        smem_bwd_s = (64 + 64 + 32 + 24 + 24) * KB / 128.0
+        smem_bwd_m = smem_bwd_s + (64 + 24) * KB / 128.0
+        smem_fwd = ((4 * 7 * 8 + 42) * KB / 128.0 + 16 * 2 * 16) / 4.0
+        n_items = items_s + items_m
+        out["smem_cycles"] = st * (items_s * smem_bwd_s + items_m * smem_bwd_m + n_items * smem_fwd) / 128.0
         out["tensor_split"] = {"forward": "3xTF32 (K = 56 for D_in = 16), tcgen05 kind::tf32",
                                "reverse_sweep": "theta: fp16 head + remainder, 3 kind::f16 + 1 kind::tf32 MMA; Q = tau P and PG = tau^T X': bf16 head + remainder "
                                                 "planes of tau from shared memory, 16 kind::f16 k-steps each (fused: one tau per stage)"}
@@ -383,10 +396,11 @@ def run_ours(args):
     pipes = {"sfu": round(pm["sfu_alg_cycles"] * per_gpu_rate / chip_cycles_per_s, 4),
              "sfu_executed": round(pm["sfu_exec_cycles"] * per_gpu_rate / chip_cycles_per_s, 4),
              "tensor": round(pm["tensor_cycles"] * per_gpu_rate / chip_cycles_per_s, 4),
+             "smem": round(pm["smem_cycles"] * per_gpu_rate / chip_cycles_per_s, 4),
              "fp32_residual": round(pm["fp32_residual_cycles"] * per_gpu_rate / chip_cycles_per_s, 4)}
-    binding = max(("sfu", "tensor", "fp32_residual"), key=lambda k: pipes[k])
+    binding = max(("sfu", "tensor", "smem", "fp32_residual"), key=lambda k: pipes[k])
     frac_fp32_alg = round(work["flops"] * per_gpu_rate / fp32_peak, 4)
-    roof = {"bound": {"sfu": "sfu", "tensor": "tensor", "fp32_residual": "fp32_fma"}[binding], "frac": pipes[binding], "pipes": pipes,
+    roof = {"bound": {"sfu": "sfu", "tensor": "tensor", "smem": "smem_pipe", "fp32_residual": "fp32_fma"}[binding], "frac": pipes[binding], "pipes": pipes,
             "achieved": round(achieved_tflops, 3), "peak": round(fp32_peak / 1e12, 2), "unit": "TFLOP/s",
             "frac_fp32_algorithmic": frac_fp32_alg,
             "traffic": TRAFFIC.get(args.workload, (None, None))[0], "traffic_source": TRAFFIC.get(args.workload, (None, None))[1],
@@ -395,7 +409,10 @@ def run_ours(args):
             "note": ("frac = the fraction of the measured time the BINDING pipe needs at its peak rate (pipes: sfu = algorithmic transcendentals, "
                      "sfu_executed = what the kernels evaluate (D <= 8: incl. the re-evaluation in the separate parameter-gradient pass; D > 8: fused, "
                      "equal to algorithmic), tensor = the executed MMAs incl. their precision splits "
-                     "at the measured issue rates, fp32_residual = algorithmic FP32 work that stays on the FMA pipe).  achieved / peak / "
+                     "at the measured issue rates, smem = the bytes the tcgen05 kernels move through the L1 / shared-memory data pipe by design "
+                     "(tau tile stored once and read by two products, operand tiles) at 128 B per cycle per SM -- ncu of the fused reverse sweep: "
+                     "l1tex data pipe 97.6 % busy (tensor-core operand reads 52.5 % + LSU 45.1 %, profiles/ncu_r02_cfg5_t3_bwd_tc.txt), "
+                     "fp32_residual = algorithmic FP32 work that stays on the FMA pipe).  achieved / peak / "
                      "frac_fp32_algorithmic keep the SURVEY 8(d) definition: ALL algorithmic flops over the FP32-pipe peak (can exceed what the "
                      "FP32 pipe really executes once the dot products run on tensor cores)."),
             "tensor_split": pm.get("tensor_split"),
