@@ -107,12 +107,12 @@ def pipe_model(w, tc_rates):
         out["tensor_cycles"] = fwd + bwd
         # L1 / shared-memory data pipe (128 B per cycle per SM), bytes the DESIGN moves per (128 states x 128 units) item:
         #   reverse: tau tile stored once by the epilogue warps (64 KB: bf16 head + remainder planes) and read by Q (64 KB) and, inducing
-        #            items, PG (64 KB); theta operands 4 MMAs x (4 + 4 KB); P tile 16 k-steps x 1.5 KB; X' 16 x 1.5 KB (inducing);
-        #            bulk-copy writes of the operand tiles 24 KB
+        #            items, PG (64 KB); theta: the 4 MMAs' unit operands 4 x 4 KB (the state operand comes from tensor memory); P tile
+        #            16 k-steps x 1.5 KB; X' 16 x 1.5 KB (inducing); bulk-copy writes of the operand tiles 24 KB
         #   forward: per block of 256 units x 2 state tiles: 4 accumulators x 7 k-steps x (4 + 4 KB), bulk-copy write 42 KB, weights read by
         #            16 warps x 2 halves x 16 broadcast LDS.128 (one 128-B wavefront each)  -> per item-equivalent a quarter of it
         KB = 1024.0
-        smem_bwd_s = (64 + 64 + 32 + 24 + 24) * KB / 128.0
+        smem_bwd_s = (64 + 64 + 16 + 24 + 24) * KB / 128.0
         smem_bwd_m = smem_bwd_s + (64 + 24) * KB / 128.0
         smem_fwd = ((4 * 7 * 8 + 42) * KB / 128.0 + 16 * 2 * 16) / 4.0
         n_items = items_s + items_m

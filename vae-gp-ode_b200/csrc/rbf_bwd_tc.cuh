@@ -40,6 +40,12 @@ namespace gpode {
 #ifndef GPODE_BT_SLEEP_NS
 #define GPODE_BT_SLEEP_NS 64   // poll interval of the epilogue warps' "I am ahead" waits (tau_empty, pg_full, q_full, xp_empty)
 #endif
+#ifndef GPODE_BT_A_TMEM
+#define GPODE_BT_A_TMEM 1   // 1: the state operand of theta (X_h | X_l | block scales) is read from tensor memory instead of shared memory:
+                            //    the kernel is bound by the L1 / shared-memory data pipe (97.6 % busy), and this operand, constant through an
+                            //    evaluation, was re-read from shared memory by all four theta MMAs of every item (16 KB per item; 31.5 -> 31.0 ms)
+#endif
+constexpr int kBtACol = 448;                   // tensor-memory columns of that operand: 8 (X_h) + 8 (X_l) + 8 (scales)
 #ifndef GPODE_BT_EXP
 #define GPODE_BT_EXP 0   // timing experiments only (wrong results): 1 no PG MMAs, 2 no Q MMAs, 4 no transcendentals, 8 no tau stores, 16 no theta MMAs, 32 no proxy fence after the tau stores
 #endif
@@ -81,6 +87,22 @@ __device__ __forceinline__ void tcu_mma_f16(uint32_t d, uint64_t a, uint64_t b, 
 __device__ __forceinline__ void tcu_mma_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b),
                "r"(idesc), "r"(acc)
+               : "memory");
+}
+// A operand from tensor memory (rows = lanes), B from shared memory
+__device__ __forceinline__ void tcu_mma_f16_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem),
+               "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void tcu_mma_tf32_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem),
+               "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),
+               "r"(r[6]), "r"(r[7])
                : "memory");
 }
 __device__ __forceinline__ void tcu_commit(uint32_t bar) {
@@ -348,6 +370,7 @@ struct RbfTcBwdPolicy {
       }
       float sn, inv;
       rbf_pow2_scale(mx, sn, inv);
+#if !GPODE_BT_A_TMEM
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t hh[4], ll[4];
@@ -363,6 +386,27 @@ struct RbfTcBwdPolicy {
         sts128(sm.sb + kBtOffA + 4096 + c * 2048 + tid * 16, ll[0], ll[1], ll[2], ll[3]);
       }
       sts128(sm.sb + kBtOffA + 8192 + tid * 16, __float_as_uint(sn), __float_as_uint(sn), 0u, 0u);
+#endif
+#if GPODE_BT_A_TMEM
+      {   // this state's operand row into tensor memory (lane = state): fp16 pairs of X_h, of X_l, then the tf32 row (s_n, s_n, 0 ..)
+        uint32_t th_[8], tl_[8], ts_[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v0 = xv[2 * i] * sn, v1 = xv[2 * i + 1] * sn;
+          const __half2 h = __floats2half2_rn(v0, v1);
+          const __half2 lo_ = __floats2half2_rn(v0 - __low2float(h), v1 - __high2float(h));
+          th_[i] = *reinterpret_cast<const uint32_t*>(&h);
+          tl_[i] = *reinterpret_cast<const uint32_t*>(&lo_);
+          ts_[i] = i < 2 ? __float_as_uint(sn) : 0u;
+        }
+        const uint32_t ta_ = sm.tmem + kBtACol + (static_cast<uint32_t>((tid >> 5) * 32) << 16);
+        tc_st8(ta_, th_);
+        tc_st8(ta_ + 8, tl_);
+        tc_st8(ta_ + 16, ts_);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      }
+#endif
     }
     if (tid < kBtEpi) {
       // the upstream gradient of this evaluation goes to shared memory here (the item loop below must not hold global loads in flight:
@@ -452,10 +496,18 @@ struct RbfTcBwdPolicy {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = sm.tmem + slot * kTcbUnits, bt = aTh + slot * kTcbThBytes;
         if (!(GPODE_BT_EXP & 16)) {
+#if GPODE_BT_A_TMEM
+        tcu_mma_f16_ts(d, sm.tmem + kBtACol, tc_desc2(bt, 2048, 128), id_th, 0u);                      // X_h G_h
+        tcu_mma_f16_ts(d, sm.tmem + kBtACol + 8, tc_desc2(bt, 2048, 128), id_th, 1u);                  // X_l G_h
+        tcu_mma_f16_ts(d, sm.tmem + kBtACol, tc_desc2(bt + 4096, 2048, 128), id_th, 1u);               // X_h G_l
+        tcu_mma_tf32_ts(d, sm.tmem + kBtACol + 16, tc_desc2(bt + 8192, 2048, 128), id_off, 1u);        // (s_n, s_n) x (off_h, off_l)
+        (void)aA;
+#else
         tcu_mma_f16(d, tc_desc2(aA, 2048, 128), tc_desc2(bt, 2048, 128), id_th, 0u);                    // X_h G_h
         tcu_mma_f16(d, tc_desc2(aA + 4096, 2048, 128), tc_desc2(bt, 2048, 128), id_th, 1u);            // X_l G_h
         tcu_mma_f16(d, tc_desc2(aA, 2048, 128), tc_desc2(bt + 4096, 2048, 128), id_th, 1u);            // X_h G_l
         tcu_mma_tf32(d, tc_desc2(aA + 8192, 2048, 128), tc_desc2(bt + 8192, 2048, 128), id_off, 1u);   // (s_n, s_n) x (off_h, off_l)
+#endif
         }
         tcu_commit(acc_full(sm, slot));
         tcu_commit(th_empty(sm, slot));
