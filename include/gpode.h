@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GPODE_VERSION 210 /* major*100 + minor */
+#define GPODE_VERSION 211 /* major*100 + minor */
 
 /* kernel variants (core/kernels.py: RBF dimwise=False / dimwise=True :29-195, DivergenceFreeKernel :201-393) */
 enum { GPODE_RBF_SHARED = 0, GPODE_RBF_DIMWISE = 1, GPODE_DF = 2 };
@@ -104,6 +104,12 @@ const char* gpode_error_string(int code);
 #define GPODE_FWD_MMA 1    /* warp-level tensor path (mma.sync) */
 #define GPODE_FWD_TCGEN05 2 /* tcgen05.mma with the accumulators in tensor memory */
 int gpode_forward_kernel(const GpodeProblem* p);
+/* Small batches (N * L <= 148 x 32 states -- the shapes the reference trains at): the sweep kernels give 32 states to a CTA of several
+ * warps and split the work of an evaluation over a thread-block cluster (RBF: the output dimensions; divergence-free kernel: the rows
+ * of every streamed chunk), all-gathering the results through distributed shared memory.  Returns the cluster size such a problem is
+ * launched with (1 ... 8; 1 also for batches that fill the chip, where every state already has its own thread), < 0 on error.
+ * Shapes decide; no CUDA call is made. */
+int gpode_cluster_size(const GpodeProblem* p);
 
 /* bytes of scratch the calls below need for this problem (T, method only matter for the rollout).
  * `workspace` must be 256-byte aligned and is clobbered by every call. */

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert sorted(_lib.EXPORTS) == declared
     L = _lib.load()
-    assert L.gpode_version() == 210
+    assert L.gpode_version() == 211
     assert b"NULL" in L.gpode_error_string(-1)
     # argument checking happens before any CUDA call: NULL problem -> 0 bytes / error code
     assert L.gpode_workspace_bytes(None, 16, 2) == 0
@@ -51,6 +51,29 @@ def test_forward_kernel_selection(monkeypatch):
     assert kind("df", 1048576, 1, 6, 256, 256) == 0
     assert kind("rbf_dimwise", 65536, 8, 16, 512, 256, _lib.FLAG_FWD_MMA) == 1
     assert kind("rbf_dimwise", 65536, 8, 16, 300, 100, _lib.FLAG_FWD_TCGEN05) == 2
+
+
+def test_small_batch_cluster_size():
+    """small batches split an evaluation over a thread-block cluster (RBF: output dimensions, DF: rows of every chunk); the size depends
+    on shapes only: as many CTAs per block of 32 states as fit the chip once, at most 8 (and at most D_out for RBF)"""
+    from gpode_b200 import _lib
+    L = _lib.load()
+
+    def csize(variant, N, Lm, D_in, D_out, M, S):
+        p = _lib.GpodeProblem()
+        p.variant, p.L, p.N, p.D_in, p.D_out, p.M, p.S = _lib.VARIANTS[variant], Lm, N, D_in, D_out, M, S
+        return L.gpode_cluster_size(ctypes.byref(p))
+
+    assert L.gpode_cluster_size(None) < 0
+    assert csize("rbf_dimwise", 25, 1, 6, 6, 100, 256) == 6        # config 1: one block of states, six outputs
+    assert csize("rbf_dimwise", 50, 1, 6, 3, 100, 256) == 3        # config 3 (order 2): three outputs
+    assert csize("rbf_dimwise", 25, 1, 6, 12, 20, 64) == 8         # capped at the portable cluster size
+    assert csize("rbf_dimwise", 25, 1, 16, 16, 100, 256) == 1      # 410 KB of parameter rows do not fit a CTA: not the small-batch policy
+    assert csize("rbf_dimwise", 1024, 4, 6, 6, 100, 256) == 1      # 128 blocks of 32 states: the chip is full already
+    assert csize("rbf_dimwise", 65536, 8, 16, 16, 512, 256) == 1   # config 5: not a small batch
+    assert csize("df", 256, 4, 6, 6, 100, 256) == 4                # config 2: 32 blocks of states x 4 fit 148 SMs
+    assert csize("df", 25, 1, 6, 6, 100, 256) == 8
+    assert csize("df", 1048576, 1, 6, 6, 256, 256) == 1
 
 
 def test_state_dict_keys_match_reference():

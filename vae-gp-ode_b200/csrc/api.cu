@@ -260,6 +260,17 @@ int gpode_forward_kernel(const GpodeProblem* p) {
   return (g.DP > 8 && rbf_fwd_use_mma(g)) ? GPODE_FWD_MMA : GPODE_FWD_FFMA;
 }
 
+int gpode_cluster_size(const GpodeProblem* p) {
+  if (!p) return GPODE_E_NULL;
+  if (p->N < 1 || p->L < 1 || p->D_out < 1) return GPODE_E_SHAPE;
+  if (p->variant == GPODE_DF) {
+    const DfGeom g = df_geom(p);
+    return df_use_small(g) ? df_cluster(g, 32) : 1;
+  }
+  const RbfGeom g = rbf_geom(p, 1);
+  return rbf_use_small(g) ? rbf_small_cluster(g) : 1;
+}
+
 const char* gpode_error_string(int code) {
   switch (code) {
     case GPODE_OK: return "ok";

@@ -99,6 +99,9 @@ cudaError_t df_launch_rollout_bwd(const DfRolloutBwdArgs& a, cudaStream_t st);
 cudaError_t df_launch_pgrad(const DfPgradArgs& a, cudaStream_t st);
 cudaError_t df_launch_pack(const DfPackArgs& a, cudaStream_t st);
 cudaError_t df_launch_finalize(const DfFinalizeArgs& a, cudaStream_t st);
+constexpr int kDfSmallW = 8;   // warps per 32 states of the small-batch instantiation DfPolicy<D, 1, kDfSmallW>
+// small batch: fewer states than one warp per SM can cover -- rows are split over the warps of a CTA and over a cluster instead
+inline bool df_use_small(const DfGeom& g) { return static_cast<long>(g.N) * g.L <= 148L * 32; }
 int df_smem_bytes(const DfGeom& g, int threads, int R, bool bwd, bool cluster = true, int W = 0);
 int df_cluster(const DfGeom& g, int states_per_cta);
 

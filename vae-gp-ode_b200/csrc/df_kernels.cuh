@@ -667,9 +667,6 @@ __global__ void __launch_bounds__(kDfPgThreads, 4) k_df_pgrad(const DfPgradArgs 
   }
 }
 
-constexpr int kDfSmallW = 8;   // warps per 32 states of the small-batch instantiation DfPolicy<D, 1, kDfSmallW>
-// small batch: fewer states than one warp per SM can cover -- rows are split over the warps of a CTA and over a cluster instead
-inline bool df_use_small(const DfGeom& g) { return static_cast<long>(g.N) * g.L <= 148L * 32; }
 // launch-shape heuristic of the DF sweep kernels (states per CTA = 128 * R)
 inline void df_pick_shape(const DfGeom& g, bool bwd, int& threads, int& R) {
   const long want = 2L * 148;

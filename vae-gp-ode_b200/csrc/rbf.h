@@ -181,6 +181,27 @@ inline void rbf_pgrad_mma_shape(const RbfGeom& g, int& MT, int& n_mblk) {
   const int per_cta = 128 * MT;
   n_mblk = (2 * g.MP2 + per_cta - 1) / per_cta;
 }
+// ---- small-batch policy (rbf_small.cuh): host-side geometry, shared with the ABI's launch-plan query ----
+constexpr int kSmWarps = 16;
+constexpr int kSmThreads = kSmWarps * 32;
+constexpr int kSmStates = 32;
+constexpr int kSmMaxCluster = 8;   // portable cluster size
+inline int rbf_small_smem_bytes(const RbfGeom& g) {
+  return (g.D_out * (g.SP2 + g.MP2) * g.row_floats + g.D_out * g.hdr_floats + 2 * g.DP * kSmStates + 2 * kSmWarps * (g.DP + 2) * kSmStates +
+          g.D_out * (g.DP + 1) + g.D_out * kSmStates + 2 * g.D_out * 2 * kSmStates + 2 * kSmMaxCluster * g.DP * kSmStates + 8) * 4;
+}
+// small batch and a parameter set that fits in shared memory next to the exchange buffers
+inline bool rbf_use_small(const RbfGeom& g) {
+  return static_cast<long>(g.N) * g.L <= 148L * 32 && rbf_small_smem_bytes(g) <= 200 * 1024;
+}
+// cluster size of a small-batch launch: as many CTAs per state block as there are outputs (<= 8), while the whole launch fits the chip
+inline int rbf_small_cluster(const RbfGeom& g) {
+  const long ctas = static_cast<long>((g.N + kSmStates - 1) / kSmStates) * g.L;
+  long c = g.D_out < kSmMaxCluster ? g.D_out : kSmMaxCluster;
+  if (c * ctas > 148) c = 148 / ctas;
+  return c < 1 ? 1 : static_cast<int>(c);
+}
+
 // launchers (one per DP instantiation unit); return cudaGetLastError()
 cudaError_t rbf_launch_field_fwd(const RbfFieldFwdArgs& a, cudaStream_t st);
 cudaError_t rbf_launch_field_bwd(const RbfFieldBwdArgs& a, cudaStream_t st);

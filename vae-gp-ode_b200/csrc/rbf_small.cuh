@@ -20,10 +20,6 @@
 
 namespace gpode {
 
-constexpr int kSmWarps = 16;
-constexpr int kSmThreads = kSmWarps * 32;
-constexpr int kSmStates = 32;
-constexpr int kSmMaxCluster = 8;   // portable cluster size
 
 __device__ __forceinline__ void cluster_sync_all() {   // release / acquire at cluster scope: orders shared::cluster and global accesses
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -47,22 +43,6 @@ struct SmallSmem {
   float* dxp;    // [2][kSmMaxCluster][DP][32] all-gathered partial J^T g
   int ev;        // running evaluation counter of this CTA (buffer parity)
 };
-
-inline int rbf_small_smem_bytes(const RbfGeom& g) {
-  return (g.D_out * (g.SP2 + g.MP2) * g.row_floats + g.D_out * g.hdr_floats + 2 * g.DP * kSmStates + 2 * kSmWarps * (g.DP + 2) * kSmStates +
-          g.D_out * (g.DP + 1) + g.D_out * kSmStates + 2 * g.D_out * 2 * kSmStates + 2 * kSmMaxCluster * g.DP * kSmStates + 8) * 4;
-}
-// small batch and a parameter set that fits in shared memory next to the exchange buffers
-inline bool rbf_use_small(const RbfGeom& g) {
-  return static_cast<long>(g.N) * g.L <= 148L * 32 && rbf_small_smem_bytes(g) <= 200 * 1024;
-}
-// cluster size of a small-batch launch: as many CTAs per state block as there are outputs (<= 8), while the whole launch fits the chip
-inline int rbf_small_cluster(const RbfGeom& g) {
-  const long ctas = static_cast<long>((g.N + kSmStates - 1) / kSmStates) * g.L;
-  long c = g.D_out < kSmMaxCluster ? g.D_out : kSmMaxCluster;
-  if (c * ctas > 148) c = 148 / ctas;
-  return c < 1 ? 1 : static_cast<int>(c);
-}
 
 template <int DP_>
 struct RbfSmallPolicy {

@@ -27,7 +27,7 @@ class GpodeParamGrads(ctypes.Structure):
     _fields_ = [("d_Z", _fp), ("d_ell", _fp), ("d_var", _fp), ("d_nu", _fp), ("d_B", _fp)]
 
 
-EXPORTS = ["gpode_version", "gpode_error_string", "gpode_forward_kernel", "gpode_workspace_bytes", "gpode_rollout_save_floats",
+EXPORTS = ["gpode_version", "gpode_error_string", "gpode_forward_kernel", "gpode_cluster_size", "gpode_workspace_bytes", "gpode_rollout_save_floats",
            "gpode_field_fwd", "gpode_field_bwd", "gpode_rollout_fwd", "gpode_rollout_bwd",
            "gpode_nu_workspace_bytes", "gpode_nu_save_floats", "gpode_compute_nu_fwd", "gpode_compute_nu_bwd",
            "gpode_inducing_sample_fwd", "gpode_inducing_sample_bwd", "gpode_kl_fwd", "gpode_kl_bwd",
@@ -53,6 +53,8 @@ def load():
     lib.gpode_error_string.argtypes = [i32]
     lib.gpode_forward_kernel.restype = i32
     lib.gpode_forward_kernel.argtypes = [P]
+    lib.gpode_cluster_size.restype = i32
+    lib.gpode_cluster_size.argtypes = [P]
     lib.gpode_workspace_bytes.restype = sz
     lib.gpode_workspace_bytes.argtypes = [P, i32, i32]
     lib.gpode_rollout_save_floats.restype = sz
